@@ -1,0 +1,285 @@
+"""CPU oracle for the DSAC-T update path.  TEST INFRASTRUCTURE, NOT PRODUCT.
+
+Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s CPU-baseline /
+`--impl reference` legs may import this module; the product path
+(`dsac-v2_b200/`) never does and fails loudly without its CUDA library.
+
+What it is: a restatement, in plain torch-CPU tensor algebra (fp32 by default,
+fp64 on request), of what one `DSAC_V2.local_update(data, iteration)` of the
+reference computes.  Each function cites the reference lines it follows
+(paths relative to the reference checkout).  Gradients come from torch
+autograd on the restated losses, exactly as the reference obtains them; the
+Adam/Polyak arithmetic is written out by hand (the reference delegates it to
+`torch.optim.Adam`, dsac_v2.py:54-59 — not vendored; formulas below are the
+single-tensor path of torch 2.11 `optim/adam.py`).
+
+Parity status: PINNED.  `tests/test_oracle_golden.py` checks this oracle
+against fixtures produced by running the unmodified reference in the build
+container (`tests/golden/make_golden.py`): all 14 deterministic `tb_info`
+scalars for up to 100 consecutive updates, gradient and parameter digests, and
+for the small cases every parameter of the post-update state.
+
+Noise is an explicit input: `noise = [eps1[B,A], eps2[B,A], z1..z6[B]]`, the
+eight standard-normal draws one update consumes (dsac_v2.py:160,228 and the
+six `__q_evaluate` calls at :230,:231,:245,:249,:306,:307).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Sequence
+
+import torch
+import torch.nn.functional as F
+
+EPS = 1e-6  # utils/act_distribution_cls.py:3
+HUBER_DELTA = 50.0  # dsac_v2.py:282-287
+STD_BIAS = 0.1  # dsac_v2.py:277
+ADAM_B1, ADAM_B2, ADAM_EPS = 0.9, 0.999, 1e-8  # torch.optim.Adam defaults (dsac_v2.py:54-59)
+
+TB_KEYS = [
+    "DSAC2/critic_avg_q1-RL iter",
+    "DSAC2/critic_avg_q2-RL iter",
+    "DSAC2/critic_avg_std1-RL iter",
+    "DSAC2/critic_avg_std2-RL iter",
+    "DSAC2/critic_avg_min_std1-RL iter",
+    "DSAC2/critic_avg_min_std2-RL iter",
+    "Loss/Actor loss-RL iter",
+    "Loss/Critic loss-RL iter",
+    "DSAC2/policy_mean-RL iter",
+    "DSAC2/policy_std-RL iter",
+    "DSAC2/entropy-RL iter",
+    "DSAC2/alpha-RL iter",
+    "DSAC2/mean_std1",
+    "DSAC2/mean_std2",
+]
+
+_ACT = {
+    "gelu": F.gelu,  # nn.GELU() exact erf, utils/common_utils.py:26-27
+    "relu": F.relu,
+    "elu": F.elu,
+    "selu": F.selu,
+    "sigmoid": torch.sigmoid,
+    "tanh": torch.tanh,
+    "linear": lambda x: x,
+}
+
+
+def mlp_forward(layers: Sequence[torch.Tensor], x: torch.Tensor, act: str) -> torch.Tensor:
+    """networks/mlp.py:15-20 — Linear+act per hidden layer, Identity on the last."""
+    n = len(layers) // 2
+    for j in range(n):
+        x = F.linear(x, layers[2 * j], layers[2 * j + 1])
+        if j < n - 1:
+            x = _ACT[act](x)
+    return x
+
+
+def huber(x: torch.Tensor, y: torch.Tensor, delta: float = HUBER_DELTA) -> torch.Tensor:
+    """torch.nn.functional.huber_loss(reduction='none') as used at dsac_v2.py:282-287."""
+    d = x - y
+    a = d.abs()
+    return torch.where(a <= delta, 0.5 * d * d, delta * (a - 0.5 * delta))
+
+
+class OracleDSACT:
+    """State + one-update arithmetic of the reference's ApproxContainer/DSAC_V2."""
+
+    NETS = ("q1", "q2", "policy")
+
+    def __init__(self, obs_dim: int, act_dim: int, hidden_q, hidden_pi, act_high, act_low,
+                 weights: Dict[str, "torch.Tensor"], *, gamma=0.99, tau=0.005, tau_b=None,
+                 delay_update=2, auto_alpha=True, alpha=0.2, value_learning_rate=1e-4,
+                 policy_learning_rate=1e-4, alpha_learning_rate=3e-4,
+                 policy_min_log_std=-20.0, policy_max_log_std=0.5, hidden_activation="gelu",
+                 dtype=torch.float32, **_ignored):
+        self.O, self.A = int(obs_dim), int(act_dim)
+        self.dtype = dtype
+        self.act = hidden_activation
+        self.gamma, self.tau = float(gamma), float(tau)
+        self.tau_b = float(tau if tau_b is None else tau_b)  # dsac_v2.py:90
+        self.delay_update = int(delay_update)
+        self.auto_alpha, self.alpha_fixed = bool(auto_alpha), float(alpha)
+        self.target_entropy = -float(act_dim)  # dsac_v2.py:84
+        self.lr = {"q1": value_learning_rate, "q2": value_learning_rate,
+                   "policy": policy_learning_rate, "log_alpha": alpha_learning_rate}
+        self.min_log_std, self.max_log_std = float(policy_min_log_std), float(policy_max_log_std)
+        self.hi = torch.as_tensor(act_high, dtype=dtype).reshape(-1)
+        self.lo = torch.as_tensor(act_low, dtype=dtype).reshape(-1)
+        nq, npi = len(hidden_q) + 1, len(hidden_pi) + 1
+        inner = {"q1": "q", "q2": "q", "policy": "policy"}
+
+        def grab(net, n_layers):
+            out = []
+            for j in range(n_layers):
+                for leaf in ("weight", "bias"):
+                    w = weights[f"{net}.{inner[net.replace('_target', '')]}.{2 * j}.{leaf}"]
+                    out.append(torch.as_tensor(w).detach().clone().to(dtype))
+            return out
+
+        self.p = {"q1": grab("q1", nq), "q2": grab("q2", nq), "policy": grab("policy", npi)}
+        self.t = {"q1": grab("q1_target", nq), "q2": grab("q2_target", nq),
+                  "policy": grab("policy_target", npi)}
+        la = weights.get("log_alpha", 1.0)  # dsac_v2.py:51
+        self.log_alpha = torch.as_tensor(la, dtype=dtype).reshape(()).clone()
+        for group in self.p.values():
+            for w in group:
+                w.requires_grad_(True)
+        self.log_alpha.requires_grad_(True)
+        # Adam state (exp_avg, exp_avg_sq, step) per optimizer, dsac_v2.py:54-59
+        self.m = {k: [torch.zeros_like(w) for w in v] for k, v in self.p.items()}
+        self.v = {k: [torch.zeros_like(w) for w in v] for k, v in self.p.items()}
+        self.m["log_alpha"], self.v["log_alpha"] = [torch.zeros((), dtype=dtype)], [torch.zeros((), dtype=dtype)]
+        self.steps = {"q1": 0, "q2": 0, "policy": 0, "log_alpha": 0}
+        self.mean_std = [None, None]  # dsac_v2.py:88-89 (-1.0 sentinel)
+        self.grads: Dict[str, List[torch.Tensor]] = {}
+
+    # ---- network pieces -------------------------------------------------
+    def policy_logits(self, layers, obs):
+        """StochaPolicy.forward, std_type='mlp_shared' (networks/mlp.py:85-100)."""
+        out = mlp_forward(layers, obs, self.act)
+        mean, log_std = torch.chunk(out, 2, dim=-1)
+        return mean, torch.clamp(log_std, self.min_log_std, self.max_log_std).exp()
+
+    def q_dist(self, layers, obs, act):
+        """ActionValueDistri.forward (networks/mlp.py:122-127): mean, softplus(std)."""
+        out = mlp_forward(layers, torch.cat([obs, act], dim=-1), self.act)
+        return out[..., 0], F.softplus(out[..., 1])
+
+    def tanh_gauss_rsample(self, mean, std, eps):
+        """TanhGaussDistribution.rsample (utils/act_distribution_cls.py:44-54)."""
+        u = mean + std * eps
+        t = torch.tanh(u)
+        scale, shift = (self.hi - self.lo) / 2, (self.hi + self.lo) / 2
+        gauss = (-((u - mean) ** 2) / (2 * std ** 2) - std.log() - math.log(math.sqrt(2 * math.pi))).sum(-1)
+        logp = gauss - torch.log(1 + EPS - t.pow(2)).sum(-1) - torch.log(scale).sum(-1)
+        return scale * t + shift, logp
+
+    def alpha(self) -> float:
+        """__get_alpha(requires_grad=False), dsac_v2.py:140-148."""
+        return float(self.log_alpha.detach().exp()) if self.auto_alpha else self.alpha_fixed
+
+    # ---- one update -----------------------------------------------------
+    def compute_gradients(self, batch: Dict[str, torch.Tensor], noise) -> Dict[str, float]:
+        """__compute_gradient (dsac_v2.py:150-206) with explicit noise."""
+        c = lambda x: torch.as_tensor(x).to(self.dtype)
+        obs, act, rew, obs2, done = (c(batch[k]) for k in ("obs", "act", "rew", "obs2", "done"))
+        eps1, eps2, _z1, _z2, z3, z4 = (c(n) for n in noise[:6])
+        B = obs.shape[0]
+        P, T = self.p, self.t
+        alpha = self.alpha()
+
+        # actor sample (dsac_v2.py:154-161)
+        mean, std = self.policy_logits(P["policy"], obs)
+        new_act, new_logp = self.tanh_gauss_rsample(mean, std, eps1)
+
+        # ---- critic loss (__compute_loss_q, dsac_v2.py:218-290)
+        with torch.no_grad():
+            mean2, std2 = self.policy_logits(T["policy"], obs2)
+            act2, logp2 = self.tanh_gauss_rsample(mean2, std2, eps2)
+        q1, s1 = self.q_dist(P["q1"], obs, act)
+        q2, s2 = self.q_dist(P["q2"], obs, act)
+        for k, s in enumerate((s1, s2)):  # dsac_v2.py:233-241
+            batch_mean = s.detach().mean()
+            self.mean_std[k] = batch_mean if self.mean_std[k] is None else \
+                (1 - self.tau_b) * self.mean_std[k] + self.tau_b * batch_mean
+        with torch.no_grad():
+            q1n, s1n = self.q_dist(T["q1"], obs2, act2)
+            q2n, s2n = self.q_dist(T["q2"], obs2, act2)
+            q1n_s = q1n + torch.clamp(z3, -3, 3) * s1n  # __q_evaluate, dsac_v2.py:208-216
+            q2n_s = q2n + torch.clamp(z4, -3, 3) * s2n
+            qn = torch.min(q1n, q2n)
+            qn_s = torch.where(q1n < q2n, q1n_s, q2n_s)  # dsac_v2.py:252-253
+            # __compute_target_q, dsac_v2.py:292-302
+            y = rew + (1 - done) * self.gamma * (qn - alpha * logp2)
+            y_s = rew + (1 - done) * self.gamma * (qn_s - alpha * logp2)
+        loss_q = 0.0
+        for q, s, m in ((q1, s1, self.mean_std[0]), (q2, s2, self.mean_std[1])):
+            qd = q.detach()
+            yb = qd + torch.clamp(y_s - qd, -3 * m, 3 * m)
+            sd = torch.clamp(s, min=0.0).detach()
+            ratio = (m.pow(2) / (sd.pow(2) + STD_BIAS)).clamp(min=0.1, max=10)  # dsac_v2.py:279-280
+            loss_q = loss_q + torch.mean(ratio * (huber(q, y) + s * (sd.pow(2) - huber(qd, yb)) / (sd + STD_BIAS)))
+        gq = torch.autograd.grad(loss_q, P["q1"] + P["q2"])
+        n1 = len(P["q1"])
+        self.grads = {"q1": list(gq[:n1]), "q2": list(gq[n1:])}
+
+        # ---- actor loss (__compute_loss_policy, dsac_v2.py:304-310); no grad to Q params (:168-181)
+        q1p, _ = self.q_dist([w.detach() for w in P["q1"]], obs, new_act)
+        q2p, _ = self.q_dist([w.detach() for w in P["q2"]], obs, new_act)
+        loss_pi = (alpha * new_logp - torch.min(q1p, q2p)).mean()
+        self.grads["policy"] = list(torch.autograd.grad(loss_pi, P["policy"]))
+        entropy = -new_logp.detach().mean()
+
+        # ---- temperature loss (__compute_loss_alpha, dsac_v2.py:312-318)
+        if self.auto_alpha:
+            loss_alpha = -self.log_alpha * (new_logp.detach() + self.target_entropy).mean()
+            self.grads["log_alpha"] = list(torch.autograd.grad(loss_alpha, [self.log_alpha]))
+
+        vals = [q1.detach().mean(), q2.detach().mean(), s1.detach().mean(), s2.detach().mean(),
+                s1.detach().min(), s2.detach().min(), loss_pi.detach(), loss_q.detach(),
+                torch.tanh(mean).mean().detach(), std.mean().detach(), entropy, alpha,
+                self.mean_std[0], self.mean_std[1]]  # dsac_v2.py:188-202
+        return {k: float(v) for k, v in zip(TB_KEYS, vals)}
+
+    def _adam(self, name, params, grads):
+        """torch.optim.Adam single-tensor step (amsgrad/weight_decay off)."""
+        self.steps[name] += 1
+        t = self.steps[name]
+        bc1, bc2 = 1 - ADAM_B1 ** t, 1 - ADAM_B2 ** t
+        step_size, bc2_sqrt = self.lr[name] / bc1, math.sqrt(bc2)
+        with torch.no_grad():
+            for w, g, m, v in zip(params, grads, self.m[name], self.v[name]):
+                m.lerp_(g, 1 - ADAM_B1)
+                v.mul_(ADAM_B2).addcmul_(g, g, value=1 - ADAM_B2)
+                denom = (v.sqrt() / bc2_sqrt).add_(ADAM_EPS)
+                w.addcdiv_(m, denom, value=-step_size)
+
+    def apply(self, iteration: int) -> None:
+        """__update (dsac_v2.py:320-347)."""
+        self._adam("q1", self.p["q1"], self.grads["q1"])
+        self._adam("q2", self.p["q2"], self.grads["q2"])
+        if iteration % self.delay_update == 0:
+            self._adam("policy", self.p["policy"], self.grads["policy"])
+            if self.auto_alpha:
+                self._adam("log_alpha", [self.log_alpha], self.grads["log_alpha"])
+            with torch.no_grad():
+                polyak = 1 - self.tau
+                for net in self.NETS:
+                    for w, wt in zip(self.p[net], self.t[net]):
+                        wt.mul_(polyak)
+                        wt.add_((1 - polyak) * w)
+
+    def update(self, batch, noise, iteration: int) -> Dict[str, float]:
+        """local_update (dsac_v2.py:102-105)."""
+        tb = self.compute_gradients(batch, noise)
+        self.apply(iteration)
+        return tb
+
+    # ---- views in the reference's state_dict schema ----------------------
+    def state_dict(self) -> Dict[str, torch.Tensor]:
+        inner = {"q1": "q", "q2": "q", "policy": "policy"}
+        out = {"log_alpha": self.log_alpha.detach()}
+        for net in self.NETS:
+            for group, suffix in ((self.p, ""), (self.t, "_target")):
+                for i, w in enumerate(group[net]):
+                    leaf = "weight" if i % 2 == 0 else "bias"
+                    out[f"{net}{suffix}.{inner[net]}.{2 * (i // 2)}.{leaf}"] = w.detach()
+        return out
+
+    def grad_dict(self) -> Dict[str, torch.Tensor]:
+        inner = {"q1": "q", "q2": "q", "policy": "policy"}
+        out = {}
+        for net in self.NETS:
+            for i, g in enumerate(self.grads[net]):
+                leaf = "weight" if i % 2 == 0 else "bias"
+                out[f"{net}.{inner[net]}.{2 * (i // 2)}.{leaf}"] = g
+        if "log_alpha" in self.grads:
+            out["log_alpha"] = self.grads["log_alpha"][0]
+        return out
+
+
+def from_config(cfg: dict, weights: dict, **hyper) -> OracleDSACT:
+    """Build from a `synth.CONFIGS` entry (+ `synth.HYPER`-style overrides)."""
+    lim = [cfg["act_lim"]] * cfg["act_dim"]
+    return OracleDSACT(cfg["obs_dim"], cfg["act_dim"], cfg["hidden"], cfg["hidden"], lim,
+                       [-x for x in lim], weights, **hyper)

@@ -1,0 +1,16 @@
+from typing import TypeVar
+
+ObsType = TypeVar("ObsType")
+ActType = TypeVar("ActType")
+
+
+class Env:
+    pass
+
+
+class Wrapper(Env):
+    def __init__(self, env):
+        self.env = env
+
+    def __getattr__(self, name):
+        return getattr(self.env, name)
