@@ -1,0 +1,803 @@
+// libdsact.so — host side of the B200-native DSAC-T update engine (C ABI in include/dsact.h).
+//
+// Orchestrates one `DSAC_V2.local_update` (reference dsac_v2.py:102-105,150-347) as a fixed sequence of
+// kernel launches on caller-owned flat fp32 buffers, optionally captured once into a CUDA graph and
+// replayed.  No CPU fallback: every entry point needs a CUDA device.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../include/dsact.h"
+#include "gemm_simt.cuh"
+#include "kernels.cuh"
+
+using namespace dsact;
+
+static thread_local char g_err[512] = "";
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define CUDA_TRY(x)                                                                       \
+  do {                                                                                    \
+    cudaError_t e_ = (x);                                                                 \
+    if (e_ != cudaSuccess) return fail(DSACT_ECUDA, "%s failed: %s", #x, cudaGetErrorString(e_)); \
+  } while (0)
+
+// ---- network geometry -------------------------------------------------------
+struct Net {
+  int L;                                   // hidden layers
+  int s[DSACT_MAX_HIDDEN + 2];             // s[0] input, s[1..L] hidden, s[L+1] output
+  int64_t w[DSACT_MAX_HIDDEN + 1], b[DSACT_MAX_HIDDEN + 1], n;  // offsets inside the net, total floats
+  void build(int in, const int32_t* hidden, int L_, int out) {
+    L = L_;
+    s[0] = in;
+    for (int j = 0; j < L; ++j) s[j + 1] = hidden[j];
+    s[L + 1] = out;
+    n = 0;
+    for (int j = 0; j <= L; ++j) {
+      w[j] = n; n += (int64_t)s[j + 1] * s[j];
+      b[j] = n; n += s[j + 1];
+    }
+  }
+};
+
+static int64_t round64(int64_t x) { return (x + 63) / 64 * 64; }
+
+// activation arena, all offsets in floats from the workspace base
+struct Arena {
+  int64_t obs, obs2, act, rew, done, logp, idx;    // gathered minibatch + int64 indices
+  int64_t eps1, eps2, z3, z4;                      // device-generated noise
+  int64_t zP[DSACT_MAX_HIDDEN], hP[DSACT_MAX_HIDDEN], hT[DSACT_MAX_HIDDEN], logitsP, logitsT;
+  int64_t new_act, act2, logp_new, logp2;
+  int64_t zQ[6][DSACT_MAX_HIDDEN], hQ[6][DSACT_MAX_HIDDEN], outQ[6];
+  int64_t dOut[6], dzQ[6][DSACT_MAX_HIDDEN], dAct[2], dlogits, dzP[DSACT_MAX_HIDDEN];
+  int64_t total;
+  void build(const dsact_config& c, const Net& q, const Net& pi) {
+    int64_t B = c.max_batch, O = c.obs_dim, A = c.act_dim, off = 0;
+    auto take = [&](int64_t n) { int64_t o = off; off += round64(n); return o; };
+    obs = take(B * O); obs2 = take(B * O); act = take(B * A); rew = take(B); done = take(B); logp = take(B); idx = take(2 * B);
+    eps1 = take(B * A); eps2 = take(B * A); z3 = take(B); z4 = take(B);
+    for (int j = 0; j < pi.L; ++j) { zP[j] = take(B * pi.s[j + 1]); hP[j] = take(B * pi.s[j + 1]); hT[j] = take(B * pi.s[j + 1]); dzP[j] = take(B * pi.s[j + 1]); }
+    logitsP = take(B * 2 * A); logitsT = take(B * 2 * A); dlogits = take(B * 2 * A);
+    new_act = take(B * A); act2 = take(B * A); logp_new = take(B); logp2 = take(B);
+    for (int p = 0; p < 6; ++p) {
+      for (int j = 0; j < q.L; ++j) { zQ[p][j] = take(B * q.s[j + 1]); hQ[p][j] = take(B * q.s[j + 1]); dzQ[p][j] = take(B * q.s[j + 1]); }
+      outQ[p] = take(B * 2); dOut[p] = take(B * 2);
+    }
+    dAct[0] = take(B * A); dAct[1] = take(B * A);
+    total = off;
+  }
+};
+
+struct GraphKey {
+  int kind; const void* p[9]; int32_t batch; int64_t gb; int64_t size; const void* idx;
+  bool operator==(const GraphKey& o) const { return memcmp(this, &o, sizeof(GraphKey)) == 0; }
+};
+struct GraphEntry { GraphKey key; cudaGraphExec_t exec; int launches; uint64_t stamp; };
+
+struct dsact_handle {
+  dsact_config cfg;
+  int device, num_sms;
+  Net q, pi;
+  Arena ar;
+  dsact_buffers buf;
+  dsact_replay rb;
+  bool bound, rb_bound;
+  uint64_t seed;
+  int64_t dev_iter;          // what state[ST_ITER] will hold when the next enqueued work runs (-1 unknown)
+  int32_t pending_batch;     // rows of the shard phase1 processed (phase2 must match)
+  dsact_batch pending;       // batch pointers of phase1
+  const float *pending_eps1, *pending_z3, *pending_z4;  // noise phase1 used (phase2 needs it again)
+  int64_t dev_rb_size;       // what state[ST_RB_SIZE] holds
+  cudaStream_t cap_stream;   // capture-only stream
+  std::vector<GraphEntry> graphs;
+  uint64_t stamp;
+  int64_t launches;
+  int32_t last_launches;
+  float* W() const { return reinterpret_cast<float*>(buf.workspace); }
+};
+
+struct Ctx {
+  cudaStream_t s;
+  int launches;
+  cudaError_t err;
+  void check() { cudaError_t e = cudaGetLastError(); if (e != cudaSuccess && err == cudaSuccess) err = e; }
+};
+
+// ---- GEMM group launch -------------------------------------------------------
+enum { V_FWD = 0, V_DGRAD = 1, V_WGRAD = 2 };
+
+template <int BM, int BN>
+static void launch_variant(const GemmGroup& g, int variant, int grid, Ctx& c) {
+  if (variant == V_FWD) gemm_kernel<BM, BN, true, true><<<grid, 256, 0, c.s>>>(g);
+  else if (variant == V_DGRAD) gemm_kernel<BM, BN, true, false><<<grid, 256, 0, c.s>>>(g);
+  else gemm_kernel<BM, BN, false, false><<<grid, 256, 0, c.s>>>(g);
+  c.launches++;
+  c.check();
+}
+
+static void launch_group(const dsact_handle* h, GemmGroup& g, int variant, Ctx& c) {
+  if (g.n == 0) return;
+  auto count = [&](int T) {
+    int total = 0;
+    for (int i = 0; i < g.n; ++i) total += ((g.p[i].M + T - 1) / T) * ((g.p[i].N + T - 1) / T);
+    return total;
+  };
+  const bool big = variant != V_WGRAD && count(128) >= h->num_sms;
+  const int T = big ? 128 : 64;
+  const int base = count(T);
+  int grid = 0;
+  for (int i = 0; i < g.n; ++i) {
+    GemmProb& p = g.p[i];
+    p.tiles_m = (p.M + T - 1) / T;
+    p.tiles_n = (p.N + T - 1) / T;
+    p.ksplit = 1;
+    if (variant == V_WGRAD) {  // reduction over the batch: split it until ~2 CTAs per SM, >= 4 k-tiles each
+      const int nt = (p.K[0] + KT - 1) / KT;
+      int want = (2 * h->num_sms + base - 1) / base;
+      int maxs = nt / 4 > 0 ? nt / 4 : 1;
+      p.ksplit = want < maxs ? want : maxs;
+      if (p.ksplit < 1) p.ksplit = 1;
+      const int per = (nt + p.ksplit - 1) / p.ksplit;
+      p.ksplit = (nt + per - 1) / per;  // no empty splits
+    }
+    p.tile_start = grid;
+    grid += p.tiles_m * p.tiles_n * p.ksplit;
+  }
+  if (big) launch_variant<128, 128>(g, variant, grid, c);
+  else launch_variant<64, 64>(g, variant, grid, c);
+}
+
+static GemmProb prob_zero() {
+  GemmProb p;
+  memset(&p, 0, sizeof(p));
+  return p;
+}
+
+// forward layer j of `net` with weights at `W`: out = act(in * W_j^T + b_j)
+static GemmProb fwd_prob(const Net& net, const float* Wbase, int j, const float* in0, int ld0, int k0,
+                         const float* in1, int ld1, int k1, float* out, float* zout, int B, int act) {
+  GemmProb p = prob_zero();
+  const float* Wj = Wbase + net.w[j];
+  const int in_dim = net.s[j];
+  p.A[0] = in0; p.lda[0] = ld0; p.K[0] = k0; p.B[0] = Wj; p.ldb[0] = in_dim;
+  if (k1 > 0) { p.A[1] = in1; p.lda[1] = ld1; p.K[1] = k1; p.B[1] = Wj + k0; p.ldb[1] = in_dim; }
+  p.M = B; p.N = net.s[j + 1]; p.C = out; p.ldc = net.s[j + 1];
+  p.bias = Wbase + net.b[j];
+  const bool last = j == net.L;
+  p.epi = last ? EPI_STORE : EPI_BIAS_ACT;
+  p.act = act;
+  p.Zout = last ? nullptr : zout;
+  return p;
+}
+
+// dgrad through layer j: dX[B, s_j] = dY[B, s_{j+1}] * W_j   (optionally * act'(Z_{j-1}) and bias-grad colsum)
+static GemmProb dgrad_prob(const Net& net, const float* Wbase, int j, const float* dY, int col0, int ncols,
+                           float* dX, const float* Zprev, float* gbias_prev, int B, int act) {
+  GemmProb p = prob_zero();
+  p.A[0] = dY; p.lda[0] = net.s[j + 1]; p.K[0] = net.s[j + 1];
+  p.B[0] = Wbase + net.w[j] + col0; p.ldb[0] = net.s[j];
+  p.M = B; p.N = ncols; p.C = dX; p.ldc = ncols;
+  if (Zprev) { p.epi = EPI_DACT; p.Zin = Zprev; p.ldz = ncols; p.colsum = gbias_prev; p.act = act; }
+  else p.epi = EPI_STORE;
+  return p;
+}
+
+// wgrad of layer j columns [col0, col0+ncols): gW[s_{j+1}, cols] += dY^T X
+static GemmProb wgrad_prob(const Net& net, float* Gbase, int j, const float* dY, const float* X, int ldx, int col0,
+                           int ncols, int B) {
+  GemmProb p = prob_zero();
+  p.A[0] = dY; p.lda[0] = net.s[j + 1]; p.K[0] = B;
+  p.B[0] = X; p.ldb[0] = ldx;
+  p.M = net.s[j + 1]; p.N = ncols; p.C = Gbase + net.w[j] + col0; p.ldc = net.s[j];
+  p.epi = EPI_ATOMIC;
+  return p;
+}
+
+// ---- enqueue: pieces of one update ---------------------------------------------
+static void enqueue_phase1(dsact_handle* h, const dsact_batch& bt, const dsact_noise* nz, Ctx& c) {
+  const dsact_config& cf = h->cfg;
+  const Net &q = h->q, &pi = h->pi;
+  const Arena& ar = h->ar;
+  float* W = h->W();
+  const int B = bt.batch, O = cf.obs_dim, A = cf.act_dim;
+  float* P = h->buf.params;
+  float* T = h->buf.targets;
+  const float *Pq[2] = {P, P + q.n}, *Ppi = P + 2 * q.n;
+  const float *Tq[2] = {T, T + q.n}, *Tpi = T + 2 * q.n;
+
+  begin_step_kernel<<<1, 32, 0, c.s>>>(h->buf.state); c.launches++;
+  cudaMemsetAsync(h->buf.grads, 0, sizeof(float) * (2 * q.n + pi.n + 1), c.s);
+
+  const float *eps1, *eps2, *z3, *z4;
+  if (nz) { eps1 = nz->eps1; eps2 = nz->eps2; z3 = nz->z3; z4 = nz->z4; }
+  else {
+    eps1 = W + ar.eps1; eps2 = W + ar.eps2; z3 = W + ar.z3; z4 = W + ar.z4;
+    const int total = (B * A + 1) / 2 * 2 + (B + 1) / 2 * 2;
+    int blocks = (total / 2 + 255) / 256; if (blocks < 1) blocks = 1;
+    noise_kernel<<<blocks, 256, 0, c.s>>>(W + ar.eps1, W + ar.eps2, W + ar.z3, W + ar.z4, B, A, h->seed, h->buf.state);
+    rng_advance_kernel<<<1, 32, 0, c.s>>>(h->buf.state);
+    c.launches += 2;
+  }
+
+  // wave A: pi(obs), pi'(obs2), Q1(s,a), Q2(s,a), layer by layer
+  const int depth = (pi.L > q.L ? pi.L : q.L) + 1;
+  for (int j = 0; j < depth; ++j) {
+    GemmGroup g; g.n = 0;
+    if (j <= pi.L) {
+      const float* inP = j == 0 ? bt.obs : W + ar.hP[j - 1];
+      const float* inT = j == 0 ? bt.obs2 : W + ar.hT[j - 1];
+      float* outP = j == pi.L ? W + ar.logitsP : W + ar.hP[j];
+      float* outT = j == pi.L ? W + ar.logitsT : W + ar.hT[j];
+      g.p[g.n++] = fwd_prob(pi, Ppi, j, inP, pi.s[j], pi.s[j], nullptr, 0, 0, outP, j == pi.L ? nullptr : W + ar.zP[j], B, cf.act_pi);
+      g.p[g.n++] = fwd_prob(pi, Tpi, j, inT, pi.s[j], pi.s[j], nullptr, 0, 0, outT, nullptr, B, cf.act_pi);
+    }
+    if (j <= q.L) {
+      for (int k = 0; k < 2; ++k) {
+        float* out = j == q.L ? W + ar.outQ[k] : W + ar.hQ[k][j];
+        float* z = j == q.L ? nullptr : W + ar.zQ[k][j];
+        if (j == 0) g.p[g.n++] = fwd_prob(q, Pq[k], 0, bt.obs, O, O, bt.act, A, A, out, z, B, cf.act_q);
+        else g.p[g.n++] = fwd_prob(q, Pq[k], j, W + ar.hQ[k][j - 1], q.s[j], q.s[j], nullptr, 0, 0, out, z, B, cf.act_q);
+      }
+    }
+    launch_group(h, g, V_FWD, c);
+  }
+
+  // rsample of both policies (utils/act_distribution_cls.py:44-54)
+  {
+    SampleArgs a;
+    a.logits[0] = W + ar.logitsP; a.logits[1] = W + ar.logitsT;
+    a.eps[0] = eps1; a.eps[1] = eps2;
+    a.act[0] = W + ar.new_act; a.act[1] = W + ar.act2;
+    a.logp[0] = W + ar.logp_new; a.logp[1] = W + ar.logp2;
+    a.hi = h->buf.act_high; a.lo = h->buf.act_low; a.state = h->buf.state;
+    a.B = B; a.A = A; a.min_log_std = (float)cf.min_log_std; a.max_log_std = (float)cf.max_log_std;
+    int blocks = (B + 7) / 8; if (blocks > 4 * h->num_sms) blocks = 4 * h->num_sms;
+    sample_kernel<<<dim3(blocks, 2), 256, 0, c.s>>>(a); c.launches++;
+  }
+
+  // wave B: Q1', Q2' on (s', a') and Q1, Q2 on (s, a~)
+  for (int j = 0; j <= q.L; ++j) {
+    GemmGroup g; g.n = 0;
+    for (int p = 2; p < 6; ++p) {
+      const int k = p & 1;
+      const bool tgt = p < 4;
+      const float* Wn = tgt ? Tq[k] : Pq[k];
+      float* out = j == q.L ? W + ar.outQ[p] : W + ar.hQ[p][j];
+      float* z = (j == q.L || tgt) ? nullptr : W + ar.zQ[p][j];
+      if (j == 0) g.p[g.n++] = fwd_prob(q, Wn, 0, tgt ? bt.obs2 : bt.obs, O, O, tgt ? W + ar.act2 : W + ar.new_act, A, A, out, z, B, cf.act_q);
+      else g.p[g.n++] = fwd_prob(q, Wn, j, W + ar.hQ[p][j - 1], q.s[j], q.s[j], nullptr, 0, 0, out, z, B, cf.act_q);
+    }
+    launch_group(h, g, V_FWD, c);
+  }
+
+  {
+    int blocks = (B + 255) / 256; if (blocks > 2 * h->num_sms) blocks = 2 * h->num_sms;
+    std_sum_kernel<<<blocks, 256, 0, c.s>>>(W + ar.outQ[0], W + ar.outQ[1], B, h->buf.state); c.launches++;
+  }
+  h->pending_eps1 = eps1; h->pending_z3 = z3; h->pending_z4 = z4;
+  c.check();
+}
+
+static void enqueue_phase2(dsact_handle* h, const dsact_batch& bt, int64_t global_batch, Ctx& c) {
+  const dsact_config& cf = h->cfg;
+  const Net &q = h->q, &pi = h->pi;
+  const Arena& ar = h->ar;
+  float* W = h->W();
+  const int B = bt.batch, O = cf.obs_dim, A = cf.act_dim;
+  float* P = h->buf.params;
+  float* G = h->buf.grads;
+  const float *Pq[2] = {P, P + q.n}, *Ppi = P + 2 * q.n;
+  float *Gq[2] = {G, G + q.n}, *Gpi = G + 2 * q.n;
+  const float invB = (float)(1.0 / (double)global_batch);
+
+  ema_kernel<<<1, 32, 0, c.s>>>(h->buf.state, P + 2 * q.n + pi.n, invB, (float)cf.tau_b, cf.auto_alpha, (float)cf.alpha_fixed);
+  c.launches++;
+  {
+    LossArgs a;
+    a.rew = bt.rew; a.done = bt.done;
+    a.z3 = h->pending_z3; a.z4 = h->pending_z4;
+    a.logp2 = W + ar.logp2; a.logp_new = W + ar.logp_new;
+    for (int k = 0; k < 2; ++k) {
+      a.out_q[k] = W + ar.outQ[k]; a.out_qt[k] = W + ar.outQ[2 + k]; a.out_qa[k] = W + ar.outQ[4 + k];
+      a.d_out_q[k] = W + ar.dOut[k]; a.d_out_qa[k] = W + ar.dOut[4 + k];
+      a.gbias_q[k] = Gq[k] + q.b[q.L];
+    }
+    a.state = h->buf.state; a.B = B; a.gamma = (float)cf.gamma; a.inv_global_batch = invB;
+    int blocks = (B + 255) / 256; if (blocks > 2 * h->num_sms) blocks = 2 * h->num_sms;
+    loss_kernel<<<blocks, 256, 0, c.s>>>(a); c.launches++;
+  }
+
+  // wave C: critic passes 0,1 (dgrad + wgrad) and actor passes 4,5 (dgrad only), top layer down
+  const int passes[4] = {0, 1, 4, 5};
+  for (int j = q.L; j >= 1; --j) {
+    GemmGroup gd; gd.n = 0;
+    GemmGroup gw; gw.n = 0;
+    for (int pp = 0; pp < 4; ++pp) {
+      const int p = passes[pp], k = p & 1;
+      const float* dY = j == q.L ? W + ar.dOut[p] : W + ar.dzQ[p][j];
+      float* gb = p < 2 ? Gq[k] + q.b[j - 1] : nullptr;
+      gd.p[gd.n++] = dgrad_prob(q, Pq[k], j, dY, 0, q.s[j], W + ar.dzQ[p][j - 1], W + ar.zQ[p][j - 1], gb, B, cf.act_q);
+      if (p < 2) gw.p[gw.n++] = wgrad_prob(q, Gq[k], j, dY, W + ar.hQ[p][j - 1], q.s[j], 0, q.s[j], B);
+    }
+    launch_group(h, gd, V_DGRAD, c);
+    launch_group(h, gw, V_WGRAD, c);
+  }
+  {
+    GemmGroup gw; gw.n = 0;
+    GemmGroup gd; gd.n = 0;
+    for (int k = 0; k < 2; ++k) {
+      gw.p[gw.n++] = wgrad_prob(q, Gq[k], 0, W + ar.dzQ[k][0], bt.obs, O, 0, O, B);
+      gw.p[gw.n++] = wgrad_prob(q, Gq[k], 0, W + ar.dzQ[k][0], bt.act, A, O, A, B);
+      gd.p[gd.n++] = dgrad_prob(q, Pq[k], 0, W + ar.dzQ[4 + k][0], O, A, W + ar.dAct[k], nullptr, nullptr, B, 0);
+    }
+    launch_group(h, gw, V_WGRAD, c);
+    launch_group(h, gd, V_DGRAD, c);
+  }
+
+  {
+    PolicyGradArgs a;
+    a.logits = W + ar.logitsP; a.eps = h->pending_eps1; a.d_act1 = W + ar.dAct[0]; a.d_act2 = W + ar.dAct[1];
+    a.hi = h->buf.act_high; a.lo = h->buf.act_low;
+    a.d_logits = W + ar.dlogits; a.gbias = Gpi + pi.b[pi.L]; a.state = h->buf.state;
+    a.B = B; a.A = A; a.min_log_std = (float)cf.min_log_std; a.max_log_std = (float)cf.max_log_std;
+    a.inv_global_batch = invB;
+    int blocks = (B + 63) / 64; if (blocks > 2 * h->num_sms) blocks = 2 * h->num_sms; if (blocks < 1) blocks = 1;
+    policy_grad_kernel<<<blocks, 256, 0, c.s>>>(a); c.launches++;
+  }
+
+  // wave D: policy backward
+  for (int j = pi.L; j >= 0; --j) {
+    const float* dY = j == pi.L ? W + ar.dlogits : W + ar.dzP[j];
+    GemmGroup gw; gw.n = 0;
+    gw.p[gw.n++] = wgrad_prob(pi, Gpi, j, dY, j == 0 ? bt.obs : W + ar.hP[j - 1], pi.s[j], 0, pi.s[j], B);
+    if (j >= 1) {
+      GemmGroup gd; gd.n = 0;
+      gd.p[gd.n++] = dgrad_prob(pi, Ppi, j, dY, 0, pi.s[j], W + ar.dzP[j - 1], W + ar.zP[j - 1], Gpi + pi.b[j - 1], B, cf.act_pi);
+      launch_group(h, gd, V_DGRAD, c);
+    }
+    launch_group(h, gw, V_WGRAD, c);
+  }
+
+  alpha_grad_kernel<<<1, 32, 0, c.s>>>(G + 2 * q.n + pi.n, h->buf.state, invB, -(float)cf.act_dim, B);
+  c.launches++;
+  c.check();
+}
+
+static void enqueue_apply(dsact_handle* h, Ctx& c) {
+  const dsact_config& cf = h->cfg;
+  ApplyArgs a;
+  a.params = h->buf.params; a.targets = h->buf.targets; a.grads = h->buf.grads; a.m = h->buf.adam_m; a.v = h->buf.adam_v;
+  a.state = h->buf.state;
+  a.n_q2 = 2 * h->q.n; a.n_all = 2 * h->q.n + h->pi.n + 1;
+  a.delay_update = cf.delay_update; a.auto_alpha = cf.auto_alpha;
+  a.lr_q = cf.lr_q; a.lr_pi = cf.lr_pi; a.lr_alpha = cf.lr_alpha;
+  a.b1 = cf.adam_beta1; a.b2 = cf.adam_beta2; a.eps = (float)cf.adam_eps; a.tau = (float)cf.tau;
+  a.omb1 = (float)(1.0 - cf.adam_beta1); a.b2f = (float)cf.adam_beta2; a.omb2 = (float)(1.0 - cf.adam_beta2);
+  int blocks = (int)((a.n_all + 255) / 256);
+  if (blocks > 8 * h->num_sms) blocks = 8 * h->num_sms;
+  apply_kernel<<<blocks, 256, 0, c.s>>>(a);
+  advance_kernel<<<1, 32, 0, c.s>>>(h->buf.state, cf.delay_update);
+  c.launches += 2;
+  c.check();
+}
+
+static void enqueue_gather(dsact_handle* h, int B, const int64_t* idx, Ctx& c) {
+  const Arena& ar = h->ar;
+  float* W = h->W();
+  const int64_t* use = idx;
+  if (!idx) {
+    int64_t* dst = reinterpret_cast<int64_t*>(W + ar.idx);
+    int blocks = ((B + 1) / 2 + 255) / 256;
+    index_kernel<<<blocks, 256, 0, c.s>>>(dst, B, h->seed, h->buf.state); c.launches++;
+    use = dst;
+  }
+  int blocks = (B + 7) / 8; if (blocks > 8 * h->num_sms) blocks = 8 * h->num_sms;
+  gather_kernel<<<blocks, 256, 0, c.s>>>(h->rb.obs, h->rb.obs2, h->rb.act, h->rb.rew, h->rb.done, h->rb.logp, use,
+                                          W + ar.obs, W + ar.obs2, W + ar.act, W + ar.rew, W + ar.done, W + ar.logp, B,
+                                          h->cfg.obs_dim, h->cfg.act_dim);
+  c.launches++;
+  c.check();
+}
+
+// ---- graph cache -------------------------------------------------------------
+enum { K_STEP = 1, K_PHASE1 = 2, K_PHASE2 = 3, K_APPLY = 4, K_GRADS = 5, K_SAMPLE = 6, K_REPLAY_STEP = 7 };
+
+static void drop_graphs(dsact_handle* h) {
+  for (auto& e : h->graphs) cudaGraphExecDestroy(e.exec);
+  h->graphs.clear();
+}
+
+template <typename F>
+static int run(dsact_handle* h, cudaStream_t user, const GraphKey& key, F enqueue) {
+  if (!h->cfg.use_graph) {
+    Ctx c{user, 0, cudaSuccess};
+    enqueue(c);
+    if (c.err != cudaSuccess) return fail(DSACT_ECUDA, "kernel launch failed: %s", cudaGetErrorString(c.err));
+    h->launches += c.launches;
+    h->last_launches = c.launches;
+    return DSACT_OK;
+  }
+  GraphEntry* hit = nullptr;
+  for (auto& e : h->graphs)
+    if (e.key == key) { hit = &e; break; }
+  if (!hit) {
+    CUDA_TRY(cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeRelaxed));
+    Ctx c{h->cap_stream, 0, cudaSuccess};
+    enqueue(c);
+    cudaGraph_t graph = nullptr;
+    cudaError_t e = cudaStreamEndCapture(h->cap_stream, &graph);
+    if (c.err != cudaSuccess || e != cudaSuccess) {
+      if (graph) cudaGraphDestroy(graph);
+      return fail(DSACT_ECUDA, "graph capture failed: %s", cudaGetErrorString(c.err != cudaSuccess ? c.err : e));
+    }
+    cudaGraphExec_t exec = nullptr;
+    e = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) return fail(DSACT_ECUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
+    if (h->graphs.size() >= 16) {  // evict the least recently used
+      size_t victim = 0;
+      for (size_t i = 1; i < h->graphs.size(); ++i)
+        if (h->graphs[i].stamp < h->graphs[victim].stamp) victim = i;
+      cudaGraphExecDestroy(h->graphs[victim].exec);
+      h->graphs.erase(h->graphs.begin() + victim);
+    }
+    h->graphs.push_back(GraphEntry{key, exec, c.launches, 0});
+    hit = &h->graphs.back();
+  }
+  hit->stamp = ++h->stamp;
+  CUDA_TRY(cudaGraphLaunch(hit->exec, user));
+  h->launches += hit->launches;
+  h->last_launches = hit->launches;
+  return DSACT_OK;
+}
+
+static GraphKey make_key(int kind, const dsact_batch* b, const dsact_noise* n, int64_t gb) {
+  GraphKey k;
+  memset(&k, 0, sizeof(k));
+  k.kind = kind;
+  if (b) { k.p[0] = b->obs; k.p[1] = b->act; k.p[2] = b->rew; k.p[3] = b->obs2; k.p[4] = b->done; k.batch = b->batch; }
+  if (n) { k.p[5] = n->eps1; k.p[6] = n->eps2; k.p[7] = n->z3; k.p[8] = n->z4; }
+  k.gb = gb;
+  return k;
+}
+
+static int check_batch(const dsact_handle* h, const dsact_batch* b) {
+  if (!h) return fail(DSACT_EINVAL, "null handle");
+  if (!h->bound) return fail(DSACT_ESTATE, "dsact_bind has not been called");
+  if (!b || !b->obs || !b->act || !b->rew || !b->obs2 || !b->done) return fail(DSACT_EINVAL, "null batch pointer");
+  if (b->batch < 1 || b->batch > h->cfg.max_batch)
+    return fail(DSACT_EINVAL, "batch %d outside [1, max_batch=%d]", b->batch, h->cfg.max_batch);
+  return DSACT_OK;
+}
+static int check_noise(const dsact_noise* n) {
+  if (n && (!n->eps1 || !n->eps2 || !n->z3 || !n->z4)) return fail(DSACT_EINVAL, "null noise pointer");
+  return DSACT_OK;
+}
+
+static int sync_iteration(dsact_handle* h, int64_t iteration, cudaStream_t s) {
+  if (iteration < 0 || iteration > 0x7fffffff) return fail(DSACT_EINVAL, "iteration out of range");
+  if (h->dev_iter != iteration) {
+    set_iter_kernel<<<1, 32, 0, s>>>(h->buf.state, (int)iteration);
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
+  }
+  return DSACT_OK;
+}
+
+// ---- C ABI ---------------------------------------------------------------------
+extern "C" {
+
+const char* dsact_last_error(void) { return g_err; }
+int dsact_abi_version(void) { return DSACT_ABI_VERSION; }
+
+static int validate(const dsact_config* c) {
+  if (!c) return fail(DSACT_EINVAL, "null config");
+  if (c->abi_version != DSACT_ABI_VERSION) return fail(DSACT_EINVAL, "abi_version %d != %d", c->abi_version, DSACT_ABI_VERSION);
+  if (c->obs_dim < 1 || c->act_dim < 1) return fail(DSACT_EINVAL, "obs_dim/act_dim must be positive");
+  if (c->n_hidden_q < 1 || c->n_hidden_q > DSACT_MAX_HIDDEN || c->n_hidden_pi < 1 || c->n_hidden_pi > DSACT_MAX_HIDDEN)
+    return fail(DSACT_EINVAL, "1..%d hidden layers supported", DSACT_MAX_HIDDEN);
+  for (int j = 0; j < c->n_hidden_q; ++j) if (c->hidden_q[j] < 1) return fail(DSACT_EINVAL, "bad value hidden size");
+  for (int j = 0; j < c->n_hidden_pi; ++j) if (c->hidden_pi[j] < 1) return fail(DSACT_EINVAL, "bad policy hidden size");
+  if (c->act_q < 0 || c->act_q > DSACT_ACT_SELU || c->act_pi < 0 || c->act_pi > DSACT_ACT_SELU)
+    return fail(DSACT_EINVAL, "unknown activation");
+  if (c->max_batch < 1) return fail(DSACT_EINVAL, "max_batch must be positive");
+  if (c->delay_update < 1) return fail(DSACT_EINVAL, "delay_update must be >= 1");
+  if (c->gemm_mode != DSACT_GEMM_FP32) return fail(DSACT_EINVAL, "gemm_mode %d not available in this build", c->gemm_mode);
+  return DSACT_OK;
+}
+
+int dsact_query_layout(const dsact_config* cfg, dsact_layout* out) {
+  int rc = validate(cfg);
+  if (rc) return rc;
+  if (!out) return fail(DSACT_EINVAL, "null out");
+  Net q, pi;
+  q.build(cfg->obs_dim + cfg->act_dim, cfg->hidden_q, cfg->n_hidden_q, 2);
+  pi.build(cfg->obs_dim, cfg->hidden_pi, cfg->n_hidden_pi, 2 * cfg->act_dim);
+  Arena ar;
+  ar.build(*cfg, q, pi);
+  out->n_q = q.n; out->n_pi = pi.n;
+  out->n_params = 2 * q.n + pi.n + 1;
+  out->n_targets = 2 * q.n + pi.n;
+  out->workspace_bytes = ar.total * (int64_t)sizeof(float);
+  out->state_floats = 64;
+  out->max_batch = cfg->max_batch;
+  return DSACT_OK;
+}
+
+int dsact_create(const dsact_config* cfg, int device, dsact_handle** out) {
+  int rc = validate(cfg);
+  if (rc) return rc;
+  if (!out) return fail(DSACT_EINVAL, "null out");
+  CUDA_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return fail(DSACT_EARCH, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+  dsact_handle* h = new dsact_handle();
+  h->cfg = *cfg;
+  h->device = device;
+  h->num_sms = prop.multiProcessorCount;
+  h->q.build(cfg->obs_dim + cfg->act_dim, cfg->hidden_q, cfg->n_hidden_q, 2);
+  h->pi.build(cfg->obs_dim, cfg->hidden_pi, cfg->n_hidden_pi, 2 * cfg->act_dim);
+  h->ar.build(*cfg, h->q, h->pi);
+  h->bound = h->rb_bound = false;
+  h->seed = 0x5DEECE66Dull;
+  h->dev_iter = -1;
+  h->dev_rb_size = -1;
+  h->pending_batch = 0;
+  h->stamp = 0; h->launches = 0; h->last_launches = 0;
+  cudaError_t e = cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) { delete h; return fail(DSACT_ECUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(e)); }
+  *out = h;
+  return DSACT_OK;
+}
+
+void dsact_destroy(dsact_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  drop_graphs(h);
+  cudaStreamDestroy(h->cap_stream);
+  delete h;
+}
+
+int dsact_bind(dsact_handle* h, const dsact_buffers* b) {
+  if (!h || !b) return fail(DSACT_EINVAL, "null argument");
+  if (!b->params || !b->targets || !b->grads || !b->adam_m || !b->adam_v || !b->act_high || !b->act_low || !b->state || !b->workspace)
+    return fail(DSACT_EINVAL, "null buffer pointer");
+  if ((reinterpret_cast<uintptr_t>(b->workspace) & 255) != 0) return fail(DSACT_EINVAL, "workspace must be 256-byte aligned");
+  h->buf = *b;
+  h->bound = true;
+  h->dev_iter = -1;
+  h->dev_rb_size = -1;
+  drop_graphs(h);
+  return DSACT_OK;
+}
+
+int dsact_seed(dsact_handle* h, uint64_t seed) {
+  if (!h) return fail(DSACT_EINVAL, "null handle");
+  h->seed = seed;
+  drop_graphs(h);  // the seed is a baked kernel argument
+  return DSACT_OK;
+}
+
+int dsact_set_carry(dsact_handle* h, float m1, float m2, int64_t tq, int64_t tp, void* stream) {
+  if (!h || !h->bound) return fail(DSACT_ESTATE, "not bound");
+  CUDA_TRY(cudaSetDevice(h->device));
+  set_carry_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(h->buf.state, m1, m2, (int)tq, (int)tp);
+  CUDA_TRY(cudaGetLastError());
+  h->launches++;
+  return DSACT_OK;
+}
+
+int dsact_grad_phase1(dsact_handle* h, const dsact_batch* batch, const dsact_noise* noise, void* stream) {
+  int rc = check_batch(h, batch);
+  if (rc || (rc = check_noise(noise))) return rc;
+  CUDA_TRY(cudaSetDevice(h->device));
+  const dsact_batch bt = *batch;
+  dsact_noise nz; const dsact_noise* np = nullptr;
+  if (noise) { nz = *noise; np = &nz; }
+  rc = run(h, (cudaStream_t)stream, make_key(K_PHASE1, &bt, np, 0), [&](Ctx& c) { enqueue_phase1(h, bt, np, c); });
+  if (rc) return rc;
+  h->pending = bt;
+  h->pending_batch = bt.batch;
+  // (a replayed graph does not run enqueue_phase1, so record the noise pointers here as well)
+  h->pending_eps1 = np ? np->eps1 : h->W() + h->ar.eps1;
+  h->pending_z3 = np ? np->z3 : h->W() + h->ar.z3;
+  h->pending_z4 = np ? np->z4 : h->W() + h->ar.z4;
+  return DSACT_OK;
+}
+
+int dsact_grad_phase2(dsact_handle* h, int64_t global_batch, void* stream) {
+  if (!h || !h->bound) return fail(DSACT_ESTATE, "not bound");
+  if (h->pending_batch < 1) return fail(DSACT_ESTATE, "dsact_grad_phase2 without a preceding dsact_grad_phase1");
+  if (global_batch < h->pending_batch) return fail(DSACT_EINVAL, "global_batch %lld < local batch %d", (long long)global_batch, h->pending_batch);
+  CUDA_TRY(cudaSetDevice(h->device));
+  const dsact_batch bt = h->pending;
+  dsact_noise nz{h->pending_eps1, nullptr, h->pending_z3, h->pending_z4};
+  GraphKey key = make_key(K_PHASE2, &bt, &nz, global_batch);
+  return run(h, (cudaStream_t)stream, key, [&](Ctx& c) { enqueue_phase2(h, bt, global_batch, c); });
+}
+
+int dsact_compute_grads(dsact_handle* h, const dsact_batch* batch, const dsact_noise* noise, void* stream) {
+  int rc = check_batch(h, batch);
+  if (rc || (rc = check_noise(noise))) return rc;
+  CUDA_TRY(cudaSetDevice(h->device));
+  const dsact_batch bt = *batch;
+  dsact_noise nz; const dsact_noise* np = nullptr;
+  if (noise) { nz = *noise; np = &nz; }
+  rc = run(h, (cudaStream_t)stream, make_key(K_GRADS, &bt, np, bt.batch), [&](Ctx& c) {
+    enqueue_phase1(h, bt, np, c);
+    enqueue_phase2(h, bt, bt.batch, c);
+  });
+  if (rc) return rc;
+  h->pending = bt; h->pending_batch = bt.batch;
+  return DSACT_OK;
+}
+
+int dsact_apply(dsact_handle* h, int64_t iteration, void* stream) {
+  if (!h || !h->bound) return fail(DSACT_ESTATE, "not bound");
+  CUDA_TRY(cudaSetDevice(h->device));
+  int rc = sync_iteration(h, iteration, (cudaStream_t)stream);
+  if (rc) return rc;
+  rc = run(h, (cudaStream_t)stream, make_key(K_APPLY, nullptr, nullptr, 0), [&](Ctx& c) { enqueue_apply(h, c); });
+  if (rc) return rc;
+  h->dev_iter = iteration + 1;
+  return DSACT_OK;
+}
+
+int dsact_step(dsact_handle* h, const dsact_batch* batch, const dsact_noise* noise, int64_t iteration, void* stream) {
+  int rc = check_batch(h, batch);
+  if (rc || (rc = check_noise(noise))) return rc;
+  CUDA_TRY(cudaSetDevice(h->device));
+  rc = sync_iteration(h, iteration, (cudaStream_t)stream);
+  if (rc) return rc;
+  const dsact_batch bt = *batch;
+  dsact_noise nz; const dsact_noise* np = nullptr;
+  if (noise) { nz = *noise; np = &nz; }
+  rc = run(h, (cudaStream_t)stream, make_key(K_STEP, &bt, np, bt.batch), [&](Ctx& c) {
+    enqueue_phase1(h, bt, np, c);
+    enqueue_phase2(h, bt, bt.batch, c);
+    enqueue_apply(h, c);
+  });
+  if (rc) return rc;
+  h->pending = bt; h->pending_batch = bt.batch;
+  h->dev_iter = iteration + 1;
+  return DSACT_OK;
+}
+
+int dsact_read_stats(dsact_handle* h, int64_t global_batch, float* host_out, void* stream) {
+  if (!h || !h->bound) return fail(DSACT_ESTATE, "not bound");
+  if (!host_out || global_batch < 1) return fail(DSACT_EINVAL, "bad argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  const float invB = (float)(1.0 / (double)global_batch);
+  const float invBA = (float)(1.0 / ((double)global_batch * h->cfg.act_dim));
+  finalize_stats_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(h->buf.state, invB, invBA);
+  CUDA_TRY(cudaGetLastError());
+  h->launches++;
+  CUDA_TRY(cudaMemcpyAsync(host_out, h->buf.state + ST_STATS, DSACT_NUM_STATS * sizeof(float), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  return DSACT_OK;
+}
+
+// ---- replay ring buffer ----------------------------------------------------------
+int dsact_replay_bind(dsact_handle* h, const dsact_replay* rb) {
+  if (!h || !rb) return fail(DSACT_EINVAL, "null argument");
+  if (!rb->obs || !rb->obs2 || !rb->act || !rb->rew || !rb->done || !rb->logp || rb->capacity < 1)
+    return fail(DSACT_EINVAL, "bad replay buffers");
+  h->rb = *rb;
+  h->rb_bound = true;
+  drop_graphs(h);
+  return DSACT_OK;
+}
+
+int dsact_replay_add(dsact_handle* h, const float* obs, const float* obs2, const float* act, const float* rew,
+                     const float* done, const float* logp, int64_t n, int64_t ptr, void* stream) {
+  if (!h || !h->rb_bound) return fail(DSACT_ESTATE, "replay buffer not bound");
+  if (n < 0 || n > h->rb.capacity || ptr < 0 || ptr >= h->rb.capacity) return fail(DSACT_EINVAL, "bad n/ptr");
+  if (n == 0) return DSACT_OK;
+  if (!obs || !obs2 || !act || !rew || !done || !logp) return fail(DSACT_EINVAL, "null staging pointer");
+  CUDA_TRY(cudaSetDevice(h->device));
+  const int64_t first = (ptr + n <= h->rb.capacity) ? n : h->rb.capacity - ptr;
+  const int64_t O = h->cfg.obs_dim, A = h->cfg.act_dim;
+  struct { float* dst; const float* src; int64_t w; } cols[6] = {
+      {h->rb.obs, obs, O}, {h->rb.obs2, obs2, O}, {h->rb.act, act, A}, {h->rb.rew, rew, 1}, {h->rb.done, done, 1}, {h->rb.logp, logp, 1}};
+  for (auto& c : cols) {
+    CUDA_TRY(cudaMemcpyAsync(c.dst + ptr * c.w, c.src, first * c.w * sizeof(float), cudaMemcpyDefault, (cudaStream_t)stream));
+    if (first < n)
+      CUDA_TRY(cudaMemcpyAsync(c.dst, c.src + first * c.w, (n - first) * c.w * sizeof(float), cudaMemcpyDefault, (cudaStream_t)stream));
+  }
+  return DSACT_OK;
+}
+
+static int sync_rb_size(dsact_handle* h, int64_t size, cudaStream_t s) {
+  if (size < 1 || size > h->rb.capacity) return fail(DSACT_EINVAL, "size %lld outside [1, capacity]", (long long)size);
+  if (h->dev_rb_size != size) {
+    set_rb_size_kernel<<<1, 32, 0, s>>>(h->buf.state, size);
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
+    h->dev_rb_size = size;
+  }
+  return DSACT_OK;
+}
+
+static dsact_batch arena_batch(const dsact_handle* h, int32_t batch) {
+  float* W = h->W();
+  dsact_batch b;
+  b.obs = W + h->ar.obs; b.act = W + h->ar.act; b.rew = W + h->ar.rew; b.obs2 = W + h->ar.obs2; b.done = W + h->ar.done;
+  b.logp = W + h->ar.logp;
+  b.batch = batch;
+  return b;
+}
+
+int dsact_replay_sample(dsact_handle* h, int32_t batch, int64_t size, const int64_t* idx, dsact_batch* out, void* stream) {
+  if (!h || !h->bound || !h->rb_bound) return fail(DSACT_ESTATE, "not bound");
+  if (batch < 1 || batch > h->cfg.max_batch) return fail(DSACT_EINVAL, "batch outside [1, max_batch]");
+  CUDA_TRY(cudaSetDevice(h->device));
+  int rc = sync_rb_size(h, size, (cudaStream_t)stream);
+  if (rc) return rc;
+  GraphKey key = make_key(K_SAMPLE, nullptr, nullptr, 0);
+  key.batch = batch; key.idx = idx;
+  rc = run(h, (cudaStream_t)stream, key, [&](Ctx& c) {
+    enqueue_gather(h, batch, idx, c);
+    if (!idx) { rng_advance_kernel<<<1, 32, 0, c.s>>>(h->buf.state); c.launches++; }
+  });
+  if (rc) return rc;
+  if (out) *out = arena_batch(h, batch);
+  return DSACT_OK;
+}
+
+int dsact_replay_step(dsact_handle* h, int32_t batch, int64_t size, const int64_t* idx, const dsact_noise* noise,
+                      int64_t iteration, void* stream) {
+  if (!h || !h->bound || !h->rb_bound) return fail(DSACT_ESTATE, "not bound");
+  if (batch < 1 || batch > h->cfg.max_batch) return fail(DSACT_EINVAL, "batch outside [1, max_batch]");
+  int rc = check_noise(noise);
+  if (rc) return rc;
+  CUDA_TRY(cudaSetDevice(h->device));
+  if ((rc = sync_rb_size(h, size, (cudaStream_t)stream))) return rc;
+  if ((rc = sync_iteration(h, iteration, (cudaStream_t)stream))) return rc;
+  const dsact_batch bt = arena_batch(h, batch);
+  dsact_noise nz; const dsact_noise* np = nullptr;
+  if (noise) { nz = *noise; np = &nz; }
+  GraphKey key = make_key(K_REPLAY_STEP, &bt, np, batch);
+  key.idx = idx;
+  rc = run(h, (cudaStream_t)stream, key, [&](Ctx& c) {
+    enqueue_gather(h, batch, idx, c);
+    if (!idx && np) { rng_advance_kernel<<<1, 32, 0, c.s>>>(h->buf.state); c.launches++; }
+    enqueue_phase1(h, bt, np, c);  // device noise (np == null) advances the counter itself, after the index draw
+    enqueue_phase2(h, bt, batch, c);
+    enqueue_apply(h, c);
+  });
+  if (rc) return rc;
+  h->pending = bt; h->pending_batch = batch;
+  h->dev_iter = iteration + 1;
+  return DSACT_OK;
+}
+
+int64_t dsact_launch_count(const dsact_handle* h) { return h ? h->launches : 0; }
+int32_t dsact_last_call_launches(const dsact_handle* h) { return h ? h->last_launches : 0; }
+
+int dsact_test_gemm(dsact_handle* h, int32_t variant, const float* A, int32_t lda, const float* B, int32_t ldb,
+                    const float* bias, float* C, int32_t ldc, int32_t M, int32_t N, int32_t K, void* stream) {
+  if (!h) return fail(DSACT_EINVAL, "null handle");
+  if (variant < 0 || variant > 2 || M < 1 || N < 1 || K < 1) return fail(DSACT_EINVAL, "bad argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  GemmGroup g; g.n = 1;
+  GemmProb p = prob_zero();
+  p.A[0] = A; p.lda[0] = lda; p.B[0] = B; p.ldb[0] = ldb; p.K[0] = K;
+  p.M = M; p.N = N; p.C = C; p.ldc = ldc; p.bias = variant == V_FWD ? bias : nullptr;
+  p.epi = variant == V_WGRAD ? EPI_ATOMIC : EPI_STORE;
+  g.p[0] = p;
+  Ctx c{(cudaStream_t)stream, 0, cudaSuccess};
+  launch_group(h, g, variant, c);
+  if (c.err != cudaSuccess) return fail(DSACT_ECUDA, "launch failed: %s", cudaGetErrorString(c.err));
+  h->launches += c.launches;
+  return DSACT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,483 @@
+// Non-GEMM kernels of the DSAC-T update: tanh-Gaussian sampling, the fused
+// target/loss/gradient kernel, the policy-head gradient, Adam + Polyak, noise
+// and index generation, replay gather.  Formulas follow SURVEY.md Appendix A;
+// reference line numbers are given per kernel.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+namespace dsact {
+
+constexpr float TG_EPS = 1e-6f;          // utils/act_distribution_cls.py:3
+constexpr float HUBER_DELTA = 50.0f;     // dsac_v2.py:282-287
+constexpr float STD_BIAS = 0.1f;         // dsac_v2.py:277
+constexpr float HALF_LOG_2PI = 0.91893853320467274f;  // log(sqrt(2*pi))
+
+// ---- persistent state (float slots; see include/dsact.h) ------------------
+enum {
+  ST_MEAN_STD1 = 0, ST_MEAN_STD2 = 1, ST_ALPHA_USED = 2,
+  ST_STDSUM = 4,                       // [4],[5] local sums of softplus std (phase1 -> phase2)
+  ST_ADAM_Q = 8, ST_ADAM_PI = 9,       // int32 step counters
+  ST_RNG_CTR = 10,                     // uint32 step counter of the device generator
+  ST_ITER = 11,                        // int32 iteration the next apply will use (dsac_v2.py:324)
+  ST_RB_SIZE = 12,                     // [12],[13] int64 number of valid replay rows
+  ST_ACC = 16,                         // 16 sums then 16 mins
+  ST_STATS = 48,
+};
+enum {  // accumulator slots (sums)
+  ACC_Q1 = 0, ACC_Q2, ACC_S1, ACC_S2, ACC_LOSS_PI, ACC_LOSS_Q, ACC_TANH_MEAN, ACC_PI_STD, ACC_LOGP,
+  ACC_MIN = 16  // [16] min std1, [17] min std2 (float bits, positive values only)
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Block-wide sum of NV values per thread; result valid in thread 0. blockDim.x multiple of 32, <= 1024.
+template <int NV>
+__device__ __forceinline__ void block_sum(float (&v)[NV], float* smem /* >= NV*32 floats */) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = warp_sum(v[i]);
+  if (lane == 0)
+#pragma unroll
+    for (int i = 0; i < NV; ++i) smem[i * 32 + w] = v[i];
+  __syncthreads();
+  if (w == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      float x = lane < nw ? smem[i * 32 + lane] : 0.f;
+      v[i] = warp_sum(x);
+    }
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ float softplus_f(float x) {  // F.softplus, beta=1, threshold=20
+  return x > 20.f ? x : log1pf(expf(x));
+}
+__device__ __forceinline__ float huber_f(float d) {
+  const float a = fabsf(d);
+  return a <= HUBER_DELTA ? 0.5f * d * d : HUBER_DELTA * (a - 0.5f * HUBER_DELTA);
+}
+
+// ---- Philox4x32-10 ---------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += 0x9E3779B9u;
+    key.y += 0xBB67AE85u;
+  }
+  return ctr;
+}
+__device__ __forceinline__ float u01(uint32_t x) { return (x + 0.5f) * 2.3283064365386963e-10f; }  // (0,1]
+__device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& n0, float& n1) {
+  const float r = sqrtf(-2.0f * logf(u01(a)));
+  float s, c;
+  sincospif(2.0f * u01(b), &s, &c);
+  n0 = r * c;
+  n1 = r * s;
+}
+
+// Start of every step: clear the accumulators (and the std sums of phase1).
+__global__ void begin_step_kernel(float* __restrict__ state) {
+  const int t = threadIdx.x;
+  if (t < 16) state[ST_ACC + t] = 0.f;
+  else if (t < 32) state[ST_ACC + t] = __int_as_float(0x7f800000);
+  if (t < 2) state[ST_STDSUM + t] = 0.f;
+}
+
+// Device noise: eps1, eps2 [B,A] and z3, z4 [B] (SURVEY Appendix B keeps only the draws that matter).
+__global__ void noise_kernel(float* __restrict__ eps1, float* __restrict__ eps2, float* __restrict__ z3,
+                             float* __restrict__ z4, int B, int A, uint64_t seed, const float* __restrict__ state) {
+  const uint32_t step = reinterpret_cast<const uint32_t*>(state)[ST_RNG_CTR];
+  const int n_pairs_ea = (B * A + 1) / 2, n_pairs_z = (B + 1) / 2;
+  const int total = 2 * n_pairs_ea + 2 * n_pairs_z;
+  const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < (total + 1) / 2; i += gridDim.x * blockDim.x) {
+    const uint4 r = philox4x32(make_uint4((uint32_t)i, step, 0x4e4f4953u, 0u), key);
+    float n[4];
+    box_muller(r.x, r.y, n[0], n[1]);
+    box_muller(r.z, r.w, n[2], n[3]);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      int p = 2 * i + h;  // pair index
+      if (p >= total) break;
+      float* dst; int len, off;
+      if (p < n_pairs_ea) { dst = eps1; len = B * A; off = p; }
+      else if (p < 2 * n_pairs_ea) { dst = eps2; len = B * A; off = p - n_pairs_ea; }
+      else if (p < 2 * n_pairs_ea + n_pairs_z) { dst = z3; len = B; off = p - 2 * n_pairs_ea; }
+      else { dst = z4; len = B; off = p - 2 * n_pairs_ea - n_pairs_z; }
+      if (2 * off < len) dst[2 * off] = n[2 * h];
+      if (2 * off + 1 < len) dst[2 * off + 1] = n[2 * h + 1];
+    }
+  }
+}
+
+// Uniform replay indices in [0, size) (np.random.randint, training/replay_buffer.py:86).
+__global__ void index_kernel(int64_t* __restrict__ idx, int B, uint64_t seed, const float* __restrict__ state) {
+  const uint32_t step = reinterpret_cast<const uint32_t*>(state)[ST_RNG_CTR];
+  const int64_t size = *reinterpret_cast<const int64_t*>(state + ST_RB_SIZE);
+  const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < (B + 1) / 2; i += gridDim.x * blockDim.x) {
+    const uint4 r = philox4x32(make_uint4((uint32_t)i, step, 0x49445853u, 0u), key);
+    const uint64_t a = ((uint64_t)r.x << 32) | r.y, b = ((uint64_t)r.z << 32) | r.w;
+    idx[2 * i] = (int64_t)__umul64hi(a, (uint64_t)size);  // floor(a / 2^64 * size)
+    if (2 * i + 1 < B) idx[2 * i + 1] = (int64_t)__umul64hi(b, (uint64_t)size);
+  }
+}
+
+// Replay gather (training/replay_buffer.py:87-90): one warp per sampled row, vectorised over obs columns.
+__global__ void gather_kernel(const float* __restrict__ r_obs, const float* __restrict__ r_obs2,
+                              const float* __restrict__ r_act, const float* __restrict__ r_rew,
+                              const float* __restrict__ r_done, const float* __restrict__ r_logp,
+                              const int64_t* __restrict__ idx, float* __restrict__ obs, float* __restrict__ obs2,
+                              float* __restrict__ act, float* __restrict__ rew, float* __restrict__ done,
+                              float* __restrict__ logp, int B, int O, int A) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const bool v4 = (O & 3) == 0;
+  for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < B; row += gridDim.x * wpb) {
+    const int64_t src = idx[row];
+    const float* so = r_obs + src * O;
+    const float* so2 = r_obs2 + src * O;
+    float* dobs = obs + (size_t)row * O;
+    float* dobs2 = obs2 + (size_t)row * O;
+    if (v4) {
+      for (int c = lane; c < O / 4; c += 32) {
+        reinterpret_cast<float4*>(dobs)[c] = __ldg(reinterpret_cast<const float4*>(so) + c);
+        reinterpret_cast<float4*>(dobs2)[c] = __ldg(reinterpret_cast<const float4*>(so2) + c);
+      }
+    } else {
+      for (int c = lane; c < O; c += 32) { dobs[c] = __ldg(so + c); dobs2[c] = __ldg(so2 + c); }
+    }
+    for (int c = lane; c < A; c += 32) act[(size_t)row * A + c] = __ldg(r_act + src * A + c);
+    if (lane == 0) { rew[row] = __ldg(r_rew + src); done[row] = __ldg(r_done + src); logp[row] = __ldg(r_logp + src); }
+  }
+}
+
+// TanhGaussDistribution.rsample (utils/act_distribution_cls.py:44-54) on the raw policy-head output
+// (mean | log_std), with StochaPolicy's std = exp(clamp(log_std)) (networks/mlp.py:89-92) folded in.
+// blockIdx.y = 0: online policy on obs with eps1 (+ the two logged means, dsac_v2.py:155-157);
+// blockIdx.y = 1: target policy on obs2 with eps2.  One warp per row.
+struct SampleArgs {
+  const float* logits[2];
+  const float* eps[2];
+  float* act[2];
+  float* logp[2];
+  const float *hi, *lo;
+  float* state;
+  int B, A;
+  float min_log_std, max_log_std;
+};
+__global__ void sample_kernel(const __grid_constant__ SampleArgs a) {
+  __shared__ float red[2 * 32];
+  const int which = blockIdx.y;
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  const int A = a.A;
+  const float* __restrict__ logits = a.logits[which];
+  const float* __restrict__ eps = a.eps[which];
+  float sums[2] = {0.f, 0.f};
+  for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < a.B; row += gridDim.x * wpb) {
+    float lp = 0.f;
+    for (int j = lane; j < A; j += 32) {
+      const float mean = logits[(size_t)row * 2 * A + j];
+      const float ls = logits[(size_t)row * 2 * A + A + j];
+      const float sd = expf(fminf(fmaxf(ls, a.min_log_std), a.max_log_std));
+      const float u = mean + sd * eps[(size_t)row * A + j];
+      const float th = tanhf(u);
+      const float scale = 0.5f * (a.hi[j] - a.lo[j]), shift = 0.5f * (a.hi[j] + a.lo[j]);
+      a.act[which][(size_t)row * A + j] = scale * th + shift;
+      const float d = u - mean;
+      lp += -(d * d) / (2.f * sd * sd) - logf(sd) - HALF_LOG_2PI - logf(1.f + TG_EPS - th * th) - logf(scale);
+      sums[0] += tanhf(mean);
+      sums[1] += sd;
+    }
+    lp = warp_sum(lp);
+    if (lane == 0) a.logp[which][row] = lp;
+  }
+  if (which == 0) {
+    block_sum<2>(sums, red);
+    if (threadIdx.x == 0) {
+      atomicAdd(a.state + ST_ACC + ACC_TANH_MEAN, sums[0]);
+      atomicAdd(a.state + ST_ACC + ACC_PI_STD, sums[1]);
+    }
+  }
+}
+
+// Sum of the critics' std over the local rows (input of the mean_std EMA, dsac_v2.py:233-241).
+__global__ void std_sum_kernel(const float* __restrict__ out_q1, const float* __restrict__ out_q2, int B,
+                               float* __restrict__ state) {
+  __shared__ float red[2 * 32];
+  float s[2] = {0.f, 0.f};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B; i += gridDim.x * blockDim.x) {
+    s[0] += softplus_f(out_q1[2 * i + 1]);
+    s[1] += softplus_f(out_q2[2 * i + 1]);
+  }
+  block_sum<2>(s, red);
+  if (threadIdx.x == 0) {
+    atomicAdd(state + ST_STDSUM, s[0]);
+    atomicAdd(state + ST_STDSUM + 1, s[1]);
+  }
+}
+
+// mean_std EMA (dsac_v2.py:233-241) + the temperature this step uses (dsac_v2.py:140-148).
+__global__ void ema_kernel(float* __restrict__ state, const float* __restrict__ log_alpha, float inv_global_batch,
+                           float tau_b, int auto_alpha, float alpha_fixed) {
+  if (threadIdx.x < 2) {
+    const float mean = state[ST_STDSUM + threadIdx.x] * inv_global_batch;
+    const float old = state[ST_MEAN_STD1 + threadIdx.x];
+    state[ST_MEAN_STD1 + threadIdx.x] = old < 0.f ? mean : (1.f - tau_b) * old + tau_b * mean;
+  }
+  if (threadIdx.x == 2) state[ST_ALPHA_USED] = auto_alpha ? expf(*log_alpha) : alpha_fixed;
+}
+
+// Fused clipped-Gaussian distributional TD target + three-refinement critic loss + actor/alpha loss terms
+// and all output-layer gradients (dsac_v2.py:218-318).  One thread per sample.
+struct LossArgs {
+  const float *rew, *done, *z3, *z4, *logp2, *logp_new;
+  const float* out_q[2];    // Q_k(s,a)    [B,2] (mean, raw std)
+  const float* out_qt[2];   // Q'_k(s',a') [B,2]
+  const float* out_qa[2];   // Q_k(s,a~)   [B,2]
+  float* d_out_q[2];        // dL/d(mean, raw std) of Q_k(s,a)
+  float* d_out_qa[2];       // dL/d(mean, raw std) of Q_k(s,a~)
+  float* gbias_q[2];        // bias gradient of the critics' output layer [2] (+=)
+  float* state;
+  int B;
+  float gamma, inv_global_batch;
+};
+__global__ void loss_kernel(const __grid_constant__ LossArgs a) {
+  __shared__ float red[10 * 32];
+  const float m[2] = {a.state[ST_MEAN_STD1], a.state[ST_MEAN_STD2]};
+  const float alpha = a.state[ST_ALPHA_USED];
+  const float invB = a.inv_global_batch;
+  // sums: q1 q2 s1 s2 loss_pi loss_q logp | gb(q1 mean, q1 raw, q2 mean) ; q2 raw handled separately below
+  float s[10] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float gb_q2_raw = 0.f;
+  float mn[2] = {__int_as_float(0x7f800000), __int_as_float(0x7f800000)};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.B; i += gridDim.x * blockDim.x) {
+    const float q1n = a.out_qt[0][2 * i], s1n = softplus_f(a.out_qt[0][2 * i + 1]);
+    const float q2n = a.out_qt[1][2 * i], s2n = softplus_f(a.out_qt[1][2 * i + 1]);
+    const float zc3 = fminf(fmaxf(a.z3[i], -3.f), 3.f), zc4 = fminf(fmaxf(a.z4[i], -3.f), 3.f);
+    const float qn = fminf(q1n, q2n);
+    const float qn_s = q1n < q2n ? q1n + zc3 * s1n : q2n + zc4 * s2n;  // dsac_v2.py:252-253
+    const float nd = (1.f - a.done[i]) * a.gamma, lp2 = a.logp2[i], r = a.rew[i];
+    const float y = r + nd * (qn - alpha * lp2);      // dsac_v2.py:293-295
+    const float ys = r + nd * (qn_s - alpha * lp2);   // dsac_v2.py:296-298
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const float q = a.out_q[k][2 * i], raw = a.out_q[k][2 * i + 1];
+      const float sd = softplus_f(raw);
+      const float b3 = 3.f * m[k];
+      const float yb = q + fminf(fmaxf(ys - q, -b3), b3);  // dsac_v2.py:299-301
+      const float w = fminf(fmaxf(m[k] * m[k] / (sd * sd + STD_BIAS), 0.1f), 10.f);  // dsac_v2.py:279-280
+      const float dq = q - y;
+      const float sterm = (sd * sd - huber_f(q - yb)) / (sd + STD_BIAS);
+      s[ACC_LOSS_Q] += w * (huber_f(dq) + sd * sterm);
+      const float g_mean = w * fminf(fmaxf(dq, -HUBER_DELTA), HUBER_DELTA) * invB;
+      const float dsoft = raw > 20.f ? 1.f : 1.f / (1.f + expf(-raw));
+      const float g_raw = w * sterm * invB * dsoft;
+      a.d_out_q[k][2 * i] = g_mean;
+      a.d_out_q[k][2 * i + 1] = g_raw;
+      s[k] += q;
+      s[2 + k] += sd;
+      mn[k] = fminf(mn[k], sd);
+      if (k == 0) { s[7] += g_mean; s[8] += g_raw; } else { s[9] += g_mean; gb_q2_raw += g_raw; }
+    }
+    // actor: L_pi = mean(alpha*logp - min(q1pi, q2pi)), dsac_v2.py:304-310; ties split like torch.min
+    const float q1p = a.out_qa[0][2 * i], q2p = a.out_qa[1][2 * i];
+    const float lpn = a.logp_new[i];
+    s[ACC_LOSS_PI] += alpha * lpn - fminf(q1p, q2p);
+    s[6] += lpn;
+    const float g1 = q1p < q2p ? -invB : (q1p == q2p ? -0.5f * invB : 0.f);
+    const float g2 = q2p < q1p ? -invB : (q1p == q2p ? -0.5f * invB : 0.f);
+    a.d_out_qa[0][2 * i] = g1; a.d_out_qa[0][2 * i + 1] = 0.f;
+    a.d_out_qa[1][2 * i] = g2; a.d_out_qa[1][2 * i + 1] = 0.f;
+  }
+  block_sum<10>(s, red);
+  float one[1] = {gb_q2_raw};
+  block_sum<1>(one, red);
+  mn[0] = warp_min(mn[0]);
+  mn[1] = warp_min(mn[1]);
+  if ((threadIdx.x & 31) == 0) {
+    atomicMin(reinterpret_cast<int*>(a.state + ST_ACC + ACC_MIN), __float_as_int(mn[0]));
+    atomicMin(reinterpret_cast<int*>(a.state + ST_ACC + ACC_MIN + 1), __float_as_int(mn[1]));
+  }
+  if (threadIdx.x == 0) {
+    float* acc = a.state + ST_ACC;
+    atomicAdd(acc + ACC_Q1, s[0]); atomicAdd(acc + ACC_Q2, s[1]);
+    atomicAdd(acc + ACC_S1, s[2]); atomicAdd(acc + ACC_S2, s[3]);
+    atomicAdd(acc + ACC_LOSS_PI, s[4]); atomicAdd(acc + ACC_LOSS_Q, s[5]);
+    atomicAdd(acc + ACC_LOGP, s[6]);
+    atomicAdd(a.gbias_q[0], s[7]); atomicAdd(a.gbias_q[0] + 1, s[8]);
+    atomicAdd(a.gbias_q[1], s[9]); atomicAdd(a.gbias_q[1] + 1, one[0]);
+  }
+}
+
+// Gradient of the actor loss w.r.t. the raw policy-head output (mean | log_std): chain rule through
+// a~ = scale*tanh(u)+shift, u = mean + std*eps, and log-prob.
+// Also accumulates the output-layer bias gradient.  One warp per row.
+struct PolicyGradArgs {
+  const float *logits, *eps, *d_act1, *d_act2;  // d_act_k: dL/da~ through critic k  [B,A]
+  const float *hi, *lo;
+  float* d_logits;   // [B,2A]
+  float* gbias;      // [2A] (+=)
+  const float* state;
+  int B, A;
+  float min_log_std, max_log_std, inv_global_batch;
+};
+__global__ void policy_grad_kernel(const __grid_constant__ PolicyGradArgs a) {
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  const int A = a.A;
+  const float coef = a.state[ST_ALPHA_USED] * a.inv_global_batch;  // dL/dlogp
+  for (int j = lane; j < A; j += 32) {
+    const float scale = 0.5f * (a.hi[j] - a.lo[j]);
+    float gb_mean = 0.f, gb_ls = 0.f;
+    for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < a.B; row += gridDim.x * wpb) {
+      const float mean = a.logits[(size_t)row * 2 * A + j];
+      const float ls = a.logits[(size_t)row * 2 * A + A + j];
+      const bool inside = ls >= a.min_log_std && ls <= a.max_log_std;
+      const float sd = expf(fminf(fmaxf(ls, a.min_log_std), a.max_log_std));
+      const float e = a.eps[(size_t)row * A + j];
+      const float th = tanhf(mean + sd * e);
+      const float om = 1.f - th * th;
+      const float da = a.d_act1[(size_t)row * A + j] + a.d_act2[(size_t)row * A + j];
+      const float gu = da * scale * om + coef * (2.f * th * om / (1.f + TG_EPS - th * th));
+      const float gsd = gu * e - coef / sd;
+      const float gls = inside ? gsd * sd : 0.f;
+      a.d_logits[(size_t)row * 2 * A + j] = gu;
+      a.d_logits[(size_t)row * 2 * A + A + j] = gls;
+      gb_mean += gu;
+      gb_ls += gls;
+    }
+    atomicAdd(a.gbias + j, gb_mean);
+    atomicAdd(a.gbias + A + j, gb_ls);
+  }
+}
+
+// __update (dsac_v2.py:320-347): Adam on q1|q2 every step; on policy|log_alpha plus Polyak of all three
+// targets when iteration % delay_update == 0.  One pass over the flat buffers; also writes the gradient
+// of log_alpha (dsac_v2.py:312-318) from the accumulated sum of log-probs.
+struct ApplyArgs {
+  float *params, *targets, *grads, *m, *v;
+  float* state;
+  int64_t n_q2;      // 2*n_q  (critic span)
+  int64_t n_all;     // 2*n_q + n_pi + 1
+  int delay_update, auto_alpha;
+  double lr_q, lr_pi, lr_alpha, b1, b2;
+  float omb1, b2f, omb2, eps, tau;  // (float)(1-beta1), (float)beta2, (float)(1-beta2) formed in double on the host
+};
+// torch.optim.Adam single-tensor step (amsgrad / weight decay off)
+__device__ __forceinline__ float adam_update(float w, float g, float& m, float& v, float step_size, float bc2_sqrt,
+                                             float omb1, float b2, float omb2, float eps) {
+  m = m + (g - m) * omb1;                  // exp_avg.lerp_(grad, 1-beta1)
+  v = v * b2 + omb2 * g * g;               // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1-beta2)
+  const float denom = sqrtf(v) / bc2_sqrt + eps;
+  return w - step_size * (m / denom);      // param.addcdiv_(exp_avg, denom, value=-lr/bias_correction1)
+}
+__global__ void apply_kernel(const __grid_constant__ ApplyArgs a) {
+  __shared__ float sh[6];
+  const int* sti = reinterpret_cast<const int*>(a.state);
+  const bool delayed = (sti[ST_ITER] % a.delay_update) == 0;
+  if (threadIdx.x == 0) {  // bias corrections in double, like the Python scalars of torch's Adam
+    const double tq = sti[ST_ADAM_Q] + 1, tp = sti[ST_ADAM_PI] + 1;
+    const double bc1q = 1.0 - pow(a.b1, tq), bc1p = 1.0 - pow(a.b1, tp);
+    sh[0] = (float)(a.lr_q / bc1q);
+    sh[1] = (float)sqrt(1.0 - pow(a.b2, tq));
+    sh[2] = (float)(a.lr_pi / bc1p);
+    sh[3] = (float)(a.lr_alpha / bc1p);
+    sh[4] = (float)sqrt(1.0 - pow(a.b2, tp));
+  }
+  __syncthreads();
+  const int64_t n_targets = a.n_all - 1;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < a.n_all; i += (int64_t)gridDim.x * blockDim.x) {
+    const bool critic = i < a.n_q2;
+    float w = a.params[i];
+    if (critic || delayed) {
+      const bool is_alpha = i == a.n_all - 1;
+      if (!(is_alpha && !a.auto_alpha)) {
+        float g = a.grads[i], m = a.m[i], v = a.v[i];
+        const float step = critic ? sh[0] : (is_alpha ? sh[3] : sh[2]);
+        w = adam_update(w, g, m, v, step, critic ? sh[1] : sh[4], a.omb1, a.b2f, a.omb2, a.eps);
+        a.params[i] = w;
+        a.m[i] = m;
+        a.v[i] = v;
+      }
+    }
+    if (delayed && i < n_targets) {
+      const float polyak = 1.f - a.tau;
+      a.targets[i] = a.targets[i] * polyak + (1.f - polyak) * w;  // p_targ.mul_(polyak).add_((1-polyak)*p)
+    }
+  }
+}
+// Runs after apply_kernel: advance the counters it read.
+__global__ void advance_kernel(float* __restrict__ state, int delay_update) {
+  int* sti = reinterpret_cast<int*>(state);
+  if (threadIdx.x == 0) {
+    sti[ST_ADAM_Q] += 1;
+    if (sti[ST_ITER] % delay_update == 0) sti[ST_ADAM_PI] += 1;
+    sti[ST_ITER] += 1;
+  }
+}
+__global__ void set_iter_kernel(float* __restrict__ state, int iteration) {
+  if (threadIdx.x == 0) reinterpret_cast<int*>(state)[ST_ITER] = iteration;
+}
+__global__ void set_rb_size_kernel(float* __restrict__ state, int64_t size) {
+  if (threadIdx.x == 0) *reinterpret_cast<int64_t*>(state + ST_RB_SIZE) = size;
+}
+__global__ void rng_advance_kernel(float* __restrict__ state) {
+  if (threadIdx.x == 0) reinterpret_cast<uint32_t*>(state)[ST_RNG_CTR] += 1u;
+}
+
+// Gradient of log_alpha (dsac_v2.py:312-318): -(mean(logp_new) + target_entropy).
+// `rows` = local shard size, so that per-rank values sum to the global gradient under data parallelism.
+__global__ void alpha_grad_kernel(float* __restrict__ grad_log_alpha, const float* __restrict__ state,
+                                  float inv_global_batch, float target_entropy, int rows) {
+  if (threadIdx.x == 0)
+    *grad_log_alpha = -(state[ST_ACC + ACC_LOGP] + (float)rows * target_entropy) * inv_global_batch;
+}
+
+// tb_info (dsac_v2.py:188-202) from the accumulators.
+__global__ void finalize_stats_kernel(float* __restrict__ state, float inv_global_batch, float inv_policy_elems) {
+  if (threadIdx.x != 0) return;
+  const float* acc = state + ST_ACC;
+  float* o = state + ST_STATS;
+  o[0] = acc[ACC_Q1] * inv_global_batch;
+  o[1] = acc[ACC_Q2] * inv_global_batch;
+  o[2] = acc[ACC_S1] * inv_global_batch;
+  o[3] = acc[ACC_S2] * inv_global_batch;
+  o[4] = acc[ACC_MIN];
+  o[5] = acc[ACC_MIN + 1];
+  o[6] = acc[ACC_LOSS_PI] * inv_global_batch;
+  o[7] = acc[ACC_LOSS_Q] * inv_global_batch;
+  o[8] = acc[ACC_TANH_MEAN] * inv_policy_elems;
+  o[9] = acc[ACC_PI_STD] * inv_policy_elems;
+  o[10] = -acc[ACC_LOGP] * inv_global_batch;
+  o[11] = state[ST_ALPHA_USED];
+  o[12] = state[ST_MEAN_STD1];
+  o[13] = state[ST_MEAN_STD2];
+  o[14] = 0.f;
+  o[15] = 0.f;
+}
+
+__global__ void set_carry_kernel(float* __restrict__ state, float m1, float m2, int tq, int tp) {
+  if (threadIdx.x == 0) {
+    state[ST_MEAN_STD1] = m1;
+    state[ST_MEAN_STD2] = m2;
+    reinterpret_cast<int*>(state)[ST_ADAM_Q] = tq;
+    reinterpret_cast<int*>(state)[ST_ADAM_PI] = tp;
+  }
+}
+
+}  // namespace dsact

@@ -1,0 +1,160 @@
+"""`training.trainer` of the drop-in: `OffSerialTrainer` with the reference's
+constructor, `step()`, `train()` and `save_apprfunc()` (reference
+training/trainer.py:15-158), reorganised around the GPU-resident engine:
+
+* the six networks live on the GPU for the whole run (no `ModuleOnDevice`
+  ping-pong, reference :64,:92); the CPU sampler and evaluator act with a CPU
+  mirror of the policy that is refreshed from the flat parameter buffer every
+  `policy_mirror_interval` iterations (1 = the reference's semantics: sample
+  with the current weights);
+* replay minibatches are gathered on the GPU (no per-step `.cuda()` copies, :72-74);
+* `tb_info` is fetched from the device only on iterations that log.
+"""
+__all__ = ["OffSerialTrainer", "create_trainer"]
+
+import os
+import time
+from math import inf
+
+import torch
+
+from dsact_host import TB_TAGS as tb_tags
+
+
+def _add_scalars(tb_info, writer, step):
+    for key, value in tb_info.items():
+        writer.add_scalar(key, value, step)
+
+
+class OffSerialTrainer:
+    def __init__(self, alg, sampler, buffer, evaluator, **kwargs):
+        self.alg = alg
+        self.sampler = sampler
+        self.buffer = buffer
+        self.evaluator = evaluator
+        self.per_flag = kwargs["buffer_name"] == "prioritized_replay_buffer"
+        if self.per_flag:
+            raise NotImplementedError("prioritized replay is not part of the B200 update path")
+
+        self.networks = self.alg.networks
+        if kwargs.get("ini_network_dir") is not None:
+            self.networks.load_state_dict(torch.load(kwargs["ini_network_dir"]))
+
+        self.replay_batch_size = kwargs["replay_batch_size"]
+        self.max_iteration = kwargs["max_iteration"]
+        self.sample_interval = kwargs.get("sample_interval", 1)
+        self.log_save_interval = kwargs["log_save_interval"]
+        self.apprfunc_save_interval = kwargs["apprfunc_save_interval"]
+        self.eval_interval = kwargs["eval_interval"]
+        self.mirror_interval = max(1, int(kwargs.get("policy_mirror_interval", 1)))
+        self.best_tar = -inf
+        self.save_folder = kwargs["save_folder"]
+        self.iteration = 0
+
+        # the update engine is CUDA-only: the networks go to the GPU whatever `use_gpu` says
+        self.use_gpu = True
+        if not kwargs.get("use_gpu", False):
+            print("dsac-v2_b200: the DSAC-T update runs on the CUDA engine; moving the networks to the GPU")
+        self.networks.cuda()
+        engine = self.networks.engine(self.replay_batch_size)
+        if hasattr(self.buffer, "attach"):
+            self.buffer.attach(engine)
+
+        # CPU mirror of the behaviour policy for sampler and evaluator (they were handed
+        # `alg.networks` itself in the reference, :24-26)
+        self.cpu_networks = self.sampler.networks
+        self.evaluator.networks = self.cpu_networks
+        self._policy_span = self._find_policy_span()
+        self._policy_host = torch.empty(self._policy_span[1] - self._policy_span[0]).pin_memory()
+        self.refresh_policy_mirror()
+
+        self.writer = None
+        if kwargs.get("dsact_tensorboard", True):
+            from torch.utils.tensorboard import SummaryWriter
+            self.writer = SummaryWriter(log_dir=self.save_folder, flush_secs=20)
+            _add_scalars({tb_tags["alg_time"]: 0, tb_tags["sampler_time"]: 0}, self.writer, 0)
+            self.writer.flush()
+
+        while self.buffer.size < kwargs["buffer_warm_size"]:
+            samples, _ = self.sampler.sample()
+            self.buffer.add_batch(samples)
+
+        self.start_time = time.time()
+
+    # ---- policy mirror ----------------------------------------------------------------
+    def _find_policy_span(self):
+        n_q = sum(p.numel() for p in self.networks.q1.parameters())
+        n_pi = sum(p.numel() for p in self.networks.policy.parameters())
+        return 2 * n_q, 2 * n_q + n_pi
+
+    def refresh_policy_mirror(self):
+        """Copy the current policy weights GPU -> pinned host -> the CPU module sampler/evaluator use."""
+        lo, hi = self._policy_span
+        eng = self.networks.engine()
+        self._policy_host.copy_(eng.params[lo:hi], non_blocking=True)
+        torch.cuda.current_stream(eng.device).synchronize()
+        off = 0
+        with torch.no_grad():
+            for p in self.cpu_networks.policy.parameters():
+                p.copy_(self._policy_host[off:off + p.numel()].view(p.shape))
+                off += p.numel()
+
+    # ---- one iteration (reference :60-138) -----------------------------------------------
+    def step(self):
+        sampler_tb_dict = {}
+        if self.iteration % self.sample_interval == 0:
+            if self.iteration % self.mirror_interval == 0:
+                self.refresh_policy_mirror()
+            sampler_samples, sampler_tb_dict = self.sampler.sample()
+            self.buffer.add_batch(sampler_samples)
+
+        replay_samples = self.buffer.sample_batch(self.replay_batch_size)
+        alg_tb_dict = self.alg.local_update(replay_samples, self.iteration)
+
+        if self.iteration % self.log_save_interval == 0:
+            print("Iter = ", self.iteration)
+            if self.writer is not None:
+                _add_scalars(alg_tb_dict, self.writer, step=self.iteration)
+                _add_scalars(sampler_tb_dict, self.writer, step=self.iteration)
+        self.last_tb = alg_tb_dict
+
+        if self.iteration % self.eval_interval == 0:
+            self.refresh_policy_mirror()
+            total_avg_return = self.evaluator.run_evaluation(self.iteration)
+            if total_avg_return >= self.best_tar and self.iteration >= self.max_iteration / 5:
+                self.best_tar = total_avg_return
+                print("Best return = {}!".format(str(self.best_tar)))
+                folder = self.save_folder + "/apprfunc/"
+                for filename in os.listdir(folder):
+                    if filename.endswith("_opt.pkl"):
+                        os.remove(folder + filename)
+                torch.save(self.networks.state_dict(), folder + "apprfunc_{}_opt.pkl".format(self.iteration))
+            if self.writer is not None:
+                w, it = self.writer, self.iteration
+                w.add_scalar(tb_tags["Buffer RAM of RL iteration"], self.buffer.__get_RAM__(), it)
+                w.add_scalar(tb_tags["TAR of RL iteration"], total_avg_return, it)
+                w.add_scalar(tb_tags["TAR of replay samples"], total_avg_return, it * self.replay_batch_size)
+                w.add_scalar(tb_tags["TAR of total time"], total_avg_return, int(time.time() - self.start_time))
+                w.add_scalar(tb_tags["TAR of collected samples"], total_avg_return,
+                             self.sampler.get_total_sample_number())
+
+        if self.iteration % self.apprfunc_save_interval == 0:
+            self.save_apprfunc()
+
+    def train(self):
+        while self.iteration < self.max_iteration:
+            self.step()
+            self.iteration += 1
+        self.save_apprfunc()
+        if self.writer is not None:
+            self.writer.flush()
+
+    def save_apprfunc(self):
+        os.makedirs(self.save_folder + "/apprfunc", exist_ok=True)
+        torch.save(self.networks.state_dict(), self.save_folder + "/apprfunc/apprfunc_{}.pkl".format(self.iteration))
+
+
+def create_trainer(alg, sampler, buffer, evaluator, **kwargs):
+    trainer = OffSerialTrainer(alg, sampler, buffer, evaluator, **kwargs)
+    print("Create trainer successfully!")
+    return trainer

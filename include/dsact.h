@@ -1,0 +1,201 @@
+/*
+ * dsact.h — C ABI of the B200-native DSAC-T update engine (libdsact.so).
+ *
+ * Drop-in boundary for ONE path of Jingliang-Duan/DSAC-v2: the per-step
+ * critic/actor/temperature update over a replay minibatch,
+ *     DSAC_V2.local_update(data, iteration)             reference dsac_v2.py:102-105
+ * plus the replay minibatch gather that feeds it,
+ *     ReplayBuffer.sample_batch(batch_size)             reference training/replay_buffer.py:85-90
+ * called from OffSerialTrainer.step                      reference training/trainer.py:69,82.
+ *
+ * Conventions
+ *  - plain C types only; every function returns 0 on success or a negative
+ *    DSACT_E* code, and `dsact_last_error()` holds a message for the caller's thread;
+ *  - the CALLER (PyTorch) owns every device allocation; the library borrows
+ *    pointers handed over in `dsact_bind*` and never frees them;
+ *  - all work is enqueued on the caller's CUDA stream (`cudaStream_t` passed as
+ *    `void*`) and is asynchronous with respect to the host;
+ *  - one handle per device and per trainer thread (not thread safe);
+ *  - all tensors are fp32, row-major, contiguous unless a leading dimension is given.
+ *
+ * Flat parameter layout (`dsact_layout`): params = [ q1 | q2 | policy | log_alpha ],
+ * targets = [ q1_target | q2_target | policy_target ]; each network is the
+ * concatenation, in `state_dict` order (reference SURVEY §4 schema), of
+ * weight_j [out_j, in_j] then bias_j [out_j].  grads / adam_m / adam_v mirror params.
+ */
+#ifndef DSACT_H
+#define DSACT_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DSACT_ABI_VERSION 1
+#define DSACT_MAX_HIDDEN 6
+#define DSACT_NUM_STATS 16
+
+enum {
+  DSACT_OK = 0,
+  DSACT_EINVAL = -1,   /* bad argument / unsupported configuration */
+  DSACT_ECUDA = -2,    /* a CUDA runtime call failed */
+  DSACT_ESTATE = -3,   /* call sequence error (e.g. step before bind) */
+  DSACT_EARCH = -4     /* device is not sm_100 */
+};
+
+/* hidden activations, reference utils/common_utils.py:16-45 */
+enum {
+  DSACT_ACT_LINEAR = 0, DSACT_ACT_RELU = 1, DSACT_ACT_GELU = 2, DSACT_ACT_TANH = 3,
+  DSACT_ACT_SIGMOID = 4, DSACT_ACT_ELU = 5, DSACT_ACT_SELU = 6
+};
+
+/* arithmetic of the dense layers */
+enum {
+  DSACT_GEMM_FP32 = 0,     /* fp32 FFMA, bit-comparable with the reference's fp32 path */
+  DSACT_GEMM_BF16X3 = 1,   /* tcgen05 bf16 split-precision (hi*hi + hi*lo + lo*hi), fp32 accumulate */
+  DSACT_GEMM_BF16 = 2      /* tcgen05 single-pass bf16, fp32 accumulate (throughput mode) */
+};
+
+/* What ApproxContainer.__init__ + DSAC_V2.__init__ read from kwargs
+ * (reference dsac_v2.py:25-59,79-90; utils/common_utils.py:48-89). */
+typedef struct dsact_config {
+  int32_t abi_version;           /* = DSACT_ABI_VERSION */
+  int32_t obs_dim;               /* obsv_dim */
+  int32_t act_dim;               /* action_dim */
+  int32_t n_hidden_q;            /* len(value_hidden_sizes) */
+  int32_t n_hidden_pi;           /* len(policy_hidden_sizes) */
+  int32_t hidden_q[DSACT_MAX_HIDDEN];
+  int32_t hidden_pi[DSACT_MAX_HIDDEN];
+  int32_t act_q;                 /* value_hidden_activation  */
+  int32_t act_pi;                /* policy_hidden_activation */
+  int32_t max_batch;             /* largest minibatch a step will see */
+  int32_t auto_alpha;            /* dsac_v2.py:85 */
+  int32_t delay_update;          /* dsac_v2.py:87 */
+  int32_t gemm_mode;             /* DSACT_GEMM_* */
+  int32_t use_graph;             /* replay captured CUDA graphs for repeated identical calls */
+  /* scalars are doubles because the reference holds them as Python floats and forms
+   * 1-beta, lr/(1-beta^t) ... in double before they touch an fp32 tensor */
+  double gamma, tau, tau_b;       /* dsac_v2.py:82,83,90 */
+  double alpha_fixed;             /* dsac_v2.py:86 (used when auto_alpha == 0) */
+  double lr_q, lr_pi, lr_alpha;   /* dsac_v2.py:54-59 */
+  double min_log_std, max_log_std;/* networks/mlp.py:73-74 */
+  double adam_beta1, adam_beta2, adam_eps; /* torch.optim.Adam defaults 0.9 / 0.999 / 1e-8 */
+} dsact_config;
+
+typedef struct dsact_layout {
+  int64_t n_q;          /* floats in one Q network */
+  int64_t n_pi;         /* floats in the policy network */
+  int64_t n_params;     /* 2*n_q + n_pi + 1 (log_alpha last) */
+  int64_t n_targets;    /* 2*n_q + n_pi */
+  int64_t workspace_bytes; /* activation / scratch arena the caller must provide */
+  int64_t state_floats; /* persistent device state (EMA, counters, accumulators, stats) */
+  int64_t max_batch;
+} dsact_layout;
+
+/* Device pointers of caller-owned tensors. */
+typedef struct dsact_buffers {
+  float *params, *targets, *grads, *adam_m, *adam_v;
+  const float *act_high, *act_low;   /* [act_dim], policy.act_high_lim / act_low_lim */
+  float *state;                      /* [state_floats], zero-initialised by the caller */
+  void *workspace;                   /* [workspace_bytes], 256-byte aligned */
+} dsact_buffers;
+
+/* One replay minibatch, device pointers (the dict `data`, dsac_v2.py:219-225). */
+typedef struct dsact_batch {
+  const float *obs, *act, *rew, *obs2, *done;
+  int32_t batch;
+  const float *logp;  /* behaviour log-prob; stored and gathered like the reference does, never read by the update */
+} dsact_batch;
+
+/* The normal draws that affect an update: eps1/eps2 [B,A]
+ * for the two rsample() calls, z3/z4 [B] for the two target __q_evaluate calls.
+ * Pass NULL instead of the struct to draw them on the device (Philox4x32-10). */
+typedef struct dsact_noise {
+  const float *eps1, *eps2, *z3, *z4;
+} dsact_noise;
+
+typedef struct dsact_handle dsact_handle;
+
+const char *dsact_last_error(void);
+int dsact_abi_version(void);
+
+/* sizes implied by a configuration; no device needed */
+int dsact_query_layout(const dsact_config *cfg, dsact_layout *out);
+
+/* replaces ApproxContainer/DSAC_V2 construction (dsac_v2.py:25-59,79-90) */
+int dsact_create(const dsact_config *cfg, int device, dsact_handle **out);
+void dsact_destroy(dsact_handle *h);
+int dsact_bind(dsact_handle *h, const dsact_buffers *bufs);
+
+/* seed / counter of the device noise generator and of replay index sampling */
+int dsact_seed(dsact_handle *h, uint64_t seed);
+
+/* overwrite the carried scalars: mean_std1/2 (< 0 = "unset", dsac_v2.py:88-89),
+ * Adam step counters of the critics and of policy/alpha */
+int dsact_set_carry(dsact_handle *h, float mean_std1, float mean_std2,
+                    int64_t adam_steps_q, int64_t adam_steps_pi, void *stream);
+
+/* DSAC_V2.local_update (dsac_v2.py:102-105): gradients + Adam + delayed Polyak */
+int dsact_step(dsact_handle *h, const dsact_batch *batch, const dsact_noise *noise,
+               int64_t iteration, void *stream);
+
+/* split form = get_remote_update_info / remote_update (dsac_v2.py:107-138).
+ * phase1: all forwards up to the per-critic sum of std over the local shard
+ *         (state[DSACT_STATE_STDSUM..+1]); phase2: EMA, losses, all backward passes
+ *         with loss means taken over `global_batch` rows.  A data-parallel caller
+ *         all-reduces the two std sums between the phases and `grads` after phase2. */
+int dsact_grad_phase1(dsact_handle *h, const dsact_batch *batch, const dsact_noise *noise, void *stream);
+int dsact_grad_phase2(dsact_handle *h, int64_t global_batch, void *stream);
+int dsact_compute_grads(dsact_handle *h, const dsact_batch *batch, const dsact_noise *noise, void *stream);
+/* DSAC_V2.__update (dsac_v2.py:320-347) on whatever is in `grads` */
+int dsact_apply(dsact_handle *h, int64_t iteration, void *stream);
+
+/* tb_info (dsac_v2.py:188-202) of the last step, in this order:
+ *  0 q1 mean, 1 q2 mean, 2 std1 mean, 3 std2 mean, 4 min std1, 5 min std2,
+ *  6 actor loss, 7 critic loss, 8 mean tanh(policy mean), 9 mean policy std,
+ * 10 entropy, 11 alpha (pre-update), 12 mean_std1, 13 mean_std2, 14/15 reserved.
+ * Finalises the accumulators over `global_batch` rows and copies 16 floats to `host_out`
+ * (pinned or pageable) asynchronously on `stream`. */
+int dsact_read_stats(dsact_handle *h, int64_t global_batch, float *host_out, void *stream);
+
+/* ---- device replay ring buffer (ReplayBuffer, training/replay_buffer.py:15-90) ---- */
+typedef struct dsact_replay {
+  float *obs, *obs2, *act, *rew, *done, *logp; /* [capacity, O], [capacity, O], [capacity, A], 3x [capacity] */
+  int64_t capacity;
+} dsact_replay;
+
+int dsact_replay_bind(dsact_handle *h, const dsact_replay *rb);
+/* store(): copy n transitions (rows of the staging arrays; host-pinned, pageable or device)
+ * into rows (ptr + i) % capacity */
+int dsact_replay_add(dsact_handle *h, const float *obs, const float *obs2, const float *act,
+                     const float *rew, const float *done, const float *logp,
+                     int64_t n, int64_t ptr, void *stream);
+/* sample_batch(): gather rows idx[i] (device int64, or NULL = draw uniformly in [0,size) on
+ * the device) into the engine's batch arena; `out` receives the arena's device pointers */
+int dsact_replay_sample(dsact_handle *h, int32_t batch, int64_t size, const int64_t *idx,
+                        dsact_batch *out, void *stream);
+/* sample_batch + local_update in one submission (no host round trip in between) */
+int dsact_replay_step(dsact_handle *h, int32_t batch, int64_t size, const int64_t *idx,
+                      const dsact_noise *noise, int64_t iteration, void *stream);
+
+/* introspection for tests/bench: number of kernel launches (graph nodes included)
+ * submitted by this handle so far, and by the most recent entry-point call */
+int64_t dsact_launch_count(const dsact_handle *h);
+int32_t dsact_last_call_launches(const dsact_handle *h);
+
+/* raw dense-layer entry for unit tests of the GEMM kernels, in the handle's gemm_mode:
+ *  variant 0 (forward): C[M,N]  = A[M,K] * B[N,K]^T (+ bias[N])
+ *  variant 1 (dgrad)  : C[M,N]  = A[M,K] * B[K,N]
+ *  variant 2 (wgrad)  : C[M,N] += A[K,M]^T * B[K,N]   (split-K, atomic accumulate) */
+int dsact_test_gemm(dsact_handle *h, int32_t variant, const float *A, int32_t lda, const float *B, int32_t ldb,
+                    const float *bias, float *C, int32_t ldc, int32_t M, int32_t N, int32_t K, void *stream);
+
+#define DSACT_STATE_STDSUM 4   /* state[4], state[5]: local sums of critic std (phase1 -> phase2) */
+#define DSACT_STATE_ACC 16     /* state[16..47]: per-step accumulators (sums first, then mins) */
+#define DSACT_STATE_STATS 48   /* state[48..63]: finalised tb_info */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DSACT_H */

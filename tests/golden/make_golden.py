@@ -24,8 +24,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REPO = os.path.dirname(os.path.dirname(HERE))
 REF = os.environ.get("DSAC_REFERENCE", "/root/reference")
 
-sys.path.insert(0, os.path.join(REPO, "dsac-v2_b200"))
-import synth  # noqa: E402
+sys.path.insert(0, REPO)
+from dsac_v2_b200 import synth  # noqa: E402
 
 sys.path.insert(0, REF)
 sys.path.insert(0, os.path.join(HERE, "gymstub"))

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-import synth
+from dsac_v2_b200 import synth
 from oracle.dsact_oracle import TB_KEYS, from_config
 
 CASES = ["tiny_b16", "ragged_b37", "tiny_fixed_alpha", "pendulum_b256", "halfcheetah_b512",
