@@ -1,0 +1,352 @@
+#!/usr/bin/env python
+"""bench.py — DSAC-T gradient-steps/sec on synthetic Humanoid-shaped minibatches.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch 4096]
+
+Workload (BASELINE.json configs[1]): obs=376, act=17, MLP [256,256,256] for the policy and both
+critics, batch 4096 per GPU, device replay ring of 1e6 synthetic transitions (3.09 GB, far larger
+than the 126 MB L2: every step gathers fresh random rows from HBM).  One "step" = one
+`DSAC_V2.local_update`-equivalent: replay gather + 8 MLP forwards + losses + 3 backward passes +
+Adam + delayed Polyak.  Nothing is skipped on any iteration.
+
+`value`   : steps/s with inputs resident in HBM (`dsact_replay_step`: index draw, gather, update
+            in one CUDA-graph submission), device-timed with CUDA events, max over ranks.
+`e2e`     : the same step through the reference-facing API `DSAC_V2.local_update(data, it)` with
+            HOST (pinned) minibatches: H2D copies inside the timed region and the critic loss
+            read back to the host every step.
+`roofline`: the grouped fp32 GEMM kernel (all dense layers), algorithmic FLOPs / event-timed
+            duration from `dsact_profile_step`, against MEASURED_PEAKS.json.
+`cpu_baseline` / `--impl reference`: the torch-CPU oracle port of the reference path (the
+            reference is pure PyTorch, so the port issues the same ATen ops) on the host cores.
+N > 1 (torchrun): data parallel, one process per GPU, batch 4096 per GPU (weak scaling),
+NCCL all-reduce of the critic-std sums and of the flat gradients; `value` counts one
+4096-row minibatch update per rank per step.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+sys.path.insert(0, os.path.join(REPO, "dsac-v2_b200", "dropin"))
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+from dsac_v2_b200 import synth  # noqa: E402
+
+FLOP_PER_SAMPLE = 2 * 3_240_448  # 6.481 MFLOP per sample per step (H dims)
+METRIC = "DSAC-T gradient-steps/sec @ batch 4096 (Humanoid-dim)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=4096)
+    ap.add_argument("--config", default="humanoid", choices=list(synth.CONFIGS))
+    ap.add_argument("--replay-size", type=int, default=1_000_000)
+    ap.add_argument("--gemm", default="fp32")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    try:
+        p = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
+        return p["bf16_tflops_sustained"], p["hbm_gbs"], "measured"
+    except Exception:
+        return 1400.0, 6650.0, "fallback"  # B200_PROFILING.md fallback (sustained)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons while the timed region runs (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def oracle_setup(cfg, batch, ring_rows=100_000):
+    from oracle.dsact_oracle import from_config
+    torch.manual_seed(0)
+    orc = from_config(cfg, synth.make_weights(cfg), **synth.HYPER)
+    g = np.random.default_rng(123)
+    O, A, lim = cfg["obs_dim"], cfg["act_dim"], cfg["act_lim"]
+    ring = {"obs": g.standard_normal((ring_rows, O), dtype=np.float32),
+            "obs2": g.standard_normal((ring_rows, O), dtype=np.float32),
+            "act": g.uniform(-lim, lim, (ring_rows, A)).astype(np.float32),
+            "rew": g.standard_normal(ring_rows, dtype=np.float32),
+            "done": (g.random(ring_rows) < 0.01).astype(np.float32)}
+
+    def step(it):
+        idx = np.random.randint(0, ring_rows, size=batch)  # training/replay_buffer.py:85-90
+        data = {k: torch.as_tensor(v[idx]) for k, v in ring.items()}
+        noise = [torch.randn(batch, A), torch.randn(batch, A)] + [torch.randn(batch) for _ in range(6)]
+        return orc.update(data, noise, it)
+
+    return step
+
+
+def time_oracle(cfg, batch, warm, max_steps, budget_s):
+    step = oracle_setup(cfg, batch)
+    for it in range(warm):
+        step(it)
+    t0, n = time.perf_counter(), 0
+    while n < max_steps and (time.perf_counter() - t0 < budget_s or n < 2):
+        step(warm + n)
+        n += 1
+    dt = time.perf_counter() - t0
+    return n / dt, n, dt
+
+
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def run_reference(args, rank, world):
+    """The reference's own CPU implementation of the path (torch-CPU port, all host threads)."""
+    if rank != 0:
+        return
+    cfg = synth.CONFIGS[args.config]
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    step = oracle_setup(cfg, args.batch)
+    t0 = time.perf_counter()
+    step(0)
+    est = time.perf_counter() - t0
+    warm = min(args.warmup, max(1, int(20.0 / max(est, 1e-3))))
+    for it in range(1, warm):
+        step(it)
+    k = args.steps if est * args.steps <= 200.0 else max(3, int(200.0 / est))
+    t0 = time.perf_counter()
+    for it in range(k):
+        step(warm + it)
+    dt = time.perf_counter() - t0
+    value = k / dt
+    sample = f"{k} full updates of batch {args.batch} (+ numpy replay gather from 1e5 rows), {warm} warm-up"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": args.gpus,
+        "steps": k, "warmup": warm, "ms_per_step": 1000 * dt / k, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"gym_humanoid-shaped synthetic, obs=376 act=17 MLP[256,256,256] batch={args.batch}, CPU torch",
+                   "global_batch": args.batch, "host": cpu_model()},
+        "cpu_baseline": {"value": value, "unit": "steps/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", 0))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+
+    import torch.distributed as dist
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+
+    import dsac_v2
+    from training.replay_buffer import ReplayBuffer
+
+    cfg = synth.CONFIGS[args.config]
+    B, O, A = args.batch, cfg["obs_dim"], cfg["act_dim"]
+    kw = synth.reference_kwargs(cfg, replay_batch_size=B, dsact_gemm=args.gemm, buffer_max_size=args.replay_size,
+                                additional_info={})
+    alg = dsac_v2.DSAC_V2(**kw)
+    sd = alg.networks.state_dict()
+    for k, v in synth.make_weights(cfg).items():
+        sd[k] = torch.from_numpy(v)
+    alg.networks.load_state_dict(sd)
+    alg.networks.cuda()
+    eng = alg.networks.engine(B)
+    eng.seed(1000 + rank)
+    buf = ReplayBuffer(**kw)
+    buf.attach(eng)
+    g = torch.Generator(device=dev).manual_seed(123 + rank)  # synthetic transitions, SURVEY §8(d)
+    r = eng.replay
+    r["obs"].normal_(generator=g); r["obs2"].normal_(generator=g); r["rew"].normal_(generator=g)
+    r["act"].uniform_(-cfg["act_lim"], cfg["act_lim"], generator=g)
+    r["done"].copy_((torch.rand(args.replay_size, device=dev, generator=g) < 0.01).float())
+    buf.size, buf.ptr = args.replay_size, 0
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def dev_step(it):
+        if world == 1:
+            eng.replay_step(B, buf.size, it)
+        else:
+            alg.local_update(buf.sample_batch(B), it)
+
+    # ---- device-resident throughput ------------------------------------------------
+    it = 0
+    for _ in range(args.warmup):
+        dev_step(it); it += 1
+    launches_per_step = eng.last_call_launches() if world == 1 else None
+    barrier()
+    l0 = eng.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        e0.record()
+        for _ in range(args.steps):
+            dev_step(it); it += 1
+        e1.record()
+        barrier()
+        extra = max(0.0, 1.2 - e0.elapsed_time(e1) / 1000)  # keep the sampler alive for a few readings
+        if extra:
+            t_end = time.time() + extra
+            while time.time() < t_end:
+                dev_step(it); it += 1
+            torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_per_step = ms.item() / args.steps
+    launches = eng.launch_count() - l0 if world == 1 else None
+    value = world * 1000.0 / ms_per_step
+
+    # ---- end to end through DSAC_V2.local_update with host minibatches ------------------
+    ring = []
+    hg = torch.Generator().manual_seed(7 + rank)
+    for _ in range(4):
+        ring.append({"obs": torch.randn(B, O, generator=hg).pin_memory(), "obs2": torch.randn(B, O, generator=hg).pin_memory(),
+                     "act": ((torch.rand(B, A, generator=hg) * 2 - 1) * cfg["act_lim"]).pin_memory(),
+                     "rew": torch.randn(B, generator=hg).pin_memory(),
+                     "done": (torch.rand(B, generator=hg) < 0.01).float().pin_memory()})
+    sink = 0.0
+    for i in range(max(3, args.warmup // 2)):
+        sink += alg.local_update(ring[i % 4], it)["Loss/Critic loss-RL iter"]; it += 1
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        tb = alg.local_update(ring[i % 4], it); it += 1
+        sink += tb["Loss/Critic loss-RL iter"]  # device -> host read of the step's result, every step
+    e1.record()
+    barrier()
+    ms2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    e2e_value = world * 1000.0 * args.steps / ms2.item()
+    assert np.isfinite(sink)
+
+    # ---- roofline of the dominant kernel (grouped GEMM), per-launch events, eager -------------------
+    peak_tf, peak_hbm, peak_src = peaks()
+    roof = None
+    if rank == 0:
+        data = buf.sample_batch(B)
+        acc = None
+        for _ in range(5):
+            p = eng.profile_step(data, it); it += 1
+            if acc is None:
+                acc = p
+            else:
+                acc["total_ms"] += p["total_ms"]
+                for k in ("other", "gemm_fwd", "gemm_dgrad", "gemm_wgrad"):
+                    for f in ("ms", "flops", "launches"):
+                        acc[k][f] += p[k][f]
+        gem = [acc[k] for k in ("gemm_fwd", "gemm_dgrad", "gemm_wgrad")]
+        g_ms, g_fl, g_n = sum(x["ms"] for x in gem), sum(x["flops"] for x in gem), sum(x["launches"] for x in gem)
+        achieved = g_fl / (g_ms * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": "dsact::gemm_kernel (grouped dense layers: forward, dgrad, wgrad)",
+                "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None,
+                "peak_source": f"bf16_tflops_sustained of {peak_src} (arithmetic here is {args.gemm})",
+                "flop_per_sample_measured": g_fl / 5 / B, "flop_per_sample_survey": FLOP_PER_SAMPLE,
+                "avg_launch_us": 1000 * g_ms / g_n, "launches_per_step": g_n // 5,
+                "share_of_step": g_ms / acc["total_ms"],
+                "by_kind": {k: {"tflops": acc[k]["flops"] / (acc[k]["ms"] * 1e-3) / 1e12, "ms_per_step": acc[k]["ms"] / 5}
+                            for k in ("gemm_fwd", "gemm_dgrad", "gemm_wgrad")},
+                "other_ms_per_step": acc["other"]["ms"] / 5, "eager_step_ms": acc["total_ms"] / 5}
+
+    # ---- CPU baseline (oracle port) on the host cores ----------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        torch.set_num_threads(threads)
+        v, n, dt = time_oracle(cfg, B, warm=2, max_steps=60, budget_s=12.0)
+        cpu = {"value": v, "unit": "steps/s", "cores": threads, "kind": "port",
+               "sample": f"{n} full updates of batch {B} incl. numpy replay gather ({dt:.1f} s), {cpu_model()}"}
+
+    if rank == 0:
+        out = {
+            "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32" if args.gemm == "fp32" else args.gemm, "data": "synthetic",
+            "config": {"workload": f"gym_{args.config} shapes (obs={O} act={A}) MLP{list(cfg['hidden'])} batch_size={B} per GPU, "
+                                   f"device replay ring {args.replay_size} rows, device index+noise generation",
+                       "global_batch": B * world, "parallelism": f"dp{world}" if world > 1 else "single",
+                       "l2": f"inputs exceed L2: each step gathers {B} random rows from a {4 * args.replay_size * (2 * O + A + 3) / 1e9:.2f} GB ring",
+                       "gemm_mode": args.gemm, "cuda_graph": True},
+            "clocks": clocks.summary(),
+            "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": 4 * B * (2 * O + A + 2),
+                    "d2h_bytes_per_step": 64, "api": "DSAC_V2.local_update(host pinned dict, iteration) + tb_info read"},
+            "gpu_launches": launches,
+            "launches_per_step": launches_per_step,
+            "tflops_algorithmic": FLOP_PER_SAMPLE * B * value / world / 1e12 if args.config == "humanoid" else None,
+            "roofline": roof,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

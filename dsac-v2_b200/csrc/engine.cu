@@ -104,11 +104,29 @@ struct dsact_handle {
   float* W() const { return reinterpret_cast<float*>(buf.workspace); }
 };
 
+enum { CLS_OTHER = 0, CLS_GEMM_FWD = 1, CLS_GEMM_DGRAD = 2, CLS_GEMM_WGRAD = 3, CLS_COUNT = 4 };
+struct Prof {  // dsact_profile_step: an event after every launch
+  std::vector<cudaEvent_t> ev;
+  std::vector<int> cls;
+  std::vector<double> flops;
+};
 struct Ctx {
   cudaStream_t s;
   int launches;
   cudaError_t err;
+  Prof* prof = nullptr;
   void check() { cudaError_t e = cudaGetLastError(); if (e != cudaSuccess && err == cudaSuccess) err = e; }
+  void done(int cls = CLS_OTHER, double flops = 0.0) {
+    launches++;
+    if (prof) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      cudaEventRecord(e, s);
+      prof->ev.push_back(e);
+      prof->cls.push_back(cls);
+      prof->flops.push_back(flops);
+    }
+  }
 };
 
 // ---- GEMM group launch -------------------------------------------------------
@@ -119,7 +137,9 @@ static void launch_variant(const GemmGroup& g, int variant, int grid, Ctx& c) {
   if (variant == V_FWD) gemm_kernel<BM, BN, true, true><<<grid, 256, 0, c.s>>>(g);
   else if (variant == V_DGRAD) gemm_kernel<BM, BN, true, false><<<grid, 256, 0, c.s>>>(g);
   else gemm_kernel<BM, BN, false, false><<<grid, 256, 0, c.s>>>(g);
-  c.launches++;
+  double flops = 0.0;
+  for (int i = 0; i < g.n; ++i) flops += 2.0 * g.p[i].M * g.p[i].N * ((double)g.p[i].K[0] + g.p[i].K[1]);
+  c.done(CLS_GEMM_FWD + variant, flops);
   c.check();
 }
 
@@ -213,7 +233,7 @@ static void enqueue_phase1(dsact_handle* h, const dsact_batch& bt, const dsact_n
   const float *Pq[2] = {P, P + q.n}, *Ppi = P + 2 * q.n;
   const float *Tq[2] = {T, T + q.n}, *Tpi = T + 2 * q.n;
 
-  begin_step_kernel<<<1, 32, 0, c.s>>>(h->buf.state); c.launches++;
+  begin_step_kernel<<<1, 32, 0, c.s>>>(h->buf.state); c.done();
   cudaMemsetAsync(h->buf.grads, 0, sizeof(float) * (2 * q.n + pi.n + 1), c.s);
 
   const float *eps1, *eps2, *z3, *z4;
@@ -223,8 +243,9 @@ static void enqueue_phase1(dsact_handle* h, const dsact_batch& bt, const dsact_n
     const int total = (B * A + 1) / 2 * 2 + (B + 1) / 2 * 2;
     int blocks = (total / 2 + 255) / 256; if (blocks < 1) blocks = 1;
     noise_kernel<<<blocks, 256, 0, c.s>>>(W + ar.eps1, W + ar.eps2, W + ar.z3, W + ar.z4, B, A, h->seed, h->buf.state);
+    c.done();
     rng_advance_kernel<<<1, 32, 0, c.s>>>(h->buf.state);
-    c.launches += 2;
+    c.done();
   }
 
   // wave A: pi(obs), pi'(obs2), Q1(s,a), Q2(s,a), layer by layer
@@ -260,7 +281,7 @@ static void enqueue_phase1(dsact_handle* h, const dsact_batch& bt, const dsact_n
     a.hi = h->buf.act_high; a.lo = h->buf.act_low; a.state = h->buf.state;
     a.B = B; a.A = A; a.min_log_std = (float)cf.min_log_std; a.max_log_std = (float)cf.max_log_std;
     int blocks = (B + 7) / 8; if (blocks > 4 * h->num_sms) blocks = 4 * h->num_sms;
-    sample_kernel<<<dim3(blocks, 2), 256, 0, c.s>>>(a); c.launches++;
+    sample_kernel<<<dim3(blocks, 2), 256, 0, c.s>>>(a); c.done();
   }
 
   // wave B: Q1', Q2' on (s', a') and Q1, Q2 on (s, a~)
@@ -280,7 +301,7 @@ static void enqueue_phase1(dsact_handle* h, const dsact_batch& bt, const dsact_n
 
   {
     int blocks = (B + 255) / 256; if (blocks > 2 * h->num_sms) blocks = 2 * h->num_sms;
-    std_sum_kernel<<<blocks, 256, 0, c.s>>>(W + ar.outQ[0], W + ar.outQ[1], B, h->buf.state); c.launches++;
+    std_sum_kernel<<<blocks, 256, 0, c.s>>>(W + ar.outQ[0], W + ar.outQ[1], B, h->buf.state); c.done();
   }
   h->pending_eps1 = eps1; h->pending_z3 = z3; h->pending_z4 = z4;
   c.check();
@@ -299,7 +320,7 @@ static void enqueue_phase2(dsact_handle* h, const dsact_batch& bt, int64_t globa
   const float invB = (float)(1.0 / (double)global_batch);
 
   ema_kernel<<<1, 32, 0, c.s>>>(h->buf.state, P + 2 * q.n + pi.n, invB, (float)cf.tau_b, cf.auto_alpha, (float)cf.alpha_fixed);
-  c.launches++;
+  c.done();
   {
     LossArgs a;
     a.rew = bt.rew; a.done = bt.done;
@@ -312,7 +333,7 @@ static void enqueue_phase2(dsact_handle* h, const dsact_batch& bt, int64_t globa
     }
     a.state = h->buf.state; a.B = B; a.gamma = (float)cf.gamma; a.inv_global_batch = invB;
     int blocks = (B + 255) / 256; if (blocks > 2 * h->num_sms) blocks = 2 * h->num_sms;
-    loss_kernel<<<blocks, 256, 0, c.s>>>(a); c.launches++;
+    loss_kernel<<<blocks, 256, 0, c.s>>>(a); c.done();
   }
 
   // wave C: critic passes 0,1 (dgrad + wgrad) and actor passes 4,5 (dgrad only), top layer down
@@ -350,7 +371,7 @@ static void enqueue_phase2(dsact_handle* h, const dsact_batch& bt, int64_t globa
     a.B = B; a.A = A; a.min_log_std = (float)cf.min_log_std; a.max_log_std = (float)cf.max_log_std;
     a.inv_global_batch = invB;
     int blocks = (B + 63) / 64; if (blocks > 2 * h->num_sms) blocks = 2 * h->num_sms; if (blocks < 1) blocks = 1;
-    policy_grad_kernel<<<blocks, 256, 0, c.s>>>(a); c.launches++;
+    policy_grad_kernel<<<blocks, 256, 0, c.s>>>(a); c.done();
   }
 
   // wave D: policy backward
@@ -367,7 +388,7 @@ static void enqueue_phase2(dsact_handle* h, const dsact_batch& bt, int64_t globa
   }
 
   alpha_grad_kernel<<<1, 32, 0, c.s>>>(G + 2 * q.n + pi.n, h->buf.state, invB, -(float)cf.act_dim, B);
-  c.launches++;
+  c.done();
   c.check();
 }
 
@@ -384,8 +405,9 @@ static void enqueue_apply(dsact_handle* h, Ctx& c) {
   int blocks = (int)((a.n_all + 255) / 256);
   if (blocks > 8 * h->num_sms) blocks = 8 * h->num_sms;
   apply_kernel<<<blocks, 256, 0, c.s>>>(a);
+  c.done();
   advance_kernel<<<1, 32, 0, c.s>>>(h->buf.state, cf.delay_update);
-  c.launches += 2;
+  c.done();
   c.check();
 }
 
@@ -396,14 +418,14 @@ static void enqueue_gather(dsact_handle* h, int B, const int64_t* idx, Ctx& c) {
   if (!idx) {
     int64_t* dst = reinterpret_cast<int64_t*>(W + ar.idx);
     int blocks = ((B + 1) / 2 + 255) / 256;
-    index_kernel<<<blocks, 256, 0, c.s>>>(dst, B, h->seed, h->buf.state); c.launches++;
+    index_kernel<<<blocks, 256, 0, c.s>>>(dst, B, h->seed, h->buf.state); c.done();
     use = dst;
   }
   int blocks = (B + 7) / 8; if (blocks > 8 * h->num_sms) blocks = 8 * h->num_sms;
   gather_kernel<<<blocks, 256, 0, c.s>>>(h->rb.obs, h->rb.obs2, h->rb.act, h->rb.rew, h->rb.done, h->rb.logp, use,
                                           W + ar.obs, W + ar.obs2, W + ar.act, W + ar.rew, W + ar.done, W + ar.logp, B,
                                           h->cfg.obs_dim, h->cfg.act_dim);
-  c.launches++;
+  c.done();
   c.check();
 }
 
@@ -745,7 +767,7 @@ int dsact_replay_sample(dsact_handle* h, int32_t batch, int64_t size, const int6
   key.batch = batch; key.idx = idx;
   rc = run(h, (cudaStream_t)stream, key, [&](Ctx& c) {
     enqueue_gather(h, batch, idx, c);
-    if (!idx) { rng_advance_kernel<<<1, 32, 0, c.s>>>(h->buf.state); c.launches++; }
+    if (!idx) { rng_advance_kernel<<<1, 32, 0, c.s>>>(h->buf.state); c.done(); }
   });
   if (rc) return rc;
   if (out) *out = arena_batch(h, batch);
@@ -768,13 +790,57 @@ int dsact_replay_step(dsact_handle* h, int32_t batch, int64_t size, const int64_
   key.idx = idx;
   rc = run(h, (cudaStream_t)stream, key, [&](Ctx& c) {
     enqueue_gather(h, batch, idx, c);
-    if (!idx && np) { rng_advance_kernel<<<1, 32, 0, c.s>>>(h->buf.state); c.launches++; }
+    if (!idx && np) { rng_advance_kernel<<<1, 32, 0, c.s>>>(h->buf.state); c.done(); }
     enqueue_phase1(h, bt, np, c);  // device noise (np == null) advances the counter itself, after the index draw
     enqueue_phase2(h, bt, batch, c);
     enqueue_apply(h, c);
   });
   if (rc) return rc;
   h->pending = bt; h->pending_batch = batch;
+  h->dev_iter = iteration + 1;
+  return DSACT_OK;
+}
+
+int dsact_profile_step(dsact_handle* h, const dsact_batch* batch, const dsact_noise* noise, int64_t iteration,
+                       void* stream, dsact_profile* out) {
+  int rc = check_batch(h, batch);
+  if (rc || (rc = check_noise(noise))) return rc;
+  if (!out) return fail(DSACT_EINVAL, "null out");
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  rc = sync_iteration(h, iteration, s);
+  if (rc) return rc;
+  const dsact_batch bt = *batch;
+  dsact_noise nz; const dsact_noise* np = nullptr;
+  if (noise) { nz = *noise; np = &nz; }
+  Prof prof;
+  Ctx c{s, 0, cudaSuccess};
+  c.prof = &prof;
+  cudaEvent_t e0;
+  CUDA_TRY(cudaEventCreate(&e0));
+  CUDA_TRY(cudaEventRecord(e0, s));
+  enqueue_phase1(h, bt, np, c);
+  enqueue_phase2(h, bt, bt.batch, c);
+  enqueue_apply(h, c);
+  cudaError_t e = cudaStreamSynchronize(s);
+  memset(out, 0, sizeof(*out));
+  cudaEvent_t prev = e0;
+  for (size_t i = 0; i < prof.ev.size(); ++i) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, prev, prof.ev[i]);
+    out->ms[prof.cls[i]] += ms;
+    out->flops[prof.cls[i]] += prof.flops[i];
+    out->launches[prof.cls[i]] += 1;
+    out->total_ms += ms;
+    prev = prof.ev[i];
+  }
+  cudaEventDestroy(e0);
+  for (auto ev : prof.ev) cudaEventDestroy(ev);
+  if (c.err != cudaSuccess || e != cudaSuccess)
+    return fail(DSACT_ECUDA, "profile step failed: %s", cudaGetErrorString(c.err != cudaSuccess ? c.err : e));
+  h->launches += c.launches;
+  h->last_launches = c.launches;
+  h->pending = bt; h->pending_batch = bt.batch;
   h->dev_iter = iteration + 1;
   return DSACT_OK;
 }

@@ -108,6 +108,7 @@ class Engine:
             self._bind()
             check(self.lib.dsact_set_carry(self.h, -1.0, -1.0, 0, 0, self._stream()))
         self.replay = None
+        self._arena = None
         self._keep = None  # tensors referenced by the last enqueued call
 
     def _bind(self):
@@ -134,7 +135,30 @@ class Engine:
         return torch.cuda.current_stream(self.device).cuda_stream
 
     # ---- argument marshalling ------------------------------------------------
+    def _stage_in(self, data):
+        """Host minibatch -> the engine's minibatch arena with async copies (pinned sources overlap);
+        fixed destination pointers, so a captured graph is replayed."""
+        B = data["obs"].shape[0]
+        if B > self.cfg.max_batch:
+            raise ValueError(f"batch {B} > max_batch {self.cfg.max_batch}")
+        if self._arena is None or self._arena[0] != B:
+            O, A, r64 = self.cfg.obs_dim, self.cfg.act_dim, lambda n: (n + 63) // 64 * 64
+            mb = self.cfg.max_batch
+            offs, off = {}, 0
+            for k, n, w in (("obs", O, O), ("obs2", O, O), ("act", A, A), ("rew", 1, 1), ("done", 1, 1)):
+                offs[k] = (off, w)
+                off += r64(mb * n)
+            views = {k: self._ws_view[o:o + B * w].view((B, w) if k in ("obs", "obs2", "act") else (B,))
+                     for k, (o, w) in offs.items()}
+            self._arena = (B, views)
+        views = self._arena[1]
+        for k, v in views.items():
+            v.copy_(data[k].reshape(v.shape), non_blocking=True)
+        return views
+
     def _batch(self, data: Dict[str, torch.Tensor]) -> Batch:
+        if data["obs"].device.type == "cpu":
+            data = self._stage_in(data)
         t = {k: _f32c(data[k], self.device) for k in ("obs", "act", "rew", "obs2", "done")}
         B = t["obs"].shape[0]
         O, A = self.cfg.obs_dim, self.cfg.act_dim
@@ -145,10 +169,26 @@ class Engine:
         return Batch(t["obs"].data_ptr(), t["act"].data_ptr(), t["rew"].data_ptr(), t["obs2"].data_ptr(),
                      t["done"].data_ptr(), B, None)
 
+    def _noise_slots(self, B):
+        O, A, r64 = self.cfg.obs_dim, self.cfg.act_dim, lambda n: (n + 63) // 64 * 64
+        mb = self.cfg.max_batch
+        off = 2 * r64(mb * O) + r64(mb * A) + 3 * r64(mb) + r64(2 * mb)  # obs obs2 act rew done logp idx
+        out = []
+        for n, shape in ((A, (B, A)), (A, (B, A)), (1, (B,)), (1, (B,))):
+            out.append(self._ws_view[off:off + B * n].view(shape))
+            off += r64(mb * n)
+        return out
+
     def _noise(self, noise, B):
         if noise is None:
             return None, None
-        eps1, eps2, z3, z4 = (_f32c(torch.as_tensor(x), self.device) for x in noise)
+        noise = [torch.as_tensor(x) for x in noise]
+        if all(x.device.type == "cpu" for x in noise):  # stage into the arena's noise slots: stable pointers
+            slots = self._noise_slots(B)
+            for dst, src in zip(slots, noise):
+                dst.copy_(src.reshape(dst.shape), non_blocking=True)
+            noise = slots
+        eps1, eps2, z3, z4 = (_f32c(x, self.device) for x in noise)
         A = self.cfg.act_dim
         if eps1.shape != (B, A) or eps2.shape != (B, A) or z3.numel() != B or z4.numel() != B:
             raise ValueError("noise shapes must be eps1/eps2 [B,A], z3/z4 [B]")
@@ -164,6 +204,18 @@ class Engine:
             self._keep_noise = keep
             check(self.lib.dsact_step(self.h, C.byref(b), n, int(iteration), self._stream()))
         self.last_batch = b.batch
+
+    def profile_step(self, data, iteration: int, noise=None) -> dict:
+        """One eager step with per-launch CUDA events (bench.py's roofline leg)."""
+        out = _lib.Profile()
+        with torch.cuda.device(self.device):
+            b = self._batch(data)
+            n, keep = self._noise(noise, b.batch)
+            check(self.lib.dsact_profile_step(self.h, C.byref(b), n, int(iteration), self._stream(), C.byref(out)))
+        self.last_batch = b.batch
+        names = ("other", "gemm_fwd", "gemm_dgrad", "gemm_wgrad")
+        return {"total_ms": out.total_ms,
+                **{k: {"ms": out.ms[i], "flops": out.flops[i], "launches": out.launches[i]} for i, k in enumerate(names)}}
 
     def compute_grads(self, data, noise=None):
         with torch.cuda.device(self.device):

@@ -184,6 +184,17 @@ int dsact_replay_step(dsact_handle *h, int32_t batch, int64_t size, const int64_
 int64_t dsact_launch_count(const dsact_handle *h);
 int32_t dsact_last_call_launches(const dsact_handle *h);
 
+/* One eager (un-graphed) dsact_step with a CUDA event after every launch; per kernel class
+ * [0 elementwise/other, 1 forward GEMM, 2 dgrad GEMM, 3 wgrad GEMM]: device milliseconds,
+ * algorithmic FLOPs (2*M*N*K of every problem) and launch count.  Synchronises the stream. */
+typedef struct dsact_profile {
+  double ms[4], flops[4];
+  int32_t launches[4];
+  double total_ms;
+} dsact_profile;
+int dsact_profile_step(dsact_handle *h, const dsact_batch *batch, const dsact_noise *noise, int64_t iteration,
+                       void *stream, dsact_profile *out);
+
 /* raw dense-layer entry for unit tests of the GEMM kernels, in the handle's gemm_mode:
  *  variant 0 (forward): C[M,N]  = A[M,K] * B[N,K]^T (+ bias[N])
  *  variant 1 (dgrad)  : C[M,N]  = A[M,K] * B[K,N]
