@@ -131,6 +131,26 @@ def oracle_setup(cfg, batch, ring_rows=100_000):
     return step
 
 
+def pick_threads(cfg, batch):
+    """torch intra-op threads for the CPU arm: the reference pins 4 (utils/init_args.py:14); more helps up to
+    a point, and a container may see far more cores than it may use.  Try a few, keep the fastest."""
+    step = oracle_setup(cfg, batch)
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    best, best_t = 4, None
+    for n in sorted({4, 8, 16, 32, min(64, cores)}):
+        if n > cores:
+            continue
+        torch.set_num_threads(n)
+        step(0)
+        t0 = time.perf_counter()
+        step(1)
+        dt = time.perf_counter() - t0
+        if best_t is None or dt < best_t:
+            best, best_t = n, dt
+    torch.set_num_threads(best)
+    return best
+
+
 def time_oracle(cfg, batch, warm, max_steps, budget_s):
     step = oracle_setup(cfg, batch)
     for it in range(warm):
@@ -158,8 +178,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     cfg = synth.CONFIGS[args.config]
-    threads = os.cpu_count() or 1
-    torch.set_num_threads(threads)
+    threads = pick_threads(cfg, args.batch)
     step = oracle_setup(cfg, args.batch)
     t0 = time.perf_counter()
     step(0)
@@ -318,8 +337,7 @@ def main():
     # ---- CPU baseline (oracle port) on the host cores ----------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        threads = os.cpu_count() or 1
-        torch.set_num_threads(threads)
+        threads = pick_threads(cfg, B)
         v, n, dt = time_oracle(cfg, B, warm=2, max_steps=60, budget_s=12.0)
         cpu = {"value": v, "unit": "steps/s", "cores": threads, "kind": "port",
                "sample": f"{n} full updates of batch {B} incl. numpy replay gather ({dt:.1f} s), {cpu_model()}"}

@@ -32,7 +32,7 @@ import networks.mlp as _mlp
 from dsact_host import TB_TAGS as tb_tags
 from dsact_host import net_kwargs
 
-from dsac_v2_b200 import _lib
+from dsac_v2_b200 import _lib, dp
 from dsac_v2_b200.engine import STAT_KEYS, Engine, make_config
 
 _TRAINABLE = ("q1", "q2", "policy")
@@ -225,10 +225,7 @@ class DSAC_V2:
         return eps1, eps2, z[2], z[3]
 
     def _world(self):
-        import torch.distributed as dist
-        if self.data_parallel and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            return dist, dist.get_world_size()
-        return None, 1
+        return dp.world() if self.data_parallel else (None, 1)
 
     def _stats(self, eng, global_batch, t0):
         if self._slots is None:
@@ -253,13 +250,8 @@ class DSAC_V2:
         if world == 1:
             eng.compute_grads(data, noise)
             return B
-        eng.grad_phase1(data, noise)
-        dist.all_reduce(eng.state[_lib.STATE_STDSUM:_lib.STATE_STDSUM + 2])
-        eng.grad_phase2(B * world)
-        dist.all_reduce(eng.grads)
-        dist.all_reduce(eng.state[_lib.STATE_ACC:_lib.STATE_ACC + 16])
-        dist.all_reduce(eng.state[_lib.STATE_ACC + 16:_lib.STATE_ACC + 18], op=dist.ReduceOp.MIN)
-        return B * world
+        # every rank holds `B` rows of the global minibatch (the trainer samples B per rank)
+        return dp.data_parallel_gradients(eng, data, noise, dist, B, B * world)
 
     # ---- reference interface ------------------------------------------------------
     def local_update(self, data: Dict, iteration: int) -> dict:

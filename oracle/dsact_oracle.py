@@ -159,12 +159,20 @@ class OracleDSACT:
         return float(self.log_alpha.detach().exp()) if self.auto_alpha else self.alpha_fixed
 
     # ---- one update -----------------------------------------------------
-    def compute_gradients(self, batch: Dict[str, torch.Tensor], noise) -> Dict[str, float]:
-        """__compute_gradient (dsac_v2.py:150-206) with explicit noise."""
+    def compute_gradients(self, batch: Dict[str, torch.Tensor], noise, *, global_batch=None,
+                          std_sum_hook=None) -> Dict[str, float]:
+        """__compute_gradient (dsac_v2.py:150-206) with explicit noise.
+
+        `global_batch` / `std_sum_hook` restate the same arithmetic for a data-parallel shard
+        (SURVEY.md §8e): batch means become sums over the local rows divided by the global row
+        count, and the two critic-std sums pass through the hook (an all-reduce) before the
+        mean_std EMA.  With the defaults this is exactly the single-process update."""
         c = lambda x: torch.as_tensor(x).to(self.dtype)
         obs, act, rew, obs2, done = (c(batch[k]) for k in ("obs", "act", "rew", "obs2", "done"))
         eps1, eps2, _z1, _z2, z3, z4 = (c(n) for n in noise[:6])
         B = obs.shape[0]
+        GB = B if global_batch is None else int(global_batch)
+        gmean = (lambda x: x.mean()) if GB == B else (lambda x: x.sum() / GB)
         P, T = self.p, self.t
         alpha = self.alpha()
 
@@ -178,8 +186,11 @@ class OracleDSACT:
             act2, logp2 = self.tanh_gauss_rsample(mean2, std2, eps2)
         q1, s1 = self.q_dist(P["q1"], obs, act)
         q2, s2 = self.q_dist(P["q2"], obs, act)
+        sums = [s1.detach().sum(), s2.detach().sum()]
+        if std_sum_hook is not None:
+            sums = std_sum_hook(sums)
         for k, s in enumerate((s1, s2)):  # dsac_v2.py:233-241
-            batch_mean = s.detach().mean()
+            batch_mean = s.detach().mean() if (GB == B and std_sum_hook is None) else sums[k] / GB
             self.mean_std[k] = batch_mean if self.mean_std[k] is None else \
                 (1 - self.tau_b) * self.mean_std[k] + self.tau_b * batch_mean
         with torch.no_grad():
@@ -198,7 +209,7 @@ class OracleDSACT:
             yb = qd + torch.clamp(y_s - qd, -3 * m, 3 * m)
             sd = torch.clamp(s, min=0.0).detach()
             ratio = (m.pow(2) / (sd.pow(2) + STD_BIAS)).clamp(min=0.1, max=10)  # dsac_v2.py:279-280
-            loss_q = loss_q + torch.mean(ratio * (huber(q, y) + s * (sd.pow(2) - huber(qd, yb)) / (sd + STD_BIAS)))
+            loss_q = loss_q + gmean(ratio * (huber(q, y) + s * (sd.pow(2) - huber(qd, yb)) / (sd + STD_BIAS)))
         gq = torch.autograd.grad(loss_q, P["q1"] + P["q2"])
         n1 = len(P["q1"])
         self.grads = {"q1": list(gq[:n1]), "q2": list(gq[n1:])}
@@ -206,13 +217,13 @@ class OracleDSACT:
         # ---- actor loss (__compute_loss_policy, dsac_v2.py:304-310); no grad to Q params (:168-181)
         q1p, _ = self.q_dist([w.detach() for w in P["q1"]], obs, new_act)
         q2p, _ = self.q_dist([w.detach() for w in P["q2"]], obs, new_act)
-        loss_pi = (alpha * new_logp - torch.min(q1p, q2p)).mean()
+        loss_pi = gmean(alpha * new_logp - torch.min(q1p, q2p))
         self.grads["policy"] = list(torch.autograd.grad(loss_pi, P["policy"]))
         entropy = -new_logp.detach().mean()
 
         # ---- temperature loss (__compute_loss_alpha, dsac_v2.py:312-318)
         if self.auto_alpha:
-            loss_alpha = -self.log_alpha * (new_logp.detach() + self.target_entropy).mean()
+            loss_alpha = -self.log_alpha * gmean(new_logp.detach() + self.target_entropy)
             self.grads["log_alpha"] = list(torch.autograd.grad(loss_alpha, [self.log_alpha]))
 
         vals = [q1.detach().mean(), q2.detach().mean(), s1.detach().mean(), s2.detach().mean(),
