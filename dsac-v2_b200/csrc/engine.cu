@@ -13,6 +13,7 @@
 #include "../../include/dsact.h"
 #include "gemm_simt.cuh"
 #include "kernels.cuh"
+#include "tc_host.cuh"
 
 using namespace dsact;
 
@@ -50,6 +51,13 @@ struct Net {
 
 static int64_t round64(int64_t x) { return (x + 63) / 64 * 64; }
 
+// bf16 image slot inside the arena (TC modes only)
+struct ImgSlot {
+  int64_t off = -1;  // floats from the workspace base
+  int rows = 0, width = 0, pitch = 0;
+  int64_t plane = 0;
+};
+
 // activation arena, all offsets in floats from the workspace base
 struct Arena {
   int64_t obs, obs2, act, rew, done, logp, idx;    // gathered minibatch + int64 indices
@@ -58,10 +66,26 @@ struct Arena {
   int64_t new_act, act2, logp_new, logp2;
   int64_t zQ[6][DSACT_MAX_HIDDEN], hQ[6][DSACT_MAX_HIDDEN], outQ[6];
   int64_t dOut[6], dzQ[6][DSACT_MAX_HIDDEN], dAct[2], dlogits, dzP[DSACT_MAX_HIDDEN];
+  // ---- tcgen05 modes: bf16 hi/lo images of every GEMM operand + wgrad split slabs
+  bool tc;
+  ImgSlot i_obs, i_obs2, i_act, i_new_act, i_act2, i_dlogits;
+  ImgSlot i_hP[DSACT_MAX_HIDDEN], i_hT[DSACT_MAX_HIDDEN], i_dzP[DSACT_MAX_HIDDEN];
+  ImgSlot i_hQ[6][DSACT_MAX_HIDDEN], i_dzQ[6][DSACT_MAX_HIDDEN], i_dOut[6];
+  ImgSlot i_wq[4][DSACT_MAX_HIDDEN + 1], i_wpi[2][DSACT_MAX_HIDDEN + 1];  // q1,q2,q1',q2' / pi,pi'
+  int kpad_q0;        // column of the act block inside the Q layer-0 weight image
+  int64_t slabs;      // [nslabs][n_params] fp32 wgrad partials
+  int nslabs;
   int64_t total;
   void build(const dsact_config& c, const Net& q, const Net& pi) {
     int64_t B = c.max_batch, O = c.obs_dim, A = c.act_dim, off = 0;
     auto take = [&](int64_t n) { int64_t o = off; off += round64(n); return o; };
+    auto img = [&](int rows, int width) {
+      ImgSlot s;
+      s.rows = rows; s.width = width; s.pitch = (width + 7) / 8 * 8;
+      s.plane = round64((int64_t)rows * s.pitch);  // elements per plane, multiple of 64
+      s.off = take(s.plane);  // 2 planes of bf16 = plane floats
+      return s;
+    };
     obs = take(B * O); obs2 = take(B * O); act = take(B * A); rew = take(B); done = take(B); logp = take(B); idx = take(2 * B);
     eps1 = take(B * A); eps2 = take(B * A); z3 = take(B); z4 = take(B);
     for (int j = 0; j < pi.L; ++j) { zP[j] = take(B * pi.s[j + 1]); hP[j] = take(B * pi.s[j + 1]); hT[j] = take(B * pi.s[j + 1]); dzP[j] = take(B * pi.s[j + 1]); }
@@ -72,6 +96,24 @@ struct Arena {
       outQ[p] = take(B * 2); dOut[p] = take(B * 2);
     }
     dAct[0] = take(B * A); dAct[1] = take(B * A);
+    tc = c.gemm_mode != DSACT_GEMM_FP32;
+    nslabs = 0; slabs = 0; kpad_q0 = (int)((O + 63) / 64 * 64);
+    if (tc) {
+      const int Bi = (int)B;
+      i_obs = img(Bi, (int)O); i_obs2 = img(Bi, (int)O); i_act = img(Bi, (int)A); i_new_act = img(Bi, (int)A); i_act2 = img(Bi, (int)A);
+      i_dlogits = img(Bi, 2 * (int)A);
+      for (int j = 0; j < pi.L; ++j) { i_hP[j] = img(Bi, pi.s[j + 1]); i_hT[j] = img(Bi, pi.s[j + 1]); i_dzP[j] = img(Bi, pi.s[j + 1]); }
+      for (int p = 0; p < 6; ++p) {
+        for (int j = 0; j < q.L; ++j) { i_hQ[p][j] = img(Bi, q.s[j + 1]); i_dzQ[p][j] = img(Bi, q.s[j + 1]); }
+        i_dOut[p] = img(Bi, 2);
+      }
+      for (int n = 0; n < 4; ++n)
+        for (int j = 0; j <= q.L; ++j) i_wq[n][j] = img(q.s[j + 1], j == 0 ? kpad_q0 + (int)A : q.s[j]);
+      for (int n = 0; n < 2; ++n)
+        for (int j = 0; j <= pi.L; ++j) i_wpi[n][j] = img(pi.s[j + 1], pi.s[j]);
+      nslabs = (int)((B + 511) / 512); if (nslabs > 8) nslabs = 8; if (nslabs < 1) nslabs = 1;
+      slabs = take((int64_t)nslabs * (2 * q.n + pi.n + 1));
+    }
     total = off;
   }
 };
@@ -101,7 +143,16 @@ struct dsact_handle {
   uint64_t stamp;
   int64_t launches;
   int32_t last_launches;
+  bool tc() const { return cfg.gemm_mode != DSACT_GEMM_FP32; }
+  int passes() const { return cfg.gemm_mode == DSACT_GEMM_BF16X3 ? 3 : 1; }
   float* W() const { return reinterpret_cast<float*>(buf.workspace); }
+  Img img(const ImgSlot& s, int rows) const {  // image handle with the live row count
+    Img i;
+    if (s.off < 0) return i;
+    i.p = reinterpret_cast<__nv_bfloat16*>(W() + s.off);
+    i.rows = rows; i.width = s.width; i.pitch = s.pitch; i.plane = s.plane;
+    return i;
+  }
 };
 
 enum { CLS_OTHER = 0, CLS_GEMM_FWD = 1, CLS_GEMM_DGRAD = 2, CLS_GEMM_WGRAD = 3, CLS_COUNT = 4 };
@@ -132,19 +183,30 @@ struct Ctx {
 // ---- GEMM group launch -------------------------------------------------------
 enum { V_FWD = 0, V_DGRAD = 1, V_WGRAD = 2 };
 
+// A group of independent problems in both lowerings: fp32 pointers (GemmGroup) and bf16 images (TcExtra).
+struct Group {
+  GemmGroup g;
+  TcExtra x[MAXG];
+  float* wg_slab = nullptr;   // wgrad split slabs (default: the arena's, addressed like the gradient buffer)
+  long long wg_stride = 0;
+  int wg_nslabs = 0;
+  Group() { g.n = 0; }
+};
+
 template <int BM, int BN>
 static void launch_variant(const GemmGroup& g, int variant, int grid, Ctx& c) {
   if (variant == V_FWD) gemm_kernel<BM, BN, true, true><<<grid, 256, 0, c.s>>>(g);
   else if (variant == V_DGRAD) gemm_kernel<BM, BN, true, false><<<grid, 256, 0, c.s>>>(g);
   else gemm_kernel<BM, BN, false, false><<<grid, 256, 0, c.s>>>(g);
-  double flops = 0.0;
-  for (int i = 0; i < g.n; ++i) flops += 2.0 * g.p[i].M * g.p[i].N * ((double)g.p[i].K[0] + g.p[i].K[1]);
-  c.done(CLS_GEMM_FWD + variant, flops);
-  c.check();
 }
 
-static void launch_group(const dsact_handle* h, GemmGroup& g, int variant, Ctx& c) {
-  if (g.n == 0) return;
+static double group_flops(const GemmGroup& g) {
+  double flops = 0.0;
+  for (int i = 0; i < g.n; ++i) flops += 2.0 * g.p[i].M * g.p[i].N * ((double)g.p[i].K[0] + g.p[i].K[1]);
+  return flops;
+}
+
+static void launch_simt(const dsact_handle* h, GemmGroup& g, int variant, Ctx& c) {
   auto count = [&](int T) {
     int total = 0;
     for (int i = 0; i < g.n; ++i) total += ((g.p[i].M + T - 1) / T) * ((g.p[i].N + T - 1) / T);
@@ -175,50 +237,182 @@ static void launch_group(const dsact_handle* h, GemmGroup& g, int variant, Ctx& 
   else launch_variant<64, 64>(g, variant, grid, c);
 }
 
+static bool g_tc_attr_done = false;
+
+// Lower the group onto tcgen05: images instead of fp32 operands, TMA tensor maps, 128 x bn tiles.
+static void launch_tc(const dsact_handle* h, Group& G, int variant, Ctx& c) {
+  static TcGroup t;  // ~5 KiB; host-side scratch (single trainer thread per process is the documented contract)
+  memset(&t, 0, sizeof(t));
+  t.n = G.g.n;
+  t.passes = h->passes();
+  const bool a_mn = variant == V_WGRAD, b_mn = variant != V_FWD;
+  int grid = 0;
+  for (int i = 0; i < G.g.n; ++i) {
+    const GemmProb& s = G.g.p[i];
+    const TcExtra& x = G.x[i];
+    TcProb& p = t.p[i];
+    p.M = s.M; p.N = s.N;
+    int bn = (s.N + 15) / 16 * 16;
+    if (bn > 256) bn = 256;
+    if (variant == V_WGRAD && bn > 128) bn = 128;  // more tiles for the (few, batch-split) weight-gradient problems
+    p.bn = bn;
+    p.tiles_m = (s.M + TC_BM - 1) / TC_BM;
+    p.tiles_n = (s.N + bn - 1) / bn;
+    for (int sgm = 0; sgm < 2; ++sgm) {
+      p.kblocks[sgm] = (s.K[sgm] + TC_BK - 1) / TC_BK;
+      p.kB0[sgm] = x.kB0[sgm];
+      if (s.K[sgm] > 0 && !make_map(&p.mapA[sgm], x.a[sgm], a_mn ? 64 : TC_BM)) { c.err = cudaErrorInvalidValue; return; }
+    }
+    if (!make_map(&p.mapB, x.b, b_mn ? 64 : bn)) { c.err = cudaErrorInvalidValue; return; }
+    p.ksplit = 1;
+    p.C = s.C; p.ldc = s.ldc; p.bias = s.bias; p.Zout = s.Zout; p.Zin = s.Zin; p.ldz = s.ldz; p.colsum = s.colsum;
+    p.epi = s.epi; p.act = s.act;
+    if (variant == V_WGRAD) {  // fixed slab count: empty splits store zeros so that the reduction is always valid
+      p.epi = EPI_PARTIAL;
+      if (G.wg_slab) { p.ksplit = G.wg_nslabs; p.C = G.wg_slab; p.split_stride = G.wg_stride; }
+      else {
+        p.ksplit = h->ar.nslabs;
+        p.C = h->W() + h->ar.slabs + (s.C - h->buf.grads);
+        p.split_stride = 2 * h->q.n + h->pi.n + 1;
+      }
+    }
+    if (x.out.p) {
+      p.img = x.out.p; p.img_pitch = x.out.pitch; p.img_plane = x.out.plane;
+      if (p.epi == EPI_BIAS_ACT || p.epi == EPI_DACT) p.C = nullptr;  // the next GEMM reads the image; no fp32 copy
+    }
+    p.tile_start = grid;
+    grid += p.tiles_m * p.tiles_n * p.ksplit;
+  }
+  const int planes = t.passes == 3 ? 2 : 1;
+  const int stages = planes == 2 ? 2 : 4;
+  const int smem = tc_smem_bytes(stages, planes);
+  if (!g_tc_attr_done) {
+    cudaFuncSetAttribute(tc_gemm_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(tc_gemm_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(tc_gemm_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    g_tc_attr_done = true;
+  }
+  if (variant == V_FWD) tc_gemm_kernel<false, false><<<grid, TC_THREADS, smem, c.s>>>(t, stages);
+  else if (variant == V_DGRAD) tc_gemm_kernel<false, true><<<grid, TC_THREADS, smem, c.s>>>(t, stages);
+  else tc_gemm_kernel<true, true><<<grid, TC_THREADS, smem, c.s>>>(t, stages);
+}
+
+static void launch_group(const dsact_handle* h, Group& G, int variant, Ctx& c) {
+  if (G.g.n == 0) return;
+  const double flops = group_flops(G.g);
+  if (h->tc()) launch_tc(h, G, variant, c);
+  else launch_simt(h, G.g, variant, c);
+  c.done(CLS_GEMM_FWD + variant, flops);
+  c.check();
+}
+
 static GemmProb prob_zero() {
   GemmProb p;
   memset(&p, 0, sizeof(p));
   return p;
 }
 
-// forward layer j of `net` with weights at `W`: out = act(in * W_j^T + b_j)
-static GemmProb fwd_prob(const Net& net, const float* Wbase, int j, const float* in0, int ld0, int k0,
-                         const float* in1, int ld1, int k1, float* out, float* zout, int B, int act) {
+// a [rows, ld] tensor as both lowerings see it
+struct Ten {
+  float* f = nullptr;
+  Img im;
+};
+struct Wt {       // one layer's weights: fp32 [out, in] + image
+  const float* f = nullptr;
+  const float* bias = nullptr;
+  Img im;
+};
+
+// forward layer j: out = act(in0 * W[:, :k0]^T + in1 * W[:, k0:k0+k1]^T + b)
+static void add_fwd(Group& G, const Net& net, int j, const Wt& w, const Ten& in0, int k0, const Ten& in1, int k1, int kB1,
+                    const Ten& out, float* zout, int B, int act) {
   GemmProb p = prob_zero();
-  const float* Wj = Wbase + net.w[j];
+  TcExtra x;
   const int in_dim = net.s[j];
-  p.A[0] = in0; p.lda[0] = ld0; p.K[0] = k0; p.B[0] = Wj; p.ldb[0] = in_dim;
-  if (k1 > 0) { p.A[1] = in1; p.lda[1] = ld1; p.K[1] = k1; p.B[1] = Wj + k0; p.ldb[1] = in_dim; }
-  p.M = B; p.N = net.s[j + 1]; p.C = out; p.ldc = net.s[j + 1];
-  p.bias = Wbase + net.b[j];
+  p.A[0] = in0.f; p.lda[0] = k0; p.K[0] = k0; p.B[0] = w.f; p.ldb[0] = in_dim;
+  x.a[0] = in0.im;
+  if (k1 > 0) {
+    p.A[1] = in1.f; p.lda[1] = k1; p.K[1] = k1; p.B[1] = w.f + k0; p.ldb[1] = in_dim;
+    x.a[1] = in1.im; x.kB0[1] = kB1;
+  }
+  x.b = w.im;
+  p.M = B; p.N = net.s[j + 1]; p.C = out.f; p.ldc = net.s[j + 1];
+  p.bias = w.bias;
   const bool last = j == net.L;
   p.epi = last ? EPI_STORE : EPI_BIAS_ACT;
   p.act = act;
   p.Zout = last ? nullptr : zout;
-  return p;
+  x.out = last ? Img() : out.im;
+  G.x[G.g.n] = x;
+  G.g.p[G.g.n++] = p;
 }
 
-// dgrad through layer j: dX[B, s_j] = dY[B, s_{j+1}] * W_j   (optionally * act'(Z_{j-1}) and bias-grad colsum)
-static GemmProb dgrad_prob(const Net& net, const float* Wbase, int j, const float* dY, int col0, int ncols,
-                           float* dX, const float* Zprev, float* gbias_prev, int B, int act) {
+// dgrad through layer j, weight columns [col0, col0+ncols): dX = dY * W[:, cols]   (* act'(Zprev), bias-grad colsum)
+static void add_dgrad(Group& G, const Net& net, int j, const Wt& w, int col0, int img_col0, int ncols, const Ten& dY,
+                      const Ten& dX, const float* Zprev, float* gbias_prev, int B, int act) {
   GemmProb p = prob_zero();
-  p.A[0] = dY; p.lda[0] = net.s[j + 1]; p.K[0] = net.s[j + 1];
-  p.B[0] = Wbase + net.w[j] + col0; p.ldb[0] = net.s[j];
-  p.M = B; p.N = ncols; p.C = dX; p.ldc = ncols;
+  TcExtra x;
+  p.A[0] = dY.f; p.lda[0] = net.s[j + 1]; p.K[0] = net.s[j + 1];
+  p.B[0] = w.f + col0; p.ldb[0] = net.s[j];
+  x.a[0] = dY.im;
+  x.b = w.im.cols(img_col0, ncols);
+  p.M = B; p.N = ncols; p.C = dX.f; p.ldc = ncols;
   if (Zprev) { p.epi = EPI_DACT; p.Zin = Zprev; p.ldz = ncols; p.colsum = gbias_prev; p.act = act; }
   else p.epi = EPI_STORE;
-  return p;
+  x.out = dX.im;
+  G.x[G.g.n] = x;
+  G.g.p[G.g.n++] = p;
 }
 
-// wgrad of layer j columns [col0, col0+ncols): gW[s_{j+1}, cols] += dY^T X
-static GemmProb wgrad_prob(const Net& net, float* Gbase, int j, const float* dY, const float* X, int ldx, int col0,
-                           int ncols, int B) {
+// wgrad of layer j, weight columns [col0, col0+ncols): gW[:, cols] += dY^T X
+static void add_wgrad(Group& G, const Net& net, int j, float* Gw, int col0, int ncols, const Ten& dY, const Ten& X, int B) {
   GemmProb p = prob_zero();
-  p.A[0] = dY; p.lda[0] = net.s[j + 1]; p.K[0] = B;
-  p.B[0] = X; p.ldb[0] = ldx;
-  p.M = net.s[j + 1]; p.N = ncols; p.C = Gbase + net.w[j] + col0; p.ldc = net.s[j];
+  TcExtra x;
+  p.A[0] = dY.f; p.lda[0] = net.s[j + 1]; p.K[0] = B;
+  p.B[0] = X.f; p.ldb[0] = ncols;
+  x.a[0] = dY.im; x.b = X.im;
+  p.M = net.s[j + 1]; p.N = ncols; p.C = Gw + col0; p.ldc = net.s[j];
   p.epi = EPI_ATOMIC;
-  return p;
+  G.x[G.g.n] = x;
+  G.g.p[G.g.n++] = p;
+}
+
+// fp32 -> image conversions (TC modes)
+struct ImgBatch {
+  ImgGroup g;
+  ImgBatch() { g.n = 0; }
+  void add(const float* src, int ld_src, const Img& dst, int rows, int w0, int w1 = 0, int dst1 = 0) {
+    ImgJob& j = g.j[g.n++];
+    memset(&j, 0, sizeof(j));
+    j.src = src; j.dst = dst.p; j.rows = rows; j.ld_src = ld_src;
+    j.seg_w[0] = w0; j.seg_src0[0] = 0; j.seg_dst0[0] = 0;
+    j.seg_w[1] = w1; j.seg_src0[1] = w0; j.seg_dst0[1] = dst1;
+    j.pitch = dst.pitch; j.fill_w = w1 > 0 ? dst1 + w1 : w0; j.plane = dst.plane;
+  }
+  void launch(const dsact_handle* h, Ctx& c) {
+    if (g.n == 0) return;
+    g.planes = h->passes() == 3 ? 2 : 1;
+    int grid = 0;
+    for (int i = 0; i < g.n; ++i) {
+      g.j[i].block_start = grid;
+      long long total = (long long)g.j[i].rows * g.j[i].fill_w;
+      int blocks = (int)((total + 1023) / 1024);
+      if (blocks < 1) blocks = 1;
+      if (blocks > 2 * h->num_sms) blocks = 2 * h->num_sms;
+      grid += blocks;
+    }
+    image_kernel<<<grid, 256, 0, c.s>>>(g);
+    c.done();
+    g.n = 0;
+  }
+};
+
+static Wt weight(const dsact_handle* h, const Net& net, const float* base, int j, const ImgSlot& slot) {
+  Wt w;
+  w.f = base + net.w[j];
+  w.bias = base + net.b[j];
+  w.im = h->img(slot, net.s[j + 1]);
+  return w;
 }
 
 // ---- enqueue: pieces of one update ---------------------------------------------
@@ -228,13 +422,39 @@ static void enqueue_phase1(dsact_handle* h, const dsact_batch& bt, const dsact_n
   const Arena& ar = h->ar;
   float* W = h->W();
   const int B = bt.batch, O = cf.obs_dim, A = cf.act_dim;
+  const bool tc = h->tc();
   float* P = h->buf.params;
   float* T = h->buf.targets;
-  const float *Pq[2] = {P, P + q.n}, *Ppi = P + 2 * q.n;
-  const float *Tq[2] = {T, T + q.n}, *Tpi = T + 2 * q.n;
+  const float* Qb[4] = {P, P + q.n, T, T + q.n};        // q1, q2, q1', q2'
+  const float* PIb[2] = {P + 2 * q.n, T + 2 * q.n};     // pi, pi'
+  auto ten = [&](const float* f, const ImgSlot& s) { Ten t; t.f = const_cast<float*>(f); t.im = h->img(s, B); return t; };
+  const ImgSlot none;
 
   begin_step_kernel<<<1, 32, 0, c.s>>>(h->buf.state); c.done();
   cudaMemsetAsync(h->buf.grads, 0, sizeof(float) * (2 * q.n + pi.n + 1), c.s);
+
+  if (tc) {  // refresh the weight images (the caller may have written params/targets through its views) + inputs
+    ImgBatch ib;
+    for (int n = 0; n < 2; ++n)
+      for (int j = 0; j <= q.L; ++j) {
+        const Img im = h->img(ar.i_wq[n][j], q.s[j + 1]);
+        if (j == 0) ib.add(Qb[n] + q.w[0], O + A, im, q.s[1], O, A, ar.kpad_q0);
+        else ib.add(Qb[n] + q.w[j], q.s[j], im, q.s[j + 1], q.s[j]);
+      }
+    for (int j = 0; j <= pi.L; ++j) ib.add(PIb[0] + pi.w[j], pi.s[j], h->img(ar.i_wpi[0][j], pi.s[j + 1]), pi.s[j + 1], pi.s[j]);
+    ib.add(bt.obs, O, h->img(ar.i_obs, B), B, O);
+    ib.launch(h, c);
+    for (int n = 2; n < 4; ++n)
+      for (int j = 0; j <= q.L; ++j) {
+        const Img im = h->img(ar.i_wq[n][j], q.s[j + 1]);
+        if (j == 0) ib.add(Qb[n] + q.w[0], O + A, im, q.s[1], O, A, ar.kpad_q0);
+        else ib.add(Qb[n] + q.w[j], q.s[j], im, q.s[j + 1], q.s[j]);
+      }
+    for (int j = 0; j <= pi.L; ++j) ib.add(PIb[1] + pi.w[j], pi.s[j], h->img(ar.i_wpi[1][j], pi.s[j + 1]), pi.s[j + 1], pi.s[j]);
+    ib.add(bt.obs2, O, h->img(ar.i_obs2, B), B, O);
+    ib.add(bt.act, A, h->img(ar.i_act, B), B, A);
+    ib.launch(h, c);
+  }
 
   const float *eps1, *eps2, *z3, *z4;
   if (nz) { eps1 = nz->eps1; eps2 = nz->eps2; z3 = nz->z3; z4 = nz->z4; }
@@ -248,27 +468,31 @@ static void enqueue_phase1(dsact_handle* h, const dsact_batch& bt, const dsact_n
     c.done();
   }
 
+  const Ten t_obs = ten(bt.obs, ar.i_obs), t_obs2 = ten(bt.obs2, ar.i_obs2), t_act = ten(bt.act, ar.i_act);
+  const Ten t_none;
+
   // wave A: pi(obs), pi'(obs2), Q1(s,a), Q2(s,a), layer by layer
   const int depth = (pi.L > q.L ? pi.L : q.L) + 1;
   for (int j = 0; j < depth; ++j) {
-    GemmGroup g; g.n = 0;
+    Group G;
     if (j <= pi.L) {
-      const float* inP = j == 0 ? bt.obs : W + ar.hP[j - 1];
-      const float* inT = j == 0 ? bt.obs2 : W + ar.hT[j - 1];
-      float* outP = j == pi.L ? W + ar.logitsP : W + ar.hP[j];
-      float* outT = j == pi.L ? W + ar.logitsT : W + ar.hT[j];
-      g.p[g.n++] = fwd_prob(pi, Ppi, j, inP, pi.s[j], pi.s[j], nullptr, 0, 0, outP, j == pi.L ? nullptr : W + ar.zP[j], B, cf.act_pi);
-      g.p[g.n++] = fwd_prob(pi, Tpi, j, inT, pi.s[j], pi.s[j], nullptr, 0, 0, outT, nullptr, B, cf.act_pi);
+      const Ten inP = j == 0 ? t_obs : ten(W + ar.hP[j - 1], ar.i_hP[j - 1]);
+      const Ten inT = j == 0 ? t_obs2 : ten(W + ar.hT[j - 1], ar.i_hT[j - 1]);
+      const Ten outP = j == pi.L ? ten(W + ar.logitsP, none) : ten(W + ar.hP[j], ar.i_hP[j]);
+      const Ten outT = j == pi.L ? ten(W + ar.logitsT, none) : ten(W + ar.hT[j], ar.i_hT[j]);
+      add_fwd(G, pi, j, weight(h, pi, PIb[0], j, ar.i_wpi[0][j]), inP, pi.s[j], t_none, 0, 0, outP, j == pi.L ? nullptr : W + ar.zP[j], B, cf.act_pi);
+      add_fwd(G, pi, j, weight(h, pi, PIb[1], j, ar.i_wpi[1][j]), inT, pi.s[j], t_none, 0, 0, outT, nullptr, B, cf.act_pi);
     }
     if (j <= q.L) {
       for (int k = 0; k < 2; ++k) {
-        float* out = j == q.L ? W + ar.outQ[k] : W + ar.hQ[k][j];
+        const Ten out = j == q.L ? ten(W + ar.outQ[k], none) : ten(W + ar.hQ[k][j], ar.i_hQ[k][j]);
         float* z = j == q.L ? nullptr : W + ar.zQ[k][j];
-        if (j == 0) g.p[g.n++] = fwd_prob(q, Pq[k], 0, bt.obs, O, O, bt.act, A, A, out, z, B, cf.act_q);
-        else g.p[g.n++] = fwd_prob(q, Pq[k], j, W + ar.hQ[k][j - 1], q.s[j], q.s[j], nullptr, 0, 0, out, z, B, cf.act_q);
+        const Wt w = weight(h, q, Qb[k], j, ar.i_wq[k][j]);
+        if (j == 0) add_fwd(G, q, 0, w, t_obs, O, t_act, A, ar.kpad_q0, out, z, B, cf.act_q);
+        else add_fwd(G, q, j, w, ten(W + ar.hQ[k][j - 1], ar.i_hQ[k][j - 1]), q.s[j], t_none, 0, 0, out, z, B, cf.act_q);
       }
     }
-    launch_group(h, g, V_FWD, c);
+    launch_group(h, G, V_FWD, c);
   }
 
   // rsample of both policies (utils/act_distribution_cls.py:44-54)
@@ -283,20 +507,28 @@ static void enqueue_phase1(dsact_handle* h, const dsact_batch& bt, const dsact_n
     int blocks = (B + 7) / 8; if (blocks > 4 * h->num_sms) blocks = 4 * h->num_sms;
     sample_kernel<<<dim3(blocks, 2), 256, 0, c.s>>>(a); c.done();
   }
+  if (tc) {
+    ImgBatch ib;
+    ib.add(W + ar.new_act, A, h->img(ar.i_new_act, B), B, A);
+    ib.add(W + ar.act2, A, h->img(ar.i_act2, B), B, A);
+    ib.launch(h, c);
+  }
 
   // wave B: Q1', Q2' on (s', a') and Q1, Q2 on (s, a~)
+  const Ten t_new_act = ten(W + ar.new_act, ar.i_new_act), t_act2 = ten(W + ar.act2, ar.i_act2);
   for (int j = 0; j <= q.L; ++j) {
-    GemmGroup g; g.n = 0;
+    Group G;
     for (int p = 2; p < 6; ++p) {
       const int k = p & 1;
       const bool tgt = p < 4;
-      const float* Wn = tgt ? Tq[k] : Pq[k];
-      float* out = j == q.L ? W + ar.outQ[p] : W + ar.hQ[p][j];
+      const int wn = tgt ? 2 + k : k;
+      const Ten out = j == q.L ? ten(W + ar.outQ[p], none) : ten(W + ar.hQ[p][j], ar.i_hQ[p][j]);
       float* z = (j == q.L || tgt) ? nullptr : W + ar.zQ[p][j];
-      if (j == 0) g.p[g.n++] = fwd_prob(q, Wn, 0, tgt ? bt.obs2 : bt.obs, O, O, tgt ? W + ar.act2 : W + ar.new_act, A, A, out, z, B, cf.act_q);
-      else g.p[g.n++] = fwd_prob(q, Wn, j, W + ar.hQ[p][j - 1], q.s[j], q.s[j], nullptr, 0, 0, out, z, B, cf.act_q);
+      const Wt w = weight(h, q, Qb[wn], j, ar.i_wq[wn][j]);
+      if (j == 0) add_fwd(G, q, 0, w, tgt ? t_obs2 : t_obs, O, tgt ? t_act2 : t_new_act, A, ar.kpad_q0, out, z, B, cf.act_q);
+      else add_fwd(G, q, j, w, ten(W + ar.hQ[p][j - 1], ar.i_hQ[p][j - 1]), q.s[j], t_none, 0, 0, out, z, B, cf.act_q);
     }
-    launch_group(h, g, V_FWD, c);
+    launch_group(h, G, V_FWD, c);
   }
 
   {
@@ -313,11 +545,14 @@ static void enqueue_phase2(dsact_handle* h, const dsact_batch& bt, int64_t globa
   const Arena& ar = h->ar;
   float* W = h->W();
   const int B = bt.batch, O = cf.obs_dim, A = cf.act_dim;
+  const bool tc = h->tc();
   float* P = h->buf.params;
-  float* G = h->buf.grads;
+  float* G_ = h->buf.grads;
   const float *Pq[2] = {P, P + q.n}, *Ppi = P + 2 * q.n;
-  float *Gq[2] = {G, G + q.n}, *Gpi = G + 2 * q.n;
+  float *Gq[2] = {G_, G_ + q.n}, *Gpi = G_ + 2 * q.n;
   const float invB = (float)(1.0 / (double)global_batch);
+  auto ten = [&](const float* f, const ImgSlot& s) { Ten t; t.f = const_cast<float*>(f); t.im = h->img(s, B); return t; };
+  const ImgSlot none;
 
   ema_kernel<<<1, 32, 0, c.s>>>(h->buf.state, P + 2 * q.n + pi.n, invB, (float)cf.tau_b, cf.auto_alpha, (float)cf.alpha_fixed);
   c.done();
@@ -335,29 +570,36 @@ static void enqueue_phase2(dsact_handle* h, const dsact_batch& bt, int64_t globa
     int blocks = (B + 255) / 256; if (blocks > 2 * h->num_sms) blocks = 2 * h->num_sms;
     loss_kernel<<<blocks, 256, 0, c.s>>>(a); c.done();
   }
+  const int passes[4] = {0, 1, 4, 5};
+  if (tc) {
+    ImgBatch ib;
+    for (int pp = 0; pp < 4; ++pp) ib.add(W + ar.dOut[passes[pp]], 2, h->img(ar.i_dOut[passes[pp]], B), B, 2);
+    ib.launch(h, c);
+  }
+  const Ten t_obs = ten(bt.obs, ar.i_obs), t_act = ten(bt.act, ar.i_act);
 
   // wave C: critic passes 0,1 (dgrad + wgrad) and actor passes 4,5 (dgrad only), top layer down
-  const int passes[4] = {0, 1, 4, 5};
   for (int j = q.L; j >= 1; --j) {
-    GemmGroup gd; gd.n = 0;
-    GemmGroup gw; gw.n = 0;
+    Group gd, gw;
     for (int pp = 0; pp < 4; ++pp) {
       const int p = passes[pp], k = p & 1;
-      const float* dY = j == q.L ? W + ar.dOut[p] : W + ar.dzQ[p][j];
+      const Ten dY = j == q.L ? ten(W + ar.dOut[p], ar.i_dOut[p]) : ten(W + ar.dzQ[p][j], ar.i_dzQ[p][j]);
       float* gb = p < 2 ? Gq[k] + q.b[j - 1] : nullptr;
-      gd.p[gd.n++] = dgrad_prob(q, Pq[k], j, dY, 0, q.s[j], W + ar.dzQ[p][j - 1], W + ar.zQ[p][j - 1], gb, B, cf.act_q);
-      if (p < 2) gw.p[gw.n++] = wgrad_prob(q, Gq[k], j, dY, W + ar.hQ[p][j - 1], q.s[j], 0, q.s[j], B);
+      add_dgrad(gd, q, j, weight(h, q, Pq[k], j, ar.i_wq[k][j]), 0, 0, q.s[j], dY, ten(W + ar.dzQ[p][j - 1], ar.i_dzQ[p][j - 1]),
+                W + ar.zQ[p][j - 1], gb, B, cf.act_q);
+      if (p < 2) add_wgrad(gw, q, j, Gq[k] + q.w[j], 0, q.s[j], dY, ten(W + ar.hQ[p][j - 1], ar.i_hQ[p][j - 1]), B);
     }
     launch_group(h, gd, V_DGRAD, c);
     launch_group(h, gw, V_WGRAD, c);
   }
   {
-    GemmGroup gw; gw.n = 0;
-    GemmGroup gd; gd.n = 0;
+    Group gw, gd;
     for (int k = 0; k < 2; ++k) {
-      gw.p[gw.n++] = wgrad_prob(q, Gq[k], 0, W + ar.dzQ[k][0], bt.obs, O, 0, O, B);
-      gw.p[gw.n++] = wgrad_prob(q, Gq[k], 0, W + ar.dzQ[k][0], bt.act, A, O, A, B);
-      gd.p[gd.n++] = dgrad_prob(q, Pq[k], 0, W + ar.dzQ[4 + k][0], O, A, W + ar.dAct[k], nullptr, nullptr, B, 0);
+      const Ten dz0 = ten(W + ar.dzQ[k][0], ar.i_dzQ[k][0]);
+      add_wgrad(gw, q, 0, Gq[k] + q.w[0], 0, O, dz0, t_obs, B);
+      add_wgrad(gw, q, 0, Gq[k] + q.w[0], O, A, dz0, t_act, B);
+      add_dgrad(gd, q, 0, weight(h, q, Pq[k], 0, ar.i_wq[k][0]), O, ar.kpad_q0, A, ten(W + ar.dzQ[4 + k][0], ar.i_dzQ[4 + k][0]),
+                ten(W + ar.dAct[k], none), nullptr, nullptr, B, 0);
     }
     launch_group(h, gw, V_WGRAD, c);
     launch_group(h, gd, V_DGRAD, c);
@@ -373,21 +615,32 @@ static void enqueue_phase2(dsact_handle* h, const dsact_batch& bt, int64_t globa
     int blocks = (B + 63) / 64; if (blocks > 2 * h->num_sms) blocks = 2 * h->num_sms; if (blocks < 1) blocks = 1;
     policy_grad_kernel<<<blocks, 256, 0, c.s>>>(a); c.done();
   }
+  if (tc) {
+    ImgBatch ib;
+    ib.add(W + ar.dlogits, 2 * A, h->img(ar.i_dlogits, B), B, 2 * A);
+    ib.launch(h, c);
+  }
 
   // wave D: policy backward
   for (int j = pi.L; j >= 0; --j) {
-    const float* dY = j == pi.L ? W + ar.dlogits : W + ar.dzP[j];
-    GemmGroup gw; gw.n = 0;
-    gw.p[gw.n++] = wgrad_prob(pi, Gpi, j, dY, j == 0 ? bt.obs : W + ar.hP[j - 1], pi.s[j], 0, pi.s[j], B);
+    const Ten dY = j == pi.L ? ten(W + ar.dlogits, ar.i_dlogits) : ten(W + ar.dzP[j], ar.i_dzP[j]);
+    Group gw;
+    add_wgrad(gw, pi, j, Gpi + pi.w[j], 0, pi.s[j], dY, j == 0 ? t_obs : ten(W + ar.hP[j - 1], ar.i_hP[j - 1]), B);
     if (j >= 1) {
-      GemmGroup gd; gd.n = 0;
-      gd.p[gd.n++] = dgrad_prob(pi, Ppi, j, dY, 0, pi.s[j], W + ar.dzP[j - 1], W + ar.zP[j - 1], Gpi + pi.b[j - 1], B, cf.act_pi);
+      Group gd;
+      add_dgrad(gd, pi, j, weight(h, pi, Ppi, j, ar.i_wpi[0][j]), 0, 0, pi.s[j], dY, ten(W + ar.dzP[j - 1], ar.i_dzP[j - 1]),
+                W + ar.zP[j - 1], Gpi + pi.b[j - 1], B, cf.act_pi);
       launch_group(h, gd, V_DGRAD, c);
     }
     launch_group(h, gw, V_WGRAD, c);
   }
 
-  alpha_grad_kernel<<<1, 32, 0, c.s>>>(G + 2 * q.n + pi.n, h->buf.state, invB, -(float)cf.act_dim, B);
+  if (tc) {  // fold the weight-gradient split slabs into the flat gradient buffer
+    const long long n = 2 * q.n + pi.n + 1;
+    int blocks = (int)((n + 255) / 256); if (blocks > 4 * h->num_sms) blocks = 4 * h->num_sms;
+    grad_reduce_kernel<<<blocks, 256, 0, c.s>>>(G_, W + ar.slabs, n, ar.nslabs, n); c.done();
+  }
+  alpha_grad_kernel<<<1, 32, 0, c.s>>>(G_ + 2 * q.n + pi.n, h->buf.state, invB, -(float)cf.act_dim, B);
   c.done();
   c.check();
 }
@@ -532,7 +785,7 @@ static int validate(const dsact_config* c) {
     return fail(DSACT_EINVAL, "unknown activation");
   if (c->max_batch < 1) return fail(DSACT_EINVAL, "max_batch must be positive");
   if (c->delay_update < 1) return fail(DSACT_EINVAL, "delay_update must be >= 1");
-  if (c->gemm_mode != DSACT_GEMM_FP32) return fail(DSACT_EINVAL, "gemm_mode %d not available in this build", c->gemm_mode);
+  if (c->gemm_mode < DSACT_GEMM_FP32 || c->gemm_mode > DSACT_GEMM_BF16) return fail(DSACT_EINVAL, "unknown gemm_mode %d", c->gemm_mode);
   return DSACT_OK;
 }
 
@@ -596,6 +849,10 @@ int dsact_bind(dsact_handle* h, const dsact_buffers* b) {
   if ((reinterpret_cast<uintptr_t>(b->workspace) & 255) != 0) return fail(DSACT_EINVAL, "workspace must be 256-byte aligned");
   h->buf = *b;
   h->bound = true;
+  if (h->tc()) {  // bias regions of the wgrad slabs are never written by a kernel: they must read as zero
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaMemset(h->W() + h->ar.slabs, 0, sizeof(float) * (size_t)h->ar.nslabs * (2 * h->q.n + h->pi.n + 1)));
+  }
   h->dev_iter = -1;
   h->dev_rb_size = -1;
   drop_graphs(h);
@@ -853,15 +1110,52 @@ int dsact_test_gemm(dsact_handle* h, int32_t variant, const float* A, int32_t ld
   if (!h) return fail(DSACT_EINVAL, "null handle");
   if (variant < 0 || variant > 2 || M < 1 || N < 1 || K < 1) return fail(DSACT_EINVAL, "bad argument");
   CUDA_TRY(cudaSetDevice(h->device));
-  GemmGroup g; g.n = 1;
+  cudaStream_t s = (cudaStream_t)stream;
+  Group G;
   GemmProb p = prob_zero();
   p.A[0] = A; p.lda[0] = lda; p.B[0] = B; p.ldb[0] = ldb; p.K[0] = K;
   p.M = M; p.N = N; p.C = C; p.ldc = ldc; p.bias = variant == V_FWD ? bias : nullptr;
   p.epi = variant == V_WGRAD ? EPI_ATOMIC : EPI_STORE;
-  g.p[0] = p;
-  Ctx c{(cudaStream_t)stream, 0, cudaSuccess};
-  launch_group(h, g, variant, c);
-  if (c.err != cudaSuccess) return fail(DSACT_ECUDA, "launch failed: %s", cudaGetErrorString(c.err));
+  G.g.p[0] = p; G.g.n = 1;
+  Ctx c{s, 0, cudaSuccess};
+  void* scratch = nullptr;
+  if (h->tc()) {  // test hook only: scratch images (and slabs) come from cudaMalloc, not from the caller
+    if (variant == V_WGRAD && ldc != N) return fail(DSACT_EINVAL, "tc wgrad test needs contiguous C");
+    const int a_rows = variant == V_WGRAD ? K : M, a_w = variant == V_WGRAD ? M : K;
+    const int b_rows = variant == V_FWD ? N : K, b_w = variant == V_FWD ? K : N;
+    auto mk = [&](int rows, int w, size_t& off) {
+      Img i; i.rows = rows; i.width = w; i.pitch = (w + 7) / 8 * 8; i.plane = round64((int64_t)rows * i.pitch);
+      off = (off + 255) / 256 * 256; size_t o = off; off += (size_t)i.plane * 4; i.p = reinterpret_cast<__nv_bfloat16*>(o);
+      return i;
+    };
+    size_t off = 0;
+    Img ia = mk(a_rows, a_w, off), ib = mk(b_rows, b_w, off);
+    const int nslabs = 4;
+    off = (off + 255) / 256 * 256;
+    const size_t slab_off = off;
+    if (variant == V_WGRAD) off += sizeof(float) * (size_t)nslabs * M * N;
+    CUDA_TRY(cudaMalloc(&scratch, off + 256));
+    ia.p = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uintptr_t>(scratch) + reinterpret_cast<uintptr_t>(ia.p));
+    ib.p = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uintptr_t>(scratch) + reinterpret_cast<uintptr_t>(ib.p));
+    ImgBatch ibt;
+    ibt.add(A, lda, ia, a_rows, a_w);
+    ibt.add(B, ldb, ib, b_rows, b_w);
+    ibt.launch(h, c);
+    G.x[0].a[0] = ia; G.x[0].b = ib;
+    if (variant == V_WGRAD) {
+      G.wg_slab = reinterpret_cast<float*>(reinterpret_cast<uintptr_t>(scratch) + slab_off);
+      G.wg_stride = (long long)M * N; G.wg_nslabs = nslabs;
+    }
+  }
+  launch_group(h, G, variant, c);
+  if (h->tc() && variant == V_WGRAD && c.err == cudaSuccess) {
+    grad_reduce_kernel<<<64, 256, 0, s>>>(C, G.wg_slab, (long long)M * N, G.wg_nslabs, (long long)M * N);
+    c.done();
+  }
+  cudaError_t e = cudaSuccess;
+  if (scratch) { e = cudaStreamSynchronize(s); cudaFree(scratch); }
+  if (c.err != cudaSuccess || e != cudaSuccess)
+    return fail(DSACT_ECUDA, "launch failed: %s", cudaGetErrorString(c.err != cudaSuccess ? c.err : e));
   h->launches += c.launches;
   return DSACT_OK;
 }

@@ -1,0 +1,404 @@
+// tcgen05 grouped GEMM for the dense layers of the DSAC-T update (DSACT_GEMM_BF16X3 / DSACT_GEMM_BF16).
+//
+// Operands are bf16 "images" of the fp32 tensors: plane 0 = hi = bf16(x), plane 1 = lo = bf16(x - hi).
+// BF16X3 accumulates hi*hi + hi*lo + lo*hi in fp32 (relative product error ~2^-16, enough for the 1e-4
+// parity gate, SURVEY.md §7 "Parity vs speed"); BF16 uses plane 0 only.
+//
+// One CTA computes one 128 x BN output tile (BN <= 256) of one problem of the group:
+//   warp 0      : TMA producer  (cp.async.bulk.tensor.3d, 128B swizzle, mbarrier complete_tx)
+//   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (accumulator in TMEM, fp32)
+//   warps 2..5  : epilogue      (tcgen05.ld 32x32b, bias/activation/derivative, fp32 + bf16-image stores)
+// The three orientations of a linear layer never need a transposed copy: the UMMA descriptors read
+// K-major or MN-major shared-memory tiles as the reduction dimension requires
+//   forward  y  = x W^T   : A K-major (x image),   B K-major  (W image)
+//   dgrad    dx = dy W    : A K-major (dy image),  B MN-major (W image)
+//   wgrad    dW = dy^T x  : A MN-major (dy image), B MN-major (x image); split over the batch, each split
+//                           stores its partial tile to a workspace slab (no atomics), reduced later.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "gemm_simt.cuh"  // activations, EPI_* enums
+
+namespace dsact {
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 64;        // bf16 elements per k-block = one 128-byte swizzle row
+constexpr int TC_MAXG = 8;
+constexpr int TC_STAGE_A = TC_BM * TC_BK * 2;   // 16 KiB per plane
+constexpr int TC_STAGE_B = 256 * TC_BK * 2;     // 32 KiB per plane
+constexpr int TC_THREADS = 192;
+
+enum { EPI_PARTIAL = 4 };  // wgrad: plain store into slab `ks`
+
+struct TcProb {
+  CUtensorMap mapA[2];      // A operand; a second K segment for cat(obs, act)
+  CUtensorMap mapB;
+  int kblocks[2];           // k-blocks (of 64) per A segment
+  int kB0[2];               // element offset of each segment along B's reduction dimension
+  int M, N, bn;             // output extents; N-tile width (multiple of 16, <= 256)
+  int tiles_m, tiles_n, ksplit, tile_start;
+  float* C;                 // fp32 output or null
+  int ldc;
+  long long split_stride;   // floats between consecutive split slabs (EPI_PARTIAL)
+  const float* bias;
+  float* Zout;              // pre-activation store (ld = ldc)
+  const float* Zin;         // pre-activation input for the derivative
+  int ldz;
+  float* colsum;            // bias gradient accumulation (EPI_DACT)
+  __nv_bfloat16* img;       // bf16 hi/lo image of the result, or null
+  int img_pitch;
+  long long img_plane;      // elements between the hi and lo planes
+  int epi, act;
+};
+
+struct TcGroup {
+  int n;
+  int passes;               // 3 = hi*hi + hi*lo + lo*hi, 1 = hi*hi
+  TcProb p[TC_MAXG];
+};
+
+// ---- PTX wrappers ------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\tWAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n\t"
+      "@P1 bra WAIT_DONE;\n\tbra WAIT_LOOP;\n\tWAIT_DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity), "r"(0x989680)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%1], %0;" ::"r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {  // arrives on `bar` when all prior MMAs of this thread finish
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc),
+      "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout), 128-byte swizzle.
+//   K-major : rows of 128 B (64 bf16 of K), 8-row groups SBO = 1024 B apart; advance K by 32 B per UMMA_K=16.
+//   MN-major: k-rows of 128 B (64 bf16 of M/N), 8-k groups SBO = 1024 B apart, 64-wide M/N blocks LBO apart.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;  // SWIZZLE_128B
+  return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): fp32 accumulate, bf16 x bf16.
+__device__ __forceinline__ uint32_t make_idesc(int m, int n, int a_mn, int b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(x);
+  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+
+// A_MN / B_MN: operand is MN-major (reduction dimension strided in global memory).
+template <bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_constant__ TcGroup g, int stages) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // 1024-byte alignment for the 128B-swizzle atoms
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int planes = g.passes == 3 ? 2 : 1;
+  const int stage_bytes = planes * (TC_STAGE_A + TC_STAGE_B);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)stages * stage_bytes);
+  uint64_t* full = bars;             // [stages]  TMA -> MMA
+  uint64_t* empty = bars + stages;   // [stages]  MMA -> TMA
+  uint64_t* acc_full = bars + 2 * stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * stages + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  int pi = 0;
+#pragma unroll
+  for (int i = 1; i < TC_MAXG; ++i)
+    if (i < g.n && (int)blockIdx.x >= g.p[i].tile_start) pi = i;
+  const TcProb& P = g.p[pi];
+  int local = blockIdx.x - P.tile_start;
+  const int tiles_mn = P.tiles_m * P.tiles_n;
+  const int ks = local / tiles_mn;
+  local -= ks * tiles_mn;
+  const int m0 = (local / P.tiles_n) * TC_BM, n0 = (local % P.tiles_n) * P.bn;
+  const int bn = P.bn;
+
+  // k-block range of this CTA (split only ever applies to single-segment problems)
+  const int nkb = P.kblocks[0] + P.kblocks[1];
+  int kb_begin = 0, kb_end = nkb;
+  if (P.ksplit > 1) {
+    const int per = (nkb + P.ksplit - 1) / P.ksplit;
+    kb_begin = ks * per;
+    kb_end = min(nkb, kb_begin + per);
+  }
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(acc_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  uint32_t tmem_cols = 32;
+  while ((int)tmem_cols < bn) tmem_cols <<= 1;
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      const int a_boxes = A_MN ? 2 : 1;                    // 64-wide feature blocks of a 128-row tile
+      const int b_boxes = B_MN ? (bn + 63) / 64 : 1;
+      const uint32_t a_bytes = A_MN ? 2u * 64 * 128 : (uint32_t)TC_STAGE_A;
+      const uint32_t b_bytes = B_MN ? (uint32_t)b_boxes * 64 * 128 : (uint32_t)bn * 128;
+      const uint32_t tx = planes * (a_bytes + b_bytes);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        mbar_expect_tx(&full[stage], tx);
+        const int seg = kb >= P.kblocks[0] ? 1 : 0;
+        const int kloc = (seg ? kb - P.kblocks[0] : kb) * TC_BK;   // offset inside the A segment
+        const int kB = P.kB0[seg] + kloc;                         // offset along B's reduction dimension
+        uint8_t* sA = smem + (size_t)stage * stage_bytes;
+        uint8_t* sB = sA + planes * TC_STAGE_A;
+        for (int pl = 0; pl < planes; ++pl) {
+          if (A_MN) {
+            for (int i = 0; i < a_boxes; ++i)
+              tma_load_3d(sA + pl * TC_STAGE_A + i * 8192, &P.mapA[seg], &full[stage], m0 + 64 * i, kloc, pl);
+          } else {
+            tma_load_3d(sA + pl * TC_STAGE_A, &P.mapA[seg], &full[stage], kloc, m0, pl);
+          }
+          if (B_MN) {
+            for (int i = 0; i < b_boxes; ++i)
+              tma_load_3d(sB + pl * TC_STAGE_B + i * 8192, &P.mapB, &full[stage], n0 + 64 * i, kB, pl);
+          } else {
+            tma_load_3d(sB + pl * TC_STAGE_B, &P.mapB, &full[stage], kB, n0, pl);
+          }
+        }
+        if (++stage == stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (one thread) =====
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(TC_BM, bn, A_MN, B_MN);
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t accumulate = 0;
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        const uint32_t sA = smem_u32(smem + (size_t)stage * stage_bytes);
+        const uint32_t sB = sA + planes * TC_STAGE_A;
+#pragma unroll
+        for (int k = 0; k < TC_BK / 16; ++k) {
+          const uint32_t a_off = A_MN ? k * 2048 : k * 32;
+          const uint32_t b_off = B_MN ? k * 2048 : k * 32;
+          const uint64_t a_hi = make_desc(sA + a_off, A_MN ? 8192 : 16, 1024);
+          const uint64_t b_hi = make_desc(sB + b_off, B_MN ? 8192 : 16, 1024);
+          tc_mma(tmem_base, a_hi, b_hi, idesc, accumulate);
+          accumulate = 1;
+          if (planes == 2) {
+            const uint64_t a_lo = make_desc(sA + TC_STAGE_A + a_off, A_MN ? 8192 : 16, 1024);
+            const uint64_t b_lo = make_desc(sB + TC_STAGE_B + b_off, B_MN ? 8192 : 16, 1024);
+            tc_mma(tmem_base, a_hi, b_lo, idesc, 1);
+            tc_mma(tmem_base, a_lo, b_hi, idesc, 1);
+          }
+        }
+        tc_commit(&empty[stage]);  // smem slot reusable once these MMAs retire
+        if (++stage == stages) { stage = 0; phase ^= 1; }
+      }
+      tc_commit(acc_full);
+    }
+  } else {
+    // ===== epilogue: 4 warps, warp w owns TMEM lanes 32*(w%4) .. +31 =====
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const int m = m0 + row;
+    const bool row_ok = m < P.M;
+    const bool have_acc = kb_begin < kb_end;
+    if (have_acc) {
+      mbar_wait(acc_full, 0);
+      tc_fence_after();
+    }
+    const int epi = P.epi, act = P.act;
+    float* C = P.C ? P.C + (epi == EPI_PARTIAL ? (size_t)ks * P.split_stride : 0) : nullptr;
+    for (int c0 = 0; c0 < bn; c0 += 16) {
+      float v[16];
+      if (have_acc) {
+        tc_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = 0.f;
+      }
+      const int n = n0 + c0;
+      const int valid = row_ok ? max(0, min(16, P.N - n)) : 0;
+      float z[16];
+      if (epi == EPI_STORE || epi == EPI_BIAS_ACT) {
+        if (P.bias)
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (n + j < P.N) v[j] += __ldg(P.bias + n + j);
+        if (epi == EPI_BIAS_ACT) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) { z[j] = v[j]; v[j] = act_fwd(v[j], act); }
+          if (P.Zout && valid > 0) {
+            float* zp = P.Zout + (size_t)m * P.ldc + n;
+            if (valid == 16 && ((reinterpret_cast<uintptr_t>(zp) & 15) == 0)) {
+#pragma unroll
+              for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(zp + j) = make_float4(z[j], z[j + 1], z[j + 2], z[j + 3]);
+            } else {
+              for (int j = 0; j < valid; ++j) zp[j] = z[j];
+            }
+          }
+        }
+      } else if (epi == EPI_DACT) {
+        const float* zp = P.Zin + (size_t)m * P.ldz + n;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = j < valid ? v[j] * act_bwd(__ldg(zp + j), act) : 0.f;
+        if (P.colsum) {  // column sums over the tile's rows: reduce-scatter across the warp, then 1 atomic per column
+          float r[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) r[j] = v[j];
+          int off = 0;
+#pragma unroll
+          for (int w = 8, bit = 16; w >= 1; w >>= 1, bit >>= 1) {
+            const bool up = lane & bit;
+#pragma unroll
+            for (int j = 0; j < w; ++j) {
+              const float send = up ? r[j] : r[j + w];
+              const float recv = __shfl_xor_sync(0xffffffffu, send, bit);
+              r[j] = (up ? r[j + w] : r[j]) + recv;
+            }
+            off += up ? w : 0;
+          }
+          r[0] += __shfl_xor_sync(0xffffffffu, r[0], 1);
+          if ((lane & 1) == 0 && n + off < P.N) atomicAdd(P.colsum + n + off, r[0]);
+        }
+      }
+      if (valid > 0) {
+        if (C) {
+          float* cp = C + (size_t)m * P.ldc + n;
+          if (valid == 16 && ((reinterpret_cast<uintptr_t>(cp) & 15) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(cp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          } else {
+            for (int j = 0; j < valid; ++j) cp[j] = v[j];
+          }
+        }
+        if (P.img) {
+          __nv_bfloat16* hp = P.img + (size_t)m * P.img_pitch + n;
+          __nv_bfloat16* lp = hp + P.img_plane;
+          __align__(16) __nv_bfloat16 hi[16], lo[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) split_bf16(v[j], hi[j], lo[j]);
+          if (valid == 16 && ((reinterpret_cast<uintptr_t>(hp) & 15) == 0) && ((P.img_plane & 7) == 0)) {
+            reinterpret_cast<uint4*>(hp)[0] = reinterpret_cast<const uint4*>(hi)[0];
+            reinterpret_cast<uint4*>(hp)[1] = reinterpret_cast<const uint4*>(hi)[1];
+            if (planes == 2) {
+              reinterpret_cast<uint4*>(lp)[0] = reinterpret_cast<const uint4*>(lo)[0];
+              reinterpret_cast<uint4*>(lp)[1] = reinterpret_cast<const uint4*>(lo)[1];
+            }
+          } else {
+            for (int j = 0; j < valid; ++j) { hp[j] = hi[j]; if (planes == 2) lp[j] = lo[j]; }
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols));
+  }
+}
+
+// fp32 -> bf16 hi/lo image conversion for tensors that elementwise kernels (or the optimiser) produce.
+// Up to two column segments let cat(obs, act)-shaped weights land with the act block on a 64-column boundary.
+struct ImgJob {
+  const float* src;
+  __nv_bfloat16* dst;
+  int rows, ld_src;
+  int seg_w[2], seg_src0[2], seg_dst0[2];
+  int pitch;            // image row pitch (elements); columns not covered by a segment are zero-filled up to `fill_w`
+  int fill_w;
+  long long plane;
+  int block_start;
+};
+struct ImgGroup {
+  int n, planes;
+  ImgJob j[16];
+};
+__global__ void image_kernel(const __grid_constant__ ImgGroup g) {
+  int ji = 0;
+#pragma unroll
+  for (int i = 1; i < 16; ++i)
+    if (i < g.n && (int)blockIdx.x >= g.j[i].block_start) ji = i;
+  const ImgJob& J = g.j[ji];
+  const long long total = (long long)J.rows * J.fill_w;
+  const int nblocks = (ji + 1 < g.n ? g.j[ji + 1].block_start : gridDim.x) - J.block_start;
+  for (long long i = (long long)(blockIdx.x - J.block_start) * blockDim.x + threadIdx.x; i < total;
+       i += (long long)nblocks * blockDim.x) {
+    const int r = (int)(i / J.fill_w), c = (int)(i - (long long)r * J.fill_w);
+    float x = 0.f;
+    if (c >= J.seg_dst0[0] && c < J.seg_dst0[0] + J.seg_w[0]) x = J.src[(size_t)r * J.ld_src + J.seg_src0[0] + (c - J.seg_dst0[0])];
+    else if (c >= J.seg_dst0[1] && c < J.seg_dst0[1] + J.seg_w[1]) x = J.src[(size_t)r * J.ld_src + J.seg_src0[1] + (c - J.seg_dst0[1])];
+    __nv_bfloat16 hi, lo;
+    split_bf16(x, hi, lo);
+    J.dst[(size_t)r * J.pitch + c] = hi;
+    if (g.planes == 2) J.dst[J.plane + (size_t)r * J.pitch + c] = lo;
+  }
+}
+
+// Sum the wgrad split slabs into the flat gradient buffer (which already holds the bias gradients).
+__global__ void grad_reduce_kernel(float* __restrict__ grads, const float* __restrict__ slabs, long long n, int nslabs,
+                                   long long slab_stride) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float s = grads[i];
+    for (int k = 0; k < nslabs; ++k) s += slabs[(size_t)k * slab_stride + i];
+    grads[i] = s;
+  }
+}
+
+}  // namespace dsact
