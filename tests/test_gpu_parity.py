@@ -160,3 +160,63 @@ def test_device_noise_statistics():
     assert abs(eps1.mean().item()) < 0.02 and abs(eps1.std().item() - 1.0) < 0.02
     assert abs((eps1 ** 4).mean().item() - 3.0) < 0.2
     eng.close(); eng2.close()
+
+
+# ---- tcgen05 paths -------------------------------------------------------------------------------------
+TC_CASES = ["tiny_b16", "ragged_b37", "halfcheetah_b512", "humanoid_b256", "humanoid_b4096"]
+
+
+@pytest.mark.parametrize("name", TC_CASES)
+def test_bf16x3_tensor_core_path_matches_reference_golden(golden_dir, name):
+    """Split-precision bf16 (hi*hi + hi*lo + lo*hi) on tcgen05: still inside the 1e-4 gate on 100 losses."""
+    z, cfg, batch, steps, over = load(golden_dir, name)
+    eng = make_engine(cfg, batch, over, use_graph=True, gemm_mode="bf16x3")
+    worst = 0.0
+    for it in range(steps):
+        b, n = feed(cfg, batch, it)
+        eng.step(b, it, n)
+        got = stats_vec(eng)
+        ref = z["tb"][it]
+        worst = max(worst, float(np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 1e-2))))
+        np.testing.assert_allclose(got, ref, rtol=RTOL, atol=1e-5, err_msg=f"{name} tb_info at step {it}")
+    names = [str(n) for n in z["param_names"]]
+    last = max(int(k.split("_")[1]) for k in z.files if k.startswith("pdigest_"))
+    if last == steps:
+        w = eng.export_weights()
+        for row, k in zip(z[f"pdigest_{last}"], names):
+            d = w[k].double().reshape(-1)
+            np.testing.assert_allclose(d.abs().sum().item(), row[1], rtol=RTOL, err_msg=f"{name} {k}")
+    print(f"{name}: worst relative tb_info deviation over {steps} steps = {worst:.2e}")
+    eng.close()
+
+
+def test_bf16x3_gradients_match_reference_golden(golden_dir):
+    z, cfg, batch, steps, over = load(golden_dir, "ragged_b37")
+    eng = make_engine(cfg, batch, over, use_graph=False, gemm_mode="bf16x3")
+    trainable = [str(n) for n in z["trainable_names"]]
+    for it in (0, 1):
+        b, n = feed(cfg, batch, it)
+        eng.compute_grads(b, n)
+        g = eng.export_weights(grads=True)
+        for k in trainable:
+            ref = z[f"grad_{it}/{k}"]
+            np.testing.assert_allclose(g[k].numpy(), ref, rtol=1e-3, atol=3e-5 * np.abs(ref).max() + 1e-12,
+                                       err_msg=f"grad {k} step {it}")
+        eng.apply(it)
+    eng.close()
+
+
+def test_bf16_single_pass_is_close_but_outside_the_parity_gate(golden_dir):
+    """Throughput mode: operands rounded to bf16 once.  It must track the reference loosely; it is NOT a parity mode."""
+    z, cfg, batch, steps, over = load(golden_dir, "humanoid_b256")
+    eng = make_engine(cfg, batch, over, use_graph=True, gemm_mode="bf16")
+    dev = []
+    for it in range(30):
+        b, n = feed(cfg, batch, it)
+        eng.step(b, it, n)
+        got = stats_vec(eng)
+        assert np.all(np.isfinite(got))
+        dev.append(abs(got[7] - z["tb"][it][7]) / abs(z["tb"][it][7]))
+    assert max(dev) < 5e-2, max(dev)
+    print(f"bf16 single pass: max critic-loss deviation over 30 steps = {max(dev):.2e}")
+    eng.close()
