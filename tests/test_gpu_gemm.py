@@ -7,7 +7,7 @@ pytestmark = pytest.mark.gpu
 
 # per-mode (rtol, atol per sqrt(K)): fp32 FFMA; bf16 split-precision on tcgen05 (products good to ~2^-16);
 # single-pass bf16 on tcgen05 (operands rounded to 8 bits)
-TOL = {"fp32": (2e-5, 2e-5), "bf16x3": (1e-4, 6e-5), "bf16": (2e-2, 1.2e-2)}
+TOL = {"fp32": (2e-5, 2e-5), "bf16x3": (1e-4, 6e-5), "bf16": (3e-2, 2.5e-2)}
 
 
 @pytest.fixture(scope="module", params=["fp32", "bf16x3", "bf16"])
