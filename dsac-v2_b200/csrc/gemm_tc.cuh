@@ -7,7 +7,8 @@
 // One CTA computes one 128 x BN output tile (BN <= 256) of one problem of the group:
 //   warp 0      : TMA producer  (cp.async.bulk.tensor.3d, 128B swizzle, mbarrier complete_tx)
 //   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (accumulator in TMEM, fp32)
-//   warps 2..5  : epilogue      (tcgen05.ld 32x32b, bias/activation/derivative, fp32 + bf16-image stores)
+//   warps 2..9  : epilogue      (tcgen05.ld 32x32b -> shared-memory transpose -> one output column per lane, so every
+//                                global access of bias/activation/derivative/fp32/bf16-image traffic is coalesced)
 // The three orientations of a linear layer never need a transposed copy: the UMMA descriptors read
 // K-major or MN-major shared-memory tiles as the reduction dimension requires
 //   forward  y  = x W^T   : A K-major (x image),   B K-major  (W image)
@@ -29,7 +30,8 @@ constexpr int TC_BK = 64;        // bf16 elements per k-block = one 128-byte swi
 constexpr int TC_MAXG = 8;
 constexpr int TC_STAGE_A = TC_BM * TC_BK * 2;   // 16 KiB per plane
 constexpr int TC_STAGE_B = 256 * TC_BK * 2;     // 32 KiB per plane
-constexpr int TC_THREADS = 192;
+constexpr int TC_EPI_WARPS = 8;
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 
 enum { EPI_PARTIAL = 4 };  // wgrad: plain store into slab `ks`
 
@@ -94,16 +96,19 @@ __device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t
 }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16]) {
-  uint32_t r[16];
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
   asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
 // Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout), 128-byte swizzle.
@@ -250,99 +255,66 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
       tc_commit(acc_full);
     }
   } else {
-    // ===== epilogue: 4 warps, warp w owns TMEM lanes 32*(w%4) .. +31 =====
+    // ===== epilogue: 8 warps; warp w may touch TMEM lanes 32*(w%4)..+31; two warps share a lane quarter and
+    // split the tile's 32-column chunks between them =====
     const int quarter = warp & 3;
-    const int row = quarter * 32 + lane;
-    const int m = m0 + row;
-    const bool row_ok = m < P.M;
+    const int half = (warp - 2) >> 2;
     const bool have_acc = kb_begin < kb_end;
     if (have_acc) {
-      mbar_wait(acc_full, 0);
+      mbar_wait(acc_full, 0);  // all MMAs retired: accumulator complete, pipeline smem is dead and reusable
       tc_fence_after();
     }
+    float* tr = reinterpret_cast<float*>(smem) + (warp - 2) * (32 * 33);  // per-warp 32x33 transpose tile
     const int epi = P.epi, act = P.act;
-    float* C = P.C ? P.C + (epi == EPI_PARTIAL ? (size_t)ks * P.split_stride : 0) : nullptr;
-    for (int c0 = 0; c0 < bn; c0 += 16) {
-      float v[16];
+    const int nch = (bn + 31) / 32, ch_lo = half ? (nch + 1) / 2 : 0, ch_hi = half ? nch : (nch + 1) / 2;
+    const int mbase = m0 + quarter * 32;
+    float* Cb = P.C ? P.C + (epi == EPI_PARTIAL ? (size_t)ks * P.split_stride : 0) : nullptr;
+    for (int ch = ch_lo; ch < ch_hi; ++ch) {
+      const int c0 = ch * 32;
+      float v[32];
       if (have_acc) {
-        tc_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
+        tc_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
       } else {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = 0.f;
+        for (int i = 0; i < 32; ++i) v[i] = 0.f;
       }
-      const int n = n0 + c0;
-      const int valid = row_ok ? max(0, min(16, P.N - n)) : 0;
-      float z[16];
-      if (epi == EPI_STORE || epi == EPI_BIAS_ACT) {
-        if (P.bias)
+      __syncwarp();
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (n + j < P.N) v[j] += __ldg(P.bias + n + j);
-        if (epi == EPI_BIAS_ACT) {
+      for (int j = 0; j < 32; ++j) tr[lane * 33 + j] = v[j];   // row = lane, column = j
+      __syncwarp();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) { z[j] = v[j]; v[j] = act_fwd(v[j], act); }
-          if (P.Zout && valid > 0) {
-            float* zp = P.Zout + (size_t)m * P.ldc + n;
-            if (valid == 16 && ((reinterpret_cast<uintptr_t>(zp) & 15) == 0)) {
-#pragma unroll
-              for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(zp + j) = make_float4(z[j], z[j + 1], z[j + 2], z[j + 3]);
-            } else {
-              for (int j = 0; j < valid; ++j) zp[j] = z[j];
-            }
-          }
+      for (int r = 0; r < 32; ++r) v[r] = tr[r * 33 + lane];   // now: this lane's column, rows 0..31
+      const int n = n0 + c0 + lane;
+      const bool col_ok = (c0 + lane) < bn && n < P.N;
+      const float bias_n = (P.bias && col_ok) ? __ldg(P.bias + n) : 0.f;
+      float csum = 0.f;
+#pragma unroll 8
+      for (int r = 0; r < 32; ++r) {
+        const int m = mbase + r;
+        const bool ok = col_ok && m < P.M;
+        float val = v[r];
+        if (epi == EPI_STORE) {
+          val += bias_n;
+        } else if (epi == EPI_BIAS_ACT) {
+          val += bias_n;
+          if (ok && P.Zout) P.Zout[(size_t)m * P.ldc + n] = val;
+          val = act_fwd(val, act);
+        } else if (epi == EPI_DACT) {
+          val = ok ? val * act_bwd(__ldg(P.Zin + (size_t)m * P.ldz + n), act) : 0.f;
+          csum += val;
         }
-      } else if (epi == EPI_DACT) {
-        const float* zp = P.Zin + (size_t)m * P.ldz + n;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = j < valid ? v[j] * act_bwd(__ldg(zp + j), act) : 0.f;
-        if (P.colsum) {  // column sums over the tile's rows: reduce-scatter across the warp, then 1 atomic per column
-          float r[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) r[j] = v[j];
-          int off = 0;
-#pragma unroll
-          for (int w = 8, bit = 16; w >= 1; w >>= 1, bit >>= 1) {
-            const bool up = lane & bit;
-#pragma unroll
-            for (int j = 0; j < w; ++j) {
-              const float send = up ? r[j] : r[j + w];
-              const float recv = __shfl_xor_sync(0xffffffffu, send, bit);
-              r[j] = (up ? r[j + w] : r[j]) + recv;
-            }
-            off += up ? w : 0;
-          }
-          r[0] += __shfl_xor_sync(0xffffffffu, r[0], 1);
-          if ((lane & 1) == 0 && n + off < P.N) atomicAdd(P.colsum + n + off, r[0]);
-        }
-      }
-      if (valid > 0) {
-        if (C) {
-          float* cp = C + (size_t)m * P.ldc + n;
-          if (valid == 16 && ((reinterpret_cast<uintptr_t>(cp) & 15) == 0)) {
-#pragma unroll
-            for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(cp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          } else {
-            for (int j = 0; j < valid; ++j) cp[j] = v[j];
-          }
-        }
-        if (P.img) {
-          __nv_bfloat16* hp = P.img + (size_t)m * P.img_pitch + n;
-          __nv_bfloat16* lp = hp + P.img_plane;
-          __align__(16) __nv_bfloat16 hi[16], lo[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) split_bf16(v[j], hi[j], lo[j]);
-          if (valid == 16 && ((reinterpret_cast<uintptr_t>(hp) & 15) == 0) && ((P.img_plane & 7) == 0)) {
-            reinterpret_cast<uint4*>(hp)[0] = reinterpret_cast<const uint4*>(hi)[0];
-            reinterpret_cast<uint4*>(hp)[1] = reinterpret_cast<const uint4*>(hi)[1];
-            if (planes == 2) {
-              reinterpret_cast<uint4*>(lp)[0] = reinterpret_cast<const uint4*>(lo)[0];
-              reinterpret_cast<uint4*>(lp)[1] = reinterpret_cast<const uint4*>(lo)[1];
-            }
-          } else {
-            for (int j = 0; j < valid; ++j) { hp[j] = hi[j]; if (planes == 2) lp[j] = lo[j]; }
+        if (ok) {
+          if (Cb) Cb[(size_t)m * P.ldc + n] = val;
+          if (P.img) {
+            __nv_bfloat16 hi, lo;
+            split_bf16(val, hi, lo);
+            __nv_bfloat16* hp = P.img + (size_t)m * P.img_pitch + n;
+            *hp = hi;
+            if (planes == 2) hp[P.img_plane] = lo;
           }
         }
       }
+      if (epi == EPI_DACT && P.colsum && col_ok) atomicAdd(P.colsum + n, csum);  // bias gradient of this tile
     }
   }
 
