@@ -7,7 +7,7 @@
 // One CTA computes one 128 x BN output tile (BN <= 256) of one problem of the group:
 //   warp 0      : TMA producer  (cp.async.bulk.tensor.3d, 128B swizzle, mbarrier complete_tx)
 //   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (accumulator in TMEM, fp32)
-//   warps 2..9  : epilogue      (tcgen05.ld 32x32b -> shared-memory transpose -> one output column per lane, so every
+//   warps 2..17 : epilogue      (tcgen05.ld 32x32b -> shared-memory transpose -> one output column per lane, so every
 //                                global access of bias/activation/derivative/fp32/bf16-image traffic is coalesced)
 // The three orientations of a linear layer never need a transposed copy: the UMMA descriptors read
 // K-major or MN-major shared-memory tiles as the reduction dimension requires
@@ -30,7 +30,7 @@ constexpr int TC_BK = 64;        // bf16 elements per k-block = one 128-byte swi
 constexpr int TC_MAXG = 8;
 constexpr int TC_STAGE_A = TC_BM * TC_BK * 2;   // 16 KiB per plane
 constexpr int TC_STAGE_B = 256 * TC_BK * 2;     // 32 KiB per plane
-constexpr int TC_EPI_WARPS = 8;
+constexpr int TC_EPI_WARPS = 16;
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 
 enum { EPI_PARTIAL = 4 };  // wgrad: plain store into slab `ks`
@@ -255,10 +255,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
       tc_commit(acc_full);
     }
   } else {
-    // ===== epilogue: 8 warps; warp w may touch TMEM lanes 32*(w%4)..+31; two warps share a lane quarter and
-    // split the tile's 32-column chunks between them =====
+    // ===== epilogue: 16 warps; warp w may touch TMEM lanes 32*(w%4)..+31; the four warps of a lane quarter
+    // take every fourth 32-column chunk.  Each phase below is fully unrolled over the 32 rows a lane holds so that
+    // the loads, the activation polynomials and the stores of different rows overlap (the phase is latency bound).
     const int quarter = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int sub = (warp - 2) >> 2;                       // 0..3
     const bool have_acc = kb_begin < kb_end;
     if (have_acc) {
       mbar_wait(acc_full, 0);  // all MMAs retired: accumulator complete, pipeline smem is dead and reusable
@@ -266,10 +267,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
     }
     float* tr = reinterpret_cast<float*>(smem) + (warp - 2) * (32 * 33);  // per-warp 32x33 transpose tile
     const int epi = P.epi, act = P.act;
-    const int nch = (bn + 31) / 32, ch_lo = half ? (nch + 1) / 2 : 0, ch_hi = half ? nch : (nch + 1) / 2;
+    const int nch = (bn + 31) / 32;
     const int mbase = m0 + quarter * 32;
+    const int rows_ok = max(0, min(32, P.M - mbase));       // rows of this quarter inside the matrix
     float* Cb = P.C ? P.C + (epi == EPI_PARTIAL ? (size_t)ks * P.split_stride : 0) : nullptr;
-    for (int ch = ch_lo; ch < ch_hi; ++ch) {
+    for (int ch = sub; ch < nch; ch += TC_EPI_WARPS / 4) {
       const int c0 = ch * 32;
       float v[32];
       if (have_acc) {
@@ -286,35 +288,52 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
       for (int r = 0; r < 32; ++r) v[r] = tr[r * 33 + lane];   // now: this lane's column, rows 0..31
       const int n = n0 + c0 + lane;
       const bool col_ok = (c0 + lane) < bn && n < P.N;
-      const float bias_n = (P.bias && col_ok) ? __ldg(P.bias + n) : 0.f;
-      float csum = 0.f;
-#pragma unroll 8
-      for (int r = 0; r < 32; ++r) {
-        const int m = mbase + r;
-        const bool ok = col_ok && m < P.M;
-        float val = v[r];
-        if (epi == EPI_STORE) {
-          val += bias_n;
-        } else if (epi == EPI_BIAS_ACT) {
-          val += bias_n;
-          if (ok && P.Zout) P.Zout[(size_t)m * P.ldc + n] = val;
-          val = act_fwd(val, act);
-        } else if (epi == EPI_DACT) {
-          val = ok ? val * act_bwd(__ldg(P.Zin + (size_t)m * P.ldz + n), act) : 0.f;
-          csum += val;
+      const int nrows = col_ok ? rows_ok : 0;
+      if (epi == EPI_STORE || epi == EPI_BIAS_ACT) {
+        const float bias_n = (P.bias && col_ok) ? __ldg(P.bias + n) : 0.f;
+#pragma unroll
+        for (int r = 0; r < 32; ++r) v[r] += bias_n;
+        if (epi == EPI_BIAS_ACT) {
+          if (P.Zout) {
+            float* zp = P.Zout + (size_t)mbase * P.ldc + n;
+#pragma unroll
+            for (int r = 0; r < 32; ++r)
+              if (r < nrows) zp[(size_t)r * P.ldc] = v[r];
+          }
+#pragma unroll
+          for (int r = 0; r < 32; ++r) v[r] = act_fwd(v[r], act);
         }
-        if (ok) {
-          if (Cb) Cb[(size_t)m * P.ldc + n] = val;
-          if (P.img) {
-            __nv_bfloat16 hi, lo;
-            split_bf16(val, hi, lo);
-            __nv_bfloat16* hp = P.img + (size_t)m * P.img_pitch + n;
-            *hp = hi;
-            if (planes == 2) hp[P.img_plane] = lo;
+      } else if (epi == EPI_DACT) {
+        const float* zp = P.Zin + (size_t)mbase * P.ldz + n;
+        float zin[32];
+#pragma unroll
+        for (int r = 0; r < 32; ++r) zin[r] = r < nrows ? __ldg(zp + (size_t)r * P.ldz) : 0.f;
+        float csum = 0.f;
+#pragma unroll
+        for (int r = 0; r < 32; ++r) {
+          v[r] = r < nrows ? v[r] * act_bwd(zin[r], act) : 0.f;
+          csum += v[r];
+        }
+        if (P.colsum && col_ok) atomicAdd(P.colsum + n, csum);  // bias gradient of this tile
+      }
+      if (Cb) {
+        float* cp = Cb + (size_t)mbase * P.ldc + n;
+#pragma unroll
+        for (int r = 0; r < 32; ++r)
+          if (r < nrows) cp[(size_t)r * P.ldc] = v[r];
+      }
+      if (P.img) {
+        __nv_bfloat16* hp = P.img + (size_t)mbase * P.img_pitch + n;
+#pragma unroll
+        for (int r = 0; r < 32; ++r) {
+          __nv_bfloat16 hi, lo;
+          split_bf16(v[r], hi, lo);
+          if (r < nrows) {
+            hp[(size_t)r * P.img_pitch] = hi;
+            if (planes == 2) hp[P.img_plane + (size_t)r * P.img_pitch] = lo;
           }
         }
       }
-      if (epi == EPI_DACT && P.colsum && col_ok) atomicAdd(P.colsum + n, csum);  // bias gradient of this tile
     }
   }
 
