@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -185,12 +186,17 @@ enum { V_FWD = 0, V_DGRAD = 1, V_WGRAD = 2 };
 
 // A group of independent problems in both lowerings: fp32 pointers (GemmGroup) and bf16 images (TcExtra).
 struct Group {
-  GemmGroup g;
-  TcExtra x[MAXG];
+  GemmGroup g;               // SIMT lowering holds at most MAXG problems per launch; tcgen05 up to TC_MAXG
+  GemmProb more[TC_MAXG - MAXG];
+  TcExtra x[TC_MAXG];
+  int n = 0;
+  GemmProb& prob(int i) { return i < MAXG ? g.p[i] : more[i - MAXG]; }
+  const GemmProb& prob(int i) const { return i < MAXG ? g.p[i] : more[i - MAXG]; }
   float* wg_slab = nullptr;   // wgrad split slabs (default: the arena's, addressed like the gradient buffer)
   long long wg_stride = 0;
   int wg_nslabs = 0;
   Group() { g.n = 0; }
+  void push(const GemmProb& p, const TcExtra& e) { x[n] = e; prob(n) = p; ++n; g.n = n < MAXG ? n : MAXG; }
 };
 
 template <int BM, int BN>
@@ -198,12 +204,6 @@ static void launch_variant(const GemmGroup& g, int variant, int grid, Ctx& c) {
   if (variant == V_FWD) gemm_kernel<BM, BN, true, true><<<grid, 256, 0, c.s>>>(g);
   else if (variant == V_DGRAD) gemm_kernel<BM, BN, true, false><<<grid, 256, 0, c.s>>>(g);
   else gemm_kernel<BM, BN, false, false><<<grid, 256, 0, c.s>>>(g);
-}
-
-static double group_flops(const GemmGroup& g) {
-  double flops = 0.0;
-  for (int i = 0; i < g.n; ++i) flops += 2.0 * g.p[i].M * g.p[i].N * ((double)g.p[i].K[0] + g.p[i].K[1]);
-  return flops;
 }
 
 static void launch_simt(const dsact_handle* h, GemmGroup& g, int variant, Ctx& c) {
@@ -243,12 +243,13 @@ static bool g_tc_attr_done = false;
 static void launch_tc(const dsact_handle* h, Group& G, int variant, Ctx& c) {
   static TcGroup t;  // ~5 KiB; host-side scratch (single trainer thread per process is the documented contract)
   memset(&t, 0, sizeof(t));
-  t.n = G.g.n;
+  t.n = G.n;
   t.passes = h->passes();
   const bool a_mn = variant == V_WGRAD, b_mn = variant != V_FWD;
   int grid = 0;
-  for (int i = 0; i < G.g.n; ++i) {
-    const GemmProb& s = G.g.p[i];
+  int bn_max = 16;
+  for (int i = 0; i < G.n; ++i) {
+    const GemmProb& s = G.prob(i);
     const TcExtra& x = G.x[i];
     TcProb& p = t.p[i];
     p.M = s.M; p.N = s.N;
@@ -256,6 +257,7 @@ static void launch_tc(const dsact_handle* h, Group& G, int variant, Ctx& c) {
     if (bn > 256) bn = 256;
     if (variant == V_WGRAD && bn > 128) bn = 128;  // more tiles for the (few, batch-split) weight-gradient problems
     p.bn = bn;
+    if (bn > bn_max) bn_max = bn;
     p.tiles_m = (s.M + TC_BM - 1) / TC_BM;
     p.tiles_n = (s.N + bn - 1) / bn;
     for (int sgm = 0; sgm < 2; ++sgm) {
@@ -283,26 +285,61 @@ static void launch_tc(const dsact_handle* h, Group& G, int variant, Ctx& c) {
     p.tile_start = grid;
     grid += p.tiles_m * p.tiles_n * p.ksplit;
   }
+  static unsigned long long* dbg = nullptr;
+  const bool debug = getenv("DSACT_TC_DEBUG") != nullptr;
+  if (debug && !dbg) cudaMalloc(&dbg, sizeof(unsigned long long) * 8 * 4096);
+  if (debug && grid <= 4096) { cudaMemsetAsync(dbg, 0, sizeof(unsigned long long) * 8 * grid, c.s); t.dbg = dbg; }
   const int planes = t.passes == 3 ? 2 : 1;
-  const int stages = planes == 2 ? 2 : 4;
-  const int smem = tc_smem_bytes(stages, planes);
+  const int stage_b = (b_mn ? (bn_max + 63) / 64 * 64 : bn_max) * 128;   // bytes of one B plane per stage
+  int stages = (200 * 1024) / (planes * (TC_STAGE_A + stage_b));
+  if (stages > 8) stages = 8;
+  const int smem = tc_smem_bytes(stages, planes, stage_b);
   if (!g_tc_attr_done) {
     cudaFuncSetAttribute(tc_gemm_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     cudaFuncSetAttribute(tc_gemm_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     cudaFuncSetAttribute(tc_gemm_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     g_tc_attr_done = true;
   }
-  if (variant == V_FWD) tc_gemm_kernel<false, false><<<grid, TC_THREADS, smem, c.s>>>(t, stages);
-  else if (variant == V_DGRAD) tc_gemm_kernel<false, true><<<grid, TC_THREADS, smem, c.s>>>(t, stages);
-  else tc_gemm_kernel<true, true><<<grid, TC_THREADS, smem, c.s>>>(t, stages);
+  if (variant == V_FWD) tc_gemm_kernel<false, false><<<grid, TC_THREADS, smem, c.s>>>(t, stages, stage_b);
+  else if (variant == V_DGRAD) tc_gemm_kernel<false, true><<<grid, TC_THREADS, smem, c.s>>>(t, stages, stage_b);
+  else tc_gemm_kernel<true, true><<<grid, TC_THREADS, smem, c.s>>>(t, stages, stage_b);
+  if (debug && t.dbg) {  // per-CTA phase breakdown (ns): setup | first TMA landed | MMA issue done | accumulator ready | epilogue | teardown
+    cudaStreamSynchronize(c.s);
+    std::vector<unsigned long long> hbuf(8 * (size_t)grid);
+    cudaMemcpy(hbuf.data(), dbg, sizeof(unsigned long long) * 8 * grid, cudaMemcpyDeviceToHost);
+    unsigned long long tmin = ~0ull, tmax = 0;
+    double ph[6] = {0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < grid; ++i) {
+      const unsigned long long* d = &hbuf[8 * (size_t)i];
+      if (d[0] < tmin) tmin = d[0];
+      if (d[6] > tmax) tmax = d[6];
+      ph[0] += (double)(d[1] - d[0]); ph[1] += (double)(d[2] - d[1]); ph[2] += (double)(d[3] - d[2]);
+      ph[3] += (double)(d[4] - d[3]); ph[4] += (double)(d[5] - d[4]); ph[5] += (double)(d[6] - d[5]);
+    }
+    fprintf(stderr, "[tc_debug] variant %d grid %d span %.1f us | per-CTA avg ns: setup %.0f, first-load %.0f, mma-issue %.0f, acc-wait %.0f, epilogue %.0f, teardown %.0f\n",
+            variant, grid, (tmax - tmin) / 1000.0, ph[0] / grid, ph[1] / grid, ph[2] / grid, ph[3] / grid, ph[4] / grid, ph[5] / grid);
+  }
 }
 
 static void launch_group(const dsact_handle* h, Group& G, int variant, Ctx& c) {
-  if (G.g.n == 0) return;
-  const double flops = group_flops(G.g);
-  if (h->tc()) launch_tc(h, G, variant, c);
-  else launch_simt(h, G.g, variant, c);
-  c.done(CLS_GEMM_FWD + variant, flops);
+  if (G.n == 0) return;
+  double flops = 0.0;
+  for (int i = 0; i < G.n; ++i) flops += 2.0 * G.prob(i).M * G.prob(i).N * ((double)G.prob(i).K[0] + G.prob(i).K[1]);
+  if (h->tc()) {
+    launch_tc(h, G, variant, c);
+    c.done(CLS_GEMM_FWD + variant, flops);
+  } else {
+    G.g.n = G.n < MAXG ? G.n : MAXG;
+    launch_simt(h, G.g, variant, c);
+    c.done(CLS_GEMM_FWD + variant, flops);
+    if (G.n > MAXG) {  // second launch for the overflow
+      GemmGroup g2;
+      g2.n = G.n - MAXG;
+      for (int i = 0; i < g2.n; ++i) g2.p[i] = G.more[i];
+      launch_simt(h, g2, variant, c);
+      c.done(CLS_GEMM_FWD + variant, 0.0);
+    }
+  }
   c.check();
 }
 
@@ -343,8 +380,7 @@ static void add_fwd(Group& G, const Net& net, int j, const Wt& w, const Ten& in0
   p.act = act;
   p.Zout = last ? nullptr : zout;
   x.out = last ? Img() : out.im;
-  G.x[G.g.n] = x;
-  G.g.p[G.g.n++] = p;
+  G.push(p, x);
 }
 
 // dgrad through layer j, weight columns [col0, col0+ncols): dX = dY * W[:, cols]   (* act'(Zprev), bias-grad colsum)
@@ -360,8 +396,7 @@ static void add_dgrad(Group& G, const Net& net, int j, const Wt& w, int col0, in
   if (Zprev) { p.epi = EPI_DACT; p.Zin = Zprev; p.ldz = ncols; p.colsum = gbias_prev; p.act = act; }
   else p.epi = EPI_STORE;
   x.out = dX.im;
-  G.x[G.g.n] = x;
-  G.g.p[G.g.n++] = p;
+  G.push(p, x);
 }
 
 // wgrad of layer j, weight columns [col0, col0+ncols): gW[:, cols] += dY^T X
@@ -373,8 +408,7 @@ static void add_wgrad(Group& G, const Net& net, int j, float* Gw, int col0, int 
   x.a[0] = dY.im; x.b = X.im;
   p.M = net.s[j + 1]; p.N = ncols; p.C = Gw + col0; p.ldc = net.s[j];
   p.epi = EPI_ATOMIC;
-  G.x[G.g.n] = x;
-  G.g.p[G.g.n++] = p;
+  G.push(p, x);
 }
 
 // fp32 -> image conversions (TC modes)
@@ -579,8 +613,9 @@ static void enqueue_phase2(dsact_handle* h, const dsact_batch& bt, int64_t globa
   const Ten t_obs = ten(bt.obs, ar.i_obs), t_act = ten(bt.act, ar.i_act);
 
   // wave C: critic passes 0,1 (dgrad + wgrad) and actor passes 4,5 (dgrad only), top layer down
+  Group gw;  // every weight-gradient problem of the two critics: independent once the dgrad chain has run
   for (int j = q.L; j >= 1; --j) {
-    Group gd, gw;
+    Group gd;
     for (int pp = 0; pp < 4; ++pp) {
       const int p = passes[pp], k = p & 1;
       const Ten dY = j == q.L ? ten(W + ar.dOut[p], ar.i_dOut[p]) : ten(W + ar.dzQ[p][j], ar.i_dzQ[p][j]);
@@ -590,10 +625,9 @@ static void enqueue_phase2(dsact_handle* h, const dsact_batch& bt, int64_t globa
       if (p < 2) add_wgrad(gw, q, j, Gq[k] + q.w[j], 0, q.s[j], dY, ten(W + ar.hQ[p][j - 1], ar.i_hQ[p][j - 1]), B);
     }
     launch_group(h, gd, V_DGRAD, c);
-    launch_group(h, gw, V_WGRAD, c);
   }
   {
-    Group gw, gd;
+    Group gd;
     for (int k = 0; k < 2; ++k) {
       const Ten dz0 = ten(W + ar.dzQ[k][0], ar.i_dzQ[k][0]);
       add_wgrad(gw, q, 0, Gq[k] + q.w[0], 0, O, dz0, t_obs, B);
@@ -622,18 +656,18 @@ static void enqueue_phase2(dsact_handle* h, const dsact_batch& bt, int64_t globa
   }
 
   // wave D: policy backward
+  Group gwp;
   for (int j = pi.L; j >= 0; --j) {
     const Ten dY = j == pi.L ? ten(W + ar.dlogits, ar.i_dlogits) : ten(W + ar.dzP[j], ar.i_dzP[j]);
-    Group gw;
-    add_wgrad(gw, pi, j, Gpi + pi.w[j], 0, pi.s[j], dY, j == 0 ? t_obs : ten(W + ar.hP[j - 1], ar.i_hP[j - 1]), B);
+    add_wgrad(gwp, pi, j, Gpi + pi.w[j], 0, pi.s[j], dY, j == 0 ? t_obs : ten(W + ar.hP[j - 1], ar.i_hP[j - 1]), B);
     if (j >= 1) {
       Group gd;
       add_dgrad(gd, pi, j, weight(h, pi, Ppi, j, ar.i_wpi[0][j]), 0, 0, pi.s[j], dY, ten(W + ar.dzP[j - 1], ar.i_dzP[j - 1]),
                 W + ar.zP[j - 1], Gpi + pi.b[j - 1], B, cf.act_pi);
       launch_group(h, gd, V_DGRAD, c);
     }
-    launch_group(h, gw, V_WGRAD, c);
   }
+  launch_group(h, gwp, V_WGRAD, c);
 
   if (tc) {  // fold the weight-gradient split slabs into the flat gradient buffer
     const long long n = 2 * q.n + pi.n + 1;
@@ -1116,7 +1150,7 @@ int dsact_test_gemm(dsact_handle* h, int32_t variant, const float* A, int32_t ld
   p.A[0] = A; p.lda[0] = lda; p.B[0] = B; p.ldb[0] = ldb; p.K[0] = K;
   p.M = M; p.N = N; p.C = C; p.ldc = ldc; p.bias = variant == V_FWD ? bias : nullptr;
   p.epi = variant == V_WGRAD ? EPI_ATOMIC : EPI_STORE;
-  G.g.p[0] = p; G.g.n = 1;
+  G.push(p, TcExtra());
   Ctx c{s, 0, cudaSuccess};
   void* scratch = nullptr;
   if (h->tc()) {  // test hook only: scratch images (and slabs) come from cudaMalloc, not from the caller

@@ -27,7 +27,7 @@ namespace dsact {
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;        // bf16 elements per k-block = one 128-byte swizzle row
-constexpr int TC_MAXG = 8;
+constexpr int TC_MAXG = 16;
 constexpr int TC_STAGE_A = TC_BM * TC_BK * 2;   // 16 KiB per plane
 constexpr int TC_STAGE_B = 256 * TC_BK * 2;     // 32 KiB per plane
 constexpr int TC_EPI_WARPS = 16;
@@ -59,6 +59,7 @@ struct TcProb {
 struct TcGroup {
   int n;
   int passes;               // 3 = hi*hi + hi*lo + lo*hi, 1 = hi*hi
+  unsigned long long* dbg;  // optional per-CTA phase timestamps (DSACT_TC_DEBUG), 8 slots per CTA
   TcProb p[TC_MAXG];
 };
 
@@ -129,6 +130,13 @@ __device__ __forceinline__ uint32_t make_idesc(int m, int n, int a_mn, int b_mn)
          ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define TC_STAMP(slot) do { if (g.dbg) g.dbg[(size_t)blockIdx.x * 8 + (slot)] = gtime(); } while (0)
+
 __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
   hi = __float2bfloat16_rn(x);
   lo = __float2bfloat16_rn(x - __bfloat162float(hi));
@@ -136,12 +144,12 @@ __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bflo
 
 // A_MN / B_MN: operand is MN-major (reduction dimension strided in global memory).
 template <bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_constant__ TcGroup g, int stages) {
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_constant__ TcGroup g, int stages, int stage_b) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment for the 128B-swizzle atoms
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int planes = g.passes == 3 ? 2 : 1;
-  const int stage_bytes = planes * (TC_STAGE_A + TC_STAGE_B);
+  const int stage_bytes = planes * (TC_STAGE_A + stage_b);  // stage_b: bytes of one B plane (widest tile of the launch)
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)stages * stage_bytes);
   uint64_t* full = bars;             // [stages]  TMA -> MMA
   uint64_t* empty = bars + stages;   // [stages]  MMA -> TMA
@@ -149,6 +157,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * stages + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) TC_STAMP(0);
 
   int pi = 0;
 #pragma unroll
@@ -186,6 +195,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) TC_STAMP(1);
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -214,9 +224,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
           }
           if (B_MN) {
             for (int i = 0; i < b_boxes; ++i)
-              tma_load_3d(sB + pl * TC_STAGE_B + i * 8192, &P.mapB, &full[stage], n0 + 64 * i, kB, pl);
+              tma_load_3d(sB + pl * stage_b + i * 8192, &P.mapB, &full[stage], n0 + 64 * i, kB, pl);
           } else {
-            tma_load_3d(sB + pl * TC_STAGE_B, &P.mapB, &full[stage], kB, n0, pl);
+            tma_load_3d(sB + pl * stage_b, &P.mapB, &full[stage], kB, n0, pl);
           }
         }
         if (++stage == stages) { stage = 0; phase ^= 1; }
@@ -232,6 +242,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
       for (int kb = kb_begin; kb < kb_end; ++kb) {
         mbar_wait(&full[stage], phase);
         tc_fence_after();
+        if (kb == kb_begin) TC_STAMP(2);
         const uint32_t sA = smem_u32(smem + (size_t)stage * stage_bytes);
         const uint32_t sB = sA + planes * TC_STAGE_A;
 #pragma unroll
@@ -244,7 +255,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
           accumulate = 1;
           if (planes == 2) {
             const uint64_t a_lo = make_desc(sA + TC_STAGE_A + a_off, A_MN ? 8192 : 16, 1024);
-            const uint64_t b_lo = make_desc(sB + TC_STAGE_B + b_off, B_MN ? 8192 : 16, 1024);
+            const uint64_t b_lo = make_desc(sB + stage_b + b_off, B_MN ? 8192 : 16, 1024);
             tc_mma(tmem_base, a_hi, b_lo, idesc, 1);
             tc_mma(tmem_base, a_lo, b_hi, idesc, 1);
           }
@@ -253,6 +264,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
         if (++stage == stages) { stage = 0; phase ^= 1; }
       }
       tc_commit(acc_full);
+      TC_STAMP(3);
     }
   } else {
     // ===== epilogue: 16 warps; warp w may touch TMEM lanes 32*(w%4)..+31; the four warps of a lane quarter
@@ -264,6 +276,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
     if (have_acc) {
       mbar_wait(acc_full, 0);  // all MMAs retired: accumulator complete, pipeline smem is dead and reusable
       tc_fence_after();
+      if (threadIdx.x == 64) TC_STAMP(4);
     }
     float* tr = reinterpret_cast<float*>(smem) + (warp - 2) * (32 * 33);  // per-warp 32x33 transpose tile
     const int epi = P.epi, act = P.act;
@@ -337,8 +350,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
     }
   }
 
+  if (lane == 0 && warp >= 2) { if (g.dbg) atomicMax(&g.dbg[(size_t)blockIdx.x * 8 + 5], gtime()); }
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) TC_STAMP(6);
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols));

@@ -50,8 +50,8 @@ struct TcExtra {
   int kB0[2] = {0, 0};
 };
 
-inline int tc_smem_bytes(int stages, int planes) {
-  return stages * planes * (TC_STAGE_A + TC_STAGE_B) + (2 * stages + 2) * 8 + 1024;
+inline int tc_smem_bytes(int stages, int planes, int stage_b) {
+  return stages * planes * (TC_STAGE_A + stage_b) + (2 * stages + 2) * 8 + 1024;
 }
 
 }  // namespace dsact
