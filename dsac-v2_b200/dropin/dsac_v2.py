@@ -15,7 +15,7 @@ the B200 engine (libdsact.so) instead of eager PyTorch.
 Extra kwargs (all optional): `dsact_noise` = "device" (Philox on the GPU, default)
 or "reference" (draw the 8 normals of one update from torch's CPU generator in the
 reference's order, SURVEY Appendix B — same seed, same numbers as the reference);
-`dsact_gemm` = "fp32"; `dsact_graph` = True; `dsact_max_batch`.
+`dsact_gemm` = "bf16x3" (tcgen05 split-precision, default) | "fp32" | "bf16" (outside the parity gate); `dsact_graph` = True; `dsact_max_batch`.
 """
 __all__ = ["ApproxContainer", "DSAC_V2"]
 
@@ -69,7 +69,7 @@ class ApproxContainer(nn.Module):
             delay_update=kwargs.get("delay_update", 2), auto_alpha=kwargs.get("auto_alpha", True),
             alpha=kwargs.get("alpha", 0.2), lr_q=kwargs["value_learning_rate"], lr_pi=kwargs["policy_learning_rate"],
             lr_alpha=kwargs["alpha_learning_rate"], min_log_std=pi_args["min_log_std"], max_log_std=pi_args["max_log_std"],
-            gemm_mode=kwargs.get("dsact_gemm", "fp32"), use_graph=kwargs.get("dsact_graph", True))
+            gemm_mode=kwargs.get("dsact_gemm", "bf16x3"), use_graph=kwargs.get("dsact_graph", True))
         if q_args["output_activation"] != "linear" or pi_args["output_activation"] != "linear":
             raise NotImplementedError("the B200 engine implements linear output activations")
         self._max_batch = int(kwargs.get("dsact_max_batch", kwargs.get("replay_batch_size", 256)))
