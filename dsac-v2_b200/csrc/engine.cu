@@ -15,6 +15,7 @@
 #include "gemm_simt.cuh"
 #include "kernels.cuh"
 #include "tc_host.cuh"
+#include "chain_tc.cuh"
 
 using namespace dsact;
 
@@ -145,6 +146,12 @@ struct dsact_handle {
   int64_t launches;
   int32_t last_launches;
   bool tc() const { return cfg.gemm_mode != DSACT_GEMM_FP32; }
+  bool fused() const {  // layer-chain kernel: every layer must fit one 256-column TMEM accumulator / A operand
+    if (!tc() || getenv("DSACT_NO_FUSE")) return false;
+    for (int j = 1; j <= q.L + 1; ++j) if (q.s[j] > 256) return false;
+    for (int j = 1; j <= pi.L + 1; ++j) if (pi.s[j] > 256) return false;
+    return cfg.act_dim <= 256;
+  }
   int passes() const { return cfg.gemm_mode == DSACT_GEMM_BF16X3 ? 3 : 1; }
   float* W() const { return reinterpret_cast<float*>(buf.workspace); }
   Img img(const ImgSlot& s, int rows) const {  // image handle with the live row count
@@ -449,6 +456,106 @@ static Wt weight(const dsact_handle* h, const Net& net, const float* base, int j
   return w;
 }
 
+
+// ---- layer-chain launches (tcgen05 modes) -------------------------------------------------------
+struct ChainBuild {
+  ChainGroup g;
+  int grid = 0, stage_b = 16 * 128;
+  double flops = 0.0;
+  bool ok = true;
+  explicit ChainBuild(int passes) { memset(&g, 0, sizeof(g)); g.passes = passes; }
+  ChainPass& begin(const Img& a0, const Img& a1, int M) {
+    ChainPass& P = g.p[g.n++];
+    P.n_layers = 0; P.M = M; P.tile_start = grid;
+    grid += (M + TC_BM - 1) / TC_BM;
+    ok = ok && make_map(&P.mapA[0], a0, TC_BM);
+    if (a1.p) ok = ok && make_map(&P.mapA[1], a1, TC_BM);
+    return P;
+  }
+  ChainLayer& layer(ChainPass& P, const Img& wimg, bool b_mn, int N, int K0, int K1, int kB1) {
+    ChainLayer& L = P.L[P.n_layers++];
+    L.N = N; L.bn = (N + 15) / 16 * 16; L.b_mn = b_mn ? 1 : 0;
+    L.kblocks[0] = (K0 + TC_BK - 1) / TC_BK; L.kblocks[1] = (K1 + TC_BK - 1) / TC_BK;
+    L.kB0[0] = 0; L.kB0[1] = kB1; L.K = K0;
+    ok = ok && make_map(&L.mapB, wimg, b_mn ? 64 : L.bn);
+    const int sb = b_mn ? (L.bn + 63) / 64 * 8192 : L.bn * 128;
+    if (sb > stage_b) stage_b = sb;
+    flops += 2.0 * P.M * N * ((double)K0 + K1);
+    return L;
+  }
+};
+
+static bool g_chain_attr_done = false;
+static void launch_chain(const dsact_handle* h, ChainBuild& cb, int cls, Ctx& c) {
+  if (cb.g.n == 0) return;
+  if (!cb.ok) { c.err = cudaErrorInvalidValue; return; }
+  static unsigned long long* dbg = nullptr;
+  const bool debug = getenv("DSACT_TC_DEBUG") != nullptr;
+  if (debug && !dbg) cudaMalloc(&dbg, sizeof(unsigned long long) * 8 * 4096);
+  if (debug && cb.grid <= 4096) { cudaMemsetAsync(dbg, 0, sizeof(unsigned long long) * 8 * cb.grid, c.s); cb.g.dbg = dbg; }
+  const int planes = cb.g.passes == 3 ? 2 : 1;
+  const int stages = planes == 2 ? 2 : 3;
+  const int smem = chain_smem_bytes(stages, planes, cb.stage_b);
+  if (!g_chain_attr_done) {
+    cudaFuncSetAttribute(tc_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    g_chain_attr_done = true;
+  }
+  tc_chain_kernel<<<cb.grid, TC_THREADS, smem, c.s>>>(cb.g, stages, cb.stage_b);
+  c.done(cls, cb.flops);
+  c.check();
+  if (debug && cb.g.dbg) {
+    cudaStreamSynchronize(c.s);
+    std::vector<unsigned long long> hbuf(8 * (size_t)cb.grid);
+    cudaMemcpy(hbuf.data(), dbg, sizeof(unsigned long long) * 8 * cb.grid, cudaMemcpyDeviceToHost);
+    unsigned long long tmin = ~0ull, tmax = 0;
+    for (int i = 0; i < cb.grid; ++i) { if (hbuf[8 * i] < tmin) tmin = hbuf[8 * i]; if (hbuf[8 * i + 6] > tmax) tmax = hbuf[8 * i + 6]; }
+    fprintf(stderr, "[chain_debug] class %d passes %d grid %d span %.1f us\n", cls, cb.g.n, cb.grid, (tmax - tmin) / 1000.0);
+  }
+}
+
+// forward chain of one pass: out = head(act(...act(in W_0^T + b_0)...))
+static void chain_fwd_pass(ChainBuild& cb, const dsact_handle* h, const Net& net, const float* Wbase, const ImgSlot* wslots,
+                           const Img& in0, int k0, const Img& in1, int k1, int kB1, int B, int act,
+                           const int64_t* zout_off, const ImgSlot* himg, float* out) {
+  ChainPass& P = cb.begin(in0, in1, B);
+  float* W = h->W();
+  for (int j = 0; j <= net.L; ++j) {
+    const Img wim = h->img(wslots[j], net.s[j + 1]);
+    ChainLayer& L = j == 0 ? cb.layer(P, wim, false, net.s[1], k0, k1, kB1) : cb.layer(P, wim, false, net.s[j + 1], net.s[j], 0, 0);
+    const bool last = j == net.L;
+    L.epi = last ? EPI_STORE : EPI_BIAS_ACT;
+    L.act = act;
+    L.bias = Wbase + net.b[j];
+    if (last) L.C = out;
+    else {
+      if (zout_off) L.Zout = W + zout_off[j];
+      if (himg) { const Img im = h->img(himg[j], B); L.img = im.p; L.img_pitch = im.pitch; L.img_plane = im.plane; }
+    }
+  }
+}
+
+// dgrad chain of one pass: dz_{j-1} = (dz_j W_j) (.) act'(z_{j-1}) for j = L..1 (+ dAct = dz_0 W_0[:, act columns])
+static void chain_dgrad_pass(ChainBuild& cb, const dsact_handle* h, const Net& net, const ImgSlot* wslots, const Img& dout,
+                             int B, int act, const int64_t* zin_off, float* gbase /*bias grads of this net or null*/,
+                             const ImgSlot* dzimg /*or null*/, float* dact_out, int act_col_img, int act_cols) {
+  const Img none;
+  ChainPass& P = cb.begin(dout, none, B);
+  float* W = h->W();
+  for (int j = net.L; j >= 1; --j) {
+    const Img wim = h->img(wslots[j], net.s[j + 1]);   // rows = reduction (outputs of layer j), width = inputs
+    ChainLayer& L = cb.layer(P, wim, true, net.s[j], net.s[j + 1], 0, 0);
+    L.epi = EPI_DACT; L.act = act;
+    L.Zin = W + zin_off[j - 1];
+    L.colsum = gbase ? gbase + net.b[j - 1] : nullptr;
+    if (dzimg) { const Img im = h->img(dzimg[j - 1], B); L.img = im.p; L.img_pitch = im.pitch; L.img_plane = im.plane; }
+  }
+  if (dact_out) {
+    const Img wim = h->img(wslots[0], net.s[1]).cols(act_col_img, act_cols);
+    ChainLayer& L = cb.layer(P, wim, true, act_cols, net.s[1], 0, 0);
+    L.epi = EPI_STORE; L.C = dact_out;
+  }
+}
+
 // ---- enqueue: pieces of one update ---------------------------------------------
 static void enqueue_phase1(dsact_handle* h, const dsact_batch& bt, const dsact_noise* nz, Ctx& c) {
   const dsact_config& cf = h->cfg;
@@ -505,8 +612,18 @@ static void enqueue_phase1(dsact_handle* h, const dsact_batch& bt, const dsact_n
   const Ten t_obs = ten(bt.obs, ar.i_obs), t_obs2 = ten(bt.obs2, ar.i_obs2), t_act = ten(bt.act, ar.i_act);
   const Ten t_none;
 
+  const bool fused = h->fused();
+  const Img i_none;
+  if (fused) {  // wave A as ONE launch: each CTA runs a 128-row block through every layer of its pass
+    ChainBuild cb(h->passes());
+    chain_fwd_pass(cb, h, pi, PIb[0], ar.i_wpi[0], t_obs.im, O, i_none, 0, 0, B, cf.act_pi, ar.zP, ar.i_hP, W + ar.logitsP);
+    chain_fwd_pass(cb, h, pi, PIb[1], ar.i_wpi[1], t_obs2.im, O, i_none, 0, 0, B, cf.act_pi, nullptr, nullptr, W + ar.logitsT);
+    for (int k = 0; k < 2; ++k)
+      chain_fwd_pass(cb, h, q, Qb[k], ar.i_wq[k], t_obs.im, O, t_act.im, A, ar.kpad_q0, B, cf.act_q, ar.zQ[k], ar.i_hQ[k], W + ar.outQ[k]);
+    launch_chain(h, cb, CLS_GEMM_FWD, c);
+  }
   // wave A: pi(obs), pi'(obs2), Q1(s,a), Q2(s,a), layer by layer
-  const int depth = (pi.L > q.L ? pi.L : q.L) + 1;
+  const int depth = fused ? 0 : (pi.L > q.L ? pi.L : q.L) + 1;
   for (int j = 0; j < depth; ++j) {
     Group G;
     if (j <= pi.L) {
@@ -550,7 +667,15 @@ static void enqueue_phase1(dsact_handle* h, const dsact_batch& bt, const dsact_n
 
   // wave B: Q1', Q2' on (s', a') and Q1, Q2 on (s, a~)
   const Ten t_new_act = ten(W + ar.new_act, ar.i_new_act), t_act2 = ten(W + ar.act2, ar.i_act2);
-  for (int j = 0; j <= q.L; ++j) {
+  if (fused) {
+    ChainBuild cb(h->passes());
+    for (int k = 0; k < 2; ++k)
+      chain_fwd_pass(cb, h, q, Qb[2 + k], ar.i_wq[2 + k], t_obs2.im, O, t_act2.im, A, ar.kpad_q0, B, cf.act_q, nullptr, nullptr, W + ar.outQ[2 + k]);
+    for (int k = 0; k < 2; ++k)
+      chain_fwd_pass(cb, h, q, Qb[k], ar.i_wq[k], t_obs.im, O, t_new_act.im, A, ar.kpad_q0, B, cf.act_q, ar.zQ[4 + k], nullptr, W + ar.outQ[4 + k]);
+    launch_chain(h, cb, CLS_GEMM_FWD, c);
+  }
+  for (int j = 0; j <= (fused ? -1 : q.L); ++j) {
     Group G;
     for (int p = 2; p < 6; ++p) {
       const int k = p & 1;
@@ -614,6 +739,16 @@ static void enqueue_phase2(dsact_handle* h, const dsact_batch& bt, int64_t globa
 
   // wave C: critic passes 0,1 (dgrad + wgrad) and actor passes 4,5 (dgrad only), top layer down
   Group gw;  // every weight-gradient problem of the two critics: independent once the dgrad chain has run
+  const bool fused = h->fused();
+  if (fused) {  // wave C dgrad as ONE launch: dz stays in tensor memory between layers
+    ChainBuild cb(h->passes());
+    for (int pp = 0; pp < 4; ++pp) {
+      const int p = passes[pp], k = p & 1;
+      chain_dgrad_pass(cb, h, q, ar.i_wq[k], h->img(ar.i_dOut[p], B), B, cf.act_q, ar.zQ[p], p < 2 ? Gq[k] : nullptr,
+                       p < 2 ? ar.i_dzQ[p] : nullptr, p < 2 ? nullptr : W + ar.dAct[k], ar.kpad_q0, A);
+    }
+    launch_chain(h, cb, CLS_GEMM_DGRAD, c);
+  }
   for (int j = q.L; j >= 1; --j) {
     Group gd;
     for (int pp = 0; pp < 4; ++pp) {
@@ -622,6 +757,7 @@ static void enqueue_phase2(dsact_handle* h, const dsact_batch& bt, int64_t globa
       float* gb = p < 2 ? Gq[k] + q.b[j - 1] : nullptr;
       add_dgrad(gd, q, j, weight(h, q, Pq[k], j, ar.i_wq[k][j]), 0, 0, q.s[j], dY, ten(W + ar.dzQ[p][j - 1], ar.i_dzQ[p][j - 1]),
                 W + ar.zQ[p][j - 1], gb, B, cf.act_q);
+      if (fused) gd.n = gd.g.n = 0;  // done by the chain launch; only the weight-gradient problems are collected here
       if (p < 2) add_wgrad(gw, q, j, Gq[k] + q.w[j], 0, q.s[j], dY, ten(W + ar.hQ[p][j - 1], ar.i_hQ[p][j - 1]), B);
     }
     launch_group(h, gd, V_DGRAD, c);
@@ -632,8 +768,9 @@ static void enqueue_phase2(dsact_handle* h, const dsact_batch& bt, int64_t globa
       const Ten dz0 = ten(W + ar.dzQ[k][0], ar.i_dzQ[k][0]);
       add_wgrad(gw, q, 0, Gq[k] + q.w[0], 0, O, dz0, t_obs, B);
       add_wgrad(gw, q, 0, Gq[k] + q.w[0], O, A, dz0, t_act, B);
-      add_dgrad(gd, q, 0, weight(h, q, Pq[k], 0, ar.i_wq[k][0]), O, ar.kpad_q0, A, ten(W + ar.dzQ[4 + k][0], ar.i_dzQ[4 + k][0]),
-                ten(W + ar.dAct[k], none), nullptr, nullptr, B, 0);
+      if (!fused)
+        add_dgrad(gd, q, 0, weight(h, q, Pq[k], 0, ar.i_wq[k][0]), O, ar.kpad_q0, A, ten(W + ar.dzQ[4 + k][0], ar.i_dzQ[4 + k][0]),
+                  ten(W + ar.dAct[k], none), nullptr, nullptr, B, 0);
     }
     launch_group(h, gw, V_WGRAD, c);
     launch_group(h, gd, V_DGRAD, c);
@@ -657,10 +794,15 @@ static void enqueue_phase2(dsact_handle* h, const dsact_batch& bt, int64_t globa
 
   // wave D: policy backward
   Group gwp;
+  if (fused) {
+    ChainBuild cb(h->passes());
+    chain_dgrad_pass(cb, h, pi, ar.i_wpi[0], h->img(ar.i_dlogits, B), B, cf.act_pi, ar.zP, Gpi, ar.i_dzP, nullptr, 0, 0);
+    launch_chain(h, cb, CLS_GEMM_DGRAD, c);
+  }
   for (int j = pi.L; j >= 0; --j) {
     const Ten dY = j == pi.L ? ten(W + ar.dlogits, ar.i_dlogits) : ten(W + ar.dzP[j], ar.i_dzP[j]);
     add_wgrad(gwp, pi, j, Gpi + pi.w[j], 0, pi.s[j], dY, j == 0 ? t_obs : ten(W + ar.hP[j - 1], ar.i_hP[j - 1]), B);
-    if (j >= 1) {
+    if (j >= 1 && !fused) {
       Group gd;
       add_dgrad(gd, pi, j, weight(h, pi, Ppi, j, ar.i_wpi[0][j]), 0, 0, pi.s[j], dY, ten(W + ar.dzP[j - 1], ar.i_dzP[j - 1]),
                 W + ar.zP[j - 1], Gpi + pi.b[j - 1], B, cf.act_pi);
