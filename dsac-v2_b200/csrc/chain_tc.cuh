@@ -199,6 +199,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_chain_kernel(const __grid_co
           if (++stage == stages) { stage = 0; phase ^= 1; }
         }
         tc_commit(acc_full);
+        TC_STAMP(8 + 3 * j);      // MMAs of layer j issued
       }
       TC_STAMP(3);
     }
@@ -216,6 +217,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_chain_kernel(const __grid_co
       mbar_wait(acc_full, (uint32_t)(j & 1));
       tc_fence_after();
       if (j == 0 && threadIdx.x == 64) TC_STAMP(4);
+      if (threadIdx.x == 64) TC_STAMP(9 + 3 * j);   // accumulator of layer j complete (seen by the epilogue)
       const int epi = Lj.epi, act = Lj.act;
       const bool global_io = Lj.Zout || Lj.Zin || Lj.C || Lj.img || Lj.colsum;
       // when the next layer reads this one from TMEM, every column up to the next multiple of 16 must be written
@@ -228,10 +230,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_chain_kernel(const __grid_co
           // pure on-chip layer (target networks): stay in row layout, bias by broadcast loads
           if (epi == EPI_BIAS_ACT) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const int n = c0 + i;
-              v[i] = n < Lj.N ? act_fwd(v[i] + __ldg(Lj.bias + n), act) : 0.f;
-            }
+            for (int i = 0; i < 32; ++i) v[i] += (c0 + i < Lj.N) ? __ldg(Lj.bias + c0 + i) : 0.f;
+            act_fwd32(v, act, tr + lane * 33);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = (c0 + i < Lj.N) ? v[i] : 0.f;
           }
         } else {
           // column layout for coalesced global traffic: lane = column, registers = rows
@@ -255,18 +257,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_chain_kernel(const __grid_co
                 for (int r = 0; r < 32; ++r)
                   if (r < nrows) zp[(size_t)r * Lj.N] = v[r];
               }
+              act_fwd32(v, act, tr + lane * 33);
 #pragma unroll
-              for (int r = 0; r < 32; ++r) v[r] = col_ok ? act_fwd(v[r], act) : 0.f;
+              for (int r = 0; r < 32; ++r) v[r] = col_ok ? v[r] : 0.f;
             }
           } else if (epi == EPI_DACT) {
             const float* zp = Lj.Zin + (size_t)mbase * Lj.N + n;
             float zin[32];
 #pragma unroll
             for (int r = 0; r < 32; ++r) zin[r] = r < nrows ? __ldg(zp + (size_t)r * Lj.N) : 0.f;
+            act_bwd32(v, zin, act, tr + lane * 33);
             float csum = 0.f;
 #pragma unroll
             for (int r = 0; r < 32; ++r) {
-              v[r] = r < nrows ? v[r] * act_bwd(zin[r], act) : 0.f;
+              v[r] = r < nrows ? v[r] : 0.f;
               csum += v[r];
             }
             if (Lj.colsum && col_ok) atomicAdd(Lj.colsum + n, csum);
@@ -312,6 +316,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_chain_kernel(const __grid_co
           if (planes == 2) tc_st16(lane_addr + CH_ALO_COL + (uint32_t)(c0 / 2), wlo);
         }
       }
+      if (threadIdx.x == 64) TC_STAMP(10 + 3 * j);  // epilogue of layer j done (first epilogue warp)
       if (feeds_next) {
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         tc_fence_before();
@@ -321,7 +326,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_chain_kernel(const __grid_co
     }
   }
 
-  if (lane == 0 && warp >= 2) { if (g.dbg) atomicMax(&g.dbg[(size_t)blockIdx.x * 8 + 5], gtime()); }
+  if (lane == 0 && warp >= 2) { if (g.dbg) atomicMax(&g.dbg[(size_t)blockIdx.x * TC_DBG_SLOTS + 5], gtime()); }
   tc_fence_before();
   __syncthreads();
   if (threadIdx.x == 0) TC_STAMP(6);

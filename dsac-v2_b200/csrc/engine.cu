@@ -294,8 +294,8 @@ static void launch_tc(const dsact_handle* h, Group& G, int variant, Ctx& c) {
   }
   static unsigned long long* dbg = nullptr;
   const bool debug = getenv("DSACT_TC_DEBUG") != nullptr;
-  if (debug && !dbg) cudaMalloc(&dbg, sizeof(unsigned long long) * 8 * 4096);
-  if (debug && grid <= 4096) { cudaMemsetAsync(dbg, 0, sizeof(unsigned long long) * 8 * grid, c.s); t.dbg = dbg; }
+  if (debug && !dbg) cudaMalloc(&dbg, sizeof(unsigned long long) * TC_DBG_SLOTS * 4096);
+  if (debug && grid <= 4096) { cudaMemsetAsync(dbg, 0, sizeof(unsigned long long) * TC_DBG_SLOTS * grid, c.s); t.dbg = dbg; }
   const int planes = t.passes == 3 ? 2 : 1;
   const int stage_b = (b_mn ? (bn_max + 63) / 64 * 64 : bn_max) * 128;   // bytes of one B plane per stage
   int stages = (200 * 1024) / (planes * (TC_STAGE_A + stage_b));
@@ -312,12 +312,12 @@ static void launch_tc(const dsact_handle* h, Group& G, int variant, Ctx& c) {
   else tc_gemm_kernel<true, true><<<grid, TC_THREADS, smem, c.s>>>(t, stages, stage_b);
   if (debug && t.dbg) {  // per-CTA phase breakdown (ns): setup | first TMA landed | MMA issue done | accumulator ready | epilogue | teardown
     cudaStreamSynchronize(c.s);
-    std::vector<unsigned long long> hbuf(8 * (size_t)grid);
-    cudaMemcpy(hbuf.data(), dbg, sizeof(unsigned long long) * 8 * grid, cudaMemcpyDeviceToHost);
+    std::vector<unsigned long long> hbuf(TC_DBG_SLOTS * (size_t)grid);
+    cudaMemcpy(hbuf.data(), dbg, sizeof(unsigned long long) * TC_DBG_SLOTS * grid, cudaMemcpyDeviceToHost);
     unsigned long long tmin = ~0ull, tmax = 0;
     double ph[6] = {0, 0, 0, 0, 0, 0};
     for (int i = 0; i < grid; ++i) {
-      const unsigned long long* d = &hbuf[8 * (size_t)i];
+      const unsigned long long* d = &hbuf[TC_DBG_SLOTS * (size_t)i];
       if (d[0] < tmin) tmin = d[0];
       if (d[6] > tmax) tmax = d[6];
       ph[0] += (double)(d[1] - d[0]); ph[1] += (double)(d[2] - d[1]); ph[2] += (double)(d[3] - d[2]);
@@ -491,8 +491,8 @@ static void launch_chain(const dsact_handle* h, ChainBuild& cb, int cls, Ctx& c)
   if (!cb.ok) { c.err = cudaErrorInvalidValue; return; }
   static unsigned long long* dbg = nullptr;
   const bool debug = getenv("DSACT_TC_DEBUG") != nullptr;
-  if (debug && !dbg) cudaMalloc(&dbg, sizeof(unsigned long long) * 8 * 4096);
-  if (debug && cb.grid <= 4096) { cudaMemsetAsync(dbg, 0, sizeof(unsigned long long) * 8 * cb.grid, c.s); cb.g.dbg = dbg; }
+  if (debug && !dbg) cudaMalloc(&dbg, sizeof(unsigned long long) * TC_DBG_SLOTS * 4096);
+  if (debug && cb.grid <= 4096) { cudaMemsetAsync(dbg, 0, sizeof(unsigned long long) * TC_DBG_SLOTS * cb.grid, c.s); cb.g.dbg = dbg; }
   const int planes = cb.g.passes == 3 ? 2 : 1;
   const int stages = planes == 2 ? 2 : 3;
   const int smem = chain_smem_bytes(stages, planes, cb.stage_b);
@@ -505,11 +505,23 @@ static void launch_chain(const dsact_handle* h, ChainBuild& cb, int cls, Ctx& c)
   c.check();
   if (debug && cb.g.dbg) {
     cudaStreamSynchronize(c.s);
-    std::vector<unsigned long long> hbuf(8 * (size_t)cb.grid);
-    cudaMemcpy(hbuf.data(), dbg, sizeof(unsigned long long) * 8 * cb.grid, cudaMemcpyDeviceToHost);
+    std::vector<unsigned long long> hbuf(TC_DBG_SLOTS * (size_t)cb.grid);
+    cudaMemcpy(hbuf.data(), dbg, sizeof(unsigned long long) * TC_DBG_SLOTS * cb.grid, cudaMemcpyDeviceToHost);
     unsigned long long tmin = ~0ull, tmax = 0;
-    for (int i = 0; i < cb.grid; ++i) { if (hbuf[8 * i] < tmin) tmin = hbuf[8 * i]; if (hbuf[8 * i + 6] > tmax) tmax = hbuf[8 * i + 6]; }
+    for (int i = 0; i < cb.grid; ++i) {
+      const unsigned long long* d = &hbuf[TC_DBG_SLOTS * (size_t)i];
+      if (d[0] < tmin) tmin = d[0];
+      if (d[6] > tmax) tmax = d[6];
+    }
     fprintf(stderr, "[chain_debug] class %d passes %d grid %d span %.1f us\n", cls, cb.g.n, cb.grid, (tmax - tmin) / 1000.0);
+    for (int pi = 0; pi < cb.g.n; ++pi) {  // first CTA of every pass: per-layer timeline relative to its start (us)
+      const unsigned long long* d = &hbuf[TC_DBG_SLOTS * (size_t)cb.g.p[pi].tile_start];
+      fprintf(stderr, "  pass %d: setup %.1f first-load %.1f |", pi, (d[1] - d[0]) / 1e3, (d[2] - d[0]) / 1e3);
+      for (int j = 0; j < cb.g.p[pi].n_layers; ++j)
+        fprintf(stderr, " L%d mma-issued %.1f acc-ready %.1f epi-done %.1f |", j, (d[8 + 3 * j] - d[0]) / 1e3, (d[9 + 3 * j] - d[0]) / 1e3,
+                (d[10 + 3 * j] - d[0]) / 1e3);
+      fprintf(stderr, " end %.1f\n", (d[6] - d[0]) / 1e3);
+    }
   }
 }
 

@@ -135,11 +135,50 @@ __device__ __forceinline__ unsigned long long gtime() {
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
-#define TC_STAMP(slot) do { if (g.dbg) g.dbg[(size_t)blockIdx.x * 8 + (slot)] = gtime(); } while (0)
+#define TC_DBG_SLOTS 32
+#define TC_STAMP(slot) do { if (g.dbg) g.dbg[(size_t)blockIdx.x * TC_DBG_SLOTS + (slot)] = gtime(); } while (0)
 
 __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
   hi = __float2bfloat16_rn(x);
   lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+
+// Activation over the 32 values a lane holds.  The dispatch is hoisted out of the unrolled loops (inlining the
+// 7-way switch per element made the kernel ~600 KB of SASS and instruction-fetch bound): GELU (the reference's
+// default) and ReLU get unrolled bodies, the rest run as a compact loop over a private shared-memory row.
+__device__ __forceinline__ void act_fwd32(float (&v)[32], int act, float* row /* 32 private floats in smem */) {
+  if (act == ACT_GELU) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = 0.5f * v[i] * (1.0f + erff(v[i] * 0.70710678118654752f));
+  } else if (act == ACT_RELU) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+  } else if (act != ACT_LINEAR) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) row[i] = v[i];
+#pragma unroll 1
+    for (int i = 0; i < 32; ++i) row[i] = act_fwd(row[i], act);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = row[i];
+  }
+}
+// v[i] *= act'(z[i])
+__device__ __forceinline__ void act_bwd32(float (&v)[32], const float (&z)[32], int act, float* row) {
+  if (act == ACT_GELU) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      v[i] *= 0.5f * (1.0f + erff(z[i] * 0.70710678118654752f)) + z[i] * 0.3989422804014327f * __expf(-0.5f * z[i] * z[i]);
+  } else if (act == ACT_RELU) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = z[i] > 0.f ? v[i] : 0.f;
+  } else if (act != ACT_LINEAR) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) row[i] = z[i];
+#pragma unroll 1
+    for (int i = 0; i < 32; ++i) row[i] = act_bwd(row[i], act);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] *= row[i];
+  }
 }
 
 // A_MN / B_MN: operand is MN-major (reduction dimension strided in global memory).
@@ -313,18 +352,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
             for (int r = 0; r < 32; ++r)
               if (r < nrows) zp[(size_t)r * P.ldc] = v[r];
           }
-#pragma unroll
-          for (int r = 0; r < 32; ++r) v[r] = act_fwd(v[r], act);
+          act_fwd32(v, act, tr + lane * 33);
         }
       } else if (epi == EPI_DACT) {
         const float* zp = P.Zin + (size_t)mbase * P.ldz + n;
         float zin[32];
 #pragma unroll
         for (int r = 0; r < 32; ++r) zin[r] = r < nrows ? __ldg(zp + (size_t)r * P.ldz) : 0.f;
+        act_bwd32(v, zin, act, tr + lane * 33);
         float csum = 0.f;
 #pragma unroll
         for (int r = 0; r < 32; ++r) {
-          v[r] = r < nrows ? v[r] * act_bwd(zin[r], act) : 0.f;
+          v[r] = r < nrows ? v[r] : 0.f;
           csum += v[r];
         }
         if (P.colsum && col_ok) atomicAdd(P.colsum + n, csum);  // bias gradient of this tile
@@ -350,7 +389,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
     }
   }
 
-  if (lane == 0 && warp >= 2) { if (g.dbg) atomicMax(&g.dbg[(size_t)blockIdx.x * 8 + 5], gtime()); }
+  if (lane == 0 && warp >= 2) { if (g.dbg) atomicMax(&g.dbg[(size_t)blockIdx.x * TC_DBG_SLOTS + 5], gtime()); }
   tc_fence_before();
   __syncthreads();
   if (threadIdx.x == 0) TC_STAMP(6);
