@@ -67,10 +67,6 @@ __device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t (&r)[16])
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 lo_k, __nv_bfloat16 hi_k) {  // lower k in the low half
-  return (uint32_t)__bfloat16_as_ushort(lo_k) | ((uint32_t)__bfloat16_as_ushort(hi_k) << 16);
-}
-
 __host__ __device__ inline int chain_ringA_bytes(int stages, int planes) {
   const int a = stages * planes * TC_STAGE_A, t = TC_EPI_WARPS * 32 * 33 * 4;
   return ((a > t ? a : t) + 1023) / 1024 * 1024;
@@ -79,10 +75,11 @@ inline int chain_smem_bytes(int stages, int planes, int stage_b) {
   return stages * planes * stage_b + chain_ringA_bytes(stages, planes) + (2 * stages + 4) * 8 + 1024;
 }
 
+template <bool PLANES2>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_chain_kernel(const __grid_constant__ ChainGroup g, int stages, int stage_b) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const int planes = g.passes == 3 ? 2 : 1;
+  constexpr int planes = PLANES2 ? 2 : 1;
   // [ B ring: stages x planes x stage_b ][ layer-0 A ring: stages x planes x 16 KiB, later the epilogue's transpose scratch ]
   uint8_t* ringB = smem;
   uint8_t* ringA = smem + (size_t)stages * planes * stage_b;
@@ -209,7 +206,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_chain_kernel(const __grid_co
     const int sub = (warp - 2) >> 2;
     float* tr = reinterpret_cast<float*>(ringA) + (warp - 2) * (32 * 33);   // A ring is dead once layer 0's MMAs retired
     const int mbase = m0 + quarter * 32;
-    const int rows_ok = max(0, min(32, P.M - mbase));
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
     for (int j = 0; j < nl; ++j) {
       const ChainLayer& Lj = P.L[j];
@@ -218,100 +214,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_chain_kernel(const __grid_co
       tc_fence_after();
       if (j == 0 && threadIdx.x == 64) TC_STAMP(4);
       if (threadIdx.x == 64) TC_STAMP(9 + 3 * j);   // accumulator of layer j complete (seen by the epilogue)
-      const int epi = Lj.epi, act = Lj.act;
-      const bool global_io = Lj.Zout || Lj.Zin || Lj.C || Lj.img || Lj.colsum;
+      EpiArgs E;
+      E.epi = Lj.epi; E.act = Lj.act; E.M = P.M; E.N = Lj.N; E.ldc = Lj.N; E.ldz = Lj.N;
+      E.bias = Lj.bias; E.Zout = Lj.Zout; E.Zin = Lj.Zin; E.colsum = Lj.colsum; E.C = Lj.C;
+      E.img = Lj.img; E.img_pitch = Lj.img_pitch; E.img_plane = Lj.img_plane;
       // when the next layer reads this one from TMEM, every column up to the next multiple of 16 must be written
       const int nch = ((feeds_next ? (Lj.N + 15) / 16 * 16 : Lj.bn) + 31) / 32;
       for (int ch = sub; ch < nch; ch += TC_EPI_WARPS / 4) {
         const int c0 = ch * 32;
         float v[32];
         tc_ld32(lane_addr + CH_ACC_COL + (uint32_t)c0, v);   // v[i] = acc[row = lane][c0 + i]
-        if (!global_io) {
-          // pure on-chip layer (target networks): stay in row layout, bias by broadcast loads
-          if (epi == EPI_BIAS_ACT) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] += (c0 + i < Lj.N) ? __ldg(Lj.bias + c0 + i) : 0.f;
-            act_fwd32(v, act, tr + lane * 33);
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = (c0 + i < Lj.N) ? v[i] : 0.f;
-          }
-        } else {
-          // column layout for coalesced global traffic: lane = column, registers = rows
-          __syncwarp();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) tr[lane * 33 + i] = v[i];
-          __syncwarp();
-#pragma unroll
-          for (int r = 0; r < 32; ++r) v[r] = tr[r * 33 + lane];
-          const int n = c0 + lane;
-          const bool col_ok = n < Lj.N;
-          const int nrows = col_ok ? rows_ok : 0;
-          if (epi == EPI_STORE || epi == EPI_BIAS_ACT) {
-            const float bias_n = (Lj.bias && col_ok) ? __ldg(Lj.bias + n) : 0.f;
-#pragma unroll
-            for (int r = 0; r < 32; ++r) v[r] += bias_n;
-            if (epi == EPI_BIAS_ACT) {
-              if (Lj.Zout) {
-                float* zp = Lj.Zout + (size_t)mbase * Lj.N + n;
-#pragma unroll
-                for (int r = 0; r < 32; ++r)
-                  if (r < nrows) zp[(size_t)r * Lj.N] = v[r];
-              }
-              act_fwd32(v, act, tr + lane * 33);
-#pragma unroll
-              for (int r = 0; r < 32; ++r) v[r] = col_ok ? v[r] : 0.f;
-            }
-          } else if (epi == EPI_DACT) {
-            const float* zp = Lj.Zin + (size_t)mbase * Lj.N + n;
-            float zin[32];
-#pragma unroll
-            for (int r = 0; r < 32; ++r) zin[r] = r < nrows ? __ldg(zp + (size_t)r * Lj.N) : 0.f;
-            act_bwd32(v, zin, act, tr + lane * 33);
-            float csum = 0.f;
-#pragma unroll
-            for (int r = 0; r < 32; ++r) {
-              v[r] = r < nrows ? v[r] : 0.f;
-              csum += v[r];
-            }
-            if (Lj.colsum && col_ok) atomicAdd(Lj.colsum + n, csum);
-          }
-          if (Lj.C) {
-            float* cp = Lj.C + (size_t)mbase * Lj.N + n;
-#pragma unroll
-            for (int r = 0; r < 32; ++r)
-              if (r < nrows) cp[(size_t)r * Lj.N] = v[r];
-          }
-          if (Lj.img) {
-            __nv_bfloat16* hp = Lj.img + (size_t)mbase * Lj.img_pitch + n;
-#pragma unroll
-            for (int r = 0; r < 32; ++r) {
-              __nv_bfloat16 hi, lo;
-              split_bf16(v[r], hi, lo);
-              if (r < nrows) {
-                hp[(size_t)r * Lj.img_pitch] = hi;
-                if (planes == 2) hp[Lj.img_plane + (size_t)r * Lj.img_pitch] = lo;
-              }
-            }
-          }
-          if (feeds_next) {  // back to row layout for the TMEM store
-            __syncwarp();
-#pragma unroll
-            for (int r = 0; r < 32; ++r) tr[r * 33 + lane] = v[r];
-            __syncwarp();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = tr[lane * 33 + i];
-          }
-        }
+        uint32_t whi[16], wlo[16];
+        epi_chunk<PLANES2>(v, E, c0, mbase, lane, tr, feeds_next, whi, wlo);
         if (feeds_next) {  // next layer's A operand: packed bf16 pairs along K, hi and lo planes
-          uint32_t whi[16], wlo[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            __nv_bfloat16 h0, l0, h1, l1;
-            split_bf16(v[2 * i], h0, l0);
-            split_bf16(v[2 * i + 1], h1, l1);
-            whi[i] = pack_bf16(h0, h1);
-            wlo[i] = pack_bf16(l0, l1);
-          }
           tc_st16(lane_addr + CH_AHI_COL + (uint32_t)(c0 / 2), whi);
           if (planes == 2) tc_st16(lane_addr + CH_ALO_COL + (uint32_t)(c0 / 2), wlo);
         }

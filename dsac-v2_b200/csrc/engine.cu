@@ -302,14 +302,23 @@ static void launch_tc(const dsact_handle* h, Group& G, int variant, Ctx& c) {
   if (stages > 8) stages = 8;
   const int smem = tc_smem_bytes(stages, planes, stage_b);
   if (!g_tc_attr_done) {
-    cudaFuncSetAttribute(tc_gemm_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    cudaFuncSetAttribute(tc_gemm_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    cudaFuncSetAttribute(tc_gemm_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(tc_gemm_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(tc_gemm_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(tc_gemm_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(tc_gemm_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(tc_gemm_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(tc_gemm_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     g_tc_attr_done = true;
   }
-  if (variant == V_FWD) tc_gemm_kernel<false, false><<<grid, TC_THREADS, smem, c.s>>>(t, stages, stage_b);
-  else if (variant == V_DGRAD) tc_gemm_kernel<false, true><<<grid, TC_THREADS, smem, c.s>>>(t, stages, stage_b);
-  else tc_gemm_kernel<true, true><<<grid, TC_THREADS, smem, c.s>>>(t, stages, stage_b);
+  if (planes == 2) {
+    if (variant == V_FWD) tc_gemm_kernel<false, false, true><<<grid, TC_THREADS, smem, c.s>>>(t, stages, stage_b);
+    else if (variant == V_DGRAD) tc_gemm_kernel<false, true, true><<<grid, TC_THREADS, smem, c.s>>>(t, stages, stage_b);
+    else tc_gemm_kernel<true, true, true><<<grid, TC_THREADS, smem, c.s>>>(t, stages, stage_b);
+  } else {
+    if (variant == V_FWD) tc_gemm_kernel<false, false, false><<<grid, TC_THREADS, smem, c.s>>>(t, stages, stage_b);
+    else if (variant == V_DGRAD) tc_gemm_kernel<false, true, false><<<grid, TC_THREADS, smem, c.s>>>(t, stages, stage_b);
+    else tc_gemm_kernel<true, true, false><<<grid, TC_THREADS, smem, c.s>>>(t, stages, stage_b);
+  }
   if (debug && t.dbg) {  // per-CTA phase breakdown (ns): setup | first TMA landed | MMA issue done | accumulator ready | epilogue | teardown
     cudaStreamSynchronize(c.s);
     std::vector<unsigned long long> hbuf(TC_DBG_SLOTS * (size_t)grid);
@@ -497,10 +506,12 @@ static void launch_chain(const dsact_handle* h, ChainBuild& cb, int cls, Ctx& c)
   const int stages = planes == 2 ? 2 : 3;
   const int smem = chain_smem_bytes(stages, planes, cb.stage_b);
   if (!g_chain_attr_done) {
-    cudaFuncSetAttribute(tc_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(tc_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(tc_chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     g_chain_attr_done = true;
   }
-  tc_chain_kernel<<<cb.grid, TC_THREADS, smem, c.s>>>(cb.g, stages, cb.stage_b);
+  if (planes == 2) tc_chain_kernel<true><<<cb.grid, TC_THREADS, smem, c.s>>>(cb.g, stages, cb.stage_b);
+  else tc_chain_kernel<false><<<cb.grid, TC_THREADS, smem, c.s>>>(cb.g, stages, cb.stage_b);
   c.done(cls, cb.flops);
   c.check();
   if (debug && cb.g.dbg) {

@@ -143,51 +143,190 @@ __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bflo
   lo = __float2bfloat16_rn(x - __bfloat162float(hi));
 }
 
-// Activation over the 32 values a lane holds.  The dispatch is hoisted out of the unrolled loops (inlining the
-// 7-way switch per element made the kernel ~600 KB of SASS and instruction-fetch bound): GELU (the reference's
-// default) and ReLU get unrolled bodies, the rest run as a compact loop over a private shared-memory row.
-__device__ __forceinline__ void act_fwd32(float (&v)[32], int act, float* row /* 32 private floats in smem */) {
+// ---- epilogue math ---------------------------------------------------------------------------------------
+// Branch-free Gaussian CDF: Phi(z) = 0.5 erfc(-z/sqrt2) with erfc(t) = 2^(-q(t)) for t = min(|z|/sqrt2, 4),
+// q = degree-8 minimax fit (abs error of erf 1.4e-7 in fp32, i.e. fp32 round-off level; fitted in this repo,
+// see DESIGN.md).  Half the instructions of erff() and no divergent branch.
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float gauss_cdf(float z) {
+  const float t = fminf(fabsf(z) * 0.70710678118654752f, 4.0f);
+  float q = 4.5354528e-05f;              // coefficients of -log2(erfc(t)) / t
+  q = fmaf(q, t, -4.4547783e-04f);
+  q = fmaf(q, t, 1.4893662e-03f);
+  q = fmaf(q, t, 7.7470759e-04f);
+  q = fmaf(q, t, -2.8253708e-02f);
+  q = fmaf(q, t, 1.4848161e-01f);
+  q = fmaf(q, t, 9.1841640e-01f);
+  q = fmaf(q, t, 1.6279086e+00f);
+  const float half_u = 0.5f * ex2f(-q * t);   // 0.5 * erfc(t)
+  return z < 0.f ? half_u : 1.0f - half_u;
+}
+__device__ __forceinline__ float gauss_pdf(float z) { return 0.3989422804014327f * ex2f(-0.72134752044448170f * z * z); }
+
+// v[i] = act(z_i) with z_i = v[i] on entry; if D != nullptr also D[i] = act'(z_i).  The dispatch is hoisted out of
+// the unrolled loops (inlining the 7-way switch per element made the kernel ~600 KB of SASS and fetch bound):
+// GELU (the reference's default) and ReLU get unrolled bodies, the rest a compact loop over a private smem row.
+template <bool WANT_D>
+__device__ __forceinline__ void act_fwd32(float (&v)[32], float (&d)[32], int act, float* row) {
   if (act == ACT_GELU) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = 0.5f * v[i] * (1.0f + erff(v[i] * 0.70710678118654752f));
+    for (int i = 0; i < 32; ++i) {
+      const float z = v[i], cdf = gauss_cdf(z);
+      v[i] = z * cdf;
+      if (WANT_D) d[i] = fmaf(z, gauss_pdf(z), cdf);
+    }
   } else if (act == ACT_RELU) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+    for (int i = 0; i < 32; ++i) {
+      if (WANT_D) d[i] = v[i] > 0.f ? 1.f : 0.f;
+      v[i] = fmaxf(v[i], 0.f);
+    }
   } else if (act != ACT_LINEAR) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) row[i] = v[i];
+    if (WANT_D) {
+#pragma unroll 1
+      for (int i = 0; i < 32; ++i) row[i] = act_bwd(row[i], act);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) { d[i] = row[i]; row[i] = v[i]; }
+    }
 #pragma unroll 1
     for (int i = 0; i < 32; ++i) row[i] = act_fwd(row[i], act);
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = row[i];
+  } else if (WANT_D) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) d[i] = 1.f;
   }
 }
-// v[i] *= act'(z[i])
-__device__ __forceinline__ void act_bwd32(float (&v)[32], const float (&z)[32], int act, float* row) {
-  if (act == ACT_GELU) {
+
+__device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 lo_k, __nv_bfloat16 hi_k) {  // lower k in the low half
+  return (uint32_t)__bfloat16_as_ushort(lo_k) | ((uint32_t)__bfloat16_as_ushort(hi_k) << 16);
+}
+
+// What one epilogue chunk needs.  In the tcgen05 modes `Zout`/`Zin` carry act'(z) (computed where erf is already
+// at hand) instead of z, so the backward epilogue is a load and a multiply.
+struct EpiArgs {
+  int epi, act, M, N, ldc, ldz;
+  const float* bias;
+  float* Zout;
+  const float* Zin;
+  float* colsum;
+  float* C;
+  __nv_bfloat16* img;
+  int img_pitch;
+  long long img_plane;
+};
+
+// One 32-column chunk of a 128-row tile.  On entry v[i] = accumulator[row = mbase + lane][col = n0c + i]
+// (TMEM "row layout").  Global traffic happens in "column layout" (lane = column, registers = rows: every
+// load/store of a warp is one contiguous row segment) reached by a transpose through the warp's private 32x33
+// shared-memory tile; the bf16 hi/lo image is written from the row layout as packed 16-byte vectors.
+// On return, if `want_rows`, whi/wlo hold the packed bf16 pairs of the result for this lane's row.
+template <bool PLANES2>
+__device__ __forceinline__ void epi_chunk(float (&v)[32], const EpiArgs& E, int n0c, int mbase, int lane, float* tr,
+                                          bool want_rows, uint32_t (&whi)[16], uint32_t (&wlo)[16]) {
+  const int rows_ok = max(0, min(32, E.M - mbase));
+  const bool global_io = E.Zout || E.Zin || E.C || E.colsum;
+  float d[32];
+  if (!global_io) {
+    // on-chip only (target networks) or image-only: stay in row layout, bias by broadcast loads
+    if (E.epi == EPI_BIAS_ACT || E.epi == EPI_STORE) {
+      if (E.bias) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i)
-      v[i] *= 0.5f * (1.0f + erff(z[i] * 0.70710678118654752f)) + z[i] * 0.3989422804014327f * __expf(-0.5f * z[i] * z[i]);
-  } else if (act == ACT_RELU) {
+        for (int i = 0; i < 32; ++i) v[i] += (n0c + i < E.N) ? __ldg(E.bias + n0c + i) : 0.f;
+      }
+      if (E.epi == EPI_BIAS_ACT) act_fwd32<false>(v, d, E.act, tr + lane * 33);
+    }
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = z[i] > 0.f ? v[i] : 0.f;
-  } else if (act != ACT_LINEAR) {
+    for (int i = 0; i < 32; ++i) v[i] = (n0c + i < E.N) ? v[i] : 0.f;
+  } else {
+    __syncwarp();
 #pragma unroll
-    for (int i = 0; i < 32; ++i) row[i] = z[i];
-#pragma unroll 1
-    for (int i = 0; i < 32; ++i) row[i] = act_bwd(row[i], act);
+    for (int i = 0; i < 32; ++i) tr[lane * 33 + i] = v[i];
+    __syncwarp();
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] *= row[i];
+    for (int r = 0; r < 32; ++r) v[r] = tr[r * 33 + lane];
+    const int n = n0c + lane;
+    const bool col_ok = n < E.N;
+    const int nrows = col_ok ? rows_ok : 0;
+    if (E.epi == EPI_STORE || E.epi == EPI_BIAS_ACT) {
+      const float bias_n = (E.bias && col_ok) ? __ldg(E.bias + n) : 0.f;
+#pragma unroll
+      for (int r = 0; r < 32; ++r) v[r] += bias_n;
+      if (E.epi == EPI_BIAS_ACT) {
+        if (E.Zout) {
+          act_fwd32<true>(v, d, E.act, tr + lane * 33);
+          float* zp = E.Zout + (size_t)mbase * E.ldc + n;
+#pragma unroll
+          for (int r = 0; r < 32; ++r)
+            if (r < nrows) zp[(size_t)r * E.ldc] = d[r];
+        } else {
+          act_fwd32<false>(v, d, E.act, tr + lane * 33);
+        }
+      }
+    } else if (E.epi == EPI_DACT) {
+      const float* zp = E.Zin + (size_t)mbase * E.ldz + n;
+#pragma unroll
+      for (int r = 0; r < 32; ++r) d[r] = r < nrows ? __ldg(zp + (size_t)r * E.ldz) : 0.f;
+      float csum = 0.f;
+#pragma unroll
+      for (int r = 0; r < 32; ++r) {
+        v[r] *= d[r];
+        csum += v[r];
+      }
+      if (E.colsum && col_ok) atomicAdd(E.colsum + n, csum);  // bias gradient of this tile
+    }
+    if (E.C) {
+      float* cp = E.C + (size_t)mbase * E.ldc + n;
+#pragma unroll
+      for (int r = 0; r < 32; ++r)
+        if (r < nrows) cp[(size_t)r * E.ldc] = v[r];
+    }
+    if (want_rows || E.img) {  // back to row layout
+#pragma unroll
+      for (int r = 0; r < 32; ++r) v[r] = (r < nrows) ? v[r] : 0.f;
+      __syncwarp();
+#pragma unroll
+      for (int r = 0; r < 32; ++r) tr[r * 33 + lane] = v[r];
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = tr[lane * 33 + i];
+    }
+  }
+  if (want_rows || E.img) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      __nv_bfloat16 h0, l0, h1, l1;
+      split_bf16(v[2 * i], h0, l0);
+      split_bf16(v[2 * i + 1], h1, l1);
+      whi[i] = pack_bf16(h0, h1);
+      wlo[i] = pack_bf16(l0, l1);
+    }
+    if (E.img && lane < rows_ok) {  // this lane's row: 32 bf16 per plane as 16-byte vectors (pitch % 8 == 0, n0c % 32 == 0)
+      __nv_bfloat16* hp = E.img + (size_t)(mbase + lane) * E.img_pitch + n0c;
+      const int nvec = max(0, min(4, ((E.N + 7) / 8 * 8 - n0c + 7) / 8));
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (q < nvec) {
+          reinterpret_cast<uint4*>(hp)[q] = make_uint4(whi[4 * q], whi[4 * q + 1], whi[4 * q + 2], whi[4 * q + 3]);
+          if (PLANES2) reinterpret_cast<uint4*>(hp + E.img_plane)[q] = make_uint4(wlo[4 * q], wlo[4 * q + 1], wlo[4 * q + 2], wlo[4 * q + 3]);
+        }
+    }
   }
 }
 
 // A_MN / B_MN: operand is MN-major (reduction dimension strided in global memory).
-template <bool A_MN, bool B_MN>
+template <bool A_MN, bool B_MN, bool PLANES2>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_constant__ TcGroup g, int stages, int stage_b) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment for the 128B-swizzle atoms
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const int planes = g.passes == 3 ? 2 : 1;
+  constexpr int planes = PLANES2 ? 2 : 1;
   const int stage_bytes = planes * (TC_STAGE_A + stage_b);  // stage_b: bytes of one B plane (widest tile of the launch)
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)stages * stage_bytes);
   uint64_t* full = bars;             // [stages]  TMA -> MMA
@@ -318,11 +457,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
       if (threadIdx.x == 64) TC_STAMP(4);
     }
     float* tr = reinterpret_cast<float*>(smem) + (warp - 2) * (32 * 33);  // per-warp 32x33 transpose tile
-    const int epi = P.epi, act = P.act;
     const int nch = (bn + 31) / 32;
     const int mbase = m0 + quarter * 32;
-    const int rows_ok = max(0, min(32, P.M - mbase));       // rows of this quarter inside the matrix
-    float* Cb = P.C ? P.C + (epi == EPI_PARTIAL ? (size_t)ks * P.split_stride : 0) : nullptr;
+    EpiArgs E;
+    E.epi = P.epi; E.act = P.act; E.M = P.M; E.N = P.N; E.ldc = P.ldc; E.ldz = P.ldz;
+    E.bias = P.bias; E.Zout = P.Zout; E.Zin = P.Zin; E.colsum = P.colsum;
+    E.C = P.C ? P.C + (P.epi == EPI_PARTIAL ? (size_t)ks * P.split_stride : 0) : nullptr;
+    E.img = P.img; E.img_pitch = P.img_pitch; E.img_plane = P.img_plane;
     for (int ch = sub; ch < nch; ch += TC_EPI_WARPS / 4) {
       const int c0 = ch * 32;
       float v[32];
@@ -332,60 +473,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = 0.f;
       }
-      __syncwarp();
-#pragma unroll
-      for (int j = 0; j < 32; ++j) tr[lane * 33 + j] = v[j];   // row = lane, column = j
-      __syncwarp();
-#pragma unroll
-      for (int r = 0; r < 32; ++r) v[r] = tr[r * 33 + lane];   // now: this lane's column, rows 0..31
-      const int n = n0 + c0 + lane;
-      const bool col_ok = (c0 + lane) < bn && n < P.N;
-      const int nrows = col_ok ? rows_ok : 0;
-      if (epi == EPI_STORE || epi == EPI_BIAS_ACT) {
-        const float bias_n = (P.bias && col_ok) ? __ldg(P.bias + n) : 0.f;
-#pragma unroll
-        for (int r = 0; r < 32; ++r) v[r] += bias_n;
-        if (epi == EPI_BIAS_ACT) {
-          if (P.Zout) {
-            float* zp = P.Zout + (size_t)mbase * P.ldc + n;
-#pragma unroll
-            for (int r = 0; r < 32; ++r)
-              if (r < nrows) zp[(size_t)r * P.ldc] = v[r];
-          }
-          act_fwd32(v, act, tr + lane * 33);
-        }
-      } else if (epi == EPI_DACT) {
-        const float* zp = P.Zin + (size_t)mbase * P.ldz + n;
-        float zin[32];
-#pragma unroll
-        for (int r = 0; r < 32; ++r) zin[r] = r < nrows ? __ldg(zp + (size_t)r * P.ldz) : 0.f;
-        act_bwd32(v, zin, act, tr + lane * 33);
-        float csum = 0.f;
-#pragma unroll
-        for (int r = 0; r < 32; ++r) {
-          v[r] = r < nrows ? v[r] : 0.f;
-          csum += v[r];
-        }
-        if (P.colsum && col_ok) atomicAdd(P.colsum + n, csum);  // bias gradient of this tile
-      }
-      if (Cb) {
-        float* cp = Cb + (size_t)mbase * P.ldc + n;
-#pragma unroll
-        for (int r = 0; r < 32; ++r)
-          if (r < nrows) cp[(size_t)r * P.ldc] = v[r];
-      }
-      if (P.img) {
-        __nv_bfloat16* hp = P.img + (size_t)mbase * P.img_pitch + n;
-#pragma unroll
-        for (int r = 0; r < 32; ++r) {
-          __nv_bfloat16 hi, lo;
-          split_bf16(v[r], hi, lo);
-          if (r < nrows) {
-            hp[(size_t)r * P.img_pitch] = hi;
-            if (planes == 2) hp[P.img_plane + (size_t)r * P.img_pitch] = lo;
-          }
-        }
-      }
+      uint32_t whi[16], wlo[16];
+      epi_chunk<PLANES2>(v, E, n0 + c0, mbase, lane, tr, false, whi, wlo);
     }
   }
 
