@@ -30,7 +30,7 @@ constexpr int TC_BK = 64;        // bf16 elements per k-block = one 128-byte swi
 constexpr int TC_MAXG = 16;
 constexpr int TC_STAGE_A = TC_BM * TC_BK * 2;   // 16 KiB per plane
 constexpr int TC_STAGE_B = 256 * TC_BK * 2;     // 32 KiB per plane
-constexpr int TC_EPI_WARPS = 16;
+constexpr int TC_EPI_WARPS = 8;
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 
 enum { EPI_PARTIAL = 4 };  // wgrad: plain store into slab `ks`
