@@ -140,6 +140,7 @@ struct dsact_handle {
   dsact_batch pending;       // batch pointers of phase1
   const float *pending_eps1, *pending_z3, *pending_z4;  // noise phase1 used (phase2 needs it again)
   int64_t dev_rb_size;       // what state[ST_RB_SIZE] holds
+  bool arena_imaged;         // the last dsact_replay_sample left bf16 images of obs/obs2/act beside the arena batch
   cudaStream_t cap_stream;   // capture-only stream
   std::vector<GraphEntry> graphs;
   uint64_t stamp;
@@ -445,8 +446,8 @@ struct ImgBatch {
     int grid = 0;
     for (int i = 0; i < g.n; ++i) {
       g.j[i].block_start = grid;
-      long long total = (long long)g.j[i].rows * g.j[i].fill_w;
-      int blocks = (int)((total + 1023) / 1024);
+      long long total = (long long)g.j[i].rows * (g.j[i].pitch / 8);
+      int blocks = (int)((total + 255) / 256);
       if (blocks < 1) blocks = 1;
       if (blocks > 2 * h->num_sms) blocks = 2 * h->num_sms;
       grid += blocks;
@@ -456,6 +457,13 @@ struct ImgBatch {
     g.n = 0;
   }
 };
+
+static ImgOut img_out(const dsact_handle* h, const ImgSlot& s) {
+  ImgOut o;
+  o.p = nullptr; o.pitch = 0; o.planes = h->passes() == 3 ? 2 : 1; o.plane = 0;
+  if (h->tc() && s.off >= 0) { o.p = reinterpret_cast<__nv_bfloat16*>(h->W() + s.off); o.pitch = s.pitch; o.plane = s.plane; }
+  return o;
+}
 
 static Wt weight(const dsact_handle* h, const Net& net, const float* base, int j, const ImgSlot& slot) {
   Wt w;
@@ -580,7 +588,7 @@ static void chain_dgrad_pass(ChainBuild& cb, const dsact_handle* h, const Net& n
 }
 
 // ---- enqueue: pieces of one update ---------------------------------------------
-static void enqueue_phase1(dsact_handle* h, const dsact_batch& bt, const dsact_noise* nz, Ctx& c) {
+static void enqueue_phase1(dsact_handle* h, const dsact_batch& bt, const dsact_noise* nz, Ctx& c, bool inputs_imaged = false) {
   const dsact_config& cf = h->cfg;
   const Net &q = h->q, &pi = h->pi;
   const Arena& ar = h->ar;
@@ -606,7 +614,7 @@ static void enqueue_phase1(dsact_handle* h, const dsact_batch& bt, const dsact_n
         else ib.add(Qb[n] + q.w[j], q.s[j], im, q.s[j + 1], q.s[j]);
       }
     for (int j = 0; j <= pi.L; ++j) ib.add(PIb[0] + pi.w[j], pi.s[j], h->img(ar.i_wpi[0][j], pi.s[j + 1]), pi.s[j + 1], pi.s[j]);
-    ib.add(bt.obs, O, h->img(ar.i_obs, B), B, O);
+    if (!inputs_imaged) ib.add(bt.obs, O, h->img(ar.i_obs, B), B, O);
     ib.launch(h, c);
     for (int n = 2; n < 4; ++n)
       for (int j = 0; j <= q.L; ++j) {
@@ -615,8 +623,10 @@ static void enqueue_phase1(dsact_handle* h, const dsact_batch& bt, const dsact_n
         else ib.add(Qb[n] + q.w[j], q.s[j], im, q.s[j + 1], q.s[j]);
       }
     for (int j = 0; j <= pi.L; ++j) ib.add(PIb[1] + pi.w[j], pi.s[j], h->img(ar.i_wpi[1][j], pi.s[j + 1]), pi.s[j + 1], pi.s[j]);
-    ib.add(bt.obs2, O, h->img(ar.i_obs2, B), B, O);
-    ib.add(bt.act, A, h->img(ar.i_act, B), B, A);
+    if (!inputs_imaged) {
+      ib.add(bt.obs2, O, h->img(ar.i_obs2, B), B, O);
+      ib.add(bt.act, A, h->img(ar.i_act, B), B, A);
+    }
     ib.launch(h, c);
   }
 
@@ -678,14 +688,9 @@ static void enqueue_phase1(dsact_handle* h, const dsact_batch& bt, const dsact_n
     a.logp[0] = W + ar.logp_new; a.logp[1] = W + ar.logp2;
     a.hi = h->buf.act_high; a.lo = h->buf.act_low; a.state = h->buf.state;
     a.B = B; a.A = A; a.min_log_std = (float)cf.min_log_std; a.max_log_std = (float)cf.max_log_std;
+    a.img[0] = img_out(h, ar.i_new_act); a.img[1] = img_out(h, ar.i_act2);
     int blocks = (B + 7) / 8; if (blocks > 4 * h->num_sms) blocks = 4 * h->num_sms;
     sample_kernel<<<dim3(blocks, 2), 256, 0, c.s>>>(a); c.done();
-  }
-  if (tc) {
-    ImgBatch ib;
-    ib.add(W + ar.new_act, A, h->img(ar.i_new_act, B), B, A);
-    ib.add(W + ar.act2, A, h->img(ar.i_act2, B), B, A);
-    ib.launch(h, c);
   }
 
   // wave B: Q1', Q2' on (s', a') and Q1, Q2 on (s, a~)
@@ -749,15 +754,11 @@ static void enqueue_phase2(dsact_handle* h, const dsact_batch& bt, int64_t globa
       a.gbias_q[k] = Gq[k] + q.b[q.L];
     }
     a.state = h->buf.state; a.B = B; a.gamma = (float)cf.gamma; a.inv_global_batch = invB;
+    for (int k = 0; k < 2; ++k) { a.img_q[k] = img_out(h, ar.i_dOut[k]); a.img_qa[k] = img_out(h, ar.i_dOut[4 + k]); }
     int blocks = (B + 255) / 256; if (blocks > 2 * h->num_sms) blocks = 2 * h->num_sms;
     loss_kernel<<<blocks, 256, 0, c.s>>>(a); c.done();
   }
   const int passes[4] = {0, 1, 4, 5};
-  if (tc) {
-    ImgBatch ib;
-    for (int pp = 0; pp < 4; ++pp) ib.add(W + ar.dOut[passes[pp]], 2, h->img(ar.i_dOut[passes[pp]], B), B, 2);
-    ib.launch(h, c);
-  }
   const Ten t_obs = ten(bt.obs, ar.i_obs), t_act = ten(bt.act, ar.i_act);
 
   // wave C: critic passes 0,1 (dgrad + wgrad) and actor passes 4,5 (dgrad only), top layer down
@@ -806,13 +807,9 @@ static void enqueue_phase2(dsact_handle* h, const dsact_batch& bt, int64_t globa
     a.d_logits = W + ar.dlogits; a.gbias = Gpi + pi.b[pi.L]; a.state = h->buf.state;
     a.B = B; a.A = A; a.min_log_std = (float)cf.min_log_std; a.max_log_std = (float)cf.max_log_std;
     a.inv_global_batch = invB;
+    a.img = img_out(h, ar.i_dlogits);
     int blocks = (B + 63) / 64; if (blocks > 2 * h->num_sms) blocks = 2 * h->num_sms; if (blocks < 1) blocks = 1;
     policy_grad_kernel<<<blocks, 256, 0, c.s>>>(a); c.done();
-  }
-  if (tc) {
-    ImgBatch ib;
-    ib.add(W + ar.dlogits, 2 * A, h->img(ar.i_dlogits, B), B, 2 * A);
-    ib.launch(h, c);
   }
 
   // wave D: policy backward
@@ -876,7 +873,7 @@ static void enqueue_gather(dsact_handle* h, int B, const int64_t* idx, Ctx& c) {
   int blocks = (B + 7) / 8; if (blocks > 8 * h->num_sms) blocks = 8 * h->num_sms;
   gather_kernel<<<blocks, 256, 0, c.s>>>(h->rb.obs, h->rb.obs2, h->rb.act, h->rb.rew, h->rb.done, h->rb.logp, use,
                                           W + ar.obs, W + ar.obs2, W + ar.act, W + ar.rew, W + ar.done, W + ar.logp, B,
-                                          h->cfg.obs_dim, h->cfg.act_dim);
+                                          h->cfg.obs_dim, h->cfg.act_dim, img_out(h, ar.i_obs), img_out(h, ar.i_obs2), img_out(h, ar.i_act));
   c.done();
   c.check();
 }
@@ -956,6 +953,13 @@ static int check_noise(const dsact_noise* n) {
   return DSACT_OK;
 }
 
+// true when `bt` is the arena minibatch that the preceding dsact_replay_sample gathered (images already there)
+static bool take_arena_images(dsact_handle* h, const dsact_batch& bt) {
+  const bool yes = h->tc() && h->arena_imaged && bt.obs == h->W() + h->ar.obs && bt.obs2 == h->W() + h->ar.obs2 &&
+                   bt.act == h->W() + h->ar.act;
+  return yes;
+}
+
 static int sync_iteration(dsact_handle* h, int64_t iteration, cudaStream_t s) {
   if (iteration < 0 || iteration > 0x7fffffff) return fail(DSACT_EINVAL, "iteration out of range");
   if (h->dev_iter != iteration) {
@@ -1026,6 +1030,7 @@ int dsact_create(const dsact_config* cfg, int device, dsact_handle** out) {
   h->dev_iter = -1;
   h->dev_rb_size = -1;
   h->pending_batch = 0;
+  h->arena_imaged = false;
   h->stamp = 0; h->launches = 0; h->last_launches = 0;
   cudaError_t e = cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) { delete h; return fail(DSACT_ECUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(e)); }
@@ -1048,6 +1053,7 @@ int dsact_bind(dsact_handle* h, const dsact_buffers* b) {
   if ((reinterpret_cast<uintptr_t>(b->workspace) & 255) != 0) return fail(DSACT_EINVAL, "workspace must be 256-byte aligned");
   h->buf = *b;
   h->bound = true;
+  h->arena_imaged = false;
   if (h->tc()) {  // bias regions of the wgrad slabs are never written by a kernel: they must read as zero
     CUDA_TRY(cudaSetDevice(h->device));
     CUDA_TRY(cudaMemset(h->W() + h->ar.slabs, 0, sizeof(float) * (size_t)h->ar.nslabs * (2 * h->q.n + h->pi.n + 1)));
@@ -1081,7 +1087,8 @@ int dsact_grad_phase1(dsact_handle* h, const dsact_batch* batch, const dsact_noi
   const dsact_batch bt = *batch;
   dsact_noise nz; const dsact_noise* np = nullptr;
   if (noise) { nz = *noise; np = &nz; }
-  rc = run(h, (cudaStream_t)stream, make_key(K_PHASE1, &bt, np, 0), [&](Ctx& c) { enqueue_phase1(h, bt, np, c); });
+  const bool imaged = take_arena_images(h, bt);
+  rc = run(h, (cudaStream_t)stream, make_key(K_PHASE1, &bt, np, imaged ? 1 : 0), [&](Ctx& c) { enqueue_phase1(h, bt, np, c, imaged); });
   if (rc) return rc;
   h->pending = bt;
   h->pending_batch = bt.batch;
@@ -1110,8 +1117,11 @@ int dsact_compute_grads(dsact_handle* h, const dsact_batch* batch, const dsact_n
   const dsact_batch bt = *batch;
   dsact_noise nz; const dsact_noise* np = nullptr;
   if (noise) { nz = *noise; np = &nz; }
-  rc = run(h, (cudaStream_t)stream, make_key(K_GRADS, &bt, np, bt.batch), [&](Ctx& c) {
-    enqueue_phase1(h, bt, np, c);
+  const bool imaged = take_arena_images(h, bt);
+  GraphKey gkey = make_key(K_GRADS, &bt, np, bt.batch);
+  gkey.size = imaged ? 1 : 0;
+  rc = run(h, (cudaStream_t)stream, gkey, [&](Ctx& c) {
+    enqueue_phase1(h, bt, np, c, imaged);
     enqueue_phase2(h, bt, bt.batch, c);
   });
   if (rc) return rc;
@@ -1139,8 +1149,11 @@ int dsact_step(dsact_handle* h, const dsact_batch* batch, const dsact_noise* noi
   const dsact_batch bt = *batch;
   dsact_noise nz; const dsact_noise* np = nullptr;
   if (noise) { nz = *noise; np = &nz; }
-  rc = run(h, (cudaStream_t)stream, make_key(K_STEP, &bt, np, bt.batch), [&](Ctx& c) {
-    enqueue_phase1(h, bt, np, c);
+  const bool imaged = take_arena_images(h, bt);
+  GraphKey skey = make_key(K_STEP, &bt, np, bt.batch);
+  skey.size = imaged ? 1 : 0;
+  rc = run(h, (cudaStream_t)stream, skey, [&](Ctx& c) {
+    enqueue_phase1(h, bt, np, c, imaged);
     enqueue_phase2(h, bt, bt.batch, c);
     enqueue_apply(h, c);
   });
@@ -1226,6 +1239,7 @@ int dsact_replay_sample(dsact_handle* h, int32_t batch, int64_t size, const int6
     if (!idx) { rng_advance_kernel<<<1, 32, 0, c.s>>>(h->buf.state); c.done(); }
   });
   if (rc) return rc;
+  h->arena_imaged = true;
   if (out) *out = arena_batch(h, batch);
   return DSACT_OK;
 }
@@ -1247,7 +1261,7 @@ int dsact_replay_step(dsact_handle* h, int32_t batch, int64_t size, const int64_
   rc = run(h, (cudaStream_t)stream, key, [&](Ctx& c) {
     enqueue_gather(h, batch, idx, c);
     if (!idx && np) { rng_advance_kernel<<<1, 32, 0, c.s>>>(h->buf.state); c.done(); }
-    enqueue_phase1(h, bt, np, c);  // device noise (np == null) advances the counter itself, after the index draw
+    enqueue_phase1(h, bt, np, c, true);  // device noise (np == null) advances the counter itself, after the index draw
     enqueue_phase2(h, bt, batch, c);
     enqueue_apply(h, c);
   });

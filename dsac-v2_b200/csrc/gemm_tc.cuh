@@ -504,24 +504,40 @@ struct ImgGroup {
   int n, planes;
   ImgJob j[16];
 };
+// One thread converts 8 consecutive columns of one row (one 16-byte store per plane).
 __global__ void image_kernel(const __grid_constant__ ImgGroup g) {
   int ji = 0;
 #pragma unroll
   for (int i = 1; i < 16; ++i)
     if (i < g.n && (int)blockIdx.x >= g.j[i].block_start) ji = i;
   const ImgJob& J = g.j[ji];
-  const long long total = (long long)J.rows * J.fill_w;
-  const int nblocks = (ji + 1 < g.n ? g.j[ji + 1].block_start : gridDim.x) - J.block_start;
-  for (long long i = (long long)(blockIdx.x - J.block_start) * blockDim.x + threadIdx.x; i < total;
-       i += (long long)nblocks * blockDim.x) {
-    const int r = (int)(i / J.fill_w), c = (int)(i - (long long)r * J.fill_w);
-    float x = 0.f;
-    if (c >= J.seg_dst0[0] && c < J.seg_dst0[0] + J.seg_w[0]) x = J.src[(size_t)r * J.ld_src + J.seg_src0[0] + (c - J.seg_dst0[0])];
-    else if (c >= J.seg_dst0[1] && c < J.seg_dst0[1] + J.seg_w[1]) x = J.src[(size_t)r * J.ld_src + J.seg_src0[1] + (c - J.seg_dst0[1])];
-    __nv_bfloat16 hi, lo;
-    split_bf16(x, hi, lo);
-    J.dst[(size_t)r * J.pitch + c] = hi;
-    if (g.planes == 2) J.dst[J.plane + (size_t)r * J.pitch + c] = lo;
+  const int vec_per_row = J.pitch >> 3;
+  const int total = J.rows * vec_per_row;
+  const int nblocks = (ji + 1 < g.n ? g.j[ji + 1].block_start : (int)gridDim.x) - J.block_start;
+  for (int i = (blockIdx.x - J.block_start) * blockDim.x + threadIdx.x; i < total; i += nblocks * blockDim.x) {
+    const int r = i / vec_per_row, c0 = (i - r * vec_per_row) * 8;
+    const float* src = J.src + (size_t)r * J.ld_src;
+    uint32_t whi[4], wlo[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float x[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int c = c0 + 2 * k + e;
+        float v = 0.f;
+        if (c < J.seg_w[0]) v = __ldg(src + c);
+        else if (c >= J.seg_dst0[1] && c < J.seg_dst0[1] + J.seg_w[1]) v = __ldg(src + J.seg_src0[1] + (c - J.seg_dst0[1]));
+        x[e] = v;
+      }
+      __nv_bfloat16 h0, l0, h1, l1;
+      split_bf16(x[0], h0, l0);
+      split_bf16(x[1], h1, l1);
+      whi[k] = pack_bf16(h0, h1);
+      wlo[k] = pack_bf16(l0, l1);
+    }
+    __nv_bfloat16* dst = J.dst + (size_t)r * J.pitch + c0;
+    *reinterpret_cast<uint4*>(dst) = make_uint4(whi[0], whi[1], whi[2], whi[3]);
+    if (g.planes == 2) *reinterpret_cast<uint4*>(dst + J.plane) = make_uint4(wlo[0], wlo[1], wlo[2], wlo[3]);
   }
 }
 

@@ -3,6 +3,7 @@
 // and index generation, replay gather.  Formulas follow SURVEY.md Appendix A;
 // reference line numbers are given per kernel.
 #pragma once
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -29,6 +30,20 @@ enum {  // accumulator slots (sums)
   ACC_Q1 = 0, ACC_Q2, ACC_S1, ACC_S2, ACC_LOSS_PI, ACC_LOSS_Q, ACC_TANH_MEAN, ACC_PI_STD, ACC_LOGP,
   ACC_MIN = 16  // [16] min std1, [17] min std2 (float bits, positive values only)
 };
+
+// Optional bf16 hi/lo image of a kernel's fp32 output (tcgen05 modes; p == nullptr otherwise): the next GEMM
+// reads the image by TMA, so producing it here saves a conversion launch.
+struct ImgOut {
+  __nv_bfloat16* p;
+  int pitch, planes;
+  long long plane;
+};
+__device__ __forceinline__ void img_put(const ImgOut& o, size_t row, int col, float x) {
+  if (!o.p) return;
+  const __nv_bfloat16 hi = __float2bfloat16_rn(x);
+  o.p[row * o.pitch + col] = hi;
+  if (o.planes == 2) o.p[o.plane + row * o.pitch + col] = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -144,7 +159,7 @@ __global__ void gather_kernel(const float* __restrict__ r_obs, const float* __re
                               const float* __restrict__ r_done, const float* __restrict__ r_logp,
                               const int64_t* __restrict__ idx, float* __restrict__ obs, float* __restrict__ obs2,
                               float* __restrict__ act, float* __restrict__ rew, float* __restrict__ done,
-                              float* __restrict__ logp, int B, int O, int A) {
+                              float* __restrict__ logp, int B, int O, int A, ImgOut i_obs, ImgOut i_obs2, ImgOut i_act) {
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   const bool v4 = (O & 3) == 0;
@@ -156,13 +171,26 @@ __global__ void gather_kernel(const float* __restrict__ r_obs, const float* __re
     float* dobs2 = obs2 + (size_t)row * O;
     if (v4) {
       for (int c = lane; c < O / 4; c += 32) {
-        reinterpret_cast<float4*>(dobs)[c] = __ldg(reinterpret_cast<const float4*>(so) + c);
-        reinterpret_cast<float4*>(dobs2)[c] = __ldg(reinterpret_cast<const float4*>(so2) + c);
+        const float4 a = __ldg(reinterpret_cast<const float4*>(so) + c), b = __ldg(reinterpret_cast<const float4*>(so2) + c);
+        reinterpret_cast<float4*>(dobs)[c] = a;
+        reinterpret_cast<float4*>(dobs2)[c] = b;
+        if (i_obs.p) {
+          img_put(i_obs, row, 4 * c, a.x); img_put(i_obs, row, 4 * c + 1, a.y); img_put(i_obs, row, 4 * c + 2, a.z); img_put(i_obs, row, 4 * c + 3, a.w);
+          img_put(i_obs2, row, 4 * c, b.x); img_put(i_obs2, row, 4 * c + 1, b.y); img_put(i_obs2, row, 4 * c + 2, b.z); img_put(i_obs2, row, 4 * c + 3, b.w);
+        }
       }
     } else {
-      for (int c = lane; c < O; c += 32) { dobs[c] = __ldg(so + c); dobs2[c] = __ldg(so2 + c); }
+      for (int c = lane; c < O; c += 32) {
+        const float a = __ldg(so + c), b = __ldg(so2 + c);
+        dobs[c] = a; dobs2[c] = b;
+        img_put(i_obs, row, c, a); img_put(i_obs2, row, c, b);
+      }
     }
-    for (int c = lane; c < A; c += 32) act[(size_t)row * A + c] = __ldg(r_act + src * A + c);
+    for (int c = lane; c < A; c += 32) {
+      const float a = __ldg(r_act + src * A + c);
+      act[(size_t)row * A + c] = a;
+      img_put(i_act, row, c, a);
+    }
     if (lane == 0) { rew[row] = __ldg(r_rew + src); done[row] = __ldg(r_done + src); logp[row] = __ldg(r_logp + src); }
   }
 }
@@ -180,6 +208,7 @@ struct SampleArgs {
   float* state;
   int B, A;
   float min_log_std, max_log_std;
+  ImgOut img[2];
 };
 __global__ void sample_kernel(const __grid_constant__ SampleArgs a) {
   __shared__ float red[2 * 32];
@@ -199,6 +228,7 @@ __global__ void sample_kernel(const __grid_constant__ SampleArgs a) {
       const float th = tanhf(u);
       const float scale = 0.5f * (a.hi[j] - a.lo[j]), shift = 0.5f * (a.hi[j] + a.lo[j]);
       a.act[which][(size_t)row * A + j] = scale * th + shift;
+      img_put(a.img[which], row, j, scale * th + shift);
       const float d = u - mean;
       lp += -(d * d) / (2.f * sd * sd) - logf(sd) - HALF_LOG_2PI - logf(1.f + TG_EPS - th * th) - logf(scale);
       sums[0] += tanhf(mean);
@@ -256,6 +286,7 @@ struct LossArgs {
   float* state;
   int B;
   float gamma, inv_global_batch;
+  ImgOut img_q[2], img_qa[2];
 };
 __global__ void loss_kernel(const __grid_constant__ LossArgs a) {
   __shared__ float red[10 * 32];
@@ -290,6 +321,8 @@ __global__ void loss_kernel(const __grid_constant__ LossArgs a) {
       const float g_raw = w * sterm * invB * dsoft;
       a.d_out_q[k][2 * i] = g_mean;
       a.d_out_q[k][2 * i + 1] = g_raw;
+      img_put(a.img_q[k], i, 0, g_mean);
+      img_put(a.img_q[k], i, 1, g_raw);
       s[k] += q;
       s[2 + k] += sd;
       mn[k] = fminf(mn[k], sd);
@@ -304,6 +337,8 @@ __global__ void loss_kernel(const __grid_constant__ LossArgs a) {
     const float g2 = q2p < q1p ? -invB : (q1p == q2p ? -0.5f * invB : 0.f);
     a.d_out_qa[0][2 * i] = g1; a.d_out_qa[0][2 * i + 1] = 0.f;
     a.d_out_qa[1][2 * i] = g2; a.d_out_qa[1][2 * i + 1] = 0.f;
+    img_put(a.img_qa[0], i, 0, g1); img_put(a.img_qa[0], i, 1, 0.f);
+    img_put(a.img_qa[1], i, 0, g2); img_put(a.img_qa[1], i, 1, 0.f);
   }
   block_sum<10>(s, red);
   float one[1] = {gb_q2_raw};
@@ -336,6 +371,7 @@ struct PolicyGradArgs {
   const float* state;
   int B, A;
   float min_log_std, max_log_std, inv_global_batch;
+  ImgOut img;
 };
 __global__ void policy_grad_kernel(const __grid_constant__ PolicyGradArgs a) {
   const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
@@ -358,6 +394,8 @@ __global__ void policy_grad_kernel(const __grid_constant__ PolicyGradArgs a) {
       const float gls = inside ? gsd * sd : 0.f;
       a.d_logits[(size_t)row * 2 * A + j] = gu;
       a.d_logits[(size_t)row * 2 * A + A + j] = gls;
+      img_put(a.img, row, j, gu);
+      img_put(a.img, row, A + j, gls);
       gb_mean += gu;
       gb_ls += gls;
     }

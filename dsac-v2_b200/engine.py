@@ -136,21 +136,16 @@ class Engine:
 
     # ---- argument marshalling ------------------------------------------------
     def _stage_in(self, data):
-        """Host minibatch -> the engine's minibatch arena with async copies (pinned sources overlap);
-        fixed destination pointers, so a captured graph is replayed."""
+        """Host minibatch -> persistent device staging tensors with async copies (pinned sources overlap);
+        fixed destination pointers, so a captured graph is replayed.  (Not the gather arena: the library may
+        keep bf16 images of the arena minibatch between `replay_sample` and the step.)"""
         B = data["obs"].shape[0]
         if B > self.cfg.max_batch:
             raise ValueError(f"batch {B} > max_batch {self.cfg.max_batch}")
         if self._arena is None or self._arena[0] != B:
-            O, A, r64 = self.cfg.obs_dim, self.cfg.act_dim, lambda n: (n + 63) // 64 * 64
-            mb = self.cfg.max_batch
-            offs, off = {}, 0
-            for k, n, w in (("obs", O, O), ("obs2", O, O), ("act", A, A), ("rew", 1, 1), ("done", 1, 1)):
-                offs[k] = (off, w)
-                off += r64(mb * n)
-            views = {k: self._ws_view[o:o + B * w].view((B, w) if k in ("obs", "obs2", "act") else (B,))
-                     for k, (o, w) in offs.items()}
-            self._arena = (B, views)
+            O, A = self.cfg.obs_dim, self.cfg.act_dim
+            z = lambda *s: torch.empty(*s, dtype=torch.float32, device=self.device)
+            self._arena = (B, {"obs": z(B, O), "obs2": z(B, O), "act": z(B, A), "rew": z(B), "done": z(B)})
         views = self._arena[1]
         for k, v in views.items():
             v.copy_(data[k].reshape(v.shape), non_blocking=True)
