@@ -30,7 +30,7 @@ constexpr int TC_BK = 64;        // bf16 elements per k-block = one 128-byte swi
 constexpr int TC_MAXG = 16;
 constexpr int TC_STAGE_A = TC_BM * TC_BK * 2;   // 16 KiB per plane
 constexpr int TC_STAGE_B = 256 * TC_BK * 2;     // 32 KiB per plane
-constexpr int TC_EPI_WARPS = 8;
+constexpr int TC_EPI_WARPS = 12;
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 
 enum { EPI_PARTIAL = 4 };  // wgrad: plain store into slab `ks`
@@ -170,37 +170,37 @@ __device__ __forceinline__ float gauss_pdf(float z) { return 0.3989422804014327f
 // v[i] = act(z_i) with z_i = v[i] on entry; if D != nullptr also D[i] = act'(z_i).  The dispatch is hoisted out of
 // the unrolled loops (inlining the 7-way switch per element made the kernel ~600 KB of SASS and fetch bound):
 // GELU (the reference's default) and ReLU get unrolled bodies, the rest a compact loop over a private smem row.
-template <bool WANT_D>
-__device__ __forceinline__ void act_fwd32(float (&v)[32], float (&d)[32], int act, float* row) {
+template <bool WANT_D, int NV>
+__device__ __forceinline__ void act_fwdN(float (&v)[NV], float (&d)[NV], int act, float* row) {
   if (act == ACT_GELU) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
+    for (int i = 0; i < NV; ++i) {
       const float z = v[i], cdf = gauss_cdf(z);
       v[i] = z * cdf;
       if (WANT_D) d[i] = fmaf(z, gauss_pdf(z), cdf);
     }
   } else if (act == ACT_RELU) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
+    for (int i = 0; i < NV; ++i) {
       if (WANT_D) d[i] = v[i] > 0.f ? 1.f : 0.f;
       v[i] = fmaxf(v[i], 0.f);
     }
   } else if (act != ACT_LINEAR) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) row[i] = v[i];
+    for (int i = 0; i < NV; ++i) row[i] = v[i];
     if (WANT_D) {
 #pragma unroll 1
-      for (int i = 0; i < 32; ++i) row[i] = act_bwd(row[i], act);
+      for (int i = 0; i < NV; ++i) row[i] = act_bwd(row[i], act);
 #pragma unroll
-      for (int i = 0; i < 32; ++i) { d[i] = row[i]; row[i] = v[i]; }
+      for (int i = 0; i < NV; ++i) { d[i] = row[i]; row[i] = v[i]; }
     }
 #pragma unroll 1
-    for (int i = 0; i < 32; ++i) row[i] = act_fwd(row[i], act);
+    for (int i = 0; i < NV; ++i) row[i] = act_fwd(row[i], act);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = row[i];
+    for (int i = 0; i < NV; ++i) v[i] = row[i];
   } else if (WANT_D) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) d[i] = 1.f;
+    for (int i = 0; i < NV; ++i) d[i] = 1.f;
   }
 }
 
@@ -232,7 +232,6 @@ __device__ __forceinline__ void epi_chunk(float (&v)[32], const EpiArgs& E, int 
                                           bool want_rows, uint32_t (&whi)[16], uint32_t (&wlo)[16]) {
   const int rows_ok = max(0, min(32, E.M - mbase));
   const bool global_io = E.Zout || E.Zin || E.C || E.colsum;
-  float d[32];
   if (!global_io) {
     // on-chip only (target networks) or image-only: stay in row layout, bias by broadcast loads
     if (E.epi == EPI_BIAS_ACT || E.epi == EPI_STORE) {
@@ -240,7 +239,10 @@ __device__ __forceinline__ void epi_chunk(float (&v)[32], const EpiArgs& E, int 
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] += (n0c + i < E.N) ? __ldg(E.bias + n0c + i) : 0.f;
       }
-      if (E.epi == EPI_BIAS_ACT) act_fwd32<false>(v, d, E.act, tr + lane * 33);
+      if (E.epi == EPI_BIAS_ACT) {
+        float dummy[32];
+        act_fwdN<false, 32>(v, dummy, E.act, tr + lane * 33);
+      }
     }
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = (n0c + i < E.N) ? v[i] : 0.f;
@@ -249,50 +251,56 @@ __device__ __forceinline__ void epi_chunk(float (&v)[32], const EpiArgs& E, int 
 #pragma unroll
     for (int i = 0; i < 32; ++i) tr[lane * 33 + i] = v[i];
     __syncwarp();
-#pragma unroll
-    for (int r = 0; r < 32; ++r) v[r] = tr[r * 33 + lane];
     const int n = n0c + lane;
     const bool col_ok = n < E.N;
     const int nrows = col_ok ? rows_ok : 0;
-    if (E.epi == EPI_STORE || E.epi == EPI_BIAS_ACT) {
-      const float bias_n = (E.bias && col_ok) ? __ldg(E.bias + n) : 0.f;
+    const float bias_n = (E.bias && col_ok) ? __ldg(E.bias + n) : 0.f;
+    const bool back = want_rows || E.img;
+    float csum = 0.f;
+    // column layout, 16 rows at a time (keeps the live register set small enough for 16 epilogue warps)
 #pragma unroll
-      for (int r = 0; r < 32; ++r) v[r] += bias_n;
-      if (E.epi == EPI_BIAS_ACT) {
-        if (E.Zout) {
-          act_fwd32<true>(v, d, E.act, tr + lane * 33);
-          float* zp = E.Zout + (size_t)mbase * E.ldc + n;
+    for (int half = 0; half < 2; ++half) {
+      const int r0 = half * 16;
+      float a[16], d[16];
 #pragma unroll
-          for (int r = 0; r < 32; ++r)
-            if (r < nrows) zp[(size_t)r * E.ldc] = d[r];
-        } else {
-          act_fwd32<false>(v, d, E.act, tr + lane * 33);
+      for (int r = 0; r < 16; ++r) a[r] = tr[(r0 + r) * 33 + lane];
+      if (E.epi == EPI_STORE || E.epi == EPI_BIAS_ACT) {
+#pragma unroll
+        for (int r = 0; r < 16; ++r) a[r] += bias_n;
+        if (E.epi == EPI_BIAS_ACT) {
+          if (E.Zout) {
+            act_fwdN<true, 16>(a, d, E.act, tr + lane * 33 + r0);   // scratch: this lane's own (already consumed) row
+            float* zp = E.Zout + (size_t)(mbase + r0) * E.ldc + n;
+#pragma unroll
+            for (int r = 0; r < 16; ++r)
+              if (r0 + r < nrows) zp[(size_t)r * E.ldc] = d[r];
+          } else {
+            act_fwdN<false, 16>(a, d, E.act, tr + lane * 33 + r0);
+          }
+        }
+      } else if (E.epi == EPI_DACT) {
+        const float* zp = E.Zin + (size_t)(mbase + r0) * E.ldz + n;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) d[r] = (r0 + r < nrows) ? __ldg(zp + (size_t)r * E.ldz) : 0.f;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+          a[r] *= d[r];
+          csum += a[r];
         }
       }
-    } else if (E.epi == EPI_DACT) {
-      const float* zp = E.Zin + (size_t)mbase * E.ldz + n;
+      if (E.C) {
+        float* cp = E.C + (size_t)(mbase + r0) * E.ldc + n;
 #pragma unroll
-      for (int r = 0; r < 32; ++r) d[r] = r < nrows ? __ldg(zp + (size_t)r * E.ldz) : 0.f;
-      float csum = 0.f;
-#pragma unroll
-      for (int r = 0; r < 32; ++r) {
-        v[r] *= d[r];
-        csum += v[r];
+        for (int r = 0; r < 16; ++r)
+          if (r0 + r < nrows) cp[(size_t)r * E.ldc] = a[r];
       }
-      if (E.colsum && col_ok) atomicAdd(E.colsum + n, csum);  // bias gradient of this tile
+      if (back) {
+#pragma unroll
+        for (int r = 0; r < 16; ++r) tr[(r0 + r) * 33 + lane] = (r0 + r < nrows) ? a[r] : 0.f;
+      }
     }
-    if (E.C) {
-      float* cp = E.C + (size_t)mbase * E.ldc + n;
-#pragma unroll
-      for (int r = 0; r < 32; ++r)
-        if (r < nrows) cp[(size_t)r * E.ldc] = v[r];
-    }
-    if (want_rows || E.img) {  // back to row layout
-#pragma unroll
-      for (int r = 0; r < 32; ++r) v[r] = (r < nrows) ? v[r] : 0.f;
-      __syncwarp();
-#pragma unroll
-      for (int r = 0; r < 32; ++r) tr[r * 33 + lane] = v[r];
+    if (E.epi == EPI_DACT && E.colsum && col_ok) atomicAdd(E.colsum + n, csum);  // bias gradient of this tile
+    if (back) {  // back to row layout
       __syncwarp();
 #pragma unroll
       for (int i = 0; i < 32; ++i) v[i] = tr[lane * 33 + i];
@@ -325,7 +333,7 @@ template <bool A_MN, bool B_MN, bool PLANES2>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_constant__ TcGroup g, int stages, int stage_b) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment for the 128B-swizzle atoms
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // pointer arithmetic on the __shared__ array keeps LDS/STS
   constexpr int planes = PLANES2 ? 2 : 1;
   const int stage_bytes = planes * (TC_STAGE_A + stage_b);  // stage_b: bytes of one B plane (widest tile of the launch)
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)stages * stage_bytes);
