@@ -260,7 +260,7 @@ def main():
     it = 0
     for _ in range(args.warmup):
         dev_step(it); it += 1
-    launches_per_step = eng.last_call_launches() if world == 1 else None
+    launches_per_step = eng.last_call_launches() if world == 1 else None   # (N > 1: three phase launches + collectives)
     barrier()
     l0 = eng.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -280,7 +280,7 @@ def main():
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_per_step = ms.item() / args.steps
-    launches = eng.launch_count() - l0 if world == 1 else None
+    launches = eng.launch_count() - l0
     value = world * 1000.0 / ms_per_step
 
     # ---- end to end through DSAC_V2.local_update with host minibatches ------------------
@@ -296,9 +296,13 @@ def main():
         sink += alg.local_update(ring[i % 4], it)["Loss/Critic loss-RL iter"]; it += 1
     barrier()
     e0.record()
+    prev = None
     for i in range(args.steps):
-        tb = alg.local_update(ring[i % 4], it); it += 1
-        sink += tb["Loss/Critic loss-RL iter"]  # device -> host read of the step's result, every step
+        tb = alg.local_update(ring[i % 4], it); it += 1   # H2D of this step's inputs (side stream) + update
+        if prev is not None:
+            sink += prev["Loss/Critic loss-RL iter"]      # device -> host read of EVERY step's result, one call late so
+        prev = tb                                         # that the next step's copy overlaps this step's kernels
+    sink += prev["Loss/Critic loss-RL iter"]
     e1.record()
     barrier()
     ms2 = torch.tensor([e0.elapsed_time(e1)], device=dev)

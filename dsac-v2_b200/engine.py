@@ -109,6 +109,8 @@ class Engine:
             check(self.lib.dsact_set_carry(self.h, -1.0, -1.0, 0, 0, self._stream()))
         self.replay = None
         self._arena = None
+        self._copy_stream = None
+        self._staged_turn = None
         self._keep = None  # tensors referenced by the last enqueued call
 
     def _bind(self):
@@ -136,20 +138,42 @@ class Engine:
 
     # ---- argument marshalling ------------------------------------------------
     def _stage_in(self, data):
-        """Host minibatch -> persistent device staging tensors with async copies (pinned sources overlap);
-        fixed destination pointers, so a captured graph is replayed.  (Not the gather arena: the library may
-        keep bf16 images of the arena minibatch between `replay_sample` and the step.)"""
+        """Host minibatch -> one of two persistent device staging sets, copied on a side stream so that the
+        H2D transfer of call k+1 overlaps the kernels of call k (pinned sources; fixed destination pointers, so
+        captured graphs are replayed).  Not the gather arena: the library may keep bf16 images of the arena
+        minibatch between `replay_sample` and the step."""
         B = data["obs"].shape[0]
         if B > self.cfg.max_batch:
             raise ValueError(f"batch {B} > max_batch {self.cfg.max_batch}")
         if self._arena is None or self._arena[0] != B:
             O, A = self.cfg.obs_dim, self.cfg.act_dim
             z = lambda *s: torch.empty(*s, dtype=torch.float32, device=self.device)
-            self._arena = (B, {"obs": z(B, O), "obs2": z(B, O), "act": z(B, A), "rew": z(B), "done": z(B)})
-        views = self._arena[1]
-        for k, v in views.items():
-            v.copy_(data[k].reshape(v.shape), non_blocking=True)
+            sets = [{"obs": z(B, O), "obs2": z(B, O), "act": z(B, A), "rew": z(B), "done": z(B)} for _ in range(2)]
+            self._arena = (B, sets, [None, None], 0)
+            if self._copy_stream is None:
+                self._copy_stream = torch.cuda.Stream(device=self.device)
+        B_, sets, done_events, turn = self._arena
+        views = sets[turn]
+        main = torch.cuda.current_stream(self.device)
+        if done_events[turn] is not None:
+            self._copy_stream.wait_event(done_events[turn])   # the step that last read this set has finished
+        with torch.cuda.stream(self._copy_stream):
+            for k, v in views.items():
+                v.copy_(data[k].reshape(v.shape), non_blocking=True)
+            ready = torch.cuda.Event()
+            ready.record(self._copy_stream)
+        main.wait_event(ready)
+        self._staged_turn = turn
+        self._arena = (B_, sets, done_events, turn ^ 1)
         return views
+
+    def _mark_staged_done(self):
+        """Record that the kernels reading the current staging set have been enqueued."""
+        if self._staged_turn is not None:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.device))
+            self._arena[2][self._staged_turn] = ev
+            self._staged_turn = None
 
     def _batch(self, data: Dict[str, torch.Tensor]) -> Batch:
         if data["obs"].device.type == "cpu":
@@ -198,6 +222,7 @@ class Engine:
             n, keep = self._noise(noise, b.batch)
             self._keep_noise = keep
             check(self.lib.dsact_step(self.h, C.byref(b), n, int(iteration), self._stream()))
+            self._mark_staged_done()
         self.last_batch = b.batch
 
     def profile_step(self, data, iteration: int, noise=None) -> dict:
@@ -218,6 +243,7 @@ class Engine:
             n, keep = self._noise(noise, b.batch)
             self._keep_noise = keep
             check(self.lib.dsact_compute_grads(self.h, C.byref(b), n, self._stream()))
+            self._mark_staged_done()
         self.last_batch = b.batch
 
     def grad_phase1(self, data, noise=None):
@@ -231,6 +257,7 @@ class Engine:
     def grad_phase2(self, global_batch: int):
         with torch.cuda.device(self.device):
             check(self.lib.dsact_grad_phase2(self.h, int(global_batch), self._stream()))
+            self._mark_staged_done()
 
     def apply(self, iteration: int):
         with torch.cuda.device(self.device):
