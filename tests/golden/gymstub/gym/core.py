@@ -14,3 +14,9 @@ class Wrapper(Env):
 
     def __getattr__(self, name):
         return getattr(self.env, name)
+
+    def step(self, action):
+        return self.env.step(action)
+
+    def reset(self, **kwargs):
+        return self.env.reset(**kwargs)
