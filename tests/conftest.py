@@ -12,6 +12,8 @@ GOLDEN = os.path.join(REPO, "tests", "golden")
 
 
 def pytest_configure(config):
+    import torch
+    torch.set_num_threads(4)  # the reference pins 4 (utils/init_args.py:14); hosts with 100+ cores crawl on tiny CPU ops otherwise
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
