@@ -57,18 +57,16 @@ __device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint
       "r"(accumulate)
       : "memory");
 }
-__device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
-      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
-      "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
-      : "memory");
+__device__ __forceinline__ void tc_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+               "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __host__ __device__ inline int chain_ringA_bytes(int stages, int planes) {
-  const int a = stages * planes * TC_STAGE_A, t = TC_EPI_WARPS * 32 * 33 * 4;
+  const int a = stages * planes * TC_STAGE_A, t = TC_EPI_WARPS * TR_FLOATS * 4;
   return ((a > t ? a : t) + 1023) / 1024 * 1024;
 }
 inline int chain_smem_bytes(int stages, int planes, int stage_b) {
@@ -204,7 +202,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_chain_kernel(const __grid_co
     // ===== epilogue =====
     const int quarter = warp & 3;
     const int sub = (warp - 2) >> 2;
-    float* tr = reinterpret_cast<float*>(ringA) + (warp - 2) * (32 * 33);   // A ring is dead once layer 0's MMAs retired
+    float* tr = reinterpret_cast<float*>(ringA) + (warp - 2) * TR_FLOATS;   // A ring is dead once layer 0's MMAs retired
     const int mbase = m0 + quarter * 32;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
     for (int j = 0; j < nl; ++j) {
@@ -219,16 +217,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_chain_kernel(const __grid_co
       E.bias = Lj.bias; E.Zout = Lj.Zout; E.Zin = Lj.Zin; E.colsum = Lj.colsum; E.C = Lj.C;
       E.img = Lj.img; E.img_pitch = Lj.img_pitch; E.img_plane = Lj.img_plane;
       // when the next layer reads this one from TMEM, every column up to the next multiple of 16 must be written
-      const int nch = ((feeds_next ? (Lj.N + 15) / 16 * 16 : Lj.bn) + 31) / 32;
+      const int nch = (Lj.bn + 15) / 16;   // bn = N rounded up to 16: every column the next layer reads gets written
       for (int ch = sub; ch < nch; ch += TC_EPI_WARPS / 4) {
-        const int c0 = ch * 32;
-        float v[32];
-        tc_ld32(lane_addr + CH_ACC_COL + (uint32_t)c0, v);   // v[i] = acc[row = lane][c0 + i]
-        uint32_t whi[16], wlo[16];
+        const int c0 = ch * 16;
+        float v[16];
+        tc_ld16(lane_addr + CH_ACC_COL + (uint32_t)c0, v);   // v[i] = acc[row = lane][c0 + i]
+        uint32_t whi[8], wlo[8];
         epi_chunk<PLANES2>(v, E, c0, mbase, lane, tr, feeds_next, whi, wlo);
         if (feeds_next) {  // next layer's A operand: packed bf16 pairs along K, hi and lo planes
-          tc_st16(lane_addr + CH_AHI_COL + (uint32_t)(c0 / 2), whi);
-          if (planes == 2) tc_st16(lane_addr + CH_ALO_COL + (uint32_t)(c0 / 2), wlo);
+          tc_st8(lane_addr + CH_AHI_COL + (uint32_t)(c0 / 2), whi);
+          if (planes == 2) tc_st8(lane_addr + CH_ALO_COL + (uint32_t)(c0 / 2), wlo);
         }
       }
       if (threadIdx.x == 64) TC_STAMP(10 + 3 * j);  // epilogue of layer j done (first epilogue warp)

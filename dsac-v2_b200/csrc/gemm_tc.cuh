@@ -30,7 +30,7 @@ constexpr int TC_BK = 64;        // bf16 elements per k-block = one 128-byte swi
 constexpr int TC_MAXG = 16;
 constexpr int TC_STAGE_A = TC_BM * TC_BK * 2;   // 16 KiB per plane
 constexpr int TC_STAGE_B = 256 * TC_BK * 2;     // 32 KiB per plane
-constexpr int TC_EPI_WARPS = 12;
+constexpr int TC_EPI_WARPS = 16;
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 
 enum { EPI_PARTIAL = 4 };  // wgrad: plain store into slab `ks`
@@ -110,6 +110,18 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
 // Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout), 128-byte swizzle.
@@ -222,14 +234,18 @@ struct EpiArgs {
   long long img_plane;
 };
 
-// One 32-column chunk of a 128-row tile.  On entry v[i] = accumulator[row = mbase + lane][col = n0c + i]
-// (TMEM "row layout").  Global traffic happens in "column layout" (lane = column, registers = rows: every
-// load/store of a warp is one contiguous row segment) reached by a transpose through the warp's private 32x33
-// shared-memory tile; the bf16 hi/lo image is written from the row layout as packed 16-byte vectors.
-// On return, if `want_rows`, whi/wlo hold the packed bf16 pairs of the result for this lane's row.
+// One 16-column chunk of a 128-row tile.  On entry v[i] = accumulator[row = mbase + lane][col = n0c + i] (TMEM "row
+// layout").  Global fp32 traffic happens in "column layout" (lane & 15 = column, lane >> 4 = which 16 of the
+// warp's 32 rows, registers = rows: every load/store of a warp is two contiguous 64-byte row segments) reached by
+// a transpose through the warp's private 32x17 shared-memory tile; the bf16 hi/lo image is written from the row
+// layout as packed 16-byte vectors.  16 columns (not 32) keep the live register set small enough for 16 epilogue
+// warps: the phase is latency bound and needs the warps.  On return, if `want_rows`, whi/wlo hold the packed bf16
+// pairs of the result for this lane's row.
+constexpr int TR_PITCH = 17;
+constexpr int TR_FLOATS = 32 * TR_PITCH;
 template <bool PLANES2>
-__device__ __forceinline__ void epi_chunk(float (&v)[32], const EpiArgs& E, int n0c, int mbase, int lane, float* tr,
-                                          bool want_rows, uint32_t (&whi)[16], uint32_t (&wlo)[16]) {
+__device__ __forceinline__ void epi_chunk(float (&v)[16], const EpiArgs& E, int n0c, int mbase, int lane, float* tr,
+                                          bool want_rows, uint32_t (&whi)[8], uint32_t (&wlo)[8]) {
   const int rows_ok = max(0, min(32, E.M - mbase));
   const bool global_io = E.Zout || E.Zin || E.C || E.colsum;
   if (!global_io) {
@@ -237,89 +253,88 @@ __device__ __forceinline__ void epi_chunk(float (&v)[32], const EpiArgs& E, int 
     if (E.epi == EPI_BIAS_ACT || E.epi == EPI_STORE) {
       if (E.bias) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] += (n0c + i < E.N) ? __ldg(E.bias + n0c + i) : 0.f;
+        for (int i = 0; i < 16; ++i) v[i] += (n0c + i < E.N) ? __ldg(E.bias + n0c + i) : 0.f;
       }
       if (E.epi == EPI_BIAS_ACT) {
-        float dummy[32];
-        act_fwdN<false, 32>(v, dummy, E.act, tr + lane * 33);
+        float dummy[16];
+        act_fwdN<false, 16>(v, dummy, E.act, tr + lane * TR_PITCH);
       }
     }
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = (n0c + i < E.N) ? v[i] : 0.f;
+    for (int i = 0; i < 16; ++i) v[i] = (n0c + i < E.N) ? v[i] : 0.f;
   } else {
     __syncwarp();
 #pragma unroll
-    for (int i = 0; i < 32; ++i) tr[lane * 33 + i] = v[i];
+    for (int i = 0; i < 16; ++i) tr[lane * TR_PITCH + i] = v[i];
     __syncwarp();
-    const int n = n0c + lane;
+    const int c = lane & 15, r0 = (lane >> 4) * 16;
+    const int n = n0c + c;
     const bool col_ok = n < E.N;
-    const int nrows = col_ok ? rows_ok : 0;
-    const float bias_n = (E.bias && col_ok) ? __ldg(E.bias + n) : 0.f;
+    const int nrows = col_ok ? max(0, min(16, rows_ok - r0)) : 0;
     const bool back = want_rows || E.img;
-    float csum = 0.f;
-    // column layout, 16 rows at a time (keeps the live register set small enough for 16 epilogue warps)
+    float a[16], d[16];
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      const int r0 = half * 16;
-      float a[16], d[16];
+    for (int r = 0; r < 16; ++r) a[r] = tr[(r0 + r) * TR_PITCH + c];
+    __syncwarp();  // everyone has read its column before rows are reused as scratch / overwritten
+    if (E.epi == EPI_STORE || E.epi == EPI_BIAS_ACT) {
+      const float bias_n = (E.bias && col_ok) ? __ldg(E.bias + n) : 0.f;
 #pragma unroll
-      for (int r = 0; r < 16; ++r) a[r] = tr[(r0 + r) * 33 + lane];
-      if (E.epi == EPI_STORE || E.epi == EPI_BIAS_ACT) {
+      for (int r = 0; r < 16; ++r) a[r] += bias_n;
+      if (E.epi == EPI_BIAS_ACT) {
+        if (E.Zout) {
+          act_fwdN<true, 16>(a, d, E.act, tr + lane * TR_PITCH);
+          float* zp = E.Zout + (size_t)(mbase + r0) * E.ldc + n;
 #pragma unroll
-        for (int r = 0; r < 16; ++r) a[r] += bias_n;
-        if (E.epi == EPI_BIAS_ACT) {
-          if (E.Zout) {
-            act_fwdN<true, 16>(a, d, E.act, tr + lane * 33 + r0);   // scratch: this lane's own (already consumed) row
-            float* zp = E.Zout + (size_t)(mbase + r0) * E.ldc + n;
-#pragma unroll
-            for (int r = 0; r < 16; ++r)
-              if (r0 + r < nrows) zp[(size_t)r * E.ldc] = d[r];
-          } else {
-            act_fwdN<false, 16>(a, d, E.act, tr + lane * 33 + r0);
-          }
-        }
-      } else if (E.epi == EPI_DACT) {
-        const float* zp = E.Zin + (size_t)(mbase + r0) * E.ldz + n;
-#pragma unroll
-        for (int r = 0; r < 16; ++r) d[r] = (r0 + r < nrows) ? __ldg(zp + (size_t)r * E.ldz) : 0.f;
-#pragma unroll
-        for (int r = 0; r < 16; ++r) {
-          a[r] *= d[r];
-          csum += a[r];
+          for (int r = 0; r < 16; ++r)
+            if (r < nrows) zp[(size_t)r * E.ldc] = d[r];
+        } else {
+          act_fwdN<false, 16>(a, d, E.act, tr + lane * TR_PITCH);
         }
       }
-      if (E.C) {
-        float* cp = E.C + (size_t)(mbase + r0) * E.ldc + n;
+    } else if (E.epi == EPI_DACT) {
+      const float* zp = E.Zin + (size_t)(mbase + r0) * E.ldz + n;
 #pragma unroll
-        for (int r = 0; r < 16; ++r)
-          if (r0 + r < nrows) cp[(size_t)r * E.ldc] = a[r];
+      for (int r = 0; r < 16; ++r) d[r] = (r < nrows) ? __ldg(zp + (size_t)r * E.ldz) : 0.f;
+      float csum = 0.f;
+#pragma unroll
+      for (int r = 0; r < 16; ++r) {
+        a[r] *= d[r];
+        csum += a[r];
       }
-      if (back) {
-#pragma unroll
-        for (int r = 0; r < 16; ++r) tr[(r0 + r) * 33 + lane] = (r0 + r < nrows) ? a[r] : 0.f;
+      if (E.colsum) {  // bias gradient of this tile: the two half-warps hold the two row halves of each column
+        csum += __shfl_xor_sync(0xffffffffu, csum, 16);
+        if (col_ok && lane < 16) atomicAdd(E.colsum + n, csum);
       }
     }
-    if (E.epi == EPI_DACT && E.colsum && col_ok) atomicAdd(E.colsum + n, csum);  // bias gradient of this tile
+    if (E.C) {
+      float* cp = E.C + (size_t)(mbase + r0) * E.ldc + n;
+#pragma unroll
+      for (int r = 0; r < 16; ++r)
+        if (r < nrows) cp[(size_t)r * E.ldc] = a[r];
+    }
     if (back) {  // back to row layout
       __syncwarp();
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = tr[lane * 33 + i];
+      for (int r = 0; r < 16; ++r) tr[(r0 + r) * TR_PITCH + c] = (r < nrows) ? a[r] : 0.f;
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = tr[lane * TR_PITCH + i];
     }
   }
   if (want_rows || E.img) {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
+    for (int i = 0; i < 8; ++i) {
       __nv_bfloat16 h0, l0, h1, l1;
       split_bf16(v[2 * i], h0, l0);
       split_bf16(v[2 * i + 1], h1, l1);
       whi[i] = pack_bf16(h0, h1);
       wlo[i] = pack_bf16(l0, l1);
     }
-    if (E.img && lane < rows_ok) {  // this lane's row: 32 bf16 per plane as 16-byte vectors (pitch % 8 == 0, n0c % 32 == 0)
+    if (E.img && lane < rows_ok) {  // this lane's row: 16 bf16 per plane as 16-byte vectors (pitch % 8 == 0, n0c % 16 == 0)
       __nv_bfloat16* hp = E.img + (size_t)(mbase + lane) * E.img_pitch + n0c;
-      const int nvec = max(0, min(4, ((E.N + 7) / 8 * 8 - n0c + 7) / 8));
+      const int nvec = max(0, min(2, ((E.N + 7) / 8 * 8 - n0c + 7) / 8));
 #pragma unroll
-      for (int q = 0; q < 4; ++q)
+      for (int q = 0; q < 2; ++q)
         if (q < nvec) {
           reinterpret_cast<uint4*>(hp)[q] = make_uint4(whi[4 * q], whi[4 * q + 1], whi[4 * q + 2], whi[4 * q + 3]);
           if (PLANES2) reinterpret_cast<uint4*>(hp + E.img_plane)[q] = make_uint4(wlo[4 * q], wlo[4 * q + 1], wlo[4 * q + 2], wlo[4 * q + 3]);
@@ -464,8 +479,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
       tc_fence_after();
       if (threadIdx.x == 64) TC_STAMP(4);
     }
-    float* tr = reinterpret_cast<float*>(smem) + (warp - 2) * (32 * 33);  // per-warp 32x33 transpose tile
-    const int nch = (bn + 31) / 32;
+    float* tr = reinterpret_cast<float*>(smem) + (warp - 2) * TR_FLOATS;  // per-warp 32x17 transpose tile
+    const int nch = (bn + 15) / 16;
     const int mbase = m0 + quarter * 32;
     EpiArgs E;
     E.epi = P.epi; E.act = P.act; E.M = P.M; E.N = P.N; E.ldc = P.ldc; E.ldz = P.ldz;
@@ -473,15 +488,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
     E.C = P.C ? P.C + (P.epi == EPI_PARTIAL ? (size_t)ks * P.split_stride : 0) : nullptr;
     E.img = P.img; E.img_pitch = P.img_pitch; E.img_plane = P.img_plane;
     for (int ch = sub; ch < nch; ch += TC_EPI_WARPS / 4) {
-      const int c0 = ch * 32;
-      float v[32];
+      const int c0 = ch * 16;
+      float v[16];
       if (have_acc) {
-        tc_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
+        tc_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
       } else {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = 0.f;
+        for (int i = 0; i < 16; ++i) v[i] = 0.f;
       }
-      uint32_t whi[16], wlo[16];
+      uint32_t whi[8], wlo[8];
       epi_chunk<PLANES2>(v, E, n0 + c0, mbase, lane, tr, false, whi, wlo);
     }
   }
