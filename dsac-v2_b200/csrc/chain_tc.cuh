@@ -36,6 +36,8 @@ struct ChainLayer {
   __nv_bfloat16* img;        // bf16 hi/lo image of the result for the weight-gradient GEMM (null: not needed)
   int img_pitch;
   long long img_plane;
+  CUtensorMap mapZ;          // fp32 [M, N] act'(z): stored by the forward epilogue (Zout) / loaded by the dgrad one (Zin); box 16 x 32
+  CUtensorMap mapImg;        // bf16 [2][M][pitch] image of the result; box 16 x 32 x 1
 };
 
 struct ChainPass {
@@ -62,15 +64,38 @@ __device__ __forceinline__ void tc_st8(uint32_t taddr, const uint32_t (&r)[8]) {
                "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                : "memory");
 }
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// Per epilogue warp: [ fp32 tile 32x16 (act' out, or act' in buffer 0) 2 KiB ][ image hi 1 KiB ][ image lo 1 KiB ] inside the
+// (dead after layer 0) A ring, plus a second act'-in buffer (2 KiB) behind it for the dgrad prefetch.
+constexpr int CH_STAGE_WARP = 4096, CH_ZIN1_WARP = 2048;
 __host__ __device__ inline int chain_ringA_bytes(int stages, int planes) {
-  const int a = stages * planes * TC_STAGE_A, t = TC_EPI_WARPS * TR_FLOATS * 4;
+  const int a = stages * planes * TC_STAGE_A, t = TC_EPI_WARPS * CH_STAGE_WARP;
   return ((a > t ? a : t) + 1023) / 1024 * 1024;
 }
 inline int chain_smem_bytes(int stages, int planes, int stage_b) {
-  return stages * planes * stage_b + chain_ringA_bytes(stages, planes) + (2 * stages + 4) * 8 + 1024;
+  return stages * planes * stage_b + chain_ringA_bytes(stages, planes) + TC_EPI_WARPS * CH_ZIN1_WARP +
+         (2 * stages + 4 + 2 * TC_EPI_WARPS) * 8 + 1024;
 }
 
 template <bool PLANES2>
@@ -82,12 +107,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_chain_kernel(const __grid_co
   uint8_t* ringB = smem;
   uint8_t* ringA = smem + (size_t)stages * planes * stage_b;
   const int ringA_bytes = chain_ringA_bytes(stages, planes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ringA + ringA_bytes);
+  uint8_t* zin1 = ringA + ringA_bytes;                                   // [warps] second act' input buffers
+  uint64_t* bars = reinterpret_cast<uint64_t*>(zin1 + TC_EPI_WARPS * CH_ZIN1_WARP);
   uint64_t* full = bars;               // [stages] TMA -> MMA
   uint64_t* empty = bars + stages;     // [stages] MMA -> TMA
   uint64_t* acc_full = bars + 2 * stages;
   uint64_t* a_ready = bars + 2 * stages + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * stages + 2);
+  uint64_t* zbar = bars + 2 * stages + 2;   // [warps][2] act' tile arrival
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(zbar + 2 * TC_EPI_WARPS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) TC_STAMP(0);
@@ -104,6 +131,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_chain_kernel(const __grid_co
     for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(acc_full, 1);
     mbar_init(a_ready, TC_EPI_WARPS);
+    for (int i = 0; i < 2 * TC_EPI_WARPS; ++i) mbar_init(&zbar[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -199,10 +227,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_chain_kernel(const __grid_co
       TC_STAMP(3);
     }
   } else {
-    // ===== epilogue =====
+    // ===== epilogue: everything stays in the TMEM row layout (lane = row).  Results that the backward pass needs
+    // go through a per-warp shared-memory tile and leave with TMA stores; act' tiles come in with TMA loads that are
+    // issued one chunk ahead; nothing here touches the LSU global path except the tiny head outputs. =====
     const int quarter = warp & 3;
     const int sub = (warp - 2) >> 2;
-    float* tr = reinterpret_cast<float*>(ringA) + (warp - 2) * TR_FLOATS;   // A ring is dead once layer 0's MMAs retired
+    const int ew = warp - 2;
+    uint8_t* st = ringA + (size_t)ew * CH_STAGE_WARP;          // A ring is dead once layer 0's MMAs retired
+    float* st_f32 = reinterpret_cast<float*>(st);              // 32 x 16 fp32
+    uint32_t* st_hi = reinterpret_cast<uint32_t*>(st + 2048);  // 32 x 8 packed bf16 pairs
+    uint32_t* st_lo = reinterpret_cast<uint32_t*>(st + 3072);
+    float* zin_buf[2] = {st_f32, reinterpret_cast<float*>(zin1 + (size_t)ew * CH_ZIN1_WARP)};
+    uint64_t* zb = zbar + 2 * ew;
+    uint32_t zphase[2] = {0, 0};
     const int mbase = m0 + quarter * 32;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
     for (int j = 0; j < nl; ++j) {
@@ -212,18 +249,121 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_chain_kernel(const __grid_co
       tc_fence_after();
       if (j == 0 && threadIdx.x == 64) TC_STAMP(4);
       if (threadIdx.x == 64) TC_STAMP(9 + 3 * j);   // accumulator of layer j complete (seen by the epilogue)
-      EpiArgs E;
-      E.epi = Lj.epi; E.act = Lj.act; E.M = P.M; E.N = Lj.N; E.ldc = Lj.N; E.ldz = Lj.N;
-      E.bias = Lj.bias; E.Zout = Lj.Zout; E.Zin = Lj.Zin; E.colsum = Lj.colsum; E.C = Lj.C;
-      E.img = Lj.img; E.img_pitch = Lj.img_pitch; E.img_plane = Lj.img_plane;
-      // when the next layer reads this one from TMEM, every column up to the next multiple of 16 must be written
+      const int epi = Lj.epi, act = Lj.act;
       const int nch = (Lj.bn + 15) / 16;   // bn = N rounded up to 16: every column the next layer reads gets written
-      for (int ch = sub; ch < nch; ch += TC_EPI_WARPS / 4) {
+      const bool dact = epi == EPI_DACT;
+      if (dact && sub < nch) {  // act' tile of this warp's first chunk
+        if (lane == 0) {
+          tma_store_wait_read();  // buffer 0 doubles as the fp32 store tile
+          mbar_expect_tx(&zb[0], 2048);
+          tma_load_2d(zin_buf[0], &Lj.mapZ, &zb[0], sub * 16, mbase);
+        }
+      }
+      int k = 0;
+      for (int ch = sub; ch < nch; ch += TC_EPI_WARPS / 4, ++k) {
         const int c0 = ch * 16;
         float v[16];
         tc_ld16(lane_addr + CH_ACC_COL + (uint32_t)c0, v);   // v[i] = acc[row = lane][c0 + i]
+        if (dact) {
+          const int nxt = ch + TC_EPI_WARPS / 4;
+          __syncwarp();  // every lane is done with the buffer the prefetch overwrites
+          if (nxt < nch && lane == 0) {  // prefetch the next act' tile into the other buffer
+            if (((k + 1) & 1) == 0) tma_store_wait_read();
+            mbar_expect_tx(&zb[(k + 1) & 1], 2048);
+            tma_load_2d(zin_buf[(k + 1) & 1], &Lj.mapZ, &zb[(k + 1) & 1], nxt * 16, mbase);
+          }
+          mbar_wait(&zb[k & 1], zphase[k & 1]);
+          zphase[k & 1] ^= 1;
+          const float4* zr = reinterpret_cast<const float4*>(zin_buf[k & 1] + lane * 16);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 d = zr[q];   // rows >= M and columns >= N arrive as zeros (TMA out-of-bounds fill)
+            v[4 * q] *= d.x; v[4 * q + 1] *= d.y; v[4 * q + 2] *= d.z; v[4 * q + 3] *= d.w;
+          }
+          if (Lj.colsum) {  // bias gradient: column sums over the warp's 32 rows by a reduce-scatter of the 16 columns
+            float r[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) r[i] = v[i];
+            int off = 0;
+#pragma unroll
+            for (int w = 8, bit = 16; w >= 1; w >>= 1, bit >>= 1) {
+              const bool up = lane & bit;
+#pragma unroll
+              for (int i = 0; i < w; ++i) {
+                const float send = up ? r[i] : r[i + w];
+                const float recv = __shfl_xor_sync(0xffffffffu, send, bit);
+                r[i] = (up ? r[i + w] : r[i]) + recv;
+              }
+              off += up ? w : 0;
+            }
+            r[0] += __shfl_xor_sync(0xffffffffu, r[0], 1);
+            if ((lane & 1) == 0 && c0 + off < Lj.N) atomicAdd(Lj.colsum + c0 + off, r[0]);
+          }
+        }
+        float d[16];
+        const bool st_z = epi == EPI_BIAS_ACT && Lj.Zout;
+        if (st_z || Lj.img) {  // the previous chunk's TMA stores must have finished reading this warp's tile
+          if (lane == 0) tma_store_wait_read();
+          __syncwarp();
+        }
+        if (epi == EPI_BIAS_ACT || epi == EPI_STORE) {
+          if (Lj.bias) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] += (c0 + i < Lj.N) ? __ldg(Lj.bias + c0 + i) : 0.f;
+          }
+          if (epi == EPI_BIAS_ACT) {
+            if (Lj.Zout) act_fwdN<true, 16>(v, d, act, st_f32 + lane * 16);
+            else act_fwdN<false, 16>(v, d, act, st_f32 + lane * 16);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = (c0 + i < Lj.N) ? v[i] : 0.f;   // padding columns feed the next layer as zeros
+        if (Lj.C) {  // narrow head outputs (N = 2, 2A, A): direct stores
+          if (mbase + lane < P.M) {
+            float* cp = Lj.C + (size_t)(mbase + lane) * Lj.N + c0;
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (c0 + i < Lj.N) cp[i] = v[i];
+          }
+        }
         uint32_t whi[8], wlo[8];
-        epi_chunk<PLANES2>(v, E, c0, mbase, lane, tr, feeds_next, whi, wlo);
+        if (feeds_next || Lj.img) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            __nv_bfloat16 h0, l0, h1, l1;
+            split_bf16(v[2 * i], h0, l0);
+            split_bf16(v[2 * i + 1], h1, l1);
+            whi[i] = pack_bf16(h0, h1);
+            wlo[i] = pack_bf16(l0, l1);
+          }
+        }
+        if (st_z || Lj.img) {  // stage in shared memory (row layout), one lane issues the TMA stores (they clip at M and N)
+          if (st_z) {
+            float4* zr = reinterpret_cast<float4*>(st_f32 + lane * 16);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) zr[q] = make_float4(d[4 * q], d[4 * q + 1], d[4 * q + 2], d[4 * q + 3]);
+          }
+          if (Lj.img) {
+            uint4* hr = reinterpret_cast<uint4*>(st_hi + lane * 8);
+            hr[0] = make_uint4(whi[0], whi[1], whi[2], whi[3]);
+            hr[1] = make_uint4(whi[4], whi[5], whi[6], whi[7]);
+            if (PLANES2) {
+              uint4* lr = reinterpret_cast<uint4*>(st_lo + lane * 8);
+              lr[0] = make_uint4(wlo[0], wlo[1], wlo[2], wlo[3]);
+              lr[1] = make_uint4(wlo[4], wlo[5], wlo[6], wlo[7]);
+            }
+          }
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            if (st_z) tma_store_2d(&Lj.mapZ, st_f32, c0, mbase);
+            if (Lj.img) {
+              tma_store_3d(&Lj.mapImg, st_hi, c0, mbase, 0);
+              if (PLANES2) tma_store_3d(&Lj.mapImg, st_lo, c0, mbase, 1);
+            }
+            tma_store_commit();
+          }
+        }
         if (feeds_next) {  // next layer's A operand: packed bf16 pairs along K, hi and lo planes
           tc_st8(lane_addr + CH_AHI_COL + (uint32_t)(c0 / 2), whi);
           if (planes == 2) tc_st8(lane_addr + CH_ALO_COL + (uint32_t)(c0 / 2), wlo);
@@ -237,6 +377,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_chain_kernel(const __grid_co
         if (lane == 0) mbar_arrive(a_ready);
       }
     }
+    if (lane == 0) tma_store_wait_read();   // shared memory must stay valid until the last stores have read it
   }
 
   if (lane == 0 && warp >= 2) { if (g.dbg) atomicMax(&g.dbg[(size_t)blockIdx.x * TC_DBG_SLOTS + 5], gtime()); }

@@ -151,6 +151,8 @@ struct dsact_handle {
     if (!tc() || getenv("DSACT_NO_FUSE")) return false;
     for (int j = 1; j <= q.L + 1; ++j) if (q.s[j] > 256) return false;
     for (int j = 1; j <= pi.L + 1; ++j) if (pi.s[j] > 256) return false;
+    for (int j = 1; j <= q.L; ++j) if (q.s[j] % 8) return false;    // hidden widths: 16-byte strides for the TMA epilogue
+    for (int j = 1; j <= pi.L; ++j) if (pi.s[j] % 8) return false;
     return cfg.act_dim <= 256;
   }
   int passes() const { return cfg.gemm_mode == DSACT_GEMM_BF16X3 ? 3 : 1; }
@@ -559,8 +561,12 @@ static void chain_fwd_pass(ChainBuild& cb, const dsact_handle* h, const Net& net
     L.bias = Wbase + net.b[j];
     if (last) L.C = out;
     else {
-      if (zout_off) L.Zout = W + zout_off[j];
-      if (himg) { const Img im = h->img(himg[j], B); L.img = im.p; L.img_pitch = im.pitch; L.img_plane = im.plane; }
+      if (zout_off) { L.Zout = W + zout_off[j]; cb.ok = cb.ok && make_map_f32(&L.mapZ, L.Zout, B, net.s[j + 1], net.s[j + 1]); }
+      if (himg) {
+        const Img im = h->img(himg[j], B);
+        L.img = im.p; L.img_pitch = im.pitch; L.img_plane = im.plane;
+        cb.ok = cb.ok && make_map_img_store(&L.mapImg, im);
+      }
     }
   }
 }
@@ -577,8 +583,13 @@ static void chain_dgrad_pass(ChainBuild& cb, const dsact_handle* h, const Net& n
     ChainLayer& L = cb.layer(P, wim, true, net.s[j], net.s[j + 1], 0, 0);
     L.epi = EPI_DACT; L.act = act;
     L.Zin = W + zin_off[j - 1];
+    cb.ok = cb.ok && make_map_f32(&L.mapZ, L.Zin, B, net.s[j], net.s[j]);
     L.colsum = gbase ? gbase + net.b[j - 1] : nullptr;
-    if (dzimg) { const Img im = h->img(dzimg[j - 1], B); L.img = im.p; L.img_pitch = im.pitch; L.img_plane = im.plane; }
+    if (dzimg) {
+      const Img im = h->img(dzimg[j - 1], B);
+      L.img = im.p; L.img_pitch = im.pitch; L.img_plane = im.plane;
+      cb.ok = cb.ok && make_map_img_store(&L.mapImg, im);
+    }
   }
   if (dact_out) {
     const Img wim = h->img(wslots[0], net.s[1]).cols(act_col_img, act_cols);

@@ -44,6 +44,29 @@ static bool make_map(CUtensorMap* m, const Img& t, int box_rows) {
             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// fp32 [rows, width] row-major tensor (leading dimension ld floats), box 16 x 32, no swizzle: epilogue act' tiles
+static bool make_map_f32(CUtensorMap* m, const float* base, int rows, int width, int ld) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)width, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {16, 32};
+  cuuint32_t estr[2] = {1, 1};
+  return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+// bf16 image as a store target: dims (width, rows, 2 planes), box 16 x 32 x 1, no swizzle
+static bool make_map_img_store(CUtensorMap* m, const Img& t) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[3] = {(cuuint64_t)t.width, (cuuint64_t)t.rows, 2};
+  cuuint64_t strides[2] = {(cuuint64_t)t.pitch * 2, (cuuint64_t)t.plane * 2};
+  cuuint32_t box[3] = {16, 32, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  return fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, t.p, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // what the tcgen05 lowering needs beyond a GemmProb
 struct TcExtra {
   Img a[2], b, out;
