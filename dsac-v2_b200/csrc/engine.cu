@@ -191,6 +191,26 @@ struct Ctx {
   }
 };
 
+// Every kernel goes out with the programmatic-dependent-launch attribute (each kernel begins with griddepcontrol.wait),
+// so that inside the captured graph a kernel's launch and prologue overlap its predecessor's tail.  DSACT_PDL=0 disables.
+static bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("DSACT_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
+template <typename... KArgs, typename... Args>
+static void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, Ctx& c, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = c.s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+  if (e != cudaSuccess && c.err == cudaSuccess) c.err = e;
+}
+
 // ---- GEMM group launch -------------------------------------------------------
 enum { V_FWD = 0, V_DGRAD = 1, V_WGRAD = 2 };
 
@@ -211,9 +231,9 @@ struct Group {
 
 template <int BM, int BN>
 static void launch_variant(const GemmGroup& g, int variant, int grid, Ctx& c) {
-  if (variant == V_FWD) gemm_kernel<BM, BN, true, true><<<grid, 256, 0, c.s>>>(g);
-  else if (variant == V_DGRAD) gemm_kernel<BM, BN, true, false><<<grid, 256, 0, c.s>>>(g);
-  else gemm_kernel<BM, BN, false, false><<<grid, 256, 0, c.s>>>(g);
+  if (variant == V_FWD) launch_k(gemm_kernel<BM, BN, true, true>, grid, 256, 0, c, g);
+  else if (variant == V_DGRAD) launch_k(gemm_kernel<BM, BN, true, false>, grid, 256, 0, c, g);
+  else launch_k(gemm_kernel<BM, BN, false, false>, grid, 256, 0, c, g);
 }
 
 static void launch_simt(const dsact_handle* h, GemmGroup& g, int variant, Ctx& c) {
@@ -314,13 +334,13 @@ static void launch_tc(const dsact_handle* h, Group& G, int variant, Ctx& c) {
     g_tc_attr_done = true;
   }
   if (planes == 2) {
-    if (variant == V_FWD) tc_gemm_kernel<false, false, true><<<grid, TC_THREADS, smem, c.s>>>(t, stages, stage_b);
-    else if (variant == V_DGRAD) tc_gemm_kernel<false, true, true><<<grid, TC_THREADS, smem, c.s>>>(t, stages, stage_b);
-    else tc_gemm_kernel<true, true, true><<<grid, TC_THREADS, smem, c.s>>>(t, stages, stage_b);
+    if (variant == V_FWD) launch_k(tc_gemm_kernel<false, false, true>, grid, TC_THREADS, smem, c, t, stages, stage_b);
+    else if (variant == V_DGRAD) launch_k(tc_gemm_kernel<false, true, true>, grid, TC_THREADS, smem, c, t, stages, stage_b);
+    else launch_k(tc_gemm_kernel<true, true, true>, grid, TC_THREADS, smem, c, t, stages, stage_b);
   } else {
-    if (variant == V_FWD) tc_gemm_kernel<false, false, false><<<grid, TC_THREADS, smem, c.s>>>(t, stages, stage_b);
-    else if (variant == V_DGRAD) tc_gemm_kernel<false, true, false><<<grid, TC_THREADS, smem, c.s>>>(t, stages, stage_b);
-    else tc_gemm_kernel<true, true, false><<<grid, TC_THREADS, smem, c.s>>>(t, stages, stage_b);
+    if (variant == V_FWD) launch_k(tc_gemm_kernel<false, false, false>, grid, TC_THREADS, smem, c, t, stages, stage_b);
+    else if (variant == V_DGRAD) launch_k(tc_gemm_kernel<false, true, false>, grid, TC_THREADS, smem, c, t, stages, stage_b);
+    else launch_k(tc_gemm_kernel<true, true, false>, grid, TC_THREADS, smem, c, t, stages, stage_b);
   }
   if (debug && t.dbg) {  // per-CTA phase breakdown (ns): setup | first TMA landed | MMA issue done | accumulator ready | epilogue | teardown
     cudaStreamSynchronize(c.s);
@@ -454,7 +474,7 @@ struct ImgBatch {
       if (blocks > 2 * h->num_sms) blocks = 2 * h->num_sms;
       grid += blocks;
     }
-    image_kernel<<<grid, 256, 0, c.s>>>(g);
+    launch_k(image_kernel, grid, 256, 0, c, g);
     c.done();
     g.n = 0;
   }
@@ -520,8 +540,8 @@ static void launch_chain(const dsact_handle* h, ChainBuild& cb, int cls, Ctx& c)
     cudaFuncSetAttribute(tc_chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     g_chain_attr_done = true;
   }
-  if (planes == 2) tc_chain_kernel<true><<<cb.grid, TC_THREADS, smem, c.s>>>(cb.g, stages, cb.stage_b);
-  else tc_chain_kernel<false><<<cb.grid, TC_THREADS, smem, c.s>>>(cb.g, stages, cb.stage_b);
+  if (planes == 2) launch_k(tc_chain_kernel<true>, cb.grid, TC_THREADS, smem, c, cb.g, stages, cb.stage_b);
+  else launch_k(tc_chain_kernel<false>, cb.grid, TC_THREADS, smem, c, cb.g, stages, cb.stage_b);
   c.done(cls, cb.flops);
   c.check();
   if (debug && cb.g.dbg) {
@@ -613,7 +633,7 @@ static void enqueue_phase1(dsact_handle* h, const dsact_batch& bt, const dsact_n
   auto ten = [&](const float* f, const ImgSlot& s) { Ten t; t.f = const_cast<float*>(f); t.im = h->img(s, B); return t; };
   const ImgSlot none;
 
-  begin_step_kernel<<<1, 32, 0, c.s>>>(h->buf.state); c.done();
+  launch_k(begin_step_kernel, 1, 32, 0, c, h->buf.state); c.done();
   cudaMemsetAsync(h->buf.grads, 0, sizeof(float) * (2 * q.n + pi.n + 1), c.s);
 
   if (tc) {  // refresh the weight images (the caller may have written params/targets through its views) + inputs
@@ -647,9 +667,9 @@ static void enqueue_phase1(dsact_handle* h, const dsact_batch& bt, const dsact_n
     eps1 = W + ar.eps1; eps2 = W + ar.eps2; z3 = W + ar.z3; z4 = W + ar.z4;
     const int total = (B * A + 1) / 2 * 2 + (B + 1) / 2 * 2;
     int blocks = (total / 2 + 255) / 256; if (blocks < 1) blocks = 1;
-    noise_kernel<<<blocks, 256, 0, c.s>>>(W + ar.eps1, W + ar.eps2, W + ar.z3, W + ar.z4, B, A, h->seed, h->buf.state);
+    launch_k(noise_kernel, blocks, 256, 0, c, W + ar.eps1, W + ar.eps2, W + ar.z3, W + ar.z4, B, A, h->seed, h->buf.state);
     c.done();
-    rng_advance_kernel<<<1, 32, 0, c.s>>>(h->buf.state);
+    launch_k(rng_advance_kernel, 1, 32, 0, c, h->buf.state);
     c.done();
   }
 
@@ -701,7 +721,7 @@ static void enqueue_phase1(dsact_handle* h, const dsact_batch& bt, const dsact_n
     a.B = B; a.A = A; a.min_log_std = (float)cf.min_log_std; a.max_log_std = (float)cf.max_log_std;
     a.img[0] = img_out(h, ar.i_new_act); a.img[1] = img_out(h, ar.i_act2);
     int blocks = (B + 7) / 8; if (blocks > 4 * h->num_sms) blocks = 4 * h->num_sms;
-    sample_kernel<<<dim3(blocks, 2), 256, 0, c.s>>>(a); c.done();
+    launch_k(sample_kernel, dim3(blocks, 2), 256, 0, c, a); c.done();
   }
 
   // wave B: Q1', Q2' on (s', a') and Q1, Q2 on (s, a~)
@@ -731,7 +751,7 @@ static void enqueue_phase1(dsact_handle* h, const dsact_batch& bt, const dsact_n
 
   {
     int blocks = (B + 255) / 256; if (blocks > 2 * h->num_sms) blocks = 2 * h->num_sms;
-    std_sum_kernel<<<blocks, 256, 0, c.s>>>(W + ar.outQ[0], W + ar.outQ[1], B, h->buf.state); c.done();
+    launch_k(std_sum_kernel, blocks, 256, 0, c, W + ar.outQ[0], W + ar.outQ[1], B, h->buf.state); c.done();
   }
   h->pending_eps1 = eps1; h->pending_z3 = z3; h->pending_z4 = z4;
   c.check();
@@ -752,7 +772,7 @@ static void enqueue_phase2(dsact_handle* h, const dsact_batch& bt, int64_t globa
   auto ten = [&](const float* f, const ImgSlot& s) { Ten t; t.f = const_cast<float*>(f); t.im = h->img(s, B); return t; };
   const ImgSlot none;
 
-  ema_kernel<<<1, 32, 0, c.s>>>(h->buf.state, P + 2 * q.n + pi.n, invB, (float)cf.tau_b, cf.auto_alpha, (float)cf.alpha_fixed);
+  launch_k(ema_kernel, 1, 32, 0, c, h->buf.state, P + 2 * q.n + pi.n, invB, (float)cf.tau_b, cf.auto_alpha, (float)cf.alpha_fixed);
   c.done();
   {
     LossArgs a;
@@ -767,7 +787,7 @@ static void enqueue_phase2(dsact_handle* h, const dsact_batch& bt, int64_t globa
     a.state = h->buf.state; a.B = B; a.gamma = (float)cf.gamma; a.inv_global_batch = invB;
     for (int k = 0; k < 2; ++k) { a.img_q[k] = img_out(h, ar.i_dOut[k]); a.img_qa[k] = img_out(h, ar.i_dOut[4 + k]); }
     int blocks = (B + 255) / 256; if (blocks > 2 * h->num_sms) blocks = 2 * h->num_sms;
-    loss_kernel<<<blocks, 256, 0, c.s>>>(a); c.done();
+    launch_k(loss_kernel, blocks, 256, 0, c, a); c.done();
   }
   const int passes[4] = {0, 1, 4, 5};
   const Ten t_obs = ten(bt.obs, ar.i_obs), t_act = ten(bt.act, ar.i_act);
@@ -820,7 +840,7 @@ static void enqueue_phase2(dsact_handle* h, const dsact_batch& bt, int64_t globa
     a.inv_global_batch = invB;
     a.img = img_out(h, ar.i_dlogits);
     int blocks = (B + 63) / 64; if (blocks > 2 * h->num_sms) blocks = 2 * h->num_sms; if (blocks < 1) blocks = 1;
-    policy_grad_kernel<<<blocks, 256, 0, c.s>>>(a); c.done();
+    launch_k(policy_grad_kernel, blocks, 256, sizeof(float) * 2 * A, c, a); c.done();
   }
 
   // wave D: policy backward
@@ -845,9 +865,9 @@ static void enqueue_phase2(dsact_handle* h, const dsact_batch& bt, int64_t globa
   if (tc) {  // fold the weight-gradient split slabs into the flat gradient buffer
     const long long n = 2 * q.n + pi.n + 1;
     int blocks = (int)((n + 255) / 256); if (blocks > 4 * h->num_sms) blocks = 4 * h->num_sms;
-    grad_reduce_kernel<<<blocks, 256, 0, c.s>>>(G_, W + ar.slabs, n, ar.nslabs, n); c.done();
+    launch_k(grad_reduce_kernel, blocks, 256, 0, c, G_, W + ar.slabs, n, ar.nslabs, n); c.done();
   }
-  alpha_grad_kernel<<<1, 32, 0, c.s>>>(G_ + 2 * q.n + pi.n, h->buf.state, invB, -(float)cf.act_dim, B);
+  launch_k(alpha_grad_kernel, 1, 32, 0, c, G_ + 2 * q.n + pi.n, h->buf.state, invB, -(float)cf.act_dim, B);
   c.done();
   c.check();
 }
@@ -864,9 +884,9 @@ static void enqueue_apply(dsact_handle* h, Ctx& c) {
   a.omb1 = (float)(1.0 - cf.adam_beta1); a.b2f = (float)cf.adam_beta2; a.omb2 = (float)(1.0 - cf.adam_beta2);
   int blocks = (int)((a.n_all + 255) / 256);
   if (blocks > 8 * h->num_sms) blocks = 8 * h->num_sms;
-  apply_kernel<<<blocks, 256, 0, c.s>>>(a);
+  launch_k(apply_kernel, blocks, 256, 0, c, a);
   c.done();
-  advance_kernel<<<1, 32, 0, c.s>>>(h->buf.state, cf.delay_update);
+  launch_k(advance_kernel, 1, 32, 0, c, h->buf.state, cf.delay_update);
   c.done();
   c.check();
 }
@@ -878,11 +898,11 @@ static void enqueue_gather(dsact_handle* h, int B, const int64_t* idx, Ctx& c) {
   if (!idx) {
     int64_t* dst = reinterpret_cast<int64_t*>(W + ar.idx);
     int blocks = ((B + 1) / 2 + 255) / 256;
-    index_kernel<<<blocks, 256, 0, c.s>>>(dst, B, h->seed, h->buf.state); c.done();
+    launch_k(index_kernel, blocks, 256, 0, c, dst, B, h->seed, h->buf.state); c.done();
     use = dst;
   }
   int blocks = (B + 7) / 8; if (blocks > 8 * h->num_sms) blocks = 8 * h->num_sms;
-  gather_kernel<<<blocks, 256, 0, c.s>>>(h->rb.obs, h->rb.obs2, h->rb.act, h->rb.rew, h->rb.done, h->rb.logp, use,
+  launch_k(gather_kernel, blocks, 256, 0, c, h->rb.obs, h->rb.obs2, h->rb.act, h->rb.rew, h->rb.done, h->rb.logp, use,
                                           W + ar.obs, W + ar.obs2, W + ar.act, W + ar.rew, W + ar.done, W + ar.logp, B,
                                           h->cfg.obs_dim, h->cfg.act_dim, img_out(h, ar.i_obs), img_out(h, ar.i_obs2), img_out(h, ar.i_act));
   c.done();
@@ -1247,7 +1267,7 @@ int dsact_replay_sample(dsact_handle* h, int32_t batch, int64_t size, const int6
   key.batch = batch; key.idx = idx;
   rc = run(h, (cudaStream_t)stream, key, [&](Ctx& c) {
     enqueue_gather(h, batch, idx, c);
-    if (!idx) { rng_advance_kernel<<<1, 32, 0, c.s>>>(h->buf.state); c.done(); }
+    if (!idx) { launch_k(rng_advance_kernel, 1, 32, 0, c, h->buf.state); c.done(); }
   });
   if (rc) return rc;
   h->arena_imaged = true;
@@ -1271,7 +1291,7 @@ int dsact_replay_step(dsact_handle* h, int32_t batch, int64_t size, const int64_
   key.idx = idx;
   rc = run(h, (cudaStream_t)stream, key, [&](Ctx& c) {
     enqueue_gather(h, batch, idx, c);
-    if (!idx && np) { rng_advance_kernel<<<1, 32, 0, c.s>>>(h->buf.state); c.done(); }
+    if (!idx && np) { launch_k(rng_advance_kernel, 1, 32, 0, c, h->buf.state); c.done(); }
     enqueue_phase1(h, bt, np, c, true);  // device noise (np == null) advances the counter itself, after the index draw
     enqueue_phase2(h, bt, batch, c);
     enqueue_apply(h, c);

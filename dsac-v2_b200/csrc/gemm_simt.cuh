@@ -100,6 +100,8 @@ __global__ void __launch_bounds__(256) gemm_kernel(const __grid_constant__ GemmG
   __shared__ __align__(16) float As[2][KT][BM + 4];
   __shared__ __align__(16) float Bs[2][KT][BN + 4];
 
+  asm volatile("griddepcontrol.wait;" ::: "memory");           // programmatic dependent launch (see kernels.cuh)
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int t = threadIdx.x;
   int pi = 0;
 #pragma unroll

@@ -396,6 +396,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // programmatic dependent launch: everything above overlapped the predecessor's tail; its memory is needed from here on
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (threadIdx.x == 0) TC_STAMP(1);
 
   if (warp == 0) {
@@ -529,6 +532,8 @@ struct ImgGroup {
 };
 // One thread converts 8 consecutive columns of one row (one 16-byte store per plane).
 __global__ void image_kernel(const __grid_constant__ ImgGroup g) {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   int ji = 0;
 #pragma unroll
   for (int i = 1; i < 16; ++i)
@@ -567,7 +572,19 @@ __global__ void image_kernel(const __grid_constant__ ImgGroup g) {
 // Sum the wgrad split slabs into the flat gradient buffer (which already holds the bias gradients).
 __global__ void grad_reduce_kernel(float* __restrict__ grads, const float* __restrict__ slabs, long long n, int nslabs,
                                    long long slab_stride) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  const bool vec = (slab_stride & 3) == 0;
+  const long long n4 = vec ? n / 4 : 0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 s = reinterpret_cast<const float4*>(grads)[i];
+    for (int k = 0; k < nslabs; ++k) {
+      const float4 p = __ldg(reinterpret_cast<const float4*>(slabs + (size_t)k * slab_stride) + i);
+      s.x += p.x; s.y += p.y; s.z += p.z; s.w += p.w;
+    }
+    reinterpret_cast<float4*>(grads)[i] = s;
+  }
+  for (long long i = n4 * 4 + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     float s = grads[i];
     for (int k = 0; k < nslabs; ++k) s += slabs[(size_t)k * slab_stride + i];
     grads[i] = s;

@@ -31,6 +31,13 @@ enum {  // accumulator slots (sums)
   ACC_MIN = 16  // [16] min std1, [17] min std2 (float bits, positive values only)
 };
 
+// Programmatic dependent launch: every kernel of the step is launched with the PDL attribute, waits here for its
+// predecessors' memory, and immediately lets its successors begin launching (their prologue overlaps our tail).
+__device__ __forceinline__ void pdl_sync() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 // Optional bf16 hi/lo image of a kernel's fp32 output (tcgen05 modes; p == nullptr otherwise): the next GEMM
 // reads the image by TMA, so producing it here saves a conversion launch.
 struct ImgOut {
@@ -107,6 +114,7 @@ __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& n0, fl
 
 // Start of every step: clear the accumulators (and the std sums of phase1).
 __global__ void begin_step_kernel(float* __restrict__ state) {
+  pdl_sync();
   const int t = threadIdx.x;
   if (t < 16) state[ST_ACC + t] = 0.f;
   else if (t < 32) state[ST_ACC + t] = __int_as_float(0x7f800000);
@@ -116,6 +124,7 @@ __global__ void begin_step_kernel(float* __restrict__ state) {
 // Device noise: eps1, eps2 [B,A] and z3, z4 [B] (SURVEY Appendix B keeps only the draws that matter).
 __global__ void noise_kernel(float* __restrict__ eps1, float* __restrict__ eps2, float* __restrict__ z3,
                              float* __restrict__ z4, int B, int A, uint64_t seed, const float* __restrict__ state) {
+  pdl_sync();
   const uint32_t step = reinterpret_cast<const uint32_t*>(state)[ST_RNG_CTR];
   const int n_pairs_ea = (B * A + 1) / 2, n_pairs_z = (B + 1) / 2;
   const int total = 2 * n_pairs_ea + 2 * n_pairs_z;
@@ -142,6 +151,7 @@ __global__ void noise_kernel(float* __restrict__ eps1, float* __restrict__ eps2,
 
 // Uniform replay indices in [0, size) (np.random.randint, training/replay_buffer.py:86).
 __global__ void index_kernel(int64_t* __restrict__ idx, int B, uint64_t seed, const float* __restrict__ state) {
+  pdl_sync();
   const uint32_t step = reinterpret_cast<const uint32_t*>(state)[ST_RNG_CTR];
   const int64_t size = *reinterpret_cast<const int64_t*>(state + ST_RB_SIZE);
   const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
@@ -160,6 +170,7 @@ __global__ void gather_kernel(const float* __restrict__ r_obs, const float* __re
                               const int64_t* __restrict__ idx, float* __restrict__ obs, float* __restrict__ obs2,
                               float* __restrict__ act, float* __restrict__ rew, float* __restrict__ done,
                               float* __restrict__ logp, int B, int O, int A, ImgOut i_obs, ImgOut i_obs2, ImgOut i_act) {
+  pdl_sync();
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   const bool v4 = (O & 3) == 0;
@@ -211,6 +222,7 @@ struct SampleArgs {
   ImgOut img[2];
 };
 __global__ void sample_kernel(const __grid_constant__ SampleArgs a) {
+  pdl_sync();
   __shared__ float red[2 * 32];
   const int which = blockIdx.y;
   const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
@@ -249,6 +261,7 @@ __global__ void sample_kernel(const __grid_constant__ SampleArgs a) {
 // Sum of the critics' std over the local rows (input of the mean_std EMA, dsac_v2.py:233-241).
 __global__ void std_sum_kernel(const float* __restrict__ out_q1, const float* __restrict__ out_q2, int B,
                                float* __restrict__ state) {
+  pdl_sync();
   __shared__ float red[2 * 32];
   float s[2] = {0.f, 0.f};
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B; i += gridDim.x * blockDim.x) {
@@ -265,6 +278,7 @@ __global__ void std_sum_kernel(const float* __restrict__ out_q1, const float* __
 // mean_std EMA (dsac_v2.py:233-241) + the temperature this step uses (dsac_v2.py:140-148).
 __global__ void ema_kernel(float* __restrict__ state, const float* __restrict__ log_alpha, float inv_global_batch,
                            float tau_b, int auto_alpha, float alpha_fixed) {
+  pdl_sync();
   if (threadIdx.x < 2) {
     const float mean = state[ST_STDSUM + threadIdx.x] * inv_global_batch;
     const float old = state[ST_MEAN_STD1 + threadIdx.x];
@@ -289,6 +303,7 @@ struct LossArgs {
   ImgOut img_q[2], img_qa[2];
 };
 __global__ void loss_kernel(const __grid_constant__ LossArgs a) {
+  pdl_sync();
   __shared__ float red[10 * 32];
   const float m[2] = {a.state[ST_MEAN_STD1], a.state[ST_MEAN_STD2]};
   const float alpha = a.state[ST_ALPHA_USED];
@@ -374,8 +389,12 @@ struct PolicyGradArgs {
   ImgOut img;
 };
 __global__ void policy_grad_kernel(const __grid_constant__ PolicyGradArgs a) {
+  pdl_sync();
+  extern __shared__ float gb[];   // [2A] block-local bias-gradient sums
   const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
   const int A = a.A;
+  for (int i = threadIdx.x; i < 2 * A; i += blockDim.x) gb[i] = 0.f;
+  __syncthreads();
   const float coef = a.state[ST_ALPHA_USED] * a.inv_global_batch;  // dL/dlogp
   for (int j = lane; j < A; j += 32) {
     const float scale = 0.5f * (a.hi[j] - a.lo[j]);
@@ -399,9 +418,11 @@ __global__ void policy_grad_kernel(const __grid_constant__ PolicyGradArgs a) {
       gb_mean += gu;
       gb_ls += gls;
     }
-    atomicAdd(a.gbias + j, gb_mean);
-    atomicAdd(a.gbias + A + j, gb_ls);
+    atomicAdd(&gb[j], gb_mean);
+    atomicAdd(&gb[A + j], gb_ls);
   }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * A; i += blockDim.x) atomicAdd(a.gbias + i, gb[i]);
 }
 
 // __update (dsac_v2.py:320-347): Adam on q1|q2 every step; on policy|log_alpha plus Polyak of all three
@@ -425,6 +446,7 @@ __device__ __forceinline__ float adam_update(float w, float g, float& m, float& 
   return w - step_size * (m / denom);      // param.addcdiv_(exp_avg, denom, value=-lr/bias_correction1)
 }
 __global__ void apply_kernel(const __grid_constant__ ApplyArgs a) {
+  pdl_sync();
   __shared__ float sh[6];
   const int* sti = reinterpret_cast<const int*>(a.state);
   const bool delayed = (sti[ST_ITER] % a.delay_update) == 0;
@@ -439,28 +461,69 @@ __global__ void apply_kernel(const __grid_constant__ ApplyArgs a) {
   }
   __syncthreads();
   const int64_t n_targets = a.n_all - 1;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < a.n_all; i += (int64_t)gridDim.x * blockDim.x) {
-    const bool critic = i < a.n_q2;
-    float w = a.params[i];
-    if (critic || delayed) {
-      const bool is_alpha = i == a.n_all - 1;
-      if (!(is_alpha && !a.auto_alpha)) {
-        float g = a.grads[i], m = a.m[i], v = a.v[i];
-        const float step = critic ? sh[0] : (is_alpha ? sh[3] : sh[2]);
-        w = adam_update(w, g, m, v, step, critic ? sh[1] : sh[4], a.omb1, a.b2f, a.omb2, a.eps);
-        a.params[i] = w;
-        a.m[i] = m;
-        a.v[i] = v;
+  const float polyak = 1.f - a.tau;
+  // 4 consecutive elements per thread (float4 traffic); a group is uniform unless it straddles the critic/policy
+  // boundary or holds log_alpha, so the per-element logic below stays cheap
+  const int64_t ngroups = (a.n_all + 3) / 4;
+  for (int64_t gi = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; gi < ngroups; gi += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i0 = gi * 4;
+    const bool full = i0 + 3 < n_targets;
+    float w[4], g[4], m[4], v[4], t[4];
+    if (full) {
+      const float4 W4 = reinterpret_cast<const float4*>(a.params)[gi], G4 = reinterpret_cast<const float4*>(a.grads)[gi];
+      const float4 M4 = reinterpret_cast<const float4*>(a.m)[gi], V4 = reinterpret_cast<const float4*>(a.v)[gi];
+      w[0] = W4.x; w[1] = W4.y; w[2] = W4.z; w[3] = W4.w; g[0] = G4.x; g[1] = G4.y; g[2] = G4.z; g[3] = G4.w;
+      m[0] = M4.x; m[1] = M4.y; m[2] = M4.z; m[3] = M4.w; v[0] = V4.x; v[1] = V4.y; v[2] = V4.z; v[3] = V4.w;
+      if (delayed) {
+        const float4 T4 = reinterpret_cast<const float4*>(a.targets)[gi];
+        t[0] = T4.x; t[1] = T4.y; t[2] = T4.z; t[3] = T4.w;
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int64_t i = i0 + e;
+        const bool in = i < a.n_all;
+        w[e] = in ? a.params[i] : 0.f; g[e] = in ? a.grads[i] : 0.f; m[e] = in ? a.m[i] : 0.f; v[e] = in ? a.v[i] : 0.f;
+        t[e] = (in && i < n_targets) ? a.targets[i] : 0.f;
       }
     }
-    if (delayed && i < n_targets) {
-      const float polyak = 1.f - a.tau;
-      a.targets[i] = a.targets[i] * polyak + (1.f - polyak) * w;  // p_targ.mul_(polyak).add_((1-polyak)*p)
+    bool touched = false;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int64_t i = i0 + e;
+      if (i >= a.n_all) continue;
+      const bool critic = i < a.n_q2;
+      if (critic || delayed) {
+        const bool is_alpha = i == a.n_all - 1;
+        if (!(is_alpha && !a.auto_alpha)) {
+          const float step = critic ? sh[0] : (is_alpha ? sh[3] : sh[2]);
+          w[e] = adam_update(w[e], g[e], m[e], v[e], step, critic ? sh[1] : sh[4], a.omb1, a.b2f, a.omb2, a.eps);
+          touched = true;
+        }
+      }
+      if (delayed && i < n_targets) t[e] = t[e] * polyak + (1.f - polyak) * w[e];  // p_targ.mul_(polyak).add_((1-polyak)*p)
+    }
+    if (full) {
+      if (touched) {
+        reinterpret_cast<float4*>(a.params)[gi] = make_float4(w[0], w[1], w[2], w[3]);
+        reinterpret_cast<float4*>(a.m)[gi] = make_float4(m[0], m[1], m[2], m[3]);
+        reinterpret_cast<float4*>(a.v)[gi] = make_float4(v[0], v[1], v[2], v[3]);
+      }
+      if (delayed) reinterpret_cast<float4*>(a.targets)[gi] = make_float4(t[0], t[1], t[2], t[3]);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int64_t i = i0 + e;
+        if (i >= a.n_all) continue;
+        if (touched) { a.params[i] = w[e]; a.m[i] = m[e]; a.v[i] = v[e]; }
+        if (delayed && i < n_targets) a.targets[i] = t[e];
+      }
     }
   }
 }
 // Runs after apply_kernel: advance the counters it read.
 __global__ void advance_kernel(float* __restrict__ state, int delay_update) {
+  pdl_sync();
   int* sti = reinterpret_cast<int*>(state);
   if (threadIdx.x == 0) {
     sti[ST_ADAM_Q] += 1;
@@ -469,12 +532,15 @@ __global__ void advance_kernel(float* __restrict__ state, int delay_update) {
   }
 }
 __global__ void set_iter_kernel(float* __restrict__ state, int iteration) {
+  pdl_sync();
   if (threadIdx.x == 0) reinterpret_cast<int*>(state)[ST_ITER] = iteration;
 }
 __global__ void set_rb_size_kernel(float* __restrict__ state, int64_t size) {
+  pdl_sync();
   if (threadIdx.x == 0) *reinterpret_cast<int64_t*>(state + ST_RB_SIZE) = size;
 }
 __global__ void rng_advance_kernel(float* __restrict__ state) {
+  pdl_sync();
   if (threadIdx.x == 0) reinterpret_cast<uint32_t*>(state)[ST_RNG_CTR] += 1u;
 }
 
@@ -482,12 +548,14 @@ __global__ void rng_advance_kernel(float* __restrict__ state) {
 // `rows` = local shard size, so that per-rank values sum to the global gradient under data parallelism.
 __global__ void alpha_grad_kernel(float* __restrict__ grad_log_alpha, const float* __restrict__ state,
                                   float inv_global_batch, float target_entropy, int rows) {
+  pdl_sync();
   if (threadIdx.x == 0)
     *grad_log_alpha = -(state[ST_ACC + ACC_LOGP] + (float)rows * target_entropy) * inv_global_batch;
 }
 
 // tb_info (dsac_v2.py:188-202) from the accumulators.
 __global__ void finalize_stats_kernel(float* __restrict__ state, float inv_global_batch, float inv_policy_elems) {
+  pdl_sync();
   if (threadIdx.x != 0) return;
   const float* acc = state + ST_ACC;
   float* o = state + ST_STATS;
@@ -510,6 +578,7 @@ __global__ void finalize_stats_kernel(float* __restrict__ state, float inv_globa
 }
 
 __global__ void set_carry_kernel(float* __restrict__ state, float m1, float m2, int tq, int tp) {
+  pdl_sync();
   if (threadIdx.x == 0) {
     state[ST_MEAN_STD1] = m1;
     state[ST_MEAN_STD2] = m2;
