@@ -111,6 +111,18 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def ncu_traffic(mode):
+    """Average dram bytes (read + write) per GEMM-class launch from the committed `ncu --set full` summary of this
+    mode (profiles/), or None if no capture is committed for it."""
+    path = os.path.join(REPO, "profiles", f"r1_{mode}_tc_full.txt")
+    try:
+        rows = [l.split(" | ") for l in open(path) if l.startswith("void ")]
+        mb = [float(r[3]) + float(r[4]) for r in rows]
+        return {"bytes_per_launch": round(1e6 * sum(mb) / len(mb)), "launches": len(mb), "source": os.path.relpath(path, REPO)}
+    except Exception:
+        return None
+
+
 def oracle_setup(cfg, batch, ring_rows=100_000):
     from oracle.dsact_oracle import from_config
     torch.manual_seed(0)
@@ -329,9 +341,11 @@ def main():
         gem = [acc[k] for k in ("gemm_fwd", "gemm_dgrad", "gemm_wgrad")]
         g_ms, g_fl, g_n = sum(x["ms"] for x in gem), sum(x["flops"] for x in gem), sum(x["launches"] for x in gem)
         achieved = g_fl / (g_ms * 1e-3) / 1e12
-        kname = "dsact::gemm_kernel (fp32 FFMA)" if args.gemm == "fp32" else "dsact::tc_gemm_kernel (tcgen05, TMA, TMEM)"
-        roof = {"bound": "tensor", "kernel": kname + " — grouped dense layers: forward, dgrad, wgrad",
-                "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None,
+        kname = "dsact::gemm_kernel (fp32 FFMA)" if args.gemm == "fp32" else \
+            "dsact::tc_chain_kernel (fused layer chains: forward, dgrad) + dsact::tc_gemm_kernel (wgrad) — tcgen05, TMA, TMEM"
+        roof = {"bound": "tensor", "kernel": kname + "; all dense layers of the step",
+                "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+                "traffic": ncu_traffic(args.gemm),
                 "peak_source": f"bf16_tflops_sustained of {peak_src}; arithmetic here is {args.gemm}"
                                + (" = 3 bf16 MMA passes per algorithmic FLOP, i.e. effective peak = peak/3" if args.gemm == "bf16x3" else ""),
                 "flop_per_sample_measured": g_fl / 5 / B, "flop_per_sample_survey": FLOP_PER_SAMPLE,
@@ -345,7 +359,7 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = pick_threads(cfg, B)
-        v, n, dt = time_oracle(cfg, B, warm=2, max_steps=60, budget_s=12.0)
+        v, n, dt = time_oracle(cfg, B, warm=3, max_steps=2000, budget_s=12.0)
         cpu = {"value": v, "unit": "steps/s", "cores": threads, "kind": "port",
                "sample": f"{n} full updates of batch {B} incl. numpy replay gather ({dt:.1f} s), {cpu_model()}"}
 
