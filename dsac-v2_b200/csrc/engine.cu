@@ -140,8 +140,11 @@ struct dsact_handle {
   dsact_batch pending;       // batch pointers of phase1
   const float *pending_eps1, *pending_z3, *pending_z4;  // noise phase1 used (phase2 needs it again)
   int64_t dev_rb_size;       // what state[ST_RB_SIZE] holds
+  bool join_pending = false; // a forked branch of the current enqueue has not been joined yet
   bool arena_imaged;         // the last dsact_replay_sample left bf16 images of obs/obs2/act beside the arena batch
   cudaStream_t cap_stream;   // capture-only stream
+  cudaStream_t side_stream;  // second branch inside a step (critic weight gradients || policy backward chain)
+  cudaEvent_t ev_fork, ev_join;
   std::vector<GraphEntry> graphs;
   uint64_t stamp;
   int64_t launches;
@@ -177,6 +180,7 @@ struct Ctx {
   int launches;
   cudaError_t err;
   Prof* prof = nullptr;
+  cudaStream_t side = nullptr;   // optional second stream for an independent branch (null: serialise on `s`)
   void check() { cudaError_t e = cudaGetLastError(); if (e != cudaSuccess && err == cudaSuccess) err = e; }
   void done(int cls = CLS_OTHER, double flops = 0.0) {
     launches++;
@@ -827,8 +831,23 @@ static void enqueue_phase2(dsact_handle* h, const dsact_batch& bt, int64_t globa
         add_dgrad(gd, q, 0, weight(h, q, Pq[k], 0, ar.i_wq[k][0]), O, ar.kpad_q0, A, ten(W + ar.dzQ[4 + k][0], ar.i_dzQ[4 + k][0]),
                   ten(W + ar.dAct[k], none), nullptr, nullptr, B, 0);
     }
-    launch_group(h, gw, V_WGRAD, c);
+    // the critics' weight gradients depend only on what has run so far; the policy backward (policy_grad -> dgrad chain
+    // of 32 CTAs -> its weight gradients) does not depend on them: run the two branches side by side inside the graph
+    bool forked = false;
+    if (c.side && fused) {
+      cudaEventRecord(h->ev_fork, c.s);
+      cudaStreamWaitEvent(c.side, h->ev_fork, 0);
+      Ctx cs{c.side, 0, cudaSuccess};
+      launch_group(h, gw, V_WGRAD, cs);
+      cudaEventRecord(h->ev_join, c.side);
+      c.launches += cs.launches;
+      if (cs.err != cudaSuccess && c.err == cudaSuccess) c.err = cs.err;
+      forked = true;
+    } else {
+      launch_group(h, gw, V_WGRAD, c);
+    }
     launch_group(h, gd, V_DGRAD, c);
+    h->join_pending = forked;
   }
 
   {
@@ -862,6 +881,7 @@ static void enqueue_phase2(dsact_handle* h, const dsact_batch& bt, int64_t globa
   }
   launch_group(h, gwp, V_WGRAD, c);
 
+  if (h->join_pending) { cudaStreamWaitEvent(c.s, h->ev_join, 0); h->join_pending = false; }
   if (tc) {  // fold the weight-gradient split slabs into the flat gradient buffer
     const long long n = 2 * q.n + pi.n + 1;
     int blocks = (int)((n + 255) / 256); if (blocks > 4 * h->num_sms) blocks = 4 * h->num_sms;
@@ -933,6 +953,7 @@ static int run(dsact_handle* h, cudaStream_t user, const GraphKey& key, F enqueu
   if (!hit) {
     CUDA_TRY(cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeRelaxed));
     Ctx c{h->cap_stream, 0, cudaSuccess};
+    c.side = h->side_stream;
     enqueue(c);
     cudaGraph_t graph = nullptr;
     cudaError_t e = cudaStreamEndCapture(h->cap_stream, &graph);
@@ -1064,6 +1085,9 @@ int dsact_create(const dsact_config* cfg, int device, dsact_handle** out) {
   h->arena_imaged = false;
   h->stamp = 0; h->launches = 0; h->last_launches = 0;
   cudaError_t e = cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
   if (e != cudaSuccess) { delete h; return fail(DSACT_ECUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(e)); }
   *out = h;
   return DSACT_OK;
@@ -1074,6 +1098,9 @@ void dsact_destroy(dsact_handle* h) {
   cudaSetDevice(h->device);
   drop_graphs(h);
   cudaStreamDestroy(h->cap_stream);
+  cudaStreamDestroy(h->side_stream);
+  cudaEventDestroy(h->ev_fork);
+  cudaEventDestroy(h->ev_join);
   delete h;
 }
 

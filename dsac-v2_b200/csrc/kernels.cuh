@@ -52,6 +52,24 @@ __device__ __forceinline__ void img_put(const ImgOut& o, size_t row, int col, fl
   if (o.planes == 2) o.p[o.plane + row * o.pitch + col] = __float2bfloat16_rn(x - __bfloat162float(hi));
 }
 
+// four consecutive columns (col % 4 == 0, pitch % 8 == 0): one 8-byte store per plane
+__device__ __forceinline__ void img_put4(const ImgOut& o, size_t row, int col, float4 x) {
+  if (!o.p) return;
+  const __nv_bfloat16 h0 = __float2bfloat16_rn(x.x), h1 = __float2bfloat16_rn(x.y), h2 = __float2bfloat16_rn(x.z), h3 = __float2bfloat16_rn(x.w);
+  uint2 hv;
+  hv.x = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+  hv.y = (uint32_t)__bfloat16_as_ushort(h2) | ((uint32_t)__bfloat16_as_ushort(h3) << 16);
+  *reinterpret_cast<uint2*>(o.p + row * o.pitch + col) = hv;
+  if (o.planes == 2) {
+    const __nv_bfloat16 l0 = __float2bfloat16_rn(x.x - __bfloat162float(h0)), l1 = __float2bfloat16_rn(x.y - __bfloat162float(h1));
+    const __nv_bfloat16 l2 = __float2bfloat16_rn(x.z - __bfloat162float(h2)), l3 = __float2bfloat16_rn(x.w - __bfloat162float(h3));
+    uint2 lv;
+    lv.x = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    lv.y = (uint32_t)__bfloat16_as_ushort(l2) | ((uint32_t)__bfloat16_as_ushort(l3) << 16);
+    *reinterpret_cast<uint2*>(o.p + o.plane + row * o.pitch + col) = lv;
+  }
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -185,10 +203,8 @@ __global__ void gather_kernel(const float* __restrict__ r_obs, const float* __re
         const float4 a = __ldg(reinterpret_cast<const float4*>(so) + c), b = __ldg(reinterpret_cast<const float4*>(so2) + c);
         reinterpret_cast<float4*>(dobs)[c] = a;
         reinterpret_cast<float4*>(dobs2)[c] = b;
-        if (i_obs.p) {
-          img_put(i_obs, row, 4 * c, a.x); img_put(i_obs, row, 4 * c + 1, a.y); img_put(i_obs, row, 4 * c + 2, a.z); img_put(i_obs, row, 4 * c + 3, a.w);
-          img_put(i_obs2, row, 4 * c, b.x); img_put(i_obs2, row, 4 * c + 1, b.y); img_put(i_obs2, row, 4 * c + 2, b.z); img_put(i_obs2, row, 4 * c + 3, b.w);
-        }
+        img_put4(i_obs, row, 4 * c, a);
+        img_put4(i_obs2, row, 4 * c, b);
       }
     } else {
       for (int c = lane; c < O; c += 32) {
