@@ -108,6 +108,25 @@ class ReplayBuffer:
         self._cur = (self._cur + 1) % self._STAGES
         self._fill = 0
 
+    # ---- full-state checkpoint ---------------------------------------
+    def state_dict(self, with_data: bool = True) -> dict:
+        """ptr/size (+ the valid transitions, fetched from the device ring) for an exact resume."""
+        self.flush()
+        out = {"ptr": self.ptr, "size": self.size, "max_size": self.max_size}
+        if with_data and self.engine is not None:
+            torch.cuda.current_stream(self.engine.device).synchronize()
+            out["data"] = {k: v[:self.size].cpu().clone() for k, v in self.engine.replay.items()}
+        return out
+
+    def load_state_dict(self, state: dict) -> None:
+        self._require_engine()
+        if state["max_size"] != self.max_size:
+            raise ValueError("replay capacity differs from the checkpoint")
+        self.ptr, self.size, self._fill = int(state["ptr"]), int(state["size"]), 0
+        if "data" in state:
+            for k, v in state["data"].items():
+                self.engine.replay[k][:self.size].copy_(v)
+
     # ---- sample -----------------------------------------------------------------------
     def sample_indices(self, batch_size: int):
         if self.index_source == "numpy":

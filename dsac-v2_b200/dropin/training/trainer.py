@@ -9,10 +9,19 @@ training/trainer.py:15-158), reorganised around the GPU-resident engine:
   with the current weights);
 * replay minibatches are gathered on the GPU (no per-step `.cuda()` copies, :72-74);
 * `tb_info` is fetched from the device only on iterations that log.
+
+Optional (kwargs, all off by default = the reference's serial semantics):
+* `dsact_async_sampler=True` — the CPU env loop runs in a background thread and feeds the replay buffer
+  asynchronously (north_star: "the off_sampler env loop stays on CPU and feeds the buffer asynchronously"); the
+  trainer drains what has been collected at each iteration instead of waiting for `sample_batch_size` env steps;
+* `dsact_full_checkpoint=True` — next to every `apprfunc_{it}.pkl` write `trainstate_{it}.pkl` (Adam moments,
+  mean_std EMA, counters, generator state, replay ring); `dsact_resume_dir=<file>` restores it.
 """
 __all__ = ["OffSerialTrainer", "create_trainer"]
 
 import os
+import queue
+import threading
 import time
 from math import inf
 
@@ -79,6 +88,17 @@ class OffSerialTrainer:
             samples, _ = self.sampler.sample()
             self.buffer.add_batch(samples)
 
+        self.full_checkpoint = bool(kwargs.get("dsact_full_checkpoint", False))
+        if kwargs.get("dsact_resume_dir"):
+            self.load_trainstate(kwargs["dsact_resume_dir"])
+
+        self.async_sampler = bool(kwargs.get("dsact_async_sampler", False))
+        self._mirror_lock = threading.Lock()
+        self._feed, self._stop, self._thread = queue.Queue(maxsize=64), threading.Event(), None
+        if self.async_sampler:
+            self._thread = threading.Thread(target=self._sampler_loop, name="dsact-sampler", daemon=True)
+            self._thread.start()
+
         self.start_time = time.time()
 
     # ---- policy mirror ----------------------------------------------------------------
@@ -94,15 +114,64 @@ class OffSerialTrainer:
         self._policy_host.copy_(eng.params[lo:hi], non_blocking=True)
         torch.cuda.current_stream(eng.device).synchronize()
         off = 0
-        with torch.no_grad():
-            for p in self.cpu_networks.policy.parameters():
-                p.copy_(self._policy_host[off:off + p.numel()].view(p.shape))
-                off += p.numel()
+        lock = getattr(self, "_mirror_lock", None)
+        if lock:
+            lock.acquire()
+        try:
+            with torch.no_grad():
+                for p in self.cpu_networks.policy.parameters():
+                    p.copy_(self._policy_host[off:off + p.numel()].view(p.shape))
+                    off += p.numel()
+        finally:
+            if lock:
+                lock.release()
+
+    # ---- asynchronous sampler feed --------------------------------------
+    def _sampler_loop(self):
+        torch.set_num_threads(1)
+        while not self._stop.is_set():
+            with self._mirror_lock:   # act with a consistent snapshot of the mirrored policy
+                samples, tb = self.sampler.sample()
+            try:
+                self._feed.put((samples, tb), timeout=1.0)
+            except queue.Full:
+                continue
+
+    def _drain_feed(self):
+        tb = {}
+        while True:
+            try:
+                samples, tb = self._feed.get_nowait()
+            except queue.Empty:
+                return tb
+            self.buffer.add_batch(samples)
+
+    def close(self):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join(timeout=5.0)
+            self._thread = None
+
+    # ---- full training state ------------------------------------------------------------------
+    def save_trainstate(self, path):
+        torch.save({"alg": self.alg.full_state_dict(), "buffer": self.buffer.state_dict(), "iteration": self.iteration,
+                    "best_tar": self.best_tar}, path)
+
+    def load_trainstate(self, path):
+        st = torch.load(path, weights_only=False)
+        self.alg.load_full_state_dict(st["alg"])
+        self.buffer.load_state_dict(st["buffer"])
+        self.iteration, self.best_tar = int(st["iteration"]), st["best_tar"]
+        self.refresh_policy_mirror()
 
     # ---- one iteration (reference :60-138) -----------------------------------------------
     def step(self):
         sampler_tb_dict = {}
-        if self.iteration % self.sample_interval == 0:
+        if self.async_sampler:
+            if self.iteration % self.mirror_interval == 0:
+                self.refresh_policy_mirror()
+            sampler_tb_dict = self._drain_feed()
+        elif self.iteration % self.sample_interval == 0:
             if self.iteration % self.mirror_interval == 0:
                 self.refresh_policy_mirror()
             sampler_samples, sampler_tb_dict = self.sampler.sample()
@@ -146,12 +215,15 @@ class OffSerialTrainer:
             self.step()
             self.iteration += 1
         self.save_apprfunc()
+        self.close()
         if self.writer is not None:
             self.writer.flush()
 
     def save_apprfunc(self):
         os.makedirs(self.save_folder + "/apprfunc", exist_ok=True)
         torch.save(self.networks.state_dict(), self.save_folder + "/apprfunc/apprfunc_{}.pkl".format(self.iteration))
+        if getattr(self, "full_checkpoint", False):
+            self.save_trainstate(self.save_folder + "/apprfunc/trainstate_{}.pkl".format(self.iteration))
 
 
 def create_trainer(alg, sampler, buffer, evaluator, **kwargs):

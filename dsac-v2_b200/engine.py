@@ -108,6 +108,7 @@ class Engine:
             self._bind()
             check(self.lib.dsact_set_carry(self.h, -1.0, -1.0, 0, 0, self._stream()))
         self.replay = None
+        self._seed = 0x5DEECE66D   # the library's default (csrc/engine.cu)
         self._arena = None
         self._copy_stream = None
         self._staged_turn = None
@@ -281,7 +282,8 @@ class Engine:
                                            int(adam_steps_pi), self._stream()))
 
     def seed(self, seed: int):
-        check(self.lib.dsact_seed(self.h, int(seed) & (2 ** 64 - 1)))
+        self._seed = int(seed) & (2 ** 64 - 1)
+        check(self.lib.dsact_seed(self.h, self._seed))
 
     # ---- replay ring buffer -------------------------------------------------------
     def bind_replay(self, capacity: int):

@@ -232,3 +232,60 @@ def test_trainer_loop_runs_and_mirrors_policy(tmp_path):
     assert np.isfinite(tb["Loss/Critic loss-RL iter"])
     ck = torch.load(tmp_path / "apprfunc" / "apprfunc_30.pkl", weights_only=True)
     assert len(ck) == 41
+
+
+def test_full_state_checkpoint_resumes_exactly(tmp_path):
+    """weights + Adam moments + EMA + counters + generator + replay ring -> identical continuation."""
+    from training.replay_buffer import ReplayBuffer
+    cfg, B = synth.CONFIGS["tiny"], 32
+
+    def make():
+        alg, kw = build_alg(cfg, B)
+        alg.networks.cuda()
+        eng = alg.networks.engine()
+        eng.seed(99)
+        buf = ReplayBuffer(**dict(kw, buffer_max_size=500, additional_info={}))
+        buf.attach(eng)
+        return alg, buf
+
+    g = np.random.default_rng(0)
+    rows = [(g.standard_normal(5).astype(np.float32), {}, g.uniform(-1, 1, 2).astype(np.float32), float(g.standard_normal()),
+             g.standard_normal(5).astype(np.float32), False, np.float32(0), {}) for _ in range(300)]
+    a, buf_a = make()
+    buf_a.add_batch(rows)
+    for it in range(6):
+        a.local_update(buf_a.sample_batch(B), it)
+    path = tmp_path / "trainstate.pkl"
+    torch.save({"alg": a.full_state_dict(), "buffer": buf_a.state_dict()}, path)
+    cont_a = [a.local_update(buf_a.sample_batch(B), it)["Loss/Critic loss-RL iter"] for it in range(6, 12)]
+
+    b, buf_b = make()
+    st = torch.load(path, weights_only=False)
+    b.load_full_state_dict(st["alg"])
+    buf_b.load_state_dict(st["buffer"])
+    assert (buf_b.size, buf_b.ptr) == (300, 300)
+    cont_b = [b.local_update(buf_b.sample_batch(B), it)["Loss/Critic loss-RL iter"] for it in range(6, 12)]
+    np.testing.assert_allclose(cont_b, cont_a, rtol=2e-5)   # same device indices and noise, same Adam state
+    for (k, va), vb in zip(a.networks.state_dict().items(), b.networks.state_dict().values()):
+        torch.testing.assert_close(va, vb, rtol=2e-5, atol=1e-7, msg=k)
+
+
+def test_async_sampler_feeds_buffer_while_training(tmp_path):
+    from training.replay_buffer import ReplayBuffer
+    from training.trainer import create_trainer
+    cfg = synth.CONFIGS["tiny"]
+    alg, kw = build_alg(cfg, 32)
+    kw = dict(kw, buffer_max_size=5000, additional_info={}, buffer_name="replay_buffer", buffer_warm_size=100,
+              max_iteration=200, log_save_interval=1000, apprfunc_save_interval=1000, eval_interval=1000,
+              save_folder=str(tmp_path), ini_network_dir=None, use_gpu=True, dsact_tensorboard=False,
+              dsact_async_sampler=True, dsact_full_checkpoint=True)
+    sampler, evaluator = _StubEnvSampler(kw, cfg), _StubEvaluator()
+    buf = ReplayBuffer(**kw)
+    trainer = create_trainer(alg, sampler, buf, evaluator, **kw)
+    size0 = buf.size
+    trainer.train()
+    assert trainer.iteration == 200 and trainer._thread is None
+    assert buf.size > size0                      # transitions arrived from the background thread
+    assert sampler.get_total_sample_number() >= buf.size - 0
+    assert np.isfinite(trainer.last_tb["Loss/Critic loss-RL iter"])
+    assert os.path.exists(tmp_path / "apprfunc" / "trainstate_200.pkl")
