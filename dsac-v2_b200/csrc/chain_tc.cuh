@@ -239,7 +239,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_chain_kernel(const __grid_co
     float* st_f32 = reinterpret_cast<float*>(st);              // 32 x 16 fp32
     uint32_t* st_hi = reinterpret_cast<uint32_t*>(st + 2048);  // 32 x 8 packed bf16 pairs
     uint32_t* st_lo = reinterpret_cast<uint32_t*>(st + 3072);
-    float* zin_buf[2] = {st_f32, reinterpret_cast<float*>(zin1 + (size_t)ew * CH_ZIN1_WARP)};
+    // act' tiles: buffer 0 = the fp32 staging tile, buffer 1 = this warp's slice of zin1.  Kept as (base, byte offset)
+    // so that the accesses stay LDS/STS (an array of pointers decays to generic loads).
+    float* const zin1w = reinterpret_cast<float*>(zin1 + (size_t)ew * CH_ZIN1_WARP);
+    const int zin1_off = (int)((zin1 + (size_t)ew * CH_ZIN1_WARP) - st) / 4;   // in floats, relative to st_f32
+#define ZIN_BUF(i) (st_f32 + ((i) ? zin1_off : 0))
     uint64_t* zb = zbar + 2 * ew;
     uint32_t zphase[2] = {0, 0};
     const int mbase = m0 + quarter * 32;
@@ -247,6 +251,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_chain_kernel(const __grid_co
     for (int j = 0; j < nl; ++j) {
       const ChainLayer& Lj = P.L[j];
       const bool feeds_next = j + 1 < nl;
+      // bias of this warp's (up to four) chunks -> the warp's private row of the act' buffer (forward passes never load
+      // act' tiles), while the MMAs of the layer are still running; the chunks then read it as broadcast float4s
+      const bool has_bias = (Lj.epi == EPI_BIAS_ACT || Lj.epi == EPI_STORE) && Lj.bias;
+      float* bw = zin1w;
+      if (has_bias) {
+        __syncwarp();
+        for (int t = lane; t < 64; t += 32) {
+          const int n = (sub + (TC_EPI_WARPS / 4) * (t >> 4)) * 16 + (t & 15);
+          bw[t] = n < Lj.N ? __ldg(Lj.bias + n) : 0.f;
+        }
+        __syncwarp();
+      }
       mbar_wait(acc_full, (uint32_t)(j & 1));
       tc_fence_after();
       if (j == 0 && threadIdx.x == 64) TC_STAMP(4);
@@ -258,7 +274,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_chain_kernel(const __grid_co
         if (lane == 0) {
           tma_store_wait_read();  // buffer 0 doubles as the fp32 store tile
           mbar_expect_tx(&zb[0], 2048);
-          tma_load_2d(zin_buf[0], &Lj.mapZ, &zb[0], sub * 16, mbase);
+          tma_load_2d(ZIN_BUF(0), &Lj.mapZ, &zb[0], sub * 16, mbase);
         }
       }
       int k = 0;
@@ -272,11 +288,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_chain_kernel(const __grid_co
           if (nxt < nch && lane == 0) {  // prefetch the next act' tile into the other buffer
             if (((k + 1) & 1) == 0) tma_store_wait_read();
             mbar_expect_tx(&zb[(k + 1) & 1], 2048);
-            tma_load_2d(zin_buf[(k + 1) & 1], &Lj.mapZ, &zb[(k + 1) & 1], nxt * 16, mbase);
+            tma_load_2d(ZIN_BUF((k + 1) & 1), &Lj.mapZ, &zb[(k + 1) & 1], nxt * 16, mbase);
           }
           mbar_wait(&zb[k & 1], zphase[k & 1]);
           zphase[k & 1] ^= 1;
-          const float4* zr = reinterpret_cast<const float4*>(zin_buf[k & 1] + lane * 16);
+          const float4* zr = reinterpret_cast<const float4*>(ZIN_BUF(k & 1) + lane * 16);
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const float4 d = zr[q];   // rows >= M and columns >= N arrive as zeros (TMA out-of-bounds fill)
@@ -304,22 +320,32 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_chain_kernel(const __grid_co
         }
         float d[16];
         const bool st_z = epi == EPI_BIAS_ACT && Lj.Zout;
-        if (st_z || Lj.img) {  // the previous chunk's TMA stores must have finished reading this warp's tile
+        // The previous chunk's TMA stores must have finished reading this warp's tile before it is written again.  Only
+        // the generic activations use the tile as scratch; for GELU/ReLU/linear the wait moves behind the math, which
+        // then overlaps the store engine's read.
+        const bool scratch = epi == EPI_BIAS_ACT && act != ACT_GELU && act != ACT_RELU && act != ACT_LINEAR;
+        if ((st_z || Lj.img) && scratch) {
           if (lane == 0) tma_store_wait_read();
           __syncwarp();
         }
         if (epi == EPI_BIAS_ACT || epi == EPI_STORE) {
-          if (Lj.bias) {
+          if (has_bias) {
+            const float4* bp = reinterpret_cast<const float4*>(bw + k * 16);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] += (c0 + i < Lj.N) ? __ldg(Lj.bias + c0 + i) : 0.f;
+            for (int q = 0; q < 4; ++q) {
+              const float4 b = bp[q];
+              v[4 * q] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w;
+            }
           }
           if (epi == EPI_BIAS_ACT) {
             if (Lj.Zout) act_fwdN<true, 16>(v, d, act, st_f32 + lane * 16);
             else act_fwdN<false, 16>(v, d, act, st_f32 + lane * 16);
           }
         }
+        if (c0 + 16 > Lj.N) {   // partial chunk: padding columns feed the next layer as zeros
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = (c0 + i < Lj.N) ? v[i] : 0.f;   // padding columns feed the next layer as zeros
+          for (int i = 0; i < 16; ++i) v[i] = (c0 + i < Lj.N) ? v[i] : 0.f;
+        }
         if (Lj.C) {  // narrow head outputs (N = 2, 2A, A): direct stores
           if (mbase + lane < P.M) {
             float* cp = Lj.C + (size_t)(mbase + lane) * Lj.N + c0;
@@ -332,14 +358,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_chain_kernel(const __grid_co
         if (feeds_next || Lj.img) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            __nv_bfloat16 h0, l0, h1, l1;
-            split_bf16(v[2 * i], h0, l0);
-            split_bf16(v[2 * i + 1], h1, l1);
-            whi[i] = pack_bf16(h0, h1);
-            wlo[i] = pack_bf16(l0, l1);
+            split_pack2(v[2 * i], v[2 * i + 1], whi[i], wlo[i]);
           }
         }
         if (st_z || Lj.img) {  // stage in shared memory (row layout), one lane issues the TMA stores (they clip at M and N)
+          if (!scratch) {
+            if (lane == 0) tma_store_wait_read();
+            __syncwarp();
+          }
           if (st_z) {
             float4* zr = reinterpret_cast<float4*>(st_f32 + lane * 16);
 #pragma unroll
@@ -380,6 +406,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_chain_kernel(const __grid_co
       }
     }
     if (lane == 0) tma_store_wait_read();   // shared memory must stay valid until the last stores have read it
+#undef ZIN_BUF
   }
 
   if (lane == 0 && warp >= 2) { if (g.dbg) atomicMax(&g.dbg[(size_t)blockIdx.x * TC_DBG_SLOTS + 5], gtime()); }

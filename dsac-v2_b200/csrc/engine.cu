@@ -77,6 +77,7 @@ struct Arena {
   int kpad_q0;        // column of the act block inside the Q layer-0 weight image
   int64_t slabs;      // [nslabs][n_params] fp32 wgrad partials
   int nslabs;
+  int64_t slab_stride;   // floats between slabs: n_params rounded up to 4 (float4 access to every slab)
   int64_t total;
   void build(const dsact_config& c, const Net& q, const Net& pi) {
     int64_t B = c.max_batch, O = c.obs_dim, A = c.act_dim, off = 0;
@@ -99,7 +100,7 @@ struct Arena {
     }
     dAct[0] = take(B * A); dAct[1] = take(B * A);
     tc = c.gemm_mode != DSACT_GEMM_FP32;
-    nslabs = 0; slabs = 0; kpad_q0 = (int)((O + 63) / 64 * 64);
+    nslabs = 0; slabs = 0; slab_stride = 0; kpad_q0 = (int)((O + 63) / 64 * 64);
     if (tc) {
       const int Bi = (int)B;
       i_obs = img(Bi, (int)O); i_obs2 = img(Bi, (int)O); i_act = img(Bi, (int)A); i_new_act = img(Bi, (int)A); i_act2 = img(Bi, (int)A);
@@ -114,7 +115,8 @@ struct Arena {
       for (int n = 0; n < 2; ++n)
         for (int j = 0; j <= pi.L; ++j) i_wpi[n][j] = img(pi.s[j + 1], pi.s[j]);
       nslabs = (int)((B + 511) / 512); if (nslabs > 8) nslabs = 8; if (nslabs < 1) nslabs = 1;
-      slabs = take((int64_t)nslabs * (2 * q.n + pi.n + 1));
+      slab_stride = (2 * q.n + pi.n + 1 + 3) / 4 * 4;
+      slabs = take((int64_t)nslabs * slab_stride);
     }
     total = off;
   }
@@ -145,6 +147,7 @@ struct dsact_handle {
   cudaStream_t cap_stream;   // capture-only stream
   cudaStream_t side_stream;  // second branch inside a step (critic weight gradients || policy backward chain)
   cudaEvent_t ev_fork, ev_join;
+  cudaEvent_t ev_pro_fork, ev_pro_join;   // prologue branch (weight images, noise, clears) beside the replay gather
   std::vector<GraphEntry> graphs;
   uint64_t stamp;
   int64_t launches;
@@ -309,7 +312,7 @@ static void launch_tc(const dsact_handle* h, Group& G, int variant, Ctx& c) {
       else {
         p.ksplit = h->ar.nslabs;
         p.C = h->W() + h->ar.slabs + (s.C - h->buf.grads);
-        p.split_stride = 2 * h->q.n + h->pi.n + 1;
+        p.split_stride = h->ar.slab_stride;
       }
     }
     if (x.out.p) {
@@ -623,7 +626,9 @@ static void chain_dgrad_pass(ChainBuild& cb, const dsact_handle* h, const Net& n
 }
 
 // ---- enqueue: pieces of one update ---------------------------------------------
-static void enqueue_phase1(dsact_handle* h, const dsact_batch& bt, const dsact_noise* nz, Ctx& c, bool inputs_imaged = false) {
+// Everything of a step that depends on neither the minibatch gather nor a forward pass: accumulator clears, the
+// gradient memset, the bf16 images of all weights (and of a caller-supplied batch), the device noise.
+static void enqueue_prologue(dsact_handle* h, const dsact_batch& bt, const dsact_noise* nz, Ctx& c, bool inputs_imaged) {
   const dsact_config& cf = h->cfg;
   const Net &q = h->q, &pi = h->pi;
   const Arena& ar = h->ar;
@@ -634,8 +639,6 @@ static void enqueue_phase1(dsact_handle* h, const dsact_batch& bt, const dsact_n
   float* T = h->buf.targets;
   const float* Qb[4] = {P, P + q.n, T, T + q.n};        // q1, q2, q1', q2'
   const float* PIb[2] = {P + 2 * q.n, T + 2 * q.n};     // pi, pi'
-  auto ten = [&](const float* f, const ImgSlot& s) { Ten t; t.f = const_cast<float*>(f); t.im = h->img(s, B); return t; };
-  const ImgSlot none;
 
   launch_k(begin_step_kernel, 1, 32, 0, c, h->buf.state); c.done();
   cudaMemsetAsync(h->buf.grads, 0, sizeof(float) * (2 * q.n + pi.n + 1), c.s);
@@ -665,16 +668,50 @@ static void enqueue_phase1(dsact_handle* h, const dsact_batch& bt, const dsact_n
     ib.launch(h, c);
   }
 
-  const float *eps1, *eps2, *z3, *z4;
-  if (nz) { eps1 = nz->eps1; eps2 = nz->eps2; z3 = nz->z3; z4 = nz->z4; }
-  else {
-    eps1 = W + ar.eps1; eps2 = W + ar.eps2; z3 = W + ar.z3; z4 = W + ar.z4;
+  if (!nz) {  // device noise; the counter it reads is advanced by the caller once every reader of this step has run
     const int total = (B * A + 1) / 2 * 2 + (B + 1) / 2 * 2;
     int blocks = (total / 2 + 255) / 256; if (blocks < 1) blocks = 1;
     launch_k(noise_kernel, blocks, 256, 0, c, W + ar.eps1, W + ar.eps2, W + ar.z3, W + ar.z4, B, A, h->seed, h->buf.state);
     c.done();
-    launch_k(rng_advance_kernel, 1, 32, 0, c, h->buf.state);
-    c.done();
+  }
+  c.check();
+}
+
+// In a captured step the prologue runs as its own branch next to whatever the main stream does first (the replay
+// gather); returns true if it was forked and must be joined (enqueue_phase1 does) before the first forward pass.
+static bool fork_prologue(dsact_handle* h, const dsact_batch& bt, const dsact_noise* nz, Ctx& c, bool inputs_imaged) {
+  if (!c.side) return false;
+  cudaEventRecord(h->ev_pro_fork, c.s);
+  cudaStreamWaitEvent(c.side, h->ev_pro_fork, 0);
+  Ctx cs{c.side, 0, cudaSuccess};
+  enqueue_prologue(h, bt, nz, cs, inputs_imaged);
+  cudaEventRecord(h->ev_pro_join, c.side);
+  c.launches += cs.launches;
+  if (cs.err != cudaSuccess && c.err == cudaSuccess) c.err = cs.err;
+  return true;
+}
+
+static void enqueue_phase1(dsact_handle* h, const dsact_batch& bt, const dsact_noise* nz, Ctx& c, bool inputs_imaged = false,
+                           bool prologue_forked = false) {
+  const dsact_config& cf = h->cfg;
+  const Net &q = h->q, &pi = h->pi;
+  const Arena& ar = h->ar;
+  float* W = h->W();
+  const int B = bt.batch, O = cf.obs_dim, A = cf.act_dim;
+  float* P = h->buf.params;
+  float* T = h->buf.targets;
+  const float* Qb[4] = {P, P + q.n, T, T + q.n};        // q1, q2, q1', q2'
+  const float* PIb[2] = {P + 2 * q.n, T + 2 * q.n};     // pi, pi'
+  auto ten = [&](const float* f, const ImgSlot& s) { Ten t; t.f = const_cast<float*>(f); t.im = h->img(s, B); return t; };
+  const ImgSlot none;
+
+  if (prologue_forked) cudaStreamWaitEvent(c.s, h->ev_pro_join, 0);
+  else enqueue_prologue(h, bt, nz, c, inputs_imaged);
+
+  const float *eps1, *eps2, *z3, *z4;
+  if (nz) { eps1 = nz->eps1; eps2 = nz->eps2; z3 = nz->z3; z4 = nz->z4; }
+  else {
+    eps1 = W + ar.eps1; eps2 = W + ar.eps2; z3 = W + ar.z3; z4 = W + ar.z4;   // sample_kernel steps the counter
   }
 
   const Ten t_obs = ten(bt.obs, ar.i_obs), t_obs2 = ten(bt.obs2, ar.i_obs2), t_act = ten(bt.act, ar.i_act);
@@ -724,6 +761,8 @@ static void enqueue_phase1(dsact_handle* h, const dsact_batch& bt, const dsact_n
     a.hi = h->buf.act_high; a.lo = h->buf.act_low; a.state = h->buf.state;
     a.B = B; a.A = A; a.min_log_std = (float)cf.min_log_std; a.max_log_std = (float)cf.max_log_std;
     a.img[0] = img_out(h, ar.i_new_act); a.img[1] = img_out(h, ar.i_act2);
+    a.out_q[0] = W + ar.outQ[0]; a.out_q[1] = W + ar.outQ[1];
+    a.advance_rng = nz ? 0 : 1;
     int blocks = (B + 7) / 8; if (blocks > 4 * h->num_sms) blocks = 4 * h->num_sms;
     launch_k(sample_kernel, dim3(blocks, 2), 256, 0, c, a); c.done();
   }
@@ -753,15 +792,15 @@ static void enqueue_phase1(dsact_handle* h, const dsact_batch& bt, const dsact_n
     launch_group(h, G, V_FWD, c);
   }
 
-  {
-    int blocks = (B + 255) / 256; if (blocks > 2 * h->num_sms) blocks = 2 * h->num_sms;
-    launch_k(std_sum_kernel, blocks, 256, 0, c, W + ar.outQ[0], W + ar.outQ[1], B, h->buf.state); c.done();
-  }
   h->pending_eps1 = eps1; h->pending_z3 = z3; h->pending_z4 = z4;
   c.check();
 }
 
-static void enqueue_phase2(dsact_handle* h, const dsact_batch& bt, int64_t global_batch, Ctx& c) {
+// `defer_reduce`: the caller enqueues enqueue_apply(.., reduce_slabs = true) next, which folds the split slabs itself
+static bool slabs_foldable(const dsact_handle* h) {
+  return h->tc() && ((uintptr_t)(h->W() + h->ar.slabs) & 15) == 0 && ((uintptr_t)h->buf.grads & 15) == 0;
+}
+static void enqueue_phase2(dsact_handle* h, const dsact_batch& bt, int64_t global_batch, Ctx& c, bool defer_reduce = false) {
   const dsact_config& cf = h->cfg;
   const Net &q = h->q, &pi = h->pi;
   const Arena& ar = h->ar;
@@ -776,10 +815,12 @@ static void enqueue_phase2(dsact_handle* h, const dsact_batch& bt, int64_t globa
   auto ten = [&](const float* f, const ImgSlot& s) { Ten t; t.f = const_cast<float*>(f); t.im = h->img(s, B); return t; };
   const ImgSlot none;
 
-  launch_k(ema_kernel, 1, 32, 0, c, h->buf.state, P + 2 * q.n + pi.n, invB, (float)cf.tau_b, cf.auto_alpha, (float)cf.alpha_fixed);
-  c.done();
+  StepScalars sc;
+  sc.tau_b = (float)cf.tau_b; sc.alpha_fixed = (float)cf.alpha_fixed; sc.inv_global_batch = invB;
+  sc.auto_alpha = cf.auto_alpha; sc.log_alpha = P + 2 * q.n + pi.n;
   {
     LossArgs a;
+    a.sc = sc;
     a.rew = bt.rew; a.done = bt.done;
     a.z3 = h->pending_z3; a.z4 = h->pending_z4;
     a.logp2 = W + ar.logp2; a.logp_new = W + ar.logp_new;
@@ -858,6 +899,7 @@ static void enqueue_phase2(dsact_handle* h, const dsact_batch& bt, int64_t globa
     a.B = B; a.A = A; a.min_log_std = (float)cf.min_log_std; a.max_log_std = (float)cf.max_log_std;
     a.inv_global_batch = invB;
     a.img = img_out(h, ar.i_dlogits);
+    a.sc = sc;
     int blocks = (B + 63) / 64; if (blocks > 2 * h->num_sms) blocks = 2 * h->num_sms; if (blocks < 1) blocks = 1;
     launch_k(policy_grad_kernel, blocks, 256, sizeof(float) * 2 * A, c, a); c.done();
   }
@@ -882,17 +924,17 @@ static void enqueue_phase2(dsact_handle* h, const dsact_batch& bt, int64_t globa
   launch_group(h, gwp, V_WGRAD, c);
 
   if (h->join_pending) { cudaStreamWaitEvent(c.s, h->ev_join, 0); h->join_pending = false; }
-  if (tc) {  // fold the weight-gradient split slabs into the flat gradient buffer
+  if (tc && !(defer_reduce && slabs_foldable(h))) {  // fold the weight-gradient split slabs into the flat gradient buffer
     const long long n = 2 * q.n + pi.n + 1;
     int blocks = (int)((n + 255) / 256); if (blocks > 4 * h->num_sms) blocks = 4 * h->num_sms;
-    launch_k(grad_reduce_kernel, blocks, 256, 0, c, G_, W + ar.slabs, n, ar.nslabs, n); c.done();
+    launch_k(grad_reduce_kernel, blocks, 256, 0, c, G_, W + ar.slabs, n, ar.nslabs, (long long)ar.slab_stride); c.done();
   }
-  launch_k(alpha_grad_kernel, 1, 32, 0, c, G_ + 2 * q.n + pi.n, h->buf.state, invB, -(float)cf.act_dim, B);
+  launch_k(phase2_tail_kernel, 1, 32, 0, c, G_ + 2 * q.n + pi.n, h->buf.state, sc, -(float)cf.act_dim, B);
   c.done();
   c.check();
 }
 
-static void enqueue_apply(dsact_handle* h, Ctx& c) {
+static void enqueue_apply(dsact_handle* h, Ctx& c, bool reduce_slabs = false) {
   const dsact_config& cf = h->cfg;
   ApplyArgs a;
   a.params = h->buf.params; a.targets = h->buf.targets; a.grads = h->buf.grads; a.m = h->buf.adam_m; a.v = h->buf.adam_v;
@@ -902,11 +944,11 @@ static void enqueue_apply(dsact_handle* h, Ctx& c) {
   a.lr_q = cf.lr_q; a.lr_pi = cf.lr_pi; a.lr_alpha = cf.lr_alpha;
   a.b1 = cf.adam_beta1; a.b2 = cf.adam_beta2; a.eps = (float)cf.adam_eps; a.tau = (float)cf.tau;
   a.omb1 = (float)(1.0 - cf.adam_beta1); a.b2f = (float)cf.adam_beta2; a.omb2 = (float)(1.0 - cf.adam_beta2);
+  a.slabs = nullptr; a.nslabs = 0; a.slab_stride = 0;
+  if (reduce_slabs && slabs_foldable(h)) { a.slabs = h->W() + h->ar.slabs; a.nslabs = h->ar.nslabs; a.slab_stride = h->ar.slab_stride; }
   int blocks = (int)((a.n_all + 255) / 256);
   if (blocks > 8 * h->num_sms) blocks = 8 * h->num_sms;
-  launch_k(apply_kernel, blocks, 256, 0, c, a);
-  c.done();
-  launch_k(advance_kernel, 1, 32, 0, c, h->buf.state, cf.delay_update);
+  launch_k(apply_kernel, blocks, 256, 0, c, a);   // its last block also advances the step counters
   c.done();
   c.check();
 }
@@ -1088,6 +1130,8 @@ int dsact_create(const dsact_config* cfg, int device, dsact_handle** out) {
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_pro_fork, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_pro_join, cudaEventDisableTiming);
   if (e != cudaSuccess) { delete h; return fail(DSACT_ECUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(e)); }
   *out = h;
   return DSACT_OK;
@@ -1101,6 +1145,8 @@ void dsact_destroy(dsact_handle* h) {
   cudaStreamDestroy(h->side_stream);
   cudaEventDestroy(h->ev_fork);
   cudaEventDestroy(h->ev_join);
+  cudaEventDestroy(h->ev_pro_fork);
+  cudaEventDestroy(h->ev_pro_join);
   delete h;
 }
 
@@ -1114,7 +1160,7 @@ int dsact_bind(dsact_handle* h, const dsact_buffers* b) {
   h->arena_imaged = false;
   if (h->tc()) {  // bias regions of the wgrad slabs are never written by a kernel: they must read as zero
     CUDA_TRY(cudaSetDevice(h->device));
-    CUDA_TRY(cudaMemset(h->W() + h->ar.slabs, 0, sizeof(float) * (size_t)h->ar.nslabs * (2 * h->q.n + h->pi.n + 1)));
+    CUDA_TRY(cudaMemset(h->W() + h->ar.slabs, 0, sizeof(float) * (size_t)h->ar.nslabs * h->ar.slab_stride));
   }
   h->dev_iter = -1;
   h->dev_rb_size = -1;
@@ -1212,8 +1258,8 @@ int dsact_step(dsact_handle* h, const dsact_batch* batch, const dsact_noise* noi
   skey.size = imaged ? 1 : 0;
   rc = run(h, (cudaStream_t)stream, skey, [&](Ctx& c) {
     enqueue_phase1(h, bt, np, c, imaged);
-    enqueue_phase2(h, bt, bt.batch, c);
-    enqueue_apply(h, c);
+    enqueue_phase2(h, bt, bt.batch, c, true);
+    enqueue_apply(h, c, true);
   });
   if (rc) return rc;
   h->pending = bt; h->pending_batch = bt.batch;
@@ -1317,11 +1363,12 @@ int dsact_replay_step(dsact_handle* h, int32_t batch, int64_t size, const int64_
   GraphKey key = make_key(K_REPLAY_STEP, &bt, np, batch);
   key.idx = idx;
   rc = run(h, (cudaStream_t)stream, key, [&](Ctx& c) {
+    const bool forked = fork_prologue(h, bt, np, c, true);   // weight images, noise, clears: beside the gather
     enqueue_gather(h, batch, idx, c);
     if (!idx && np) { launch_k(rng_advance_kernel, 1, 32, 0, c, h->buf.state); c.done(); }
-    enqueue_phase1(h, bt, np, c, true);  // device noise (np == null) advances the counter itself, after the index draw
-    enqueue_phase2(h, bt, batch, c);
-    enqueue_apply(h, c);
+    enqueue_phase1(h, bt, np, c, true, forked);  // device noise (np == null): phase1 advances the counter after the join
+    enqueue_phase2(h, bt, batch, c, true);
+    enqueue_apply(h, c, true);
   });
   if (rc) return rc;
   h->pending = bt; h->pending_batch = batch;
@@ -1348,8 +1395,8 @@ int dsact_profile_step(dsact_handle* h, const dsact_batch* batch, const dsact_no
   CUDA_TRY(cudaEventCreate(&e0));
   CUDA_TRY(cudaEventRecord(e0, s));
   enqueue_phase1(h, bt, np, c);
-  enqueue_phase2(h, bt, bt.batch, c);
-  enqueue_apply(h, c);
+  enqueue_phase2(h, bt, bt.batch, c, true);
+  enqueue_apply(h, c, true);
   cudaError_t e = cudaStreamSynchronize(s);
   memset(out, 0, sizeof(*out));
   cudaEvent_t prev = e0;

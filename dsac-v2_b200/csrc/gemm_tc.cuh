@@ -219,6 +219,17 @@ __device__ __forceinline__ void act_fwdN(float (&v)[NV], float (&d)[NV], int act
 __device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 lo_k, __nv_bfloat16 hi_k) {  // lower k in the low half
   return (uint32_t)__bfloat16_as_ushort(lo_k) | ((uint32_t)__bfloat16_as_ushort(hi_k) << 16);
 }
+// hi/lo split of two neighbouring K elements straight into packed words (x0 = lower k -> low half).  The packed
+// convert (F2FP.BF16.PACK_AB) runs on the ALU; two scalar F2F per element would queue on the 16-lane XU next to MUFU.
+__device__ __forceinline__ uint32_t cvt_bf16x2(float lo_k, float hi_k) {
+  uint32_t w;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w) : "f"(hi_k), "f"(lo_k));
+  return w;
+}
+__device__ __forceinline__ void split_pack2(float x0, float x1, uint32_t& whi, uint32_t& wlo) {
+  whi = cvt_bf16x2(x0, x1);
+  wlo = cvt_bf16x2(x0 - __uint_as_float(whi << 16), x1 - __uint_as_float(whi & 0xffff0000u));
+}
 
 // What one epilogue chunk needs.  In the tcgen05 modes `Zout`/`Zin` carry act'(z) (computed where erf is already
 // at hand) instead of z, so the backward epilogue is a load and a multiply.
@@ -324,11 +335,7 @@ __device__ __forceinline__ void epi_chunk(float (&v)[16], const EpiArgs& E, int 
   if (want_rows || E.img) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      __nv_bfloat16 h0, l0, h1, l1;
-      split_bf16(v[2 * i], h0, l0);
-      split_bf16(v[2 * i + 1], h1, l1);
-      whi[i] = pack_bf16(h0, h1);
-      wlo[i] = pack_bf16(l0, l1);
+      split_pack2(v[2 * i], v[2 * i + 1], whi[i], wlo[i]);
     }
     if (E.img && lane < rows_ok) {  // this lane's row: 16 bf16 per plane as 16-byte vectors (pitch % 8 == 0, n0c % 16 == 0)
       __nv_bfloat16* hp = E.img + (size_t)(mbase + lane) * E.img_pitch + n0c;
@@ -557,11 +564,7 @@ __global__ void image_kernel(const __grid_constant__ ImgGroup g) {
         else if (c >= J.seg_dst0[1] && c < J.seg_dst0[1] + J.seg_w[1]) v = __ldg(src + J.seg_src0[1] + (c - J.seg_dst0[1]));
         x[e] = v;
       }
-      __nv_bfloat16 h0, l0, h1, l1;
-      split_bf16(x[0], h0, l0);
-      split_bf16(x[1], h1, l1);
-      whi[k] = pack_bf16(h0, h1);
-      wlo[k] = pack_bf16(l0, l1);
+      split_pack2(x[0], x[1], whi[k], wlo[k]);
     }
     __nv_bfloat16* dst = J.dst + (size_t)r * J.pitch + c0;
     *reinterpret_cast<uint4*>(dst) = make_uint4(whi[0], whi[1], whi[2], whi[3]);

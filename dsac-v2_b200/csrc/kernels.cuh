@@ -23,6 +23,7 @@ enum {
   ST_RNG_CTR = 10,                     // uint32 step counter of the device generator
   ST_ITER = 11,                        // int32 iteration the next apply will use (dsac_v2.py:324)
   ST_RB_SIZE = 12,                     // [12],[13] int64 number of valid replay rows
+  ST_TICKET = 14,                      // int32: blocks of apply_kernel that have finished (the last one advances the counters)
   ST_ACC = 16,                         // 16 sums then 16 mins
   ST_STATS = 48,
 };
@@ -137,6 +138,7 @@ __global__ void begin_step_kernel(float* __restrict__ state) {
   if (t < 16) state[ST_ACC + t] = 0.f;
   else if (t < 32) state[ST_ACC + t] = __int_as_float(0x7f800000);
   if (t < 2) state[ST_STDSUM + t] = 0.f;
+  if (t == 2) reinterpret_cast<int*>(state)[ST_TICKET] = 0;
 }
 
 // Device noise: eps1, eps2 [B,A] and z3, z4 [B] (SURVEY Appendix B keeps only the draws that matter).
@@ -236,11 +238,15 @@ struct SampleArgs {
   int B, A;
   float min_log_std, max_log_std;
   ImgOut img[2];
+  const float* out_q[2];   // Q_k(s,a) [B,2]: the blockIdx.y = 1 half also sums softplus(raw std) into ST_STDSUM, the
+                           // input of the mean_std EMA (dsac_v2.py:233-241)
+  int advance_rng;         // device noise/indices were drawn with the current counter: step it (all readers are done)
 };
 __global__ void sample_kernel(const __grid_constant__ SampleArgs a) {
   pdl_sync();
   __shared__ float red[2 * 32];
   const int which = blockIdx.y;
+  if (a.advance_rng && blockIdx.x == 0 && which == 0 && threadIdx.x == 0) reinterpret_cast<uint32_t*>(a.state)[ST_RNG_CTR] += 1u;
   const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
   const int A = a.A;
   const float* __restrict__ logits = a.logits[which];
@@ -271,37 +277,34 @@ __global__ void sample_kernel(const __grid_constant__ SampleArgs a) {
       atomicAdd(a.state + ST_ACC + ACC_TANH_MEAN, sums[0]);
       atomicAdd(a.state + ST_ACC + ACC_PI_STD, sums[1]);
     }
+  } else {
+    float sd[2] = {0.f, 0.f};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.B; i += gridDim.x * blockDim.x) {
+      sd[0] += softplus_f(a.out_q[0][2 * i + 1]);
+      sd[1] += softplus_f(a.out_q[1][2 * i + 1]);
+    }
+    block_sum<2>(sd, red);
+    if (threadIdx.x == 0) {
+      atomicAdd(a.state + ST_STDSUM, sd[0]);
+      atomicAdd(a.state + ST_STDSUM + 1, sd[1]);
+    }
   }
 }
 
-// Sum of the critics' std over the local rows (input of the mean_std EMA, dsac_v2.py:233-241).
-__global__ void std_sum_kernel(const float* __restrict__ out_q1, const float* __restrict__ out_q2, int B,
-                               float* __restrict__ state) {
-  pdl_sync();
-  __shared__ float red[2 * 32];
-  float s[2] = {0.f, 0.f};
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B; i += gridDim.x * blockDim.x) {
-    s[0] += softplus_f(out_q1[2 * i + 1]);
-    s[1] += softplus_f(out_q2[2 * i + 1]);
-  }
-  block_sum<2>(s, red);
-  if (threadIdx.x == 0) {
-    atomicAdd(state + ST_STDSUM, s[0]);
-    atomicAdd(state + ST_STDSUM + 1, s[1]);
-  }
+// mean_std EMA (dsac_v2.py:233-241) and the temperature this step uses (dsac_v2.py:140-148), from the carried state
+// and the (all-reduced) std sums of phase 1.  Every block of the loss / policy-gradient kernels evaluates these three
+// scalars itself; phase2_tail_kernel commits them to the state at the end of the backward pass.
+struct StepScalars {
+  float tau_b, alpha_fixed, inv_global_batch;
+  int auto_alpha;
+  const float* log_alpha;
+};
+__device__ __forceinline__ float step_mean_std(const float* state, const StepScalars& p, int k) {
+  const float mean = state[ST_STDSUM + k] * p.inv_global_batch;
+  const float old = state[ST_MEAN_STD1 + k];
+  return old < 0.f ? mean : (1.f - p.tau_b) * old + p.tau_b * mean;
 }
-
-// mean_std EMA (dsac_v2.py:233-241) + the temperature this step uses (dsac_v2.py:140-148).
-__global__ void ema_kernel(float* __restrict__ state, const float* __restrict__ log_alpha, float inv_global_batch,
-                           float tau_b, int auto_alpha, float alpha_fixed) {
-  pdl_sync();
-  if (threadIdx.x < 2) {
-    const float mean = state[ST_STDSUM + threadIdx.x] * inv_global_batch;
-    const float old = state[ST_MEAN_STD1 + threadIdx.x];
-    state[ST_MEAN_STD1 + threadIdx.x] = old < 0.f ? mean : (1.f - tau_b) * old + tau_b * mean;
-  }
-  if (threadIdx.x == 2) state[ST_ALPHA_USED] = auto_alpha ? expf(*log_alpha) : alpha_fixed;
-}
+__device__ __forceinline__ float step_alpha(const StepScalars& p) { return p.auto_alpha ? expf(*p.log_alpha) : p.alpha_fixed; }
 
 // Fused clipped-Gaussian distributional TD target + three-refinement critic loss + actor/alpha loss terms
 // and all output-layer gradients (dsac_v2.py:218-318).  One thread per sample.
@@ -317,12 +320,13 @@ struct LossArgs {
   int B;
   float gamma, inv_global_batch;
   ImgOut img_q[2], img_qa[2];
+  StepScalars sc;
 };
 __global__ void loss_kernel(const __grid_constant__ LossArgs a) {
   pdl_sync();
   __shared__ float red[10 * 32];
-  const float m[2] = {a.state[ST_MEAN_STD1], a.state[ST_MEAN_STD2]};
-  const float alpha = a.state[ST_ALPHA_USED];
+  const float m[2] = {step_mean_std(a.state, a.sc, 0), step_mean_std(a.state, a.sc, 1)};
+  const float alpha = step_alpha(a.sc);
   const float invB = a.inv_global_batch;
   // sums: q1 q2 s1 s2 loss_pi loss_q logp | gb(q1 mean, q1 raw, q2 mean) ; q2 raw handled separately below
   float s[10] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -403,6 +407,7 @@ struct PolicyGradArgs {
   int B, A;
   float min_log_std, max_log_std, inv_global_batch;
   ImgOut img;
+  StepScalars sc;
 };
 __global__ void policy_grad_kernel(const __grid_constant__ PolicyGradArgs a) {
   pdl_sync();
@@ -411,7 +416,7 @@ __global__ void policy_grad_kernel(const __grid_constant__ PolicyGradArgs a) {
   const int A = a.A;
   for (int i = threadIdx.x; i < 2 * A; i += blockDim.x) gb[i] = 0.f;
   __syncthreads();
-  const float coef = a.state[ST_ALPHA_USED] * a.inv_global_batch;  // dL/dlogp
+  const float coef = step_alpha(a.sc) * a.inv_global_batch;  // dL/dlogp
   for (int j = lane; j < A; j += 32) {
     const float scale = 0.5f * (a.hi[j] - a.lo[j]);
     float gb_mean = 0.f, gb_ls = 0.f;
@@ -452,6 +457,11 @@ struct ApplyArgs {
   int delay_update, auto_alpha;
   double lr_q, lr_pi, lr_alpha, b1, b2;
   float omb1, b2f, omb2, eps, tau;  // (float)(1-beta1), (float)beta2, (float)(1-beta2) formed in double on the host
+  // tcgen05 modes, single-call steps: the weight-gradient split slabs are folded in here (grads += sum of slabs, stored
+  // back so that the caller's .grad views hold the totals) instead of by a separate grad_reduce launch
+  const float* slabs;
+  int nslabs;
+  long long slab_stride;
 };
 // torch.optim.Adam single-tensor step (amsgrad / weight decay off)
 __device__ __forceinline__ float adam_update(float w, float g, float& m, float& v, float step_size, float bc2_sqrt,
@@ -494,6 +504,13 @@ __global__ void apply_kernel(const __grid_constant__ ApplyArgs a) {
         const float4 T4 = reinterpret_cast<const float4*>(a.targets)[gi];
         t[0] = T4.x; t[1] = T4.y; t[2] = T4.z; t[3] = T4.w;
       }
+      if (a.nslabs > 0) {
+        for (int k = 0; k < a.nslabs; ++k) {
+          const float4 p = __ldg(reinterpret_cast<const float4*>(a.slabs + (size_t)k * a.slab_stride) + gi);
+          g[0] += p.x; g[1] += p.y; g[2] += p.z; g[3] += p.w;
+        }
+        reinterpret_cast<float4*>(a.grads)[gi] = make_float4(g[0], g[1], g[2], g[3]);
+      }
     } else {
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
@@ -501,6 +518,10 @@ __global__ void apply_kernel(const __grid_constant__ ApplyArgs a) {
         const bool in = i < a.n_all;
         w[e] = in ? a.params[i] : 0.f; g[e] = in ? a.grads[i] : 0.f; m[e] = in ? a.m[i] : 0.f; v[e] = in ? a.v[i] : 0.f;
         t[e] = (in && i < n_targets) ? a.targets[i] : 0.f;
+        if (in && a.nslabs > 0) {
+          for (int k = 0; k < a.nslabs; ++k) g[e] += a.slabs[(size_t)k * a.slab_stride + i];
+          a.grads[i] = g[e];
+        }
       }
     }
     bool touched = false;
@@ -536,15 +557,17 @@ __global__ void apply_kernel(const __grid_constant__ ApplyArgs a) {
       }
     }
   }
-}
-// Runs after apply_kernel: advance the counters it read.
-__global__ void advance_kernel(float* __restrict__ state, int delay_update) {
-  pdl_sync();
-  int* sti = reinterpret_cast<int*>(state);
+  // the block that finishes last advances the counters every block read at its start
+  __syncthreads();
   if (threadIdx.x == 0) {
-    sti[ST_ADAM_Q] += 1;
-    if (sti[ST_ITER] % delay_update == 0) sti[ST_ADAM_PI] += 1;
-    sti[ST_ITER] += 1;
+    int* stw = reinterpret_cast<int*>(a.state);
+    __threadfence();
+    if (atomicAdd(stw + ST_TICKET, 1) == (int)gridDim.x - 1) {
+      stw[ST_ADAM_Q] += 1;
+      if (delayed) stw[ST_ADAM_PI] += 1;
+      stw[ST_ITER] += 1;
+      stw[ST_TICKET] = 0;
+    }
   }
 }
 __global__ void set_iter_kernel(float* __restrict__ state, int iteration) {
@@ -560,13 +583,20 @@ __global__ void rng_advance_kernel(float* __restrict__ state) {
   if (threadIdx.x == 0) reinterpret_cast<uint32_t*>(state)[ST_RNG_CTR] += 1u;
 }
 
-// Gradient of log_alpha (dsac_v2.py:312-318): -(mean(logp_new) + target_entropy).
+// End of the backward pass: gradient of log_alpha (dsac_v2.py:312-318) = -(mean(logp_new) + target_entropy), and the
+// commit of this step's mean_std EMA and temperature to the state (every earlier reader used the carried values).
 // `rows` = local shard size, so that per-rank values sum to the global gradient under data parallelism.
-__global__ void alpha_grad_kernel(float* __restrict__ grad_log_alpha, const float* __restrict__ state,
-                                  float inv_global_batch, float target_entropy, int rows) {
+__global__ void phase2_tail_kernel(float* __restrict__ grad_log_alpha, float* __restrict__ state, const StepScalars sc,
+                                   float target_entropy, int rows) {
   pdl_sync();
-  if (threadIdx.x == 0)
-    *grad_log_alpha = -(state[ST_ACC + ACC_LOGP] + (float)rows * target_entropy) * inv_global_batch;
+  const int t = threadIdx.x;
+  float val = 0.f;
+  if (t < 2) val = step_mean_std(state, sc, t);
+  else if (t == 2) val = step_alpha(sc);
+  else if (t == 3) *grad_log_alpha = -(state[ST_ACC + ACC_LOGP] + (float)rows * target_entropy) * sc.inv_global_batch;
+  __syncwarp();
+  if (t < 2) state[ST_MEAN_STD1 + t] = val;
+  else if (t == 2) state[ST_ALPHA_USED] = val;
 }
 
 // tb_info (dsac_v2.py:188-202) from the accumulators.
