@@ -246,6 +246,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_chain_kernel(const __grid_co
 #define ZIN_BUF(i) (st_f32 + ((i) ? zin1_off : 0))
     uint64_t* zb = zbar + 2 * ew;
     uint32_t zphase[2] = {0, 0};
+    // shared-memory side of the TMA tiles is swizzled (tc_host.cuh): 16-byte chunk index of this lane's row
+    const int sw64 = (lane >> 1) & 3, sw32 = (lane >> 2) & 1;
     const int mbase = m0 + quarter * 32;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
     for (int j = 0; j < nl; ++j) {
@@ -295,7 +297,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_chain_kernel(const __grid_co
           const float4* zr = reinterpret_cast<const float4*>(ZIN_BUF(k & 1) + lane * 16);
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const float4 d = zr[q];   // rows >= M and columns >= N arrive as zeros (TMA out-of-bounds fill)
+            const float4 d = zr[q ^ sw64];   // rows >= M and columns >= N arrive as zeros (TMA out-of-bounds fill)
             v[4 * q] *= d.x; v[4 * q + 1] *= d.y; v[4 * q + 2] *= d.z; v[4 * q + 3] *= d.w;
           }
           if (Lj.colsum) {  // bias gradient: column sums over the warp's 32 rows by a reduce-scatter of the 16 columns
@@ -369,16 +371,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_chain_kernel(const __grid_co
           if (st_z) {
             float4* zr = reinterpret_cast<float4*>(st_f32 + lane * 16);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) zr[q] = make_float4(d[4 * q], d[4 * q + 1], d[4 * q + 2], d[4 * q + 3]);
+            for (int q = 0; q < 4; ++q) zr[q ^ sw64] = make_float4(d[4 * q], d[4 * q + 1], d[4 * q + 2], d[4 * q + 3]);
           }
           if (Lj.img) {
             uint4* hr = reinterpret_cast<uint4*>(st_hi + lane * 8);
-            hr[0] = make_uint4(whi[0], whi[1], whi[2], whi[3]);
-            hr[1] = make_uint4(whi[4], whi[5], whi[6], whi[7]);
+            hr[sw32] = make_uint4(whi[0], whi[1], whi[2], whi[3]);
+            hr[sw32 ^ 1] = make_uint4(whi[4], whi[5], whi[6], whi[7]);
             if (PLANES2) {
               uint4* lr = reinterpret_cast<uint4*>(st_lo + lane * 8);
-              lr[0] = make_uint4(wlo[0], wlo[1], wlo[2], wlo[3]);
-              lr[1] = make_uint4(wlo[4], wlo[5], wlo[6], wlo[7]);
+              lr[sw32] = make_uint4(wlo[0], wlo[1], wlo[2], wlo[3]);
+              lr[sw32 ^ 1] = make_uint4(wlo[4], wlo[5], wlo[6], wlo[7]);
             }
           }
           fence_async_smem();

@@ -199,10 +199,11 @@ struct Ctx {
 };
 
 // Every kernel goes out with the programmatic-dependent-launch attribute (each kernel begins with griddepcontrol.wait),
-// so that inside the captured graph a kernel's launch and prologue overlap its predecessor's tail.  DSACT_PDL=1 enables (measured neutral at B=4096, so it is off by default).
+// so that inside the captured graph a kernel's launch and prologue overlap its predecessor's tail (measured: -18 us of
+// a 280 us step at B=4096, tools/pdl_ab.sh).  DSACT_PDL=0 turns it off.
 static bool pdl_enabled() {
   static int v = -1;
-  if (v < 0) { const char* e = getenv("DSACT_PDL"); v = (e && e[0] == '1') ? 1 : 0; }  // measured neutral inside the graph: off unless asked
+  if (v < 0) { const char* e = getenv("DSACT_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
   return v == 1;
 }
 template <typename... KArgs, typename... Args>
@@ -277,7 +278,9 @@ static void launch_simt(const dsact_handle* h, GemmGroup& g, int variant, Ctx& c
 static bool g_tc_attr_done = false;
 
 // Lower the group onto tcgen05: images instead of fp32 operands, TMA tensor maps, 128 x bn tiles.
-static void launch_tc(const dsact_handle* h, Group& G, int variant, Ctx& c) {
+// `max_ctas` > 0: issue the group as several launches of at most that many CTAs (one CTA occupies an SM), which leaves
+// the remaining SMs to a concurrent branch of the step graph for the whole duration.
+static void launch_tc(const dsact_handle* h, Group& G, int variant, Ctx& c, int max_ctas = 0) {
   static TcGroup t;  // ~5 KiB; host-side scratch (single trainer thread per process is the documented contract)
   memset(&t, 0, sizeof(t));
   t.n = G.n;
@@ -340,15 +343,26 @@ static void launch_tc(const dsact_handle* h, Group& G, int variant, Ctx& c) {
     cudaFuncSetAttribute(tc_gemm_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     g_tc_attr_done = true;
   }
-  if (planes == 2) {
-    if (variant == V_FWD) launch_k(tc_gemm_kernel<false, false, true>, grid, TC_THREADS, smem, c, t, stages, stage_b);
-    else if (variant == V_DGRAD) launch_k(tc_gemm_kernel<false, true, true>, grid, TC_THREADS, smem, c, t, stages, stage_b);
-    else launch_k(tc_gemm_kernel<true, true, true>, grid, TC_THREADS, smem, c, t, stages, stage_b);
-  } else {
-    if (variant == V_FWD) launch_k(tc_gemm_kernel<false, false, false>, grid, TC_THREADS, smem, c, t, stages, stage_b);
-    else if (variant == V_DGRAD) launch_k(tc_gemm_kernel<false, true, false>, grid, TC_THREADS, smem, c, t, stages, stage_b);
-    else launch_k(tc_gemm_kernel<true, true, false>, grid, TC_THREADS, smem, c, t, stages, stage_b);
+  const int total = grid;
+  if (max_ctas > 0 && !debug && total > max_ctas) {  // equal slices, none above the bound
+    const int parts = (total + max_ctas - 1) / max_ctas;
+    grid = (total + parts - 1) / parts;
   }
+  for (int t0 = 0; t0 < total; t0 += grid) {
+    t.tile0 = t0;
+    const int n = total - t0 < grid ? total - t0 : grid;
+    if (t0 > 0) c.launches++;
+    if (planes == 2) {
+      if (variant == V_FWD) launch_k(tc_gemm_kernel<false, false, true>, n, TC_THREADS, smem, c, t, stages, stage_b);
+      else if (variant == V_DGRAD) launch_k(tc_gemm_kernel<false, true, true>, n, TC_THREADS, smem, c, t, stages, stage_b);
+      else launch_k(tc_gemm_kernel<true, true, true>, n, TC_THREADS, smem, c, t, stages, stage_b);
+    } else {
+      if (variant == V_FWD) launch_k(tc_gemm_kernel<false, false, false>, n, TC_THREADS, smem, c, t, stages, stage_b);
+      else if (variant == V_DGRAD) launch_k(tc_gemm_kernel<false, true, false>, n, TC_THREADS, smem, c, t, stages, stage_b);
+      else launch_k(tc_gemm_kernel<true, true, false>, n, TC_THREADS, smem, c, t, stages, stage_b);
+    }
+  }
+  grid = total;
   if (debug && t.dbg) {  // per-CTA phase breakdown (ns): setup | first TMA landed | MMA issue done | accumulator ready | epilogue | teardown
     cudaStreamSynchronize(c.s);
     std::vector<unsigned long long> hbuf(TC_DBG_SLOTS * (size_t)grid);
@@ -367,12 +381,12 @@ static void launch_tc(const dsact_handle* h, Group& G, int variant, Ctx& c) {
   }
 }
 
-static void launch_group(const dsact_handle* h, Group& G, int variant, Ctx& c) {
+static void launch_group(const dsact_handle* h, Group& G, int variant, Ctx& c, int max_ctas = 0) {
   if (G.n == 0) return;
   double flops = 0.0;
   for (int i = 0; i < G.n; ++i) flops += 2.0 * G.prob(i).M * G.prob(i).N * ((double)G.prob(i).K[0] + G.prob(i).K[1]);
   if (h->tc()) {
-    launch_tc(h, G, variant, c);
+    launch_tc(h, G, variant, c, max_ctas);
     c.done(CLS_GEMM_FWD + variant, flops);
   } else {
     G.g.n = G.n < MAXG ? G.n : MAXG;
@@ -460,8 +474,10 @@ static void add_wgrad(Group& G, const Net& net, int j, float* Gw, int col0, int 
 // fp32 -> image conversions (TC modes)
 struct ImgBatch {
   ImgGroup g;
+  bool overflow = false;
   ImgBatch() { g.n = 0; }
   void add(const float* src, int ld_src, const Img& dst, int rows, int w0, int w1 = 0, int dst1 = 0) {
+    if (g.n >= IMG_MAXJ) { overflow = true; return; }
     ImgJob& j = g.j[g.n++];
     memset(&j, 0, sizeof(j));
     j.src = src; j.dst = dst.p; j.rows = rows; j.ld_src = ld_src;
@@ -469,7 +485,9 @@ struct ImgBatch {
     j.seg_w[1] = w1; j.seg_src0[1] = w0; j.seg_dst0[1] = dst1;
     j.pitch = dst.pitch; j.fill_w = w1 > 0 ? dst1 + w1 : w0; j.plane = dst.plane;
   }
+  void reserve(const dsact_handle* h, Ctx& c, int jobs) { if (g.n + jobs > IMG_MAXJ) launch(h, c); }   // flush when full
   void launch(const dsact_handle* h, Ctx& c) {
+    if (overflow) { c.err = cudaErrorInvalidValue; return; }
     if (g.n == 0) return;
     g.planes = h->passes() == 3 ? 2 : 1;
     int grid = 0;
@@ -628,7 +646,17 @@ static void chain_dgrad_pass(ChainBuild& cb, const dsact_handle* h, const Net& n
 // ---- enqueue: pieces of one update ---------------------------------------------
 // Everything of a step that depends on neither the minibatch gather nor a forward pass: accumulator clears, the
 // gradient memset, the bf16 images of all weights (and of a caller-supplied batch), the device noise.
-static void enqueue_prologue(dsact_handle* h, const dsact_batch& bt, const dsact_noise* nz, Ctx& c, bool inputs_imaged) {
+static void enqueue_noise(dsact_handle* h, int B, Ctx& c) {
+  const Arena& ar = h->ar;
+  float* W = h->W();
+  const int A = h->cfg.act_dim;
+  const int total = (B * A + 1) / 2 * 2 + (B + 1) / 2 * 2;
+  int blocks = (total / 2 + 255) / 256; if (blocks < 1) blocks = 1;
+  launch_k(noise_kernel, blocks, 256, 0, c, W + ar.eps1, W + ar.eps2, W + ar.z3, W + ar.z4, B, A, h->seed, h->buf.state);
+  c.done();
+}
+static void enqueue_prologue(dsact_handle* h, const dsact_batch& bt, const dsact_noise* nz, Ctx& c, bool inputs_imaged,
+                             bool with_noise = true) {
   const dsact_config& cf = h->cfg;
   const Net &q = h->q, &pi = h->pi;
   const Arena& ar = h->ar;
@@ -647,19 +675,22 @@ static void enqueue_prologue(dsact_handle* h, const dsact_batch& bt, const dsact
     ImgBatch ib;
     for (int n = 0; n < 2; ++n)
       for (int j = 0; j <= q.L; ++j) {
+        ib.reserve(h, c, 1);
         const Img im = h->img(ar.i_wq[n][j], q.s[j + 1]);
         if (j == 0) ib.add(Qb[n] + q.w[0], O + A, im, q.s[1], O, A, ar.kpad_q0);
         else ib.add(Qb[n] + q.w[j], q.s[j], im, q.s[j + 1], q.s[j]);
       }
+    ib.reserve(h, c, pi.L + 2);
     for (int j = 0; j <= pi.L; ++j) ib.add(PIb[0] + pi.w[j], pi.s[j], h->img(ar.i_wpi[0][j], pi.s[j + 1]), pi.s[j + 1], pi.s[j]);
     if (!inputs_imaged) ib.add(bt.obs, O, h->img(ar.i_obs, B), B, O);
-    ib.launch(h, c);
     for (int n = 2; n < 4; ++n)
       for (int j = 0; j <= q.L; ++j) {
+        ib.reserve(h, c, 1);
         const Img im = h->img(ar.i_wq[n][j], q.s[j + 1]);
         if (j == 0) ib.add(Qb[n] + q.w[0], O + A, im, q.s[1], O, A, ar.kpad_q0);
         else ib.add(Qb[n] + q.w[j], q.s[j], im, q.s[j + 1], q.s[j]);
       }
+    ib.reserve(h, c, pi.L + 3);
     for (int j = 0; j <= pi.L; ++j) ib.add(PIb[1] + pi.w[j], pi.s[j], h->img(ar.i_wpi[1][j], pi.s[j + 1]), pi.s[j + 1], pi.s[j]);
     if (!inputs_imaged) {
       ib.add(bt.obs2, O, h->img(ar.i_obs2, B), B, O);
@@ -668,12 +699,8 @@ static void enqueue_prologue(dsact_handle* h, const dsact_batch& bt, const dsact
     ib.launch(h, c);
   }
 
-  if (!nz) {  // device noise; the counter it reads is advanced by the caller once every reader of this step has run
-    const int total = (B * A + 1) / 2 * 2 + (B + 1) / 2 * 2;
-    int blocks = (total / 2 + 255) / 256; if (blocks < 1) blocks = 1;
-    launch_k(noise_kernel, blocks, 256, 0, c, W + ar.eps1, W + ar.eps2, W + ar.z3, W + ar.z4, B, A, h->seed, h->buf.state);
-    c.done();
-  }
+  // device noise; the counter it reads is stepped by sample_kernel, once every reader of this step has run
+  if (!nz && with_noise) enqueue_noise(h, B, c);
   c.check();
 }
 
@@ -684,7 +711,7 @@ static bool fork_prologue(dsact_handle* h, const dsact_batch& bt, const dsact_no
   cudaEventRecord(h->ev_pro_fork, c.s);
   cudaStreamWaitEvent(c.side, h->ev_pro_fork, 0);
   Ctx cs{c.side, 0, cudaSuccess};
-  enqueue_prologue(h, bt, nz, cs, inputs_imaged);
+  enqueue_prologue(h, bt, nz, cs, inputs_imaged, false);   // the noise goes behind the gather: balances the two branches
   cudaEventRecord(h->ev_pro_join, c.side);
   c.launches += cs.launches;
   if (cs.err != cudaSuccess && c.err == cudaSuccess) c.err = cs.err;
@@ -705,8 +732,12 @@ static void enqueue_phase1(dsact_handle* h, const dsact_batch& bt, const dsact_n
   auto ten = [&](const float* f, const ImgSlot& s) { Ten t; t.f = const_cast<float*>(f); t.im = h->img(s, B); return t; };
   const ImgSlot none;
 
-  if (prologue_forked) cudaStreamWaitEvent(c.s, h->ev_pro_join, 0);
-  else enqueue_prologue(h, bt, nz, c, inputs_imaged);
+  if (prologue_forked) {
+    if (!nz) enqueue_noise(h, B, c);
+    cudaStreamWaitEvent(c.s, h->ev_pro_join, 0);
+  } else {
+    enqueue_prologue(h, bt, nz, c, inputs_imaged);
+  }
 
   const float *eps1, *eps2, *z3, *z4;
   if (nz) { eps1 = nz->eps1; eps2 = nz->eps2; z3 = nz->z3; z4 = nz->z4; }
@@ -831,8 +862,8 @@ static void enqueue_phase2(dsact_handle* h, const dsact_batch& bt, int64_t globa
     }
     a.state = h->buf.state; a.B = B; a.gamma = (float)cf.gamma; a.inv_global_batch = invB;
     for (int k = 0; k < 2; ++k) { a.img_q[k] = img_out(h, ar.i_dOut[k]); a.img_qa[k] = img_out(h, ar.i_dOut[4 + k]); }
-    int blocks = (B + 255) / 256; if (blocks > 2 * h->num_sms) blocks = 2 * h->num_sms;
-    launch_k(loss_kernel, blocks, 256, 0, c, a); c.done();
+    int blocks = (B + 63) / 64; if (blocks > 4 * h->num_sms) blocks = 4 * h->num_sms;   // latency bound: spread over the SMs
+    launch_k(loss_kernel, blocks, 64, 0, c, a); c.done();
   }
   const int passes[4] = {0, 1, 4, 5};
   const Ten t_obs = ten(bt.obs, ar.i_obs), t_act = ten(bt.act, ar.i_act);
@@ -879,7 +910,10 @@ static void enqueue_phase2(dsact_handle* h, const dsact_batch& bt, int64_t globa
       cudaEventRecord(h->ev_fork, c.s);
       cudaStreamWaitEvent(c.side, h->ev_fork, 0);
       Ctx cs{c.side, 0, cudaSuccess};
-      launch_group(h, gw, V_WGRAD, cs);
+      // the policy backward chain needs ceil(B/128) whole SMs: keep them free of weight-gradient CTAs
+      const int chain_ctas = (B + TC_BM - 1) / TC_BM;
+      const int cap = h->num_sms - chain_ctas;
+      launch_group(h, gw, V_WGRAD, cs, cap >= h->num_sms / 2 ? cap : 0);
       cudaEventRecord(h->ev_join, c.side);
       c.launches += cs.launches;
       if (cs.err != cudaSuccess && c.err == cudaSuccess) c.err = cs.err;
@@ -900,7 +934,7 @@ static void enqueue_phase2(dsact_handle* h, const dsact_batch& bt, int64_t globa
     a.inv_global_batch = invB;
     a.img = img_out(h, ar.i_dlogits);
     a.sc = sc;
-    int blocks = (B + 63) / 64; if (blocks > 2 * h->num_sms) blocks = 2 * h->num_sms; if (blocks < 1) blocks = 1;
+    int blocks = (B + 7) / 8; if (blocks > 8 * h->num_sms) blocks = 8 * h->num_sms; if (blocks < 1) blocks = 1;   // a warp per row
     launch_k(policy_grad_kernel, blocks, 256, sizeof(float) * 2 * A, c, a); c.done();
   }
 

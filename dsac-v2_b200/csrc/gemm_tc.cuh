@@ -60,6 +60,7 @@ struct TcGroup {
   int n;
   int passes;               // 3 = hi*hi + hi*lo + lo*hi, 1 = hi*hi
   unsigned long long* dbg;  // optional per-CTA phase timestamps (DSACT_TC_DEBUG), 8 slots per CTA
+  int tile0;                // first tile of this launch (a group may be issued as several launches of bounded size)
   TcProb p[TC_MAXG];
 };
 
@@ -367,12 +368,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) TC_STAMP(0);
 
+  const int tile_id = (int)blockIdx.x + g.tile0;
   int pi = 0;
 #pragma unroll
   for (int i = 1; i < TC_MAXG; ++i)
-    if (i < g.n && (int)blockIdx.x >= g.p[i].tile_start) pi = i;
+    if (i < g.n && tile_id >= g.p[i].tile_start) pi = i;
   const TcProb& P = g.p[pi];
-  int local = blockIdx.x - P.tile_start;
+  int local = tile_id - P.tile_start;
   const int tiles_mn = P.tiles_m * P.tiles_n;
   const int ks = local / tiles_mn;
   local -= ks * tiles_mn;
@@ -533,9 +535,10 @@ struct ImgJob {
   long long plane;
   int block_start;
 };
+constexpr int IMG_MAXJ = 32;   // every weight of the six networks + a caller-supplied batch in one launch
 struct ImgGroup {
   int n, planes;
-  ImgJob j[16];
+  ImgJob j[IMG_MAXJ];
 };
 // One thread converts 8 consecutive columns of one row (one 16-byte store per plane).
 __global__ void image_kernel(const __grid_constant__ ImgGroup g) {
@@ -543,7 +546,7 @@ __global__ void image_kernel(const __grid_constant__ ImgGroup g) {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   int ji = 0;
 #pragma unroll
-  for (int i = 1; i < 16; ++i)
+  for (int i = 1; i < IMG_MAXJ; ++i)
     if (i < g.n && (int)blockIdx.x >= g.j[i].block_start) ji = i;
   const ImgJob& J = g.j[ji];
   const int vec_per_row = J.pitch >> 3;

@@ -505,9 +505,15 @@ __global__ void apply_kernel(const __grid_constant__ ApplyArgs a) {
         t[0] = T4.x; t[1] = T4.y; t[2] = T4.z; t[3] = T4.w;
       }
       if (a.nslabs > 0) {
-        for (int k = 0; k < a.nslabs; ++k) {
-          const float4 p = __ldg(reinterpret_cast<const float4*>(a.slabs + (size_t)k * a.slab_stride) + gi);
-          g[0] += p.x; g[1] += p.y; g[2] += p.z; g[3] += p.w;
+        float4 p[8];   // independent loads first (the arena never has more than 8 slabs), then the sum in slab order
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          p[k] = k < a.nslabs ? __ldg(reinterpret_cast<const float4*>(a.slabs + (size_t)k * a.slab_stride) + gi) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { g[0] += p[k].x; g[1] += p[k].y; g[2] += p[k].z; g[3] += p[k].w; }
+        for (int k = 8; k < a.nslabs; ++k) {
+          const float4 q = __ldg(reinterpret_cast<const float4*>(a.slabs + (size_t)k * a.slab_stride) + gi);
+          g[0] += q.x; g[1] += q.y; g[2] += q.z; g[3] += q.w;
         }
         reinterpret_cast<float4*>(a.grads)[gi] = make_float4(g[0], g[1], g[2], g[3]);
       }

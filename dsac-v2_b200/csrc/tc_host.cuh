@@ -44,7 +44,9 @@ static bool make_map(CUtensorMap* m, const Img& t, int box_rows) {
             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-// fp32 [rows, width] row-major tensor (leading dimension ld floats), box 16 x 32, no swizzle: epilogue act' tiles
+// fp32 [rows, width] row-major tensor (leading dimension ld floats), box 16 x 32: epilogue act' tiles.  64-byte swizzle
+// on the shared-memory side (16-byte chunk ^= (row >> 1) & 3): the epilogue's lane-per-row float4 accesses, 64 bytes
+// apart, are then bank-conflict free (unswizzled they are 4-way conflicts).
 static bool make_map_f32(CUtensorMap* m, const float* base, int rows, int width, int ld) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return false;
@@ -53,9 +55,9 @@ static bool make_map_f32(CUtensorMap* m, const float* base, int rows, int width,
   cuuint32_t box[2] = {16, 32};
   cuuint32_t estr[2] = {1, 1};
   return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+            CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
-// bf16 image as a store target: dims (width, rows, 2 planes), box 16 x 32 x 1, no swizzle
+// bf16 image as a store target: dims (width, rows, 2 planes), box 16 x 32 x 1, 32-byte swizzle (16-byte chunk ^= (row >> 2) & 1)
 static bool make_map_img_store(CUtensorMap* m, const Img& t) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return false;
@@ -64,7 +66,7 @@ static bool make_map_img_store(CUtensorMap* m, const Img& t) {
   cuuint32_t box[3] = {16, 32, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   return fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, t.p, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+            CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 // what the tcgen05 lowering needs beyond a GemmProb
