@@ -387,10 +387,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_chain_kernel(const __grid_co
           __syncwarp();
           if (lane == 0) {
             if (st_z) tma_store_2d(&Lj.mapZ, st_f32, c0, mbase);
-            if (Lj.img) {
-              tma_store_3d(&Lj.mapImg, st_hi, c0, mbase, 0);
-              if (PLANES2) tma_store_3d(&Lj.mapImg, st_lo, c0, mbase, 1);
-            }
+            if (Lj.img) tma_store_3d(&Lj.mapImg, st_hi, c0, mbase, 0);   // box depth = planes: hi and lo in one request
             tma_store_commit();
           }
         }

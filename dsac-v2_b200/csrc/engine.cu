@@ -114,7 +114,9 @@ struct Arena {
         for (int j = 0; j <= q.L; ++j) i_wq[n][j] = img(q.s[j + 1], j == 0 ? kpad_q0 + (int)A : q.s[j]);
       for (int n = 0; n < 2; ++n)
         for (int j = 0; j <= pi.L; ++j) i_wpi[n][j] = img(pi.s[j + 1], pi.s[j]);
-      nslabs = (int)((B + 511) / 512); if (nslabs > 8) nslabs = 8; if (nslabs < 1) nslabs = 1;
+      // batch split of the weight-gradient GEMMs: at most 4 slabs of >= 256 rows (about one wave of CTAs at B = 4096;
+      // 8 slabs of 512 rows measured 5 % slower end to end: twice the partial tiles to write and to fold in apply)
+      nslabs = (int)(B / 256); if (nslabs > 4) nslabs = 4; if (nslabs < 1) nslabs = 1;
       slab_stride = (2 * q.n + pi.n + 1 + 3) / 4 * 4;
       slabs = take((int64_t)nslabs * slab_stride);
     }
@@ -610,7 +612,7 @@ static void chain_fwd_pass(ChainBuild& cb, const dsact_handle* h, const Net& net
       if (himg) {
         const Img im = h->img(himg[j], B);
         L.img = im.p; L.img_pitch = im.pitch; L.img_plane = im.plane;
-        cb.ok = cb.ok && make_map_img_store(&L.mapImg, im);
+        cb.ok = cb.ok && make_map_img_store(&L.mapImg, im, h->passes() == 3 ? 2 : 1);
       }
     }
   }
@@ -633,7 +635,7 @@ static void chain_dgrad_pass(ChainBuild& cb, const dsact_handle* h, const Net& n
     if (dzimg) {
       const Img im = h->img(dzimg[j - 1], B);
       L.img = im.p; L.img_pitch = im.pitch; L.img_plane = im.plane;
-      cb.ok = cb.ok && make_map_img_store(&L.mapImg, im);
+      cb.ok = cb.ok && make_map_img_store(&L.mapImg, im, h->passes() == 3 ? 2 : 1);
     }
   }
   if (dact_out) {
@@ -668,8 +670,11 @@ static void enqueue_prologue(dsact_handle* h, const dsact_batch& bt, const dsact
   const float* Qb[4] = {P, P + q.n, T, T + q.n};        // q1, q2, q1', q2'
   const float* PIb[2] = {P + 2 * q.n, T + 2 * q.n};     // pi, pi'
 
-  launch_k(begin_step_kernel, 1, 32, 0, c, h->buf.state); c.done();
-  cudaMemsetAsync(h->buf.grads, 0, sizeof(float) * (2 * q.n + pi.n + 1), c.s);
+  {
+    const long long n = 2 * q.n + pi.n + 1;
+    int blocks = (int)((n / 4 + 255) / 256); if (blocks > 2 * h->num_sms) blocks = 2 * h->num_sms; if (blocks < 1) blocks = 1;
+    launch_k(begin_step_kernel, blocks, 256, 0, c, h->buf.state, h->buf.grads, n); c.done();
+  }
 
   if (tc) {  // refresh the weight images (the caller may have written params/targets through its views) + inputs
     ImgBatch ib;
@@ -711,7 +716,7 @@ static bool fork_prologue(dsact_handle* h, const dsact_batch& bt, const dsact_no
   cudaEventRecord(h->ev_pro_fork, c.s);
   cudaStreamWaitEvent(c.side, h->ev_pro_fork, 0);
   Ctx cs{c.side, 0, cudaSuccess};
-  enqueue_prologue(h, bt, nz, cs, inputs_imaged, false);   // the noise goes behind the gather: balances the two branches
+  enqueue_prologue(h, bt, nz, cs, inputs_imaged, true);
   cudaEventRecord(h->ev_pro_join, c.side);
   c.launches += cs.launches;
   if (cs.err != cudaSuccess && c.err == cudaSuccess) c.err = cs.err;
@@ -733,7 +738,6 @@ static void enqueue_phase1(dsact_handle* h, const dsact_batch& bt, const dsact_n
   const ImgSlot none;
 
   if (prologue_forked) {
-    if (!nz) enqueue_noise(h, B, c);
     cudaStreamWaitEvent(c.s, h->ev_pro_join, 0);
   } else {
     enqueue_prologue(h, bt, nz, c, inputs_imaged);
@@ -963,7 +967,8 @@ static void enqueue_phase2(dsact_handle* h, const dsact_batch& bt, int64_t globa
     int blocks = (int)((n + 255) / 256); if (blocks > 4 * h->num_sms) blocks = 4 * h->num_sms;
     launch_k(grad_reduce_kernel, blocks, 256, 0, c, G_, W + ar.slabs, n, ar.nslabs, (long long)ar.slab_stride); c.done();
   }
-  launch_k(phase2_tail_kernel, 1, 32, 0, c, G_ + 2 * q.n + pi.n, h->buf.state, sc, -(float)cf.act_dim, B);
+  AdamHyper hy{cf.lr_q, cf.lr_pi, cf.lr_alpha, cf.adam_beta1, cf.adam_beta2};
+  launch_k(phase2_tail_kernel, 1, 32, 0, c, G_ + 2 * q.n + pi.n, h->buf.state, sc, -(float)cf.act_dim, B, hy, defer_reduce ? 1 : 0);
   c.done();
   c.check();
 }
@@ -975,8 +980,9 @@ static void enqueue_apply(dsact_handle* h, Ctx& c, bool reduce_slabs = false) {
   a.state = h->buf.state;
   a.n_q2 = 2 * h->q.n; a.n_all = 2 * h->q.n + h->pi.n + 1;
   a.delay_update = cf.delay_update; a.auto_alpha = cf.auto_alpha;
-  a.lr_q = cf.lr_q; a.lr_pi = cf.lr_pi; a.lr_alpha = cf.lr_alpha;
-  a.b1 = cf.adam_beta1; a.b2 = cf.adam_beta2; a.eps = (float)cf.adam_eps; a.tau = (float)cf.tau;
+  a.hy = AdamHyper{cf.lr_q, cf.lr_pi, cf.lr_alpha, cf.adam_beta1, cf.adam_beta2};
+  a.scalars_ready = reduce_slabs ? 1 : 0;   // single-call steps: the phase-2 tail of this very step computed them
+  a.eps = (float)cf.adam_eps; a.tau = (float)cf.tau;
   a.omb1 = (float)(1.0 - cf.adam_beta1); a.b2f = (float)cf.adam_beta2; a.omb2 = (float)(1.0 - cf.adam_beta2);
   a.slabs = nullptr; a.nslabs = 0; a.slab_stride = 0;
   if (reduce_slabs && slabs_foldable(h)) { a.slabs = h->W() + h->ar.slabs; a.nslabs = h->ar.nslabs; a.slab_stride = h->ar.slab_stride; }
@@ -1133,7 +1139,7 @@ int dsact_query_layout(const dsact_config* cfg, dsact_layout* out) {
   out->n_params = 2 * q.n + pi.n + 1;
   out->n_targets = 2 * q.n + pi.n;
   out->workspace_bytes = ar.total * (int64_t)sizeof(float);
-  out->state_floats = 64;
+  out->state_floats = ST_FLOATS;
   out->max_batch = cfg->max_batch;
   return DSACT_OK;
 }

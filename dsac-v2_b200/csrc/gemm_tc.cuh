@@ -556,19 +556,31 @@ __global__ void image_kernel(const __grid_constant__ ImgGroup g) {
     const int r = i / vec_per_row, c0 = (i - r * vec_per_row) * 8;
     const float* src = J.src + (size_t)r * J.ld_src;
     uint32_t whi[4], wlo[4];
+    float x[8];
+    const uintptr_t addr = reinterpret_cast<uintptr_t>(src + c0);
+    if (c0 + 8 <= J.seg_w[0] && (addr & 7) == 0) {   // the common case: eight columns of the first segment, vector loads
+      if ((addr & 15) == 0) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(src + c0)), b = __ldg(reinterpret_cast<const float4*>(src + c0) + 1);
+        x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+      } else {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      float x[2];
+        for (int k = 0; k < 4; ++k) {
+          const float2 a = __ldg(reinterpret_cast<const float2*>(src + c0) + k);
+          x[2 * k] = a.x; x[2 * k + 1] = a.y;
+        }
+      }
+    } else {
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int c = c0 + 2 * k + e;
+      for (int e = 0; e < 8; ++e) {
+        const int c = c0 + e;
         float v = 0.f;
         if (c < J.seg_w[0]) v = __ldg(src + c);
         else if (c >= J.seg_dst0[1] && c < J.seg_dst0[1] + J.seg_w[1]) v = __ldg(src + J.seg_src0[1] + (c - J.seg_dst0[1]));
         x[e] = v;
       }
-      split_pack2(x[0], x[1], whi[k], wlo[k]);
     }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) split_pack2(x[2 * k], x[2 * k + 1], whi[k], wlo[k]);
     __nv_bfloat16* dst = J.dst + (size_t)r * J.pitch + c0;
     *reinterpret_cast<uint4*>(dst) = make_uint4(whi[0], whi[1], whi[2], whi[3]);
     if (g.planes == 2) *reinterpret_cast<uint4*>(dst + J.plane) = make_uint4(wlo[0], wlo[1], wlo[2], wlo[3]);

@@ -26,6 +26,8 @@ enum {
   ST_TICKET = 14,                      // int32: blocks of apply_kernel that have finished (the last one advances the counters)
   ST_ACC = 16,                         // 16 sums then 16 mins
   ST_STATS = 48,
+  ST_ADAM_SC = 64,                     // [64..68] Adam step sizes / bias corrections of this step (phase2 tail -> apply)
+  ST_FLOATS = 80,
 };
 enum {  // accumulator slots (sums)
   ACC_Q1 = 0, ACC_Q2, ACC_S1, ACC_S2, ACC_LOSS_PI, ACC_LOSS_Q, ACC_TANH_MEAN, ACC_PI_STD, ACC_LOGP,
@@ -131,14 +133,22 @@ __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& n0, fl
   n1 = r * s;
 }
 
-// Start of every step: clear the accumulators (and the std sums of phase1).
-__global__ void begin_step_kernel(float* __restrict__ state) {
+// Start of every step: clear the accumulators (and the std sums of phase1) and zero the flat gradient buffer
+// (bias gradients and column sums accumulate into it with atomics).
+__global__ void begin_step_kernel(float* __restrict__ state, float* __restrict__ grads, long long n) {
   pdl_sync();
   const int t = threadIdx.x;
-  if (t < 16) state[ST_ACC + t] = 0.f;
-  else if (t < 32) state[ST_ACC + t] = __int_as_float(0x7f800000);
-  if (t < 2) state[ST_STDSUM + t] = 0.f;
-  if (t == 2) reinterpret_cast<int*>(state)[ST_TICKET] = 0;
+  if (blockIdx.x == 0) {
+    if (t < 16) state[ST_ACC + t] = 0.f;
+    else if (t < 32) state[ST_ACC + t] = __int_as_float(0x7f800000);
+    if (t < 2) state[ST_STDSUM + t] = 0.f;
+    if (t == 2) reinterpret_cast<int*>(state)[ST_TICKET] = 0;
+  }
+  const bool vec = (reinterpret_cast<uintptr_t>(grads) & 15) == 0;
+  const long long n4 = vec ? n / 4 : 0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + t; i < n4; i += (long long)gridDim.x * blockDim.x)
+    reinterpret_cast<float4*>(grads)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (long long i = n4 * 4 + blockIdx.x * (long long)blockDim.x + t; i < n; i += (long long)gridDim.x * blockDim.x) grads[i] = 0.f;
 }
 
 // Device noise: eps1, eps2 [B,A] and z3, z4 [B] (SURVEY Appendix B keeps only the draws that matter).
@@ -449,13 +459,27 @@ __global__ void policy_grad_kernel(const __grid_constant__ PolicyGradArgs a) {
 // __update (dsac_v2.py:320-347): Adam on q1|q2 every step; on policy|log_alpha plus Polyak of all three
 // targets when iteration % delay_update == 0.  One pass over the flat buffers; also writes the gradient
 // of log_alpha (dsac_v2.py:312-318) from the accumulated sum of log-probs.
+// Step sizes lr/(1-beta1^t) and sqrt(1-beta2^t) in double, like the Python scalars of torch's Adam:
+// out = {lr_q/bc1q, sqrt(bc2q), lr_pi/bc1p, lr_alpha/bc1p, sqrt(bc2p)}.  A few hundred dependent FP64 instructions: done
+// once per step by the phase-2 tail (single-call steps) instead of by thread 0 of every apply block.
+struct AdamHyper { double lr_q, lr_pi, lr_alpha, b1, b2; };
+__device__ __forceinline__ void adam_scalars(const int* sti, const AdamHyper& a, float* out) {
+  const double tq = sti[ST_ADAM_Q] + 1, tp = sti[ST_ADAM_PI] + 1;
+  const double bc1q = 1.0 - pow(a.b1, tq), bc1p = 1.0 - pow(a.b1, tp);
+  out[0] = (float)(a.lr_q / bc1q);
+  out[1] = (float)sqrt(1.0 - pow(a.b2, tq));
+  out[2] = (float)(a.lr_pi / bc1p);
+  out[3] = (float)(a.lr_alpha / bc1p);
+  out[4] = (float)sqrt(1.0 - pow(a.b2, tp));
+}
 struct ApplyArgs {
   float *params, *targets, *grads, *m, *v;
   float* state;
   int64_t n_q2;      // 2*n_q  (critic span)
   int64_t n_all;     // 2*n_q + n_pi + 1
   int delay_update, auto_alpha;
-  double lr_q, lr_pi, lr_alpha, b1, b2;
+  AdamHyper hy;
+  int scalars_ready;   // state[ST_ADAM_SC..] was written by phase2_tail_kernel of this step
   float omb1, b2f, omb2, eps, tau;  // (float)(1-beta1), (float)beta2, (float)(1-beta2) formed in double on the host
   // tcgen05 modes, single-call steps: the weight-gradient split slabs are folded in here (grads += sum of slabs, stored
   // back so that the caller's .grad views hold the totals) instead of by a separate grad_reduce launch
@@ -476,14 +500,10 @@ __global__ void apply_kernel(const __grid_constant__ ApplyArgs a) {
   __shared__ float sh[6];
   const int* sti = reinterpret_cast<const int*>(a.state);
   const bool delayed = (sti[ST_ITER] % a.delay_update) == 0;
-  if (threadIdx.x == 0) {  // bias corrections in double, like the Python scalars of torch's Adam
-    const double tq = sti[ST_ADAM_Q] + 1, tp = sti[ST_ADAM_PI] + 1;
-    const double bc1q = 1.0 - pow(a.b1, tq), bc1p = 1.0 - pow(a.b1, tp);
-    sh[0] = (float)(a.lr_q / bc1q);
-    sh[1] = (float)sqrt(1.0 - pow(a.b2, tq));
-    sh[2] = (float)(a.lr_pi / bc1p);
-    sh[3] = (float)(a.lr_alpha / bc1p);
-    sh[4] = (float)sqrt(1.0 - pow(a.b2, tp));
+  if (a.scalars_ready) {
+    if (threadIdx.x < 5) sh[threadIdx.x] = a.state[ST_ADAM_SC + threadIdx.x];
+  } else if (threadIdx.x == 0) {
+    adam_scalars(sti, a.hy, sh);
   }
   __syncthreads();
   const int64_t n_targets = a.n_all - 1;
@@ -593,9 +613,10 @@ __global__ void rng_advance_kernel(float* __restrict__ state) {
 // commit of this step's mean_std EMA and temperature to the state (every earlier reader used the carried values).
 // `rows` = local shard size, so that per-rank values sum to the global gradient under data parallelism.
 __global__ void phase2_tail_kernel(float* __restrict__ grad_log_alpha, float* __restrict__ state, const StepScalars sc,
-                                   float target_entropy, int rows) {
+                                   float target_entropy, int rows, const AdamHyper hy, int with_adam) {
   pdl_sync();
   const int t = threadIdx.x;
+  if (with_adam && t == 4) adam_scalars(reinterpret_cast<const int*>(state), hy, state + ST_ADAM_SC);
   float val = 0.f;
   if (t < 2) val = step_mean_std(state, sc, t);
   else if (t == 2) val = step_alpha(sc);

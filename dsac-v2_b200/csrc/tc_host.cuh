@@ -58,12 +58,13 @@ static bool make_map_f32(CUtensorMap* m, const float* base, int rows, int width,
             CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 // bf16 image as a store target: dims (width, rows, 2 planes), box 16 x 32 x 1, 32-byte swizzle (16-byte chunk ^= (row >> 2) & 1)
-static bool make_map_img_store(CUtensorMap* m, const Img& t) {
+// `planes` = 2: one request stores the hi tile and the lo tile behind it (shared memory: [hi 1 KiB][lo 1 KiB])
+static bool make_map_img_store(CUtensorMap* m, const Img& t, int planes) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return false;
   cuuint64_t dims[3] = {(cuuint64_t)t.width, (cuuint64_t)t.rows, 2};
   cuuint64_t strides[2] = {(cuuint64_t)t.pitch * 2, (cuuint64_t)t.plane * 2};
-  cuuint32_t box[3] = {16, 32, 1};
+  cuuint32_t box[3] = {16, 32, (cuuint32_t)planes};
   cuuint32_t estr[3] = {1, 1, 1};
   return fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, t.p, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;

@@ -205,6 +205,7 @@ int dsact_test_gemm(dsact_handle *h, int32_t variant, const float *A, int32_t ld
 #define DSACT_STATE_STDSUM 4   /* state[4], state[5]: local sums of critic std (phase1 -> phase2) */
 #define DSACT_STATE_ACC 16     /* state[16..47]: per-step accumulators (sums first, then mins) */
 #define DSACT_STATE_STATS 48   /* state[48..63]: finalised tb_info */
+#define DSACT_STATE_ADAM 64    /* state[64..68]: Adam step sizes / bias corrections of the running step (internal) */
 
 #ifdef __cplusplus
 }
