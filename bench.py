@@ -56,6 +56,8 @@ def parse():
     ap.add_argument("--gemm", default="bf16x3", choices=["fp32", "bf16x3", "bf16"],
                     help="dense-layer arithmetic; bf16x3 (default) and fp32 pass the 1e-4 parity gate, bf16 does not")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dp", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: exchanges inside the step's kernels over NVLink peer memory, or torch.distributed/NCCL")
     return ap.parse_args()
 
 
@@ -262,9 +264,17 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    peer_dp = False
+    if world > 1 and args.dp != "nccl":   # exchange buffers mapped over NVLink (CUDA IPC); NCCL path if that fails
+        from dsac_v2_b200 import dp as dpmod
+        peer_dp = dpmod.connect_peers(eng, dist)
+        alg._peer_dp = peer_dp
+
     def dev_step(it):
         if world == 1:
             eng.replay_step(B, buf.size, it)
+        elif peer_dp:
+            eng.dp_replay_step(B, buf.size, it, B * world)   # one graph per rank, exchanges inside its kernels
         else:
             alg.local_update(buf.sample_batch(B), it)
 
@@ -283,11 +293,12 @@ def main():
         e1.record()
         barrier()
         extra = max(0.0, 1.2 - e0.elapsed_time(e1) / 1000)  # keep the sampler alive for a few readings
-        if extra:
-            t_end = time.time() + extra
-            while time.time() < t_end:
-                dev_step(it); it += 1
-            torch.cuda.synchronize()
+        n_extra = torch.tensor([int(extra * 1000 / max(e0.elapsed_time(e1) / args.steps, 1e-3))], device=dev)
+        if world > 1:   # data-parallel steps are collective: every rank must run the same number of them
+            dist.all_reduce(n_extra, op=dist.ReduceOp.MAX)
+        for _ in range(int(n_extra.item())):
+            dev_step(it); it += 1
+        torch.cuda.synchronize()
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -370,7 +381,7 @@ def main():
             "vs_baseline": None, "dtype": "f32" if args.gemm == "fp32" else args.gemm, "data": "synthetic",
             "config": {"workload": f"gym_{args.config} shapes (obs={O} act={A}) MLP{list(cfg['hidden'])} batch_size={B} per GPU, "
                                    f"device replay ring {args.replay_size} rows, device index+noise generation",
-                       "global_batch": B * world, "parallelism": f"dp{world}" if world > 1 else "single",
+                       "global_batch": B * world, "parallelism": (f"dp{world}" + ("-peer" if peer_dp else "-nccl")) if world > 1 else "single",
                        "l2": f"inputs exceed L2: each step gathers {B} random rows from a {4 * args.replay_size * (2 * O + A + 3) / 1e9:.2f} GB ring",
                        "gemm_mode": args.gemm, "cuda_graph": True},
             "clocks": clocks.summary(),

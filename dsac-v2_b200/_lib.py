@@ -72,6 +72,9 @@ class Replay(C.Structure):
 
 
 # every symbol include/dsact.h declares: (restype, argtypes)
+IPC_HANDLE_BYTES = 64   # DSACT_IPC_HANDLE_BYTES
+DP_MAX_RANKS = 8        # DSACT_DP_MAX_RANKS
+
 SYMBOLS = {
     "dsact_last_error": (C.c_char_p, []),
     "dsact_abi_version": (C.c_int, []),
@@ -91,6 +94,11 @@ SYMBOLS = {
     "dsact_replay_add": (C.c_int, [C.c_void_p] + [C.c_void_p] * 6 + [C.c_int64, C.c_int64, C.c_void_p]),
     "dsact_replay_sample": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.POINTER(Batch), C.c_void_p]),
     "dsact_replay_step": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.POINTER(Noise), C.c_int64, C.c_void_p]),
+    "dsact_dp_export": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_int64)]),
+    "dsact_dp_connect": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
+    "dsact_dp_step": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.POINTER(Noise), C.c_int64, C.c_int64, C.c_void_p]),
+    "dsact_dp_replay_step": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.POINTER(Noise), C.c_int64, C.c_int64,
+                                       C.c_void_p]),
     "dsact_profile_step": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.POINTER(Noise), C.c_int64, C.c_void_p, C.POINTER(Profile)]),
     "dsact_launch_count": (C.c_int64, [C.c_void_p]),
     "dsact_last_call_launches": (C.c_int32, [C.c_void_p]),

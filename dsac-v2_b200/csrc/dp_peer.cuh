@@ -1,0 +1,120 @@
+// Data-parallel replicas over NVLink peer memory: the two exchanges of a data-parallel DSAC-T step
+// (critic-std sums before the loss; gradients + logged sums before Adam) done by the step's own kernels on buffers
+// that every rank maps with CUDA IPC, so that the whole step stays ONE captured graph per rank: no host round trip,
+// no NCCL launch between the phases.
+//
+// Per rank one cudaMalloc'd exchange buffer (floats):
+//   [0, 64)                       arrival flags (uint32 epochs): flag[kind * 16 + source_rank]
+//   [64, 64 + 2*2*R*32)           small payloads: small[kind][parity][source_rank][32]
+//   [DP_GRADS_OFF, + n_params)    this rank's local gradient sum of the running step
+// kind 0 = after the forward passes (2 std sums, SUM), kind 1 = before Adam (16 logged sums SUM + 2 minima MIN; it is
+// also the "local gradients are complete" barrier).  Every rank pushes its payload into every peer's buffer, raises
+// its flag there (release, system scope) and polls only its own memory.  Reductions run in rank order on every rank,
+// so the replicas stay bit-identical.  Reuse is safe without further barriers: a rank overwrites its gradient block
+// in phase 2 of step t+1, i.e. after the kind-0 barrier of t+1, which every peer reaches only after its apply of t.
+#pragma once
+#include <stdint.h>
+
+#include "kernels.cuh"
+
+namespace dsact {
+
+constexpr int DP_MAX_RANKS = 8;
+constexpr int DP_FLAGS = 64;
+constexpr int DP_SMALL = 32;
+constexpr int DP_SMALL_OFF = DP_FLAGS;
+constexpr int DP_GRADS_OFF = 2048;   // floats; 8 KiB header
+
+struct DpComm {
+  float* peer[DP_MAX_RANKS];   // peer[rank] = this rank's own buffer
+  int rank, world;
+};
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 ld_sys_f4(const float* p) {   // coherent at the owner's L2, never the read-only path
+  float4 v;
+  asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float ld_sys_f(const float* p) {
+  float v;
+  asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long dp_time_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+// One block of 32 * world threads.  kind 0: all-reduce state[ST_STDSUM..+1] (SUM) and open epoch e = epoch + 1;
+// kind 1: all-reduce the 16 sums (SUM) and 2 minima (MIN) of state[ST_ACC..] at the epoch kind 0 opened.
+// A peer that does not arrive within `timeout_ns` sets state[ST_DP_ERR] instead of hanging the GPU.
+__global__ void dp_exchange_kernel(const DpComm c, float* __restrict__ state, int kind, unsigned long long timeout_ns) {
+  pdl_sync();
+  int* sti = reinterpret_cast<int*>(state);
+  const uint32_t e = (uint32_t)sti[ST_DP_EPOCH] + (kind == 0 ? 1u : 0u);
+  const int par = (int)(e & 1u);
+  const int n = kind == 0 ? 2 : 18;
+  float* src = kind == 0 ? state + ST_STDSUM : state + ST_ACC;   // (the 2 minima sit at ST_ACC + 16, 17)
+  const int t = threadIdx.x, p = t >> 5, i = t & 31;
+  // 1. push my payload into every rank's small[kind][par][my rank][...]
+  if (p < c.world && i < n) {
+    float* dst = c.peer[p] + DP_SMALL_OFF + ((kind * 2 + par) * DP_MAX_RANKS + c.rank) * DP_SMALL;
+    dst[i] = src[i];
+    __threadfence_system();
+  }
+  __syncthreads();
+  // 2. raise my flag at every rank, then wait for every rank's flag here
+  if (t < c.world) {
+    st_release_sys(reinterpret_cast<uint32_t*>(c.peer[t]) + kind * 16 + c.rank, e);
+    const uint32_t* mine = reinterpret_cast<const uint32_t*>(c.peer[c.rank]) + kind * 16 + t;
+    const unsigned long long t0 = dp_time_ns();
+    while ((int32_t)(ld_acquire_sys(mine) - e) < 0) {
+      if (dp_time_ns() - t0 > timeout_ns) { sti[ST_DP_ERR] = 1 + t; break; }
+      __nanosleep(64);
+    }
+  }
+  __syncthreads();
+  // 3. reduce in rank order (identical on every rank)
+  if (t < n) {
+    const float* base = c.peer[c.rank] + DP_SMALL_OFF + (kind * 2 + par) * DP_MAX_RANKS * DP_SMALL;
+    float acc = ld_sys_f(base + t);
+    for (int r = 1; r < c.world; ++r) {
+      const float v = ld_sys_f(base + r * DP_SMALL + t);
+      acc = (kind == 1 && t >= 16) ? fminf(acc, v) : acc + v;
+    }
+    src[t] = acc;
+  }
+  if (kind == 0 && t == 0) sti[ST_DP_EPOCH] = (int)e;
+}
+
+// grads_out[i] = grads[i] + sum of the weight-gradient slabs (the local total, into the exchange buffer)
+__global__ void dp_grad_fold_kernel(float* __restrict__ out, const float* __restrict__ grads, const float* __restrict__ slabs,
+                                    long long n, int nslabs, long long slab_stride) {
+  pdl_sync();
+  const bool vec = (slab_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(grads) & 15) == 0 && (reinterpret_cast<uintptr_t>(slabs) & 15) == 0;
+  const long long n4 = vec ? n / 4 : 0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 s = reinterpret_cast<const float4*>(grads)[i];
+    for (int k = 0; k < nslabs; ++k) {
+      const float4 q = __ldg(reinterpret_cast<const float4*>(slabs + (size_t)k * slab_stride) + i);
+      s.x += q.x; s.y += q.y; s.z += q.z; s.w += q.w;
+    }
+    reinterpret_cast<float4*>(out)[i] = s;
+  }
+  for (long long i = n4 * 4 + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float s = grads[i];
+    for (int k = 0; k < nslabs; ++k) s += slabs[(size_t)k * slab_stride + i];
+    out[i] = s;
+  }
+}
+
+}  // namespace dsact

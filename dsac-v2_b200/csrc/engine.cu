@@ -16,6 +16,7 @@
 #include "kernels.cuh"
 #include "tc_host.cuh"
 #include "chain_tc.cuh"
+#include "dp_peer.cuh"
 
 using namespace dsact;
 
@@ -150,6 +151,11 @@ struct dsact_handle {
   cudaStream_t side_stream;  // second branch inside a step (critic weight gradients || policy backward chain)
   cudaEvent_t ev_fork, ev_join;
   cudaEvent_t ev_pro_fork, ev_pro_join;   // prologue branch (weight images, noise, clears) beside the replay gather
+  // peer-memory data parallelism (dp_peer.cuh)
+  float* dp_buf = nullptr;            // this rank's exchange buffer (cudaMalloc, exported with CUDA IPC)
+  void* dp_opened[DP_MAX_RANKS] = {}; // peers' buffers as opened here
+  DpComm dp = {};
+  bool dp_ready = false;
   std::vector<GraphEntry> graphs;
   uint64_t stamp;
   int64_t launches;
@@ -835,7 +841,9 @@ static void enqueue_phase1(dsact_handle* h, const dsact_batch& bt, const dsact_n
 static bool slabs_foldable(const dsact_handle* h) {
   return h->tc() && ((uintptr_t)(h->W() + h->ar.slabs) & 15) == 0 && ((uintptr_t)h->buf.grads & 15) == 0;
 }
-static void enqueue_phase2(dsact_handle* h, const dsact_batch& bt, int64_t global_batch, Ctx& c, bool defer_reduce = false) {
+enum { REDUCE_INPLACE = 0, REDUCE_DEFER = 1, REDUCE_DP = 2 };   // where the weight-gradient slabs get folded
+static void enqueue_phase2(dsact_handle* h, const dsact_batch& bt, int64_t global_batch, Ctx& c, int reduce_mode = REDUCE_INPLACE) {
+  const bool defer_reduce = reduce_mode != REDUCE_INPLACE;
   const dsact_config& cf = h->cfg;
   const Net &q = h->q, &pi = h->pi;
   const Arena& ar = h->ar;
@@ -962,7 +970,7 @@ static void enqueue_phase2(dsact_handle* h, const dsact_batch& bt, int64_t globa
   launch_group(h, gwp, V_WGRAD, c);
 
   if (h->join_pending) { cudaStreamWaitEvent(c.s, h->ev_join, 0); h->join_pending = false; }
-  if (tc && !(defer_reduce && slabs_foldable(h))) {  // fold the weight-gradient split slabs into the flat gradient buffer
+  if (tc && reduce_mode != REDUCE_DP && !(defer_reduce && slabs_foldable(h))) {  // fold the weight-gradient split slabs into the flat gradient buffer
     const long long n = 2 * q.n + pi.n + 1;
     int blocks = (int)((n + 255) / 256); if (blocks > 4 * h->num_sms) blocks = 4 * h->num_sms;
     launch_k(grad_reduce_kernel, blocks, 256, 0, c, G_, W + ar.slabs, n, ar.nslabs, (long long)ar.slab_stride); c.done();
@@ -970,10 +978,17 @@ static void enqueue_phase2(dsact_handle* h, const dsact_batch& bt, int64_t globa
   AdamHyper hy{cf.lr_q, cf.lr_pi, cf.lr_alpha, cf.adam_beta1, cf.adam_beta2};
   launch_k(phase2_tail_kernel, 1, 32, 0, c, G_ + 2 * q.n + pi.n, h->buf.state, sc, -(float)cf.act_dim, B, hy, defer_reduce ? 1 : 0);
   c.done();
+  if (reduce_mode == REDUCE_DP) {  // local total (bias gradients + slabs + log_alpha) -> this rank's block of the exchange buffer
+    const long long n = 2 * q.n + pi.n + 1;
+    int blocks = (int)((n / 4 + 255) / 256); if (blocks > 4 * h->num_sms) blocks = 4 * h->num_sms; if (blocks < 1) blocks = 1;
+    launch_k(dp_grad_fold_kernel, blocks, 256, 0, c, h->dp_buf + DP_GRADS_OFF, (const float*)G_, (const float*)(tc ? W + ar.slabs : G_), n,
+             tc ? ar.nslabs : 0, (long long)(tc ? ar.slab_stride : 4));
+    c.done();
+  }
   c.check();
 }
 
-static void enqueue_apply(dsact_handle* h, Ctx& c, bool reduce_slabs = false) {
+static void enqueue_apply(dsact_handle* h, Ctx& c, bool reduce_slabs = false, bool dp = false) {
   const dsact_config& cf = h->cfg;
   ApplyArgs a;
   a.params = h->buf.params; a.targets = h->buf.targets; a.grads = h->buf.grads; a.m = h->buf.adam_m; a.v = h->buf.adam_v;
@@ -981,11 +996,17 @@ static void enqueue_apply(dsact_handle* h, Ctx& c, bool reduce_slabs = false) {
   a.n_q2 = 2 * h->q.n; a.n_all = 2 * h->q.n + h->pi.n + 1;
   a.delay_update = cf.delay_update; a.auto_alpha = cf.auto_alpha;
   a.hy = AdamHyper{cf.lr_q, cf.lr_pi, cf.lr_alpha, cf.adam_beta1, cf.adam_beta2};
-  a.scalars_ready = reduce_slabs ? 1 : 0;   // single-call steps: the phase-2 tail of this very step computed them
+  a.scalars_ready = (reduce_slabs || dp) ? 1 : 0;   // single-call steps: the phase-2 tail of this very step computed them
+  a.dp_world = 0;
+  for (int r = 0; r < 8; ++r) a.dp_grads[r] = nullptr;
+  if (dp) {
+    a.dp_world = h->dp.world;
+    for (int r = 0; r < h->dp.world; ++r) a.dp_grads[r] = h->dp.peer[r] + DP_GRADS_OFF;
+  }
   a.eps = (float)cf.adam_eps; a.tau = (float)cf.tau;
   a.omb1 = (float)(1.0 - cf.adam_beta1); a.b2f = (float)cf.adam_beta2; a.omb2 = (float)(1.0 - cf.adam_beta2);
   a.slabs = nullptr; a.nslabs = 0; a.slab_stride = 0;
-  if (reduce_slabs && slabs_foldable(h)) { a.slabs = h->W() + h->ar.slabs; a.nslabs = h->ar.nslabs; a.slab_stride = h->ar.slab_stride; }
+  if (reduce_slabs && !dp && slabs_foldable(h)) { a.slabs = h->W() + h->ar.slabs; a.nslabs = h->ar.nslabs; a.slab_stride = h->ar.slab_stride; }
   int blocks = (int)((a.n_all + 255) / 256);
   if (blocks > 8 * h->num_sms) blocks = 8 * h->num_sms;
   launch_k(apply_kernel, blocks, 256, 0, c, a);   // its last block also advances the step counters
@@ -1012,7 +1033,7 @@ static void enqueue_gather(dsact_handle* h, int B, const int64_t* idx, Ctx& c) {
 }
 
 // ---- graph cache -------------------------------------------------------------
-enum { K_STEP = 1, K_PHASE1 = 2, K_PHASE2 = 3, K_APPLY = 4, K_GRADS = 5, K_SAMPLE = 6, K_REPLAY_STEP = 7 };
+enum { K_STEP = 1, K_PHASE1 = 2, K_PHASE2 = 3, K_APPLY = 4, K_GRADS = 5, K_SAMPLE = 6, K_REPLAY_STEP = 7, K_DP_STEP = 8, K_DP_REPLAY_STEP = 9 };
 
 static void drop_graphs(dsact_handle* h) {
   for (auto& e : h->graphs) cudaGraphExecDestroy(e.exec);
@@ -1187,6 +1208,8 @@ void dsact_destroy(dsact_handle* h) {
   cudaEventDestroy(h->ev_join);
   cudaEventDestroy(h->ev_pro_fork);
   cudaEventDestroy(h->ev_pro_join);
+  for (int r = 0; r < DP_MAX_RANKS; ++r) if (h->dp_opened[r]) cudaIpcCloseMemHandle(h->dp_opened[r]);
+  if (h->dp_buf) cudaFree(h->dp_buf);
   delete h;
 }
 
@@ -1298,7 +1321,7 @@ int dsact_step(dsact_handle* h, const dsact_batch* batch, const dsact_noise* noi
   skey.size = imaged ? 1 : 0;
   rc = run(h, (cudaStream_t)stream, skey, [&](Ctx& c) {
     enqueue_phase1(h, bt, np, c, imaged);
-    enqueue_phase2(h, bt, bt.batch, c, true);
+    enqueue_phase2(h, bt, bt.batch, c, REDUCE_DEFER);
     enqueue_apply(h, c, true);
   });
   if (rc) return rc;
@@ -1407,8 +1430,123 @@ int dsact_replay_step(dsact_handle* h, int32_t batch, int64_t size, const int64_
     enqueue_gather(h, batch, idx, c);
     if (!idx && np) { launch_k(rng_advance_kernel, 1, 32, 0, c, h->buf.state); c.done(); }
     enqueue_phase1(h, bt, np, c, true, forked);  // device noise (np == null): phase1 advances the counter after the join
-    enqueue_phase2(h, bt, batch, c, true);
+    enqueue_phase2(h, bt, batch, c, REDUCE_DEFER);
     enqueue_apply(h, c, true);
+  });
+  if (rc) return rc;
+  h->pending = bt; h->pending_batch = batch;
+  h->dev_iter = iteration + 1;
+  return DSACT_OK;
+}
+
+// ---- data parallelism over peer memory (dp_peer.cuh) ------------------------------------------------------------
+static void enqueue_dp_exchange(dsact_handle* h, int kind, Ctx& c) {
+  static const unsigned long long timeout_ns =
+      (unsigned long long)(getenv("DSACT_DP_TIMEOUT_MS") ? atoll(getenv("DSACT_DP_TIMEOUT_MS")) : 10000) * 1000000ull;
+  launch_k(dp_exchange_kernel, 1, 32 * h->dp.world, 0, c, h->dp, h->buf.state, kind, timeout_ns);
+  c.done();
+}
+
+int dsact_dp_export(dsact_handle* h, void* handle_out, int64_t* bytes_out) {
+  if (!h || !handle_out) return fail(DSACT_EINVAL, "null argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  const size_t bytes = sizeof(float) * (size_t)(DP_GRADS_OFF + (2 * h->q.n + h->pi.n + 1 + 3) / 4 * 4);
+  if (!h->dp_buf) {
+    CUDA_TRY(cudaMalloc(&h->dp_buf, bytes));
+    CUDA_TRY(cudaMemset(h->dp_buf, 0, bytes));
+  }
+  cudaIpcMemHandle_t ipc;
+  CUDA_TRY(cudaIpcGetMemHandle(&ipc, h->dp_buf));
+  static_assert(sizeof(ipc) == DSACT_IPC_HANDLE_BYTES, "IPC handle size");
+  memcpy(handle_out, &ipc, sizeof(ipc));
+  if (bytes_out) *bytes_out = (int64_t)bytes;
+  return DSACT_OK;
+}
+
+int dsact_dp_connect(dsact_handle* h, int32_t rank, int32_t world, const void* handles) {
+  if (!h || !handles) return fail(DSACT_EINVAL, "null argument");
+  if (!h->bound) return fail(DSACT_ESTATE, "dsact_bind has not been called");
+  if (!h->dp_buf) return fail(DSACT_ESTATE, "dsact_dp_export has not been called");
+  if (world < 2 || world > DP_MAX_RANKS || rank < 0 || rank >= world) return fail(DSACT_EINVAL, "rank %d / world %d outside [2, %d]", rank, world, DP_MAX_RANKS);
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaDeviceSynchronize());
+  drop_graphs(h);
+  for (int r = 0; r < DP_MAX_RANKS; ++r)
+    if (h->dp_opened[r]) { cudaIpcCloseMemHandle(h->dp_opened[r]); h->dp_opened[r] = nullptr; }
+  h->dp.rank = rank; h->dp.world = world;
+  for (int r = 0; r < world; ++r) {
+    if (r == rank) { h->dp.peer[r] = h->dp_buf; continue; }
+    cudaIpcMemHandle_t ipc;
+    memcpy(&ipc, static_cast<const char*>(handles) + (size_t)r * sizeof(ipc), sizeof(ipc));
+    void* p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, ipc, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(DSACT_ECUDA, "cudaIpcOpenMemHandle(rank %d): %s", r, cudaGetErrorString(e)); }
+    h->dp_opened[r] = p;
+    h->dp.peer[r] = static_cast<float*>(p);
+  }
+  // every rank starts at epoch 0 with clear flags (the caller synchronises the ranks after this call)
+  CUDA_TRY(cudaMemset(h->dp_buf, 0, sizeof(float) * DP_GRADS_OFF));
+  CUDA_TRY(cudaMemset(h->buf.state + ST_DP_EPOCH, 0, sizeof(float)));
+  CUDA_TRY(cudaMemset(h->buf.state + ST_DP_ERR, 0, sizeof(float)));
+  CUDA_TRY(cudaDeviceSynchronize());
+  h->dp_ready = true;
+  return DSACT_OK;
+}
+
+// One data-parallel update as one submission: forward, std-sum exchange, losses + backward scaled by 1/global_batch,
+// gradient + statistics exchange, Adam on the rank-ordered global sum.  Every rank must call it for the same iteration.
+int dsact_dp_step(dsact_handle* h, const dsact_batch* batch, const dsact_noise* noise, int64_t global_batch, int64_t iteration,
+                  void* stream) {
+  int rc = check_batch(h, batch);
+  if (rc || (rc = check_noise(noise))) return rc;
+  if (!h->dp_ready) return fail(DSACT_ESTATE, "dsact_dp_connect has not been called");
+  if (global_batch < batch->batch) return fail(DSACT_EINVAL, "global_batch %lld < local batch %d", (long long)global_batch, batch->batch);
+  CUDA_TRY(cudaSetDevice(h->device));
+  if ((rc = sync_iteration(h, iteration, (cudaStream_t)stream))) return rc;
+  const dsact_batch bt = *batch;
+  dsact_noise nz; const dsact_noise* np = nullptr;
+  if (noise) { nz = *noise; np = &nz; }
+  const bool imaged = take_arena_images(h, bt);
+  GraphKey key = make_key(K_DP_STEP, &bt, np, global_batch);
+  key.size = imaged ? 1 : 0;
+  rc = run(h, (cudaStream_t)stream, key, [&](Ctx& c) {
+    enqueue_phase1(h, bt, np, c, imaged);
+    enqueue_dp_exchange(h, 0, c);
+    enqueue_phase2(h, bt, global_batch, c, REDUCE_DP);
+    enqueue_dp_exchange(h, 1, c);
+    enqueue_apply(h, c, false, true);
+  });
+  if (rc) return rc;
+  h->pending = bt; h->pending_batch = bt.batch;
+  h->dev_iter = iteration + 1;
+  return DSACT_OK;
+}
+
+int dsact_dp_replay_step(dsact_handle* h, int32_t batch, int64_t size, const int64_t* idx, const dsact_noise* noise,
+                         int64_t global_batch, int64_t iteration, void* stream) {
+  if (!h || !h->bound || !h->rb_bound) return fail(DSACT_ESTATE, "not bound");
+  if (!h->dp_ready) return fail(DSACT_ESTATE, "dsact_dp_connect has not been called");
+  if (batch < 1 || batch > h->cfg.max_batch) return fail(DSACT_EINVAL, "batch outside [1, max_batch]");
+  if (global_batch < batch) return fail(DSACT_EINVAL, "global_batch %lld < local batch %d", (long long)global_batch, batch);
+  int rc = check_noise(noise);
+  if (rc) return rc;
+  CUDA_TRY(cudaSetDevice(h->device));
+  if ((rc = sync_rb_size(h, size, (cudaStream_t)stream))) return rc;
+  if ((rc = sync_iteration(h, iteration, (cudaStream_t)stream))) return rc;
+  const dsact_batch bt = arena_batch(h, batch);
+  dsact_noise nz; const dsact_noise* np = nullptr;
+  if (noise) { nz = *noise; np = &nz; }
+  GraphKey key = make_key(K_DP_REPLAY_STEP, &bt, np, global_batch);
+  key.idx = idx;
+  rc = run(h, (cudaStream_t)stream, key, [&](Ctx& c) {
+    const bool forked = fork_prologue(h, bt, np, c, true);
+    enqueue_gather(h, batch, idx, c);
+    if (!idx && np) { launch_k(rng_advance_kernel, 1, 32, 0, c, h->buf.state); c.done(); }
+    enqueue_phase1(h, bt, np, c, true, forked);
+    enqueue_dp_exchange(h, 0, c);
+    enqueue_phase2(h, bt, global_batch, c, REDUCE_DP);
+    enqueue_dp_exchange(h, 1, c);
+    enqueue_apply(h, c, false, true);
   });
   if (rc) return rc;
   h->pending = bt; h->pending_batch = batch;
@@ -1435,7 +1573,7 @@ int dsact_profile_step(dsact_handle* h, const dsact_batch* batch, const dsact_no
   CUDA_TRY(cudaEventCreate(&e0));
   CUDA_TRY(cudaEventRecord(e0, s));
   enqueue_phase1(h, bt, np, c);
-  enqueue_phase2(h, bt, bt.batch, c, true);
+  enqueue_phase2(h, bt, bt.batch, c, REDUCE_DEFER);
   enqueue_apply(h, c, true);
   cudaError_t e = cudaStreamSynchronize(s);
   memset(out, 0, sizeof(*out));

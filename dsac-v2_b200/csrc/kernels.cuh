@@ -23,7 +23,9 @@ enum {
   ST_RNG_CTR = 10,                     // uint32 step counter of the device generator
   ST_ITER = 11,                        // int32 iteration the next apply will use (dsac_v2.py:324)
   ST_RB_SIZE = 12,                     // [12],[13] int64 number of valid replay rows
+  ST_DP_ERR = 7,                       // int32: nonzero = a peer did not arrive in time (1 + its rank), dp_peer.cuh
   ST_TICKET = 14,                      // int32: blocks of apply_kernel that have finished (the last one advances the counters)
+  ST_DP_EPOCH = 15,                    // int32: exchanges completed by the peer-memory data-parallel path
   ST_ACC = 16,                         // 16 sums then 16 mins
   ST_STATS = 48,
   ST_ADAM_SC = 64,                     // [64..68] Adam step sizes / bias corrections of this step (phase2 tail -> apply)
@@ -486,6 +488,9 @@ struct ApplyArgs {
   const float* slabs;
   int nslabs;
   long long slab_stride;
+  // peer-memory data parallelism (dp_peer.cuh): the global gradient is the rank-ordered sum of every rank's block
+  const float* dp_grads[8];
+  int dp_world;
 };
 // torch.optim.Adam single-tensor step (amsgrad / weight decay off)
 __device__ __forceinline__ float adam_update(float w, float g, float& m, float& v, float step_size, float bc2_sqrt,
@@ -524,7 +529,20 @@ __global__ void apply_kernel(const __grid_constant__ ApplyArgs a) {
         const float4 T4 = reinterpret_cast<const float4*>(a.targets)[gi];
         t[0] = T4.x; t[1] = T4.y; t[2] = T4.z; t[3] = T4.w;
       }
-      if (a.nslabs > 0) {
+      if (a.dp_world > 0) {
+        float4 p[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+          if (r < a.dp_world) {
+            asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(p[r].x), "=f"(p[r].y), "=f"(p[r].z), "=f"(p[r].w) : "l"(a.dp_grads[r] + 4 * gi) : "memory");
+          }
+        g[0] = p[0].x; g[1] = p[0].y; g[2] = p[0].z; g[3] = p[0].w;
+#pragma unroll
+        for (int r = 1; r < 8; ++r)
+          if (r < a.dp_world) { g[0] += p[r].x; g[1] += p[r].y; g[2] += p[r].z; g[3] += p[r].w; }
+        reinterpret_cast<float4*>(a.grads)[gi] = make_float4(g[0], g[1], g[2], g[3]);
+      } else if (a.nslabs > 0) {
         float4 p[8];   // independent loads first (the arena never has more than 8 slabs), then the sum in slab order
 #pragma unroll
         for (int k = 0; k < 8; ++k)
@@ -544,7 +562,16 @@ __global__ void apply_kernel(const __grid_constant__ ApplyArgs a) {
         const bool in = i < a.n_all;
         w[e] = in ? a.params[i] : 0.f; g[e] = in ? a.grads[i] : 0.f; m[e] = in ? a.m[i] : 0.f; v[e] = in ? a.v[i] : 0.f;
         t[e] = (in && i < n_targets) ? a.targets[i] : 0.f;
-        if (in && a.nslabs > 0) {
+        if (in && a.dp_world > 0) {
+          float acc = 0.f;
+          for (int r = 0; r < a.dp_world; ++r) {
+            float v;
+            asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(a.dp_grads[r] + i) : "memory");
+            acc = r == 0 ? v : acc + v;
+          }
+          g[e] = acc;
+          a.grads[i] = acc;
+        } else if (in && a.nslabs > 0) {
           for (int k = 0; k < a.nslabs; ++k) g[e] += a.slabs[(size_t)k * a.slab_stride + i];
           a.grads[i] = g[e];
         }
@@ -646,7 +673,7 @@ __global__ void finalize_stats_kernel(float* __restrict__ state, float inv_globa
   o[11] = state[ST_ALPHA_USED];
   o[12] = state[ST_MEAN_STD1];
   o[13] = state[ST_MEAN_STD2];
-  o[14] = 0.f;
+  o[14] = (float)reinterpret_cast<const int*>(state)[ST_DP_ERR];   // 0, or 1 + rank of the peer that timed out
   o[15] = 0.f;
 }
 

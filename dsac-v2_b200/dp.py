@@ -7,8 +7,10 @@ shard the minibatch across ranks, exchange
      (each rank already scales its loss terms by 1/global_batch);
   3. the logged accumulators (16 sums, 2 minima).
 
-Collectives go through `torch.distributed` (NCCL over NVLink on GPUs; gloo in the CPU
-tests).  `engine` is anything with grad_phase1 / grad_phase2 / state / grads — the CUDA
+Two transports.  `connect_peers` + `engine.dp_step`: the exchanges run inside the step's own
+kernels over NVLink peer memory (CUDA IPC), the whole data-parallel step is one graph launch
+per rank.  `data_parallel_gradients`: the same seam through `torch.distributed` (NCCL on
+GPUs; gloo in the CPU tests) — the fallback, and the path of the split gradient API.  `engine` is anything with grad_phase1 / grad_phase2 / state / grads — the CUDA
 `Engine`, or a CPU stand-in in tests/test_dp_gloo.py.
 """
 from __future__ import annotations
@@ -40,6 +42,36 @@ def data_parallel_gradients(engine, data, noise, dist, local_rows: int, global_r
     dist.all_reduce(engine.state[_lib.STATE_ACC:_lib.STATE_ACC + 16])
     dist.all_reduce(engine.state[_lib.STATE_ACC + 16:_lib.STATE_ACC + 18], op=dist.ReduceOp.MIN)
     return global_rows
+
+
+def connect_peers(engine, dist) -> bool:
+    """Map the ranks' exchange buffers into each other (CUDA IPC) so that `engine.dp_step` can run the exchanges inside
+    the step's own kernels (include/dsact.h, csrc/dp_peer.cuh).  Collective: every rank must call it.  Returns False —
+    on every rank alike — if any rank cannot export or map a buffer (no peer access, IPC disabled in the container,
+    more than DSACT_DP_MAX_RANKS ranks); the caller then stays on the NCCL path above."""
+    world_size, rank = dist.get_world_size(), dist.get_rank()
+    handle, err = None, None
+    if world_size > _lib.DP_MAX_RANKS:
+        err = f"world size {world_size} > {_lib.DP_MAX_RANKS}"
+    else:
+        try:
+            handle = engine.dp_export()
+        except _lib.DsactError as e:
+            err = str(e)
+    gathered = [None] * world_size
+    dist.all_gather_object(gathered, (handle, err))
+    ok = all(e is None for _, e in gathered)
+    if ok:
+        try:
+            engine.dp_connect(rank, [h for h, _ in gathered])
+        except _lib.DsactError as e:
+            ok, err = False, str(e)
+    flags = [None] * world_size
+    dist.all_gather_object(flags, ok)     # also the barrier that dsact_dp_connect asks for
+    if not all(flags):
+        engine.dp_world = 0
+        return False
+    return True
 
 
 def global_rows(dist, local_rows: int, device) -> int:

@@ -166,6 +166,8 @@ class _LazyTbInfo(Mapping):
     def _materialise(self):
         if self._vals is None:
             self._event.synchronize()
+            if float(self._slot[14]) != 0.0:   # include/dsact.h: tb_info slot 14 = 1 + rank of a peer that never arrived
+                raise _lib.DsactError(f"data-parallel exchange timed out waiting for rank {int(self._slot[14]) - 1}")
             vals = {k: float(self._slot[i]) for i, k in enumerate(STAT_KEYS)}
             vals[tb_tags["alg_time"]] = self._alg_ms
             self._vals, self._slot = vals, None
@@ -200,6 +202,10 @@ class DSAC_V2:
         if self.noise_source not in ("device", "reference"):
             raise ValueError("dsact_noise must be 'device' or 'reference'")
         self.data_parallel = kwargs.get("dsact_data_parallel", True)
+        # "peer": exchanges inside the step's kernels over NVLink peer memory (falls back to NCCL if the ranks cannot
+        # map each other's buffers); "nccl": torch.distributed all-reduces between three graph launches
+        self.dp_transport = kwargs.get("dsact_dp_transport", "peer")
+        self._peer_dp = None
         self._slots, self._owners, self._cursor = None, [None] * self._RING, 0
 
     @property
@@ -289,9 +295,15 @@ class DSAC_V2:
         t0 = time.time()
         B = data["obs"].shape[0]
         eng = self.networks.engine(B)
-        if self._world()[1] == 1:
+        dist, world = self._world()
+        if world == 1:
             eng.step(data, iteration, self._noise(B))
             return self._stats(eng, B, t0)
+        if self._peer_dp is None:   # first data-parallel update: try to map the ranks' exchange buffers (collective)
+            self._peer_dp = self.dp_transport != "nccl" and dp.connect_peers(eng, dist)
+        if self._peer_dp:           # one graph launch; exchanges inside the step's kernels over NVLink peer memory
+            eng.dp_step(data, iteration, B * world, self._noise(B))
+            return self._stats(eng, B * world, t0)
         gb = self._gradients(data, eng)
         eng.apply(iteration)
         return self._stats(eng, gb, t0)

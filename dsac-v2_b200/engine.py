@@ -108,6 +108,7 @@ class Engine:
             self._bind()
             check(self.lib.dsact_set_carry(self.h, -1.0, -1.0, 0, 0, self._stream()))
         self.replay = None
+        self.dp_world = 0          # > 1 once dp_connect has mapped the peers
         self._seed = 0x5DEECE66D   # the library's default (csrc/engine.cu)
         self._arena = None
         self._copy_stream = None
@@ -274,6 +275,8 @@ class Engine:
     def read_stats(self, global_batch: Optional[int] = None) -> Dict[str, float]:
         out = self.read_stats_async(global_batch)
         torch.cuda.current_stream(self.device).synchronize()
+        if float(out[14]) != 0.0:   # include/dsact.h: slot 14 = 1 + rank of a peer that never arrived (dsact_dp_step)
+            raise _lib.DsactError(f"data-parallel exchange timed out waiting for rank {int(out[14]) - 1}")
         return {k: float(out[i]) for i, k in enumerate(STAT_KEYS)}
 
     def set_carry(self, mean_std1=-1.0, mean_std2=-1.0, adam_steps_q=0, adam_steps_pi=0):
@@ -335,6 +338,46 @@ class Engine:
             n, keep = self._noise(noise, batch)
             self._keep_noise = keep
             check(self.lib.dsact_replay_step(self.h, int(batch), int(size), _ptr(idx), n, int(iteration), self._stream()))
+        self.last_batch = int(batch)
+
+    # ---- data-parallel replicas over NVLink peer memory (include/dsact.h) ---------------------
+    def dp_export(self) -> bytes:
+        """Allocate this rank's exchange buffer; its CUDA IPC handle (to be handed to every other rank)."""
+        buf = C.create_string_buffer(_lib.IPC_HANDLE_BYTES)
+        n = C.c_int64(0)
+        with torch.cuda.device(self.device):
+            check(self.lib.dsact_dp_export(self.h, buf, C.byref(n)))
+        return buf.raw
+
+    def dp_connect(self, rank: int, handles: Sequence[bytes]):
+        """Map every rank's exchange buffer (`handles` in rank order, one per rank including this one)."""
+        blob = b"".join(handles)
+        if len(blob) != _lib.IPC_HANDLE_BYTES * len(handles):
+            raise ValueError("malformed IPC handle list")
+        with torch.cuda.device(self.device):
+            check(self.lib.dsact_dp_connect(self.h, int(rank), len(handles), blob))
+        self.dp_world = len(handles)
+
+    def dp_step(self, data, iteration: int, global_batch: int, noise=None):
+        """dsact_step on this rank's shard with the exchanges done in-kernel over peer memory."""
+        with torch.cuda.device(self.device):
+            b = self._batch(data)
+            n, keep = self._noise(noise, b.batch)
+            self._keep_noise = keep
+            check(self.lib.dsact_dp_step(self.h, C.byref(b), n, int(global_batch), int(iteration), self._stream()))
+            self._mark_staged_done()
+        self.last_batch = b.batch
+
+    def dp_replay_step(self, batch: int, size: int, iteration: int, global_batch: int, idx: Optional[torch.Tensor] = None,
+                       noise=None):
+        with torch.cuda.device(self.device):
+            if idx is not None:
+                idx = idx.to(device=self.device, dtype=torch.int64).contiguous()
+                self._keep_idx = idx
+            n, keep = self._noise(noise, batch)
+            self._keep_noise = keep
+            check(self.lib.dsact_dp_replay_step(self.h, int(batch), int(size), _ptr(idx), n, int(global_batch), int(iteration),
+                                                self._stream()))
         self.last_batch = int(batch)
 
     # ---- weights in the reference's state_dict schema -----------------------------------

@@ -179,6 +179,27 @@ int dsact_replay_sample(dsact_handle *h, int32_t batch, int64_t size, const int6
 int dsact_replay_step(dsact_handle *h, int32_t batch, int64_t size, const int64_t *idx,
                       const dsact_noise *noise, int64_t iteration, void *stream);
 
+/* ---- data-parallel replicas over NVLink peer memory (one process per GPU) ---------------------------------------
+ * Replaces, for the same path, what `dsac-v2_b200/dp.py` does with three graph launches and four NCCL all-reduces
+ * (reference: the reduction semantics of DSAC_V2.__compute_gradient, dsac_v2.py:150-206/233-241, under data
+ * parallelism; the reference itself has no multi-GPU path).  Set-up, once, on every rank:
+ *   dsact_dp_export  -> allocate this rank's exchange buffer, return its CUDA IPC handle (DSACT_IPC_HANDLE_BYTES);
+ *   (exchange the handles between the processes: any host transport, e.g. torch.distributed.all_gather_object)
+ *   dsact_dp_connect -> map every peer's buffer (`handles` = world x DSACT_IPC_HANDLE_BYTES, rank order), reset epochs;
+ *   (host barrier between the ranks).
+ * Then dsact_dp_step / dsact_dp_replay_step = dsact_step / dsact_replay_step on this rank's shard, with the critic-std
+ * sums, the gradients and the logged sums reduced over all ranks inside the step's own kernels (rank-ordered sums: the
+ * replicas stay bit-identical).  `global_batch` = sum of the ranks' batch sizes.  A peer that never arrives makes
+ * tb_info slot 14 non-zero (1 + its rank) after DSACT_DP_TIMEOUT_MS (default 10 s) instead of hanging the GPU. */
+#define DSACT_IPC_HANDLE_BYTES 64
+#define DSACT_DP_MAX_RANKS 8
+int dsact_dp_export(dsact_handle *h, void *handle_out, int64_t *bytes_out);
+int dsact_dp_connect(dsact_handle *h, int32_t rank, int32_t world, const void *handles);
+int dsact_dp_step(dsact_handle *h, const dsact_batch *batch, const dsact_noise *noise, int64_t global_batch,
+                  int64_t iteration, void *stream);
+int dsact_dp_replay_step(dsact_handle *h, int32_t batch, int64_t size, const int64_t *idx, const dsact_noise *noise,
+                         int64_t global_batch, int64_t iteration, void *stream);
+
 /* introspection for tests/bench: number of kernel launches (graph nodes included)
  * submitted by this handle so far, and by the most recent entry-point call */
 int64_t dsact_launch_count(const dsact_handle *h);

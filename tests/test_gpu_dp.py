@@ -1,5 +1,6 @@
-"""Data-parallel update on 2 GPUs over NCCL == single-GPU update on the concatenated minibatch.
-Needs >= 2 CUDA devices (`gpurun --gpus 2`); skipped on a single-GPU box."""
+"""Data-parallel update on 2 GPUs == single-GPU update on the concatenated minibatch, for both transports:
+"peer" (exchanges inside the step's kernels over NVLink peer memory, one graph per rank: dsact_dp_step) and "nccl"
+(torch.distributed all-reduces between the phase launches).  Needs >= 2 CUDA devices (`gpurun --gpus 2`)."""
 import os
 import sys
 
@@ -12,7 +13,7 @@ pytestmark = pytest.mark.gpu
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, out_dir, gemm):
+def _worker(rank, world, port, out_dir, gemm, transport):
     sys.path.insert(0, REPO)
     sys.path.insert(0, os.path.join(REPO, "dsac-v2_b200", "dropin"))
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
@@ -30,6 +31,8 @@ def _worker(rank, world, port, out_dir, gemm):
     alg.networks.load_state_dict(sd)
     alg.networks.cuda()
     eng = alg.networks.engine()
+    if transport == "peer":
+        assert dp.connect_peers(eng, dist), "the ranks could not map each other's exchange buffers"
     tbs = []
     for it in range(5):
         full, noise = synth.make_batch(cfg, B, it), synth.make_noise(cfg, B, it)
@@ -37,24 +40,31 @@ def _worker(rank, world, port, out_dir, gemm):
         shard = {k: torch.from_numpy(v[lo:hi]).cuda() for k, v in full.items()}
         nz = tuple(torch.from_numpy(noise[i][lo:hi]).cuda() for i in (0, 1, 4, 5))
         # the engine-level sequence DSAC_V2.local_update runs under torch.distributed, with explicit noise
-        gb = dp.data_parallel_gradients(eng, shard, nz, dist, hi - lo, B)
-        eng.apply(it)
+        if transport == "peer":
+            eng.dp_step(shard, it, B, nz)
+            gb = B
+        else:
+            gb = dp.data_parallel_gradients(eng, shard, nz, dist, hi - lo, B)
+            eng.apply(it)
         tbs.append([eng.read_stats(gb)[k] for k in ("Loss/Critic loss-RL iter", "Loss/Actor loss-RL iter",
                                                     "DSAC2/critic_avg_min_std1-RL iter", "DSAC2/mean_std1")])
+    assert int(eng.state[:16].view(torch.int32)[7]) == 0, "a peer timed out"
     np.savez(os.path.join(out_dir, f"rank{rank}.npz"), params=eng.params.cpu().numpy(), targets=eng.targets.cpu().numpy(),
-             tb=np.array(tbs))
+             grads=eng.grads.cpu().numpy(), tb=np.array(tbs))
     dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("transport", ["peer", "nccl"])
 @pytest.mark.parametrize("gemm", ["fp32", "bf16x3"])
-def test_two_gpu_data_parallel_equals_single_gpu(tmp_path, gemm):
+def test_two_gpu_data_parallel_equals_single_gpu(tmp_path, gemm, transport):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
-    port = 29600 + os.getpid() % 1000
-    mp.spawn(_worker, args=(2, port, str(tmp_path), gemm), nprocs=2, join=True)
+    port = 29600 + (os.getpid() + (7 if transport == "peer" else 0)) % 1000
+    mp.spawn(_worker, args=(2, port, str(tmp_path), gemm, transport), nprocs=2, join=True)
     r0, r1 = np.load(tmp_path / "rank0.npz"), np.load(tmp_path / "rank1.npz")
     np.testing.assert_array_equal(r0["params"], r1["params"])   # replicas stay bit-identical
     np.testing.assert_array_equal(r0["targets"], r1["targets"])
+    np.testing.assert_array_equal(r0["grads"], r1["grads"])     # every rank holds the global gradient
     # single GPU on the full minibatch
     sys.path.insert(0, os.path.join(REPO, "dsac-v2_b200", "dropin"))
     from dsac_v2_b200 import synth
