@@ -296,6 +296,12 @@ static void launch_tc(const dsact_handle* h, Group& G, int variant, Ctx& c, int 
   const bool a_mn = variant == V_WGRAD, b_mn = variant != V_FWD;
   int grid = 0;
   int bn_max = 16;
+  int wg_bn = 128;
+  if (variant == V_WGRAD) {  // a launch that would leave most SMs idle at 128-wide tiles gets 64-wide ones
+    int ctas = 0;
+    for (int i = 0; i < G.n; ++i) ctas += ((G.prob(i).M + TC_BM - 1) / TC_BM) * ((G.prob(i).N + 127) / 128) * (G.wg_slab ? G.wg_nslabs : h->ar.nslabs);
+    if (ctas * 2 <= h->num_sms) wg_bn = 64;
+  }
   for (int i = 0; i < G.n; ++i) {
     const GemmProb& s = G.prob(i);
     const TcExtra& x = G.x[i];
@@ -303,7 +309,7 @@ static void launch_tc(const dsact_handle* h, Group& G, int variant, Ctx& c, int 
     p.M = s.M; p.N = s.N;
     int bn = (s.N + 15) / 16 * 16;
     if (bn > 256) bn = 256;
-    if (variant == V_WGRAD && bn > 128) bn = 128;  // more tiles for the (few, batch-split) weight-gradient problems
+    if (variant == V_WGRAD && bn > wg_bn) bn = wg_bn;  // more tiles for the (few, batch-split) weight-gradient problems
     p.bn = bn;
     if (bn > bn_max) bn_max = bn;
     p.tiles_m = (s.M + TC_BM - 1) / TC_BM;
