@@ -154,7 +154,8 @@ int dsact_apply(dsact_handle *h, int64_t iteration, void *stream);
 /* tb_info (dsac_v2.py:188-202) of the last step, in this order:
  *  0 q1 mean, 1 q2 mean, 2 std1 mean, 3 std2 mean, 4 min std1, 5 min std2,
  *  6 actor loss, 7 critic loss, 8 mean tanh(policy mean), 9 mean policy std,
- * 10 entropy, 11 alpha (pre-update), 12 mean_std1, 13 mean_std2, 14/15 reserved.
+ * 10 entropy, 11 alpha (pre-update), 12 mean_std1, 13 mean_std2,
+ * 14 data-parallel exchange status (0 = ok, 1 + r = rank r never arrived, see dsact_dp_step), 15 reserved.
  * Finalises the accumulators over `global_batch` rows and copies 16 floats to `host_out`
  * (pinned or pageable) asynchronously on `stream`. */
 int dsact_read_stats(dsact_handle *h, int64_t global_batch, float *host_out, void *stream);
@@ -227,6 +228,8 @@ int dsact_test_gemm(dsact_handle *h, int32_t variant, const float *A, int32_t ld
 #define DSACT_STATE_ACC 16     /* state[16..47]: per-step accumulators (sums first, then mins) */
 #define DSACT_STATE_STATS 48   /* state[48..63]: finalised tb_info */
 #define DSACT_STATE_ADAM 64    /* state[64..68]: Adam step sizes / bias corrections of the running step (internal) */
+#define DSACT_STATE_DP_ERR 7    /* int32: 0, or 1 + rank of the peer a dsact_dp_step exchange timed out on */
+#define DSACT_STATE_DP_EPOCH 15 /* int32: exchanges opened by dsact_dp_step so far (reset by dsact_dp_connect) */
 
 #ifdef __cplusplus
 }
