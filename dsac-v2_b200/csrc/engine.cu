@@ -151,6 +151,7 @@ struct dsact_handle {
   cudaStream_t side_stream;  // second branch inside a step (critic weight gradients || policy backward chain)
   cudaEvent_t ev_fork, ev_join;
   cudaEvent_t ev_pro_fork, ev_pro_join;   // prologue branch (weight images, noise, clears) beside the replay gather
+  cudaEvent_t ev_dp_fork, ev_dp_join;     // std-sum exchange of the data-parallel step beside the second forward chain
   // peer-memory data parallelism (dp_peer.cuh)
   float* dp_buf = nullptr;            // this rank's exchange buffer (cudaMalloc, exported with CUDA IPC)
   void* dp_opened[DP_MAX_RANKS] = {}; // peers' buffers as opened here
@@ -216,8 +217,7 @@ static bool pdl_enabled() {
 }
 template <typename... KArgs, typename... Args>
 static void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, Ctx& c, Args&&... args) {
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
+  cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = c.s;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -735,8 +735,19 @@ static bool fork_prologue(dsact_handle* h, const dsact_batch& bt, const dsact_no
   return true;
 }
 
+// One exchange of the peer-memory data-parallel path (dp_peer.cuh): kind 0 = critic-std sums, 1 = logged sums.
+static void enqueue_dp_exchange(dsact_handle* h, int kind, Ctx& c) {
+  static const unsigned long long timeout_ns =
+      (unsigned long long)(getenv("DSACT_DP_TIMEOUT_MS") ? atoll(getenv("DSACT_DP_TIMEOUT_MS")) : 10000) * 1000000ull;
+  launch_k(dp_exchange_kernel, 1, 32 * h->dp.world, 0, c, h->dp, h->buf.state, kind, timeout_ns);
+  c.done();
+}
+
+// `dp_std_exchange`: the std sums are complete once sample_kernel has run, one whole forward chain before the loss needs
+// them: in a captured step their exchange (kernel + NVLink flag round trip + whatever the ranks are skewed by) runs as a
+// side branch under that chain.
 static void enqueue_phase1(dsact_handle* h, const dsact_batch& bt, const dsact_noise* nz, Ctx& c, bool inputs_imaged = false,
-                           bool prologue_forked = false) {
+                           bool prologue_forked = false, bool dp_std_exchange = false) {
   const dsact_config& cf = h->cfg;
   const Net &q = h->q, &pi = h->pi;
   const Arena& ar = h->ar;
@@ -813,6 +824,21 @@ static void enqueue_phase1(dsact_handle* h, const dsact_batch& bt, const dsact_n
     int blocks = (B + 7) / 8; if (blocks > 4 * h->num_sms) blocks = 4 * h->num_sms;
     launch_k(sample_kernel, dim3(blocks, 2), 256, 0, c, a); c.done();
   }
+  bool dp_forked = false;
+  if (dp_std_exchange) {
+    if (c.side) {
+      cudaEventRecord(h->ev_dp_fork, c.s);
+      cudaStreamWaitEvent(c.side, h->ev_dp_fork, 0);
+      Ctx cs{c.side, 0, cudaSuccess};
+      enqueue_dp_exchange(h, 0, cs);
+      cudaEventRecord(h->ev_dp_join, c.side);
+      c.launches += cs.launches;
+      if (cs.err != cudaSuccess && c.err == cudaSuccess) c.err = cs.err;
+      dp_forked = true;
+    } else {
+      enqueue_dp_exchange(h, 0, c);
+    }
+  }
 
   // wave B: Q1', Q2' on (s', a') and Q1, Q2 on (s, a~)
   const Ten t_new_act = ten(W + ar.new_act, ar.i_new_act), t_act2 = ten(W + ar.act2, ar.i_act2);
@@ -839,6 +865,7 @@ static void enqueue_phase1(dsact_handle* h, const dsact_batch& bt, const dsact_n
     launch_group(h, G, V_FWD, c);
   }
 
+  if (dp_forked) cudaStreamWaitEvent(c.s, h->ev_dp_join, 0);
   h->pending_eps1 = eps1; h->pending_z3 = z3; h->pending_z4 = z4;
   c.check();
 }
@@ -1199,6 +1226,8 @@ int dsact_create(const dsact_config* cfg, int device, dsact_handle** out) {
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_pro_fork, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_pro_join, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_dp_fork, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_dp_join, cudaEventDisableTiming);
   if (e != cudaSuccess) { delete h; return fail(DSACT_ECUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(e)); }
   *out = h;
   return DSACT_OK;
@@ -1214,6 +1243,8 @@ void dsact_destroy(dsact_handle* h) {
   cudaEventDestroy(h->ev_join);
   cudaEventDestroy(h->ev_pro_fork);
   cudaEventDestroy(h->ev_pro_join);
+  cudaEventDestroy(h->ev_dp_fork);
+  cudaEventDestroy(h->ev_dp_join);
   for (int r = 0; r < DP_MAX_RANKS; ++r) if (h->dp_opened[r]) cudaIpcCloseMemHandle(h->dp_opened[r]);
   if (h->dp_buf) cudaFree(h->dp_buf);
   delete h;
@@ -1446,13 +1477,6 @@ int dsact_replay_step(dsact_handle* h, int32_t batch, int64_t size, const int64_
 }
 
 // ---- data parallelism over peer memory (dp_peer.cuh) ------------------------------------------------------------
-static void enqueue_dp_exchange(dsact_handle* h, int kind, Ctx& c) {
-  static const unsigned long long timeout_ns =
-      (unsigned long long)(getenv("DSACT_DP_TIMEOUT_MS") ? atoll(getenv("DSACT_DP_TIMEOUT_MS")) : 10000) * 1000000ull;
-  launch_k(dp_exchange_kernel, 1, 32 * h->dp.world, 0, c, h->dp, h->buf.state, kind, timeout_ns);
-  c.done();
-}
-
 int dsact_dp_export(dsact_handle* h, void* handle_out, int64_t* bytes_out) {
   if (!h || !handle_out) return fail(DSACT_EINVAL, "null argument");
   CUDA_TRY(cudaSetDevice(h->device));
@@ -1516,8 +1540,7 @@ int dsact_dp_step(dsact_handle* h, const dsact_batch* batch, const dsact_noise* 
   GraphKey key = make_key(K_DP_STEP, &bt, np, global_batch);
   key.size = imaged ? 1 : 0;
   rc = run(h, (cudaStream_t)stream, key, [&](Ctx& c) {
-    enqueue_phase1(h, bt, np, c, imaged);
-    enqueue_dp_exchange(h, 0, c);
+    enqueue_phase1(h, bt, np, c, imaged, false, true);
     enqueue_phase2(h, bt, global_batch, c, REDUCE_DP);
     enqueue_dp_exchange(h, 1, c);
     enqueue_apply(h, c, false, true);
@@ -1548,8 +1571,7 @@ int dsact_dp_replay_step(dsact_handle* h, int32_t batch, int64_t size, const int
     const bool forked = fork_prologue(h, bt, np, c, true);
     enqueue_gather(h, batch, idx, c);
     if (!idx && np) { launch_k(rng_advance_kernel, 1, 32, 0, c, h->buf.state); c.done(); }
-    enqueue_phase1(h, bt, np, c, true, forked);
-    enqueue_dp_exchange(h, 0, c);
+    enqueue_phase1(h, bt, np, c, true, forked, true);
     enqueue_phase2(h, bt, global_batch, c, REDUCE_DP);
     enqueue_dp_exchange(h, 1, c);
     enqueue_apply(h, c, false, true);
