@@ -193,6 +193,7 @@ struct Ctx {
   cudaError_t err;
   Prof* prof = nullptr;
   cudaStream_t side = nullptr;   // optional second stream for an independent branch (null: serialise on `s`)
+  bool pdl = true;               // programmatic dependent launch for this enqueue (off in fp32 mode, see pdl_enabled)
   void check() { cudaError_t e = cudaGetLastError(); if (e != cudaSuccess && err == cudaSuccess) err = e; }
   void done(int cls = CLS_OTHER, double flops = 0.0) {
     launches++;
@@ -209,7 +210,8 @@ struct Ctx {
 
 // Every kernel goes out with the programmatic-dependent-launch attribute (each kernel begins with griddepcontrol.wait),
 // so that inside the captured graph a kernel's launch and prologue overlap its predecessor's tail (measured: -18 us of
-// a 280 us step at B=4096, tools/pdl_ab.sh).  DSACT_PDL=0 turns it off.
+// a 280 us step at B=4096, tools/pdl_ab.sh).  DSACT_PDL=0 turns it off.  The fp32 SIMT mode launches without it: its
+// multi-wave GEMM grids lose SM slots to early-launched dependents (measured 514 vs 566 steps/s).
 static bool pdl_enabled() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("DSACT_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
@@ -222,7 +224,7 @@ static void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cfg.attrs = at; cfg.numAttrs = (pdl_enabled() && c.pdl) ? 1 : 0;
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
   if (e != cudaSuccess && c.err == cudaSuccess) c.err = e;
 }
@@ -728,6 +730,7 @@ static bool fork_prologue(dsact_handle* h, const dsact_batch& bt, const dsact_no
   cudaEventRecord(h->ev_pro_fork, c.s);
   cudaStreamWaitEvent(c.side, h->ev_pro_fork, 0);
   Ctx cs{c.side, 0, cudaSuccess};
+  cs.pdl = c.pdl;
   enqueue_prologue(h, bt, nz, cs, inputs_imaged, true);
   cudaEventRecord(h->ev_pro_join, c.side);
   c.launches += cs.launches;
@@ -830,6 +833,7 @@ static void enqueue_phase1(dsact_handle* h, const dsact_batch& bt, const dsact_n
       cudaEventRecord(h->ev_dp_fork, c.s);
       cudaStreamWaitEvent(c.side, h->ev_dp_fork, 0);
       Ctx cs{c.side, 0, cudaSuccess};
+      cs.pdl = c.pdl;
       enqueue_dp_exchange(h, 0, cs);
       cudaEventRecord(h->ev_dp_join, c.side);
       c.launches += cs.launches;
@@ -955,6 +959,7 @@ static void enqueue_phase2(dsact_handle* h, const dsact_batch& bt, int64_t globa
       cudaEventRecord(h->ev_fork, c.s);
       cudaStreamWaitEvent(c.side, h->ev_fork, 0);
       Ctx cs{c.side, 0, cudaSuccess};
+      cs.pdl = c.pdl;
       // the policy backward chain needs ceil(B/128) whole SMs: keep them free of weight-gradient CTAs
       const int chain_ctas = (B + TC_BM - 1) / TC_BM;
       const int cap = h->num_sms - chain_ctas;
@@ -1077,6 +1082,7 @@ template <typename F>
 static int run(dsact_handle* h, cudaStream_t user, const GraphKey& key, F enqueue) {
   if (!h->cfg.use_graph) {
     Ctx c{user, 0, cudaSuccess};
+    c.pdl = h->tc();
     enqueue(c);
     if (c.err != cudaSuccess) return fail(DSACT_ECUDA, "kernel launch failed: %s", cudaGetErrorString(c.err));
     h->launches += c.launches;
@@ -1089,6 +1095,7 @@ static int run(dsact_handle* h, cudaStream_t user, const GraphKey& key, F enqueu
   if (!hit) {
     CUDA_TRY(cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeRelaxed));
     Ctx c{h->cap_stream, 0, cudaSuccess};
+    c.pdl = h->tc();
     c.side = h->side_stream;
     enqueue(c);
     cudaGraph_t graph = nullptr;
@@ -1596,6 +1603,7 @@ int dsact_profile_step(dsact_handle* h, const dsact_batch* batch, const dsact_no
   if (noise) { nz = *noise; np = &nz; }
   Prof prof;
   Ctx c{s, 0, cudaSuccess};
+  c.pdl = h->tc();
   c.prof = &prof;
   cudaEvent_t e0;
   CUDA_TRY(cudaEventCreate(&e0));
@@ -1642,6 +1650,7 @@ int dsact_test_gemm(dsact_handle* h, int32_t variant, const float* A, int32_t ld
   p.epi = variant == V_WGRAD ? EPI_ATOMIC : EPI_STORE;
   G.push(p, TcExtra());
   Ctx c{s, 0, cudaSuccess};
+  c.pdl = h->tc();
   void* scratch = nullptr;
   if (h->tc()) {  // test hook only: scratch images (and slabs) come from cudaMalloc, not from the caller
     if (variant == V_WGRAD && ldc != N) return fail(DSACT_EINVAL, "tc wgrad test needs contiguous C");
