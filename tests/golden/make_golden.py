@@ -45,6 +45,11 @@ CASES = [
     ("humanoid_b4096", "humanoid", 4096, 6, (), {}),
     # fixed temperature + different delay / tau_b: exercises the non-default branches
     ("tiny_fixed_alpha", "tiny", 16, 12, (1, 12), {"auto_alpha": False, "alpha": 0.2, "delay_update": 3, "tau_b": 0.05}),
+] + [
+    # the reference's other hidden activations (utils/common_utils.py:16-43), same one in critics and policy
+    (f"{cfg}_{act}", cfg, batch, 10, (10,), {"value_hidden_activation": act, "policy_hidden_activation": act})
+    for cfg, batch, act in (("tiny", 16, "relu"), ("tiny", 33, "tanh"), ("ragged", 19, "elu"), ("ragged", 37, "selu"),
+                            ("tiny", 8, "sigmoid"))
 ]
 
 TB_KEYS = [

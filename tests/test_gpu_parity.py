@@ -26,6 +26,9 @@ def make_engine(cfg, batch, over=None, **kw):
     from dsac_v2_b200.engine import Engine, make_config
     hyper = dict(synth.HYPER)
     hyper.update(over or {})
+    if "value_hidden_activation" in hyper:   # goldens of the reference's other activations
+        kw.setdefault("act_q", hyper.pop("value_hidden_activation"))
+        kw.setdefault("act_pi", hyper.pop("policy_hidden_activation"))
     c = make_config(cfg["obs_dim"], cfg["act_dim"], cfg["hidden"], cfg["hidden"], max_batch=batch,
                     gamma=hyper["gamma"], tau=hyper["tau"], tau_b=hyper.get("tau_b"), delay_update=hyper["delay_update"],
                     auto_alpha=hyper["auto_alpha"], alpha=hyper["alpha"], lr_q=hyper["value_learning_rate"],
@@ -50,7 +53,7 @@ def stats_vec(eng):
 
 
 CASES = ["tiny_b16", "ragged_b37", "tiny_fixed_alpha", "pendulum_b256", "halfcheetah_b512", "humanoid_b256",
-         "humanoid_b4096"]
+         "humanoid_b4096", "tiny_relu", "tiny_tanh", "ragged_elu", "ragged_selu", "tiny_sigmoid"]
 
 
 @pytest.mark.parametrize("use_graph", [False, True])
@@ -163,7 +166,9 @@ def test_device_noise_statistics():
 
 
 # ---- tcgen05 paths -------------------------------------------------------------------------------------
-TC_CASES = ["tiny_b16", "ragged_b37", "halfcheetah_b512", "humanoid_b256", "humanoid_b4096"]
+TC_CASES = ["tiny_b16", "ragged_b37", "halfcheetah_b512", "humanoid_b256", "humanoid_b4096",
+            # the generic-activation branch of the fused chain epilogue (GELU and ReLU have their own)
+            "tiny_relu", "tiny_tanh", "ragged_elu", "ragged_selu", "tiny_sigmoid"]
 
 
 @pytest.mark.parametrize("name", TC_CASES)

@@ -11,7 +11,9 @@ from dsac_v2_b200 import synth
 from oracle.dsact_oracle import TB_KEYS, from_config
 
 CASES = ["tiny_b16", "ragged_b37", "tiny_fixed_alpha", "pendulum_b256", "halfcheetah_b512",
-         "humanoid_b256", "humanoid_b4096"]
+         "humanoid_b256", "humanoid_b4096",
+         # the reference's other hidden activations (utils/common_utils.py:16-43)
+         "tiny_relu", "tiny_tanh", "ragged_elu", "ragged_selu", "tiny_sigmoid"]
 MAX_STEPS = {"humanoid_b256": 100, "pendulum_b256": 100}
 
 
@@ -28,7 +30,9 @@ def test_oracle_matches_reference(golden_dir, name):
     assert list(z["tb_keys"]) == TB_KEYS
     hyper = dict(synth.HYPER)
     hyper.update(over)
-    orc = from_config(cfg, synth.make_weights(cfg), **hyper)
+    act = hyper.pop("value_hidden_activation", "gelu")
+    assert hyper.pop("policy_hidden_activation", act) == act
+    orc = from_config(cfg, synth.make_weights(cfg), hidden_activation=act, **hyper)
     names = [str(n) for n in z["param_names"]]
     trainable = [str(n) for n in z["trainable_names"]]
     for it in range(steps):
