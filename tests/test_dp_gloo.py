@@ -107,3 +107,51 @@ def test_shard_rows_partition(n, world):
     assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
     sizes = [hi - lo for lo, hi in spans]
     assert max(sizes) - min(sizes) <= 1
+
+
+class _PeerStub:
+    """dp_export / dp_connect of the CUDA engine, scripted: which rank fails where."""
+
+    def __init__(self, rank, fail_export_on=None, fail_connect_on=None):
+        self.rank, self.fail_export_on, self.fail_connect_on = rank, fail_export_on, fail_connect_on
+        self.dp_world, self.connected = 0, None
+
+    def dp_export(self):
+        from dsac_v2_b200 import _lib
+        if self.rank == self.fail_export_on:
+            raise _lib.DsactError("cudaIpcGetMemHandle: not supported")
+        return bytes([self.rank]) * _lib.IPC_HANDLE_BYTES
+
+    def dp_connect(self, rank, handles):
+        from dsac_v2_b200 import _lib
+        if rank == self.fail_connect_on:
+            raise _lib.DsactError("cudaIpcOpenMemHandle: peer access denied")
+        self.connected, self.dp_world = list(handles), len(handles)
+
+
+def _peer_worker(rank, world, port, out_dir):
+    sys.path.insert(0, REPO)
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from dsac_v2_b200 import _lib, dp
+    results = []
+    ok = _PeerStub(rank)
+    results.append(dp.connect_peers(ok, dist))                       # every rank fine: handles in rank order everywhere
+    assert ok.connected == [bytes([r]) * _lib.IPC_HANDLE_BYTES for r in range(world)] and ok.dp_world == world
+    bad_export = _PeerStub(rank, fail_export_on=1)
+    results.append(dp.connect_peers(bad_export, dist))               # one rank cannot export: nobody connects
+    assert bad_export.connected is None and bad_export.dp_world == 0
+    bad_connect = _PeerStub(rank, fail_connect_on=0)
+    results.append(dp.connect_peers(bad_connect, dist))              # one rank cannot map a peer: all fall back alike
+    assert bad_connect.dp_world == 0
+    np.save(os.path.join(out_dir, f"peer{rank}.npy"), np.array(results))
+    dist.destroy_process_group()
+
+
+def test_peer_setup_is_all_or_nothing(tmp_path):
+    """`dp.connect_peers` must return the same answer on every rank, whichever rank fails to export or map a buffer
+    (a split decision would leave some ranks spinning on peers that took the NCCL path)."""
+    port = 29800 + os.getpid() % 1000
+    mp.spawn(_peer_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r0, r1 = np.load(tmp_path / "peer0.npy"), np.load(tmp_path / "peer1.npy")
+    assert r0.tolist() == r1.tolist() == [True, False, False]
