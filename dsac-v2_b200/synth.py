@@ -27,6 +27,17 @@ CONFIGS = {
     "ragged": dict(obs_dim=11, act_dim=3, hidden=(40, 24, 72), act_lim=1.5),
 }
 
+# BASELINE.json config 5 (gym_carracingraw): conv encoder `type_2` + separate mean / log_std
+# heads.  Oracle-level only so far (oracle/dsact_oracle.py:OracleDSACTCNN, tests/golden/cnn_carracing_b4.npz).
+CNN_CONFIGS = {
+    "carracing": dict(obs_dim=(3, 96, 96), act_dim=3, act_lim=1.0, conv_type="type_2"),
+}
+# reference networks/cnn.py:201-216 (type_2) and :163-170 (type_1): kernel sizes, channels, strides, head widths
+CONV_TYPES = {
+    "type_1": dict(kernels=(8, 4, 3), channels=(32, 64, 64), strides=(4, 2, 1), heads=(512, 256)),
+    "type_2": dict(kernels=(4, 3, 3, 3, 3, 3), channels=(8, 16, 32, 64, 128, 256), strides=(2, 2, 2, 2, 1, 1), heads=(256, 256, 256)),
+}
+
 HYPER = dict(
     gamma=0.99,
     tau=0.005,
@@ -126,5 +137,66 @@ def reference_kwargs(cfg: dict, **over) -> dict:
         cnn_shared=False,
     )
     kw.update(HYPER)
+    kw.update(over)
+    return kw
+
+
+# ---- CNN variant (config 5) -----------------------------------------------------------------------------------------
+def conv_feature_dim(cfg: dict) -> int:
+    c, h, w = cfg["obs_dim"]
+    t = CONV_TYPES[cfg["conv_type"]]
+    for k, s_ in zip(t["kernels"], t["strides"]):
+        h, w = (h - k) // s_ + 1, (w - k) // s_ + 1
+    return t["channels"][-1] * h * w
+
+
+def make_cnn_weights(cfg: dict, seed: int = 0) -> dict:
+    """state_dict-shaped fp32 arrays in the schema of the reference's CNN `StochaPolicy` / `ActionValueDistri`
+    (networks/cnn.py:151-240, 383-461): `{net}.conv.{0,2,..}.{weight,bias}`, `{net}.mean.{0,2,..}`, `{net}.log_std.{0,2,..}`;
+    U(-1/sqrt(fan_in), 1/sqrt(fan_in)) like the torch defaults; targets are copies."""
+    t = CONV_TYPES[cfg["conv_type"]]
+    feat, A = conv_feature_dim(cfg), cfg["act_dim"]
+    out = {}
+    for n, (net, extra, width) in enumerate((("q1", A, 1), ("q2", A, 1), ("policy", 0, A))):
+        g = _rng(seed, 44, n)
+        cin = cfg["obs_dim"][0]
+        for j, (k, cout) in enumerate(zip(t["kernels"], t["channels"])):
+            bound = 1.0 / np.sqrt(cin * k * k)
+            out[f"{net}.conv.{2 * j}.weight"] = g.uniform(-bound, bound, (cout, cin, k, k)).astype(np.float32)
+            out[f"{net}.conv.{2 * j}.bias"] = g.uniform(-bound, bound, (cout,)).astype(np.float32)
+            cin = cout
+        sizes = [feat + extra] + list(t["heads"]) + [width]
+        for head in ("mean", "log_std"):
+            for j in range(len(sizes) - 1):
+                bound = 1.0 / np.sqrt(sizes[j])
+                out[f"{net}.{head}.{2 * j}.weight"] = g.uniform(-bound, bound, (sizes[j + 1], sizes[j])).astype(np.float32)
+                out[f"{net}.{head}.{2 * j}.bias"] = g.uniform(-bound, bound, (sizes[j + 1],)).astype(np.float32)
+    for src, dst in (("q1", "q1_target"), ("q2", "q2_target"), ("policy", "policy_target")):
+        for k in [k for k in out if k.startswith(src + ".")]:
+            out[dst + k[len(src):]] = out[k].copy()
+    return out
+
+
+def make_cnn_batch(cfg: dict, batch: int, step: int, seed: int = 123) -> dict:
+    """Image minibatch: obs/obs2 ~ U(0,1) [B,C,H,W] (pixel-like), the rest as `make_batch`."""
+    g = _rng(seed, 55, step)
+    A, lim = cfg["act_dim"], cfg["act_lim"]
+    shape = (batch,) + tuple(cfg["obs_dim"])
+    return {
+        "obs": g.random(shape, dtype=np.float32),
+        "act": g.uniform(-lim, lim, size=(batch, A)).astype(np.float32),
+        "rew": g.standard_normal(batch).astype(np.float32),
+        "obs2": g.random(shape, dtype=np.float32),
+        "done": (g.random(batch) < 0.01).astype(np.float32),
+    }
+
+
+def cnn_reference_kwargs(cfg: dict, **over) -> dict:
+    """kwargs of example_train/dsacv2_cnn_carracing_offasync.py:53-79 for `DSAC_V2` / `ApproxContainer`."""
+    kw = reference_kwargs(dict(obs_dim=0, act_dim=cfg["act_dim"], act_lim=cfg["act_lim"], hidden=()))
+    for k in ("value_hidden_sizes", "policy_hidden_sizes"):
+        kw.pop(k)
+    kw.update(obsv_dim=tuple(cfg["obs_dim"]), value_func_type="CNN", policy_func_type="CNN",
+              value_conv_type=cfg["conv_type"], policy_conv_type=cfg["conv_type"])
     kw.update(over)
     return kw

@@ -105,20 +105,7 @@ class OracleDSACT:
         self.min_log_std, self.max_log_std = float(policy_min_log_std), float(policy_max_log_std)
         self.hi = torch.as_tensor(act_high, dtype=dtype).reshape(-1)
         self.lo = torch.as_tensor(act_low, dtype=dtype).reshape(-1)
-        nq, npi = len(hidden_q) + 1, len(hidden_pi) + 1
-        inner = {"q1": "q", "q2": "q", "policy": "policy"}
-
-        def grab(net, n_layers):
-            out = []
-            for j in range(n_layers):
-                for leaf in ("weight", "bias"):
-                    w = weights[f"{net}.{inner[net.replace('_target', '')]}.{2 * j}.{leaf}"]
-                    out.append(torch.as_tensor(w).detach().clone().to(dtype))
-            return out
-
-        self.p = {"q1": grab("q1", nq), "q2": grab("q2", nq), "policy": grab("policy", npi)}
-        self.t = {"q1": grab("q1_target", nq), "q2": grab("q2_target", nq),
-                  "policy": grab("policy_target", npi)}
+        self._load_weights(weights, len(hidden_q) + 1, len(hidden_pi) + 1)
         la = weights.get("log_alpha", 1.0)  # dsac_v2.py:51
         self.log_alpha = torch.as_tensor(la, dtype=dtype).reshape(()).clone()
         for group in self.p.values():
@@ -132,6 +119,22 @@ class OracleDSACT:
         self.steps = {"q1": 0, "q2": 0, "policy": 0, "log_alpha": 0}
         self.mean_std = [None, None]  # dsac_v2.py:88-89 (-1.0 sentinel)
         self.grads: Dict[str, List[torch.Tensor]] = {}
+
+    def _load_weights(self, weights, nq, npi):
+        """Parameter lists per network, in the reference's named_parameters order."""
+        inner = {"q1": "q", "q2": "q", "policy": "policy"}
+
+        def grab(net, n_layers):
+            out = []
+            for j in range(n_layers):
+                for leaf in ("weight", "bias"):
+                    w = weights[f"{net}.{inner[net.replace('_target', '')]}.{2 * j}.{leaf}"]
+                    out.append(torch.as_tensor(w).detach().clone().to(self.dtype))
+            return out
+
+        self.p = {"q1": grab("q1", nq), "q2": grab("q2", nq), "policy": grab("policy", npi)}
+        self.t = {"q1": grab("q1_target", nq), "q2": grab("q2_target", nq),
+                  "policy": grab("policy_target", npi)}
 
     # ---- network pieces -------------------------------------------------
     def policy_logits(self, layers, obs):
@@ -287,6 +290,84 @@ class OracleDSACT:
         if "log_alpha" in self.grads:
             out["log_alpha"] = self.grads["log_alpha"][0]
         return out
+
+
+class OracleDSACTCNN(OracleDSACT):
+    """The same update with the reference's CNN approximators (BASELINE config 5): a private conv
+    encoder per network (`CNN()`, networks/cnn.py:30-53, ReLU between convs) followed by two separate MLP heads `mean`
+    and `log_std` (StochaPolicy networks/cnn.py:151-240; ActionValueDistri :383-461, which concatenates the action to
+    the flattened feature, :455-456).  Loss, Adam and Polyak arithmetic are inherited unchanged.
+
+    Parity status: PINNED on `tests/golden/cnn_carracing_b4.npz` (tests/test_oracle_golden.py).  No CUDA path yet."""
+
+    def __init__(self, obs_dim, act_dim, conv_strides, act_high, act_low, weights, **hyper):
+        self.conv_strides = tuple(int(x) for x in conv_strides)
+        self.names = {}
+        super().__init__(0, act_dim, (), (), act_high, act_low, weights, **hyper)
+        self.O = tuple(obs_dim)
+
+    def _load_weights(self, weights, nq, npi):
+        order = {"conv": 0, "mean": 1, "log_std": 2}   # attribute order of the reference modules = named_parameters order
+
+        def grab(net):
+            keys = [k for k in weights if k.startswith(net + ".")]
+            keys.sort(key=lambda k: (order[k.split(".")[1]], int(k.split(".")[2]), k.split(".")[3] == "bias"))
+            self.names[net.replace("_target", "")] = [k[len(net) + 1:] for k in keys]
+            return [torch.as_tensor(weights[k]).detach().clone().to(self.dtype) for k in keys]
+
+        self.p = {n: grab(n) for n in self.NETS}
+        self.t = {n: grab(n + "_target") for n in self.NETS}
+
+    def _features(self, w, obs):
+        x, j = obs, 0
+        while f"conv.{2 * j}.weight" in w:   # Conv2d + ReLU per layer, networks/cnn.py:41-52
+            x = F.relu(F.conv2d(x, w[f"conv.{2 * j}.weight"], w[f"conv.{2 * j}.bias"], stride=self.conv_strides[j]))
+            j += 1
+        return x.reshape(x.shape[0], -1)     # img.view(img.size(0), -1), networks/cnn.py:234-235
+
+    def _head(self, w, head, x):
+        layers, j = [], 0
+        while f"{head}.{2 * j}.weight" in w:
+            layers += [w[f"{head}.{2 * j}.weight"], w[f"{head}.{2 * j}.bias"]]
+            j += 1
+        return mlp_forward(layers, x, self.act)
+
+    def policy_logits(self, layers, obs):
+        """StochaPolicy.forward (networks/cnn.py:233-240): mean head, exp(clamp(log_std head))."""
+        w = dict(zip(self.names["policy"], layers))
+        f = self._features(w, obs)
+        return self._head(w, "mean", f), torch.clamp(self._head(w, "log_std", f), self.min_log_std, self.max_log_std).exp()
+
+    def q_dist(self, layers, obs, act):
+        """ActionValueDistri.forward (networks/cnn.py:454-461): heads on cat(feature, act); softplus on the std head."""
+        w = dict(zip(self.names["q1"], layers))
+        f = torch.cat([self._features(w, obs), act], dim=-1)
+        return self._head(w, "mean", f)[..., 0], F.softplus(self._head(w, "log_std", f)[..., 0])
+
+    def state_dict(self):
+        out = {"log_alpha": self.log_alpha.detach()}
+        for net in self.NETS:
+            for group, suffix in ((self.p, ""), (self.t, "_target")):
+                for name, w in zip(self.names[net], group[net]):
+                    out[f"{net}{suffix}.{name}"] = w.detach()
+        return out
+
+    def grad_dict(self):
+        out = {}
+        for net in self.NETS:
+            for name, g in zip(self.names[net], self.grads[net]):
+                out[f"{net}.{name}"] = g
+        if "log_alpha" in self.grads:
+            out["log_alpha"] = self.grads["log_alpha"][0]
+        return out
+
+
+def cnn_from_config(cfg: dict, weights: dict, **hyper) -> OracleDSACTCNN:
+    """Build from a `synth.CNN_CONFIGS` entry."""
+    from dsac_v2_b200.synth import CONV_TYPES
+    lim = [cfg["act_lim"]] * cfg["act_dim"]
+    return OracleDSACTCNN(cfg["obs_dim"], cfg["act_dim"], CONV_TYPES[cfg["conv_type"]]["strides"], lim, [-x for x in lim],
+                          weights, **hyper)
 
 
 def from_config(cfg: dict, weights: dict, **hyper) -> OracleDSACT:

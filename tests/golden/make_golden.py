@@ -45,6 +45,8 @@ CASES = [
     ("humanoid_b4096", "humanoid", 4096, 6, (), {}),
     # fixed temperature + different delay / tau_b: exercises the non-default branches
     ("tiny_fixed_alpha", "tiny", 16, 12, (1, 12), {"auto_alpha": False, "alpha": 0.2, "delay_update": 3, "tau_b": 0.05}),
+    # CNN approximators (example_train/dsacv2_cnn_carracing_offasync.py: type_2 encoder, 3x96x96 observations); digests only
+    ("cnn_carracing_b4", "carracing", 4, 6, (), {}),
 ] + [
     # the reference's other hidden activations (utils/common_utils.py:16-43), same one in critics and policy
     (f"{cfg}_{act}", cfg, batch, 10, (10,), {"value_hidden_activation": act, "policy_hidden_activation": act})
@@ -111,11 +113,12 @@ def digest(t) -> np.ndarray:
 
 
 def run_case(name, cfg_name, batch, steps, snaps, over):
-    cfg = synth.CONFIGS[cfg_name]
+    cnn = cfg_name in synth.CNN_CONFIGS   # BASELINE config 5: conv encoder + separate heads (networks/cnn.py)
+    cfg = synth.CNN_CONFIGS[cfg_name] if cnn else synth.CONFIGS[cfg_name]
     torch.manual_seed(0)
-    alg = ref_dsac.DSAC_V2(**synth.reference_kwargs(cfg, **over))
+    alg = ref_dsac.DSAC_V2(**(synth.cnn_reference_kwargs(cfg, **over) if cnn else synth.reference_kwargs(cfg, **over)))
     sd = alg.networks.state_dict()
-    for k, v in synth.make_weights(cfg).items():
+    for k, v in (synth.make_cnn_weights(cfg) if cnn else synth.make_weights(cfg)).items():
         assert tuple(sd[k].shape) == v.shape, k
         sd[k] = torch.from_numpy(v)
     alg.networks.load_state_dict(sd)
@@ -127,7 +130,7 @@ def run_case(name, cfg_name, batch, steps, snaps, over):
     out = {"tb": np.zeros((steps, len(TB_KEYS)))}
     try:
         for it in range(steps):
-            data = {k: torch.from_numpy(v) for k, v in synth.make_batch(cfg, batch, it).items()}
+            data = {k: torch.from_numpy(v) for k, v in (synth.make_cnn_batch if cnn else synth.make_batch)(cfg, batch, it).items()}
             feed.queue = synth.make_noise(cfg, batch, it)
             tb = alg.local_update(data, it)
             assert not feed.queue

@@ -8,19 +8,22 @@ import pytest
 import torch
 
 from dsac_v2_b200 import synth
-from oracle.dsact_oracle import TB_KEYS, from_config
+from oracle.dsact_oracle import TB_KEYS, cnn_from_config, from_config
 
 CASES = ["tiny_b16", "ragged_b37", "tiny_fixed_alpha", "pendulum_b256", "halfcheetah_b512",
          "humanoid_b256", "humanoid_b4096",
          # the reference's other hidden activations (utils/common_utils.py:16-43)
-         "tiny_relu", "tiny_tanh", "ragged_elu", "ragged_selu", "tiny_sigmoid"]
+         "tiny_relu", "tiny_tanh", "ragged_elu", "ragged_selu", "tiny_sigmoid",
+         # CNN approximators (BASELINE config 5; oracle-level groundwork for SURVEY.md 8f rank 1)
+         "cnn_carracing_b4"]
 MAX_STEPS = {"humanoid_b256": 100, "pendulum_b256": 100}
 
 
 def load(golden_dir, name):
     z = np.load(os.path.join(golden_dir, name + ".npz"))
     cfg_name, batch, steps, over = z["meta"]
-    return z, synth.CONFIGS[str(cfg_name)], int(batch), int(steps), dict(ast.literal_eval(str(over)))
+    cfg = synth.CNN_CONFIGS[str(cfg_name)] if str(cfg_name) in synth.CNN_CONFIGS else synth.CONFIGS[str(cfg_name)]
+    return z, cfg, int(batch), int(steps), dict(ast.literal_eval(str(over)))
 
 
 @pytest.mark.parametrize("name", CASES)
@@ -32,11 +35,16 @@ def test_oracle_matches_reference(golden_dir, name):
     hyper.update(over)
     act = hyper.pop("value_hidden_activation", "gelu")
     assert hyper.pop("policy_hidden_activation", act) == act
-    orc = from_config(cfg, synth.make_weights(cfg), hidden_activation=act, **hyper)
+    cnn = "conv_type" in cfg
+    if cnn:
+        orc = cnn_from_config(cfg, synth.make_cnn_weights(cfg), hidden_activation=act, **hyper)
+    else:
+        orc = from_config(cfg, synth.make_weights(cfg), hidden_activation=act, **hyper)
+    make_batch = synth.make_cnn_batch if cnn else synth.make_batch
     names = [str(n) for n in z["param_names"]]
     trainable = [str(n) for n in z["trainable_names"]]
     for it in range(steps):
-        tb = orc.update(synth.make_batch(cfg, batch, it), synth.make_noise(cfg, batch, it), it)
+        tb = orc.update(make_batch(cfg, batch, it), synth.make_noise(cfg, batch, it), it)
         got = np.array([tb[k] for k in TB_KEYS])
         # same ATen ops in the same order: expect (near) bitwise agreement
         np.testing.assert_allclose(got, z["tb"][it], rtol=2e-6, atol=1e-7, err_msg=f"{name} step {it}")
