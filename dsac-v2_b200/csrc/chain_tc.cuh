@@ -26,6 +26,7 @@ struct ChainLayer {
   int kB0[2];                // offset of each segment along B's reduction dimension
   int K;                     // reduction length of layers >= 1 (= width of the previous layer)
   int N, bn;                 // outputs; tile width (multiple of 16, <= 256)
+  int nh;                    // split kernel: 2 = the layer runs as two 128-column halves (bn == 256), else 1
   int b_mn;
   int epi, act;              // EPI_BIAS_ACT | EPI_DACT | EPI_STORE
   const float* bias;
@@ -98,7 +99,19 @@ inline int chain_smem_bytes(int stages, int planes, int stage_b) {
          (2 * stages + 4 + 2 * TC_EPI_WARPS) * 8 + 1024;
 }
 
-template <bool PLANES2>
+// Split variant (SPLIT = true, bf16x3 only; opt-in with DSACT_CHAIN_SPLIT=1 until it has been validated on hardware):
+// a 256-wide layer is issued as two 128-column halves.  The weight ring holds four half-tiles (16 KiB per plane) in
+// the order (half 0: k-blocks 0..), (half 1: k-blocks 0..), each half commits its own accumulator barrier, and the
+// epilogue warps start on columns [0,128) while the MMAs of columns [128,256) are still running: the tensor pipe and
+// the epilogue overlap inside one layer without any extra tensor memory.  Layer 0 (A from shared memory) keeps the
+// k-block-major order (both halves of a k-block share the A tile) and finishes both halves together.
+constexpr int CH_SPLIT_STAGES = 4, CH_SPLIT_STAGE_B = 16384;
+inline int chain_smem_bytes_split(int planes) {
+  return CH_SPLIT_STAGES * planes * CH_SPLIT_STAGE_B + chain_ringA_bytes(2, planes) + TC_EPI_WARPS * CH_ZIN1_WARP +
+         (2 * CH_SPLIT_STAGES + 6 + 2 * TC_EPI_WARPS) * 8 + 1024;
+}
+
+template <bool PLANES2, bool SPLIT = false>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_chain_kernel(const __grid_constant__ ChainGroup g, int stages, int stage_b) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared address space (LDS/STS)
@@ -106,14 +119,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_chain_kernel(const __grid_co
   // [ B ring: stages x planes x stage_b ][ layer-0 A ring: stages x planes x 16 KiB, later the epilogue's transpose scratch ]
   uint8_t* ringB = smem;
   uint8_t* ringA = smem + (size_t)stages * planes * stage_b;
-  const int ringA_bytes = chain_ringA_bytes(stages, planes);
+  const int ringA_bytes = chain_ringA_bytes(SPLIT ? 2 : stages, planes);   // split: 4 weight half-stages, 2 A stages
   uint8_t* zin1 = ringA + ringA_bytes;                                   // [warps] second act' input buffers
   uint64_t* bars = reinterpret_cast<uint64_t*>(zin1 + TC_EPI_WARPS * CH_ZIN1_WARP);
   uint64_t* full = bars;               // [stages] TMA -> MMA
   uint64_t* empty = bars + stages;     // [stages] MMA -> TMA
-  uint64_t* acc_full = bars + 2 * stages;
-  uint64_t* a_ready = bars + 2 * stages + 1;
-  uint64_t* zbar = bars + 2 * stages + 2;   // [warps][2] act' tile arrival
+  uint64_t* acc_full = bars + 2 * stages;          // [2]: columns [0,128) / [128,256) in the split kernel; [0] otherwise
+  uint64_t* a_free = bars + 2 * stages + 2;        // split kernel: MMAs of columns [128,256) are past k-blocks 0 and 1 of A
+  uint64_t* a_ready = bars + 2 * stages + (SPLIT ? 3 : 1);
+  uint64_t* zbar = a_ready + 1;             // [warps][2] act' tile arrival
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(zbar + 2 * TC_EPI_WARPS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -129,7 +143,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_chain_kernel(const __grid_co
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    mbar_init(acc_full, 1);
+    mbar_init(&acc_full[0], 1);
+    if (SPLIT) { mbar_init(&acc_full[1], 1); mbar_init(a_free, 1); }
     mbar_init(a_ready, TC_EPI_WARPS);
     for (int i = 0; i < 2 * TC_EPI_WARPS; ++i) mbar_init(&zbar[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -148,7 +163,56 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_chain_kernel(const __grid_co
 
   if (warp == 0) {
     // ===== TMA producer: runs ahead of the epilogues, bounded only by free ring slots =====
-    if (lane == 0) {
+    if (SPLIT && lane == 0) {
+      // half-stage sequence number `it`: stage = it % 4, phase = (it / 4) & 1, identical in the MMA warp
+      int it = 0;
+      int a_last[2] = {-1, -1};   // `it` of the last half-stage that read A ring slot 0 / 1 (layer 0 only)
+      for (int j = 0; j < nl; ++j) {
+        const ChainLayer& Lj = P.L[j];
+        const int nkb = Lj.kblocks[0] + Lj.kblocks[1];
+        const int nh = Lj.nh;
+        const int rows = nh == 2 ? 128 : Lj.bn;                     // columns of the layer held by one half-tile
+        const int b_boxes = Lj.b_mn ? (rows + 63) / 64 : 1;
+        const uint32_t b_bytes = Lj.b_mn ? (uint32_t)b_boxes * 8192 : (uint32_t)rows * 128;
+        auto load_b = [&](int h, int kB, int s) {
+          uint8_t* sB = ringB + (size_t)s * planes * stage_b;
+          for (int pl = 0; pl < planes; ++pl) {
+            if (Lj.b_mn) {
+              for (int i = 0; i < b_boxes; ++i) tma_load_3d(sB + pl * stage_b + i * 8192, &Lj.mapB, &full[s], 128 * h + 64 * i, kB, pl);
+            } else {
+              tma_load_3d(sB + pl * stage_b, &Lj.mapB, &full[s], kB, 128 * h, pl);
+            }
+          }
+        };
+        if (j == 0) {   // k-block major: the A tile of a k-block serves both halves
+          for (int kb = 0; kb < nkb; ++kb) {
+            const int seg = kb >= Lj.kblocks[0] ? 1 : 0;
+            const int kloc = (seg ? kb - Lj.kblocks[0] : kb) * TC_BK;
+            const int kB = Lj.kB0[seg] + kloc;
+            const int a_slot = kb & 1;
+            if (a_last[a_slot] >= 0) mbar_wait(&empty[a_last[a_slot] % CH_SPLIT_STAGES], (uint32_t)((a_last[a_slot] / CH_SPLIT_STAGES) & 1));
+            for (int h = 0; h < nh; ++h, ++it) {
+              const int s = it % CH_SPLIT_STAGES;
+              mbar_wait(&empty[s], (uint32_t)(((it / CH_SPLIT_STAGES) & 1) ^ 1));
+              mbar_expect_tx(&full[s], planes * (b_bytes + (h == 0 ? (uint32_t)TC_STAGE_A : 0u)));
+              if (h == 0)
+                for (int pl = 0; pl < planes; ++pl)
+                  tma_load_3d(ringA + (size_t)(a_slot * planes + pl) * TC_STAGE_A, &P.mapA[seg], &full[s], kloc, m0, pl);
+              load_b(h, kB, s);
+            }
+            a_last[a_slot] = it - 1;
+          }
+        } else {        // half major: all k-blocks of columns [0,128), then all of [128,256)
+          for (int h = 0; h < nh; ++h)
+            for (int kb = 0; kb < nkb; ++kb, ++it) {
+              const int s = it % CH_SPLIT_STAGES;
+              mbar_wait(&empty[s], (uint32_t)(((it / CH_SPLIT_STAGES) & 1) ^ 1));
+              mbar_expect_tx(&full[s], planes * b_bytes);
+              load_b(h, Lj.kB0[0] + kb * TC_BK, s);
+            }
+        }
+      }
+    } else if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
       for (int j = 0; j < nl; ++j) {
@@ -179,7 +243,74 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_chain_kernel(const __grid_co
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
-    if (lane == 0) {
+    if (SPLIT && lane == 0) {
+      int it = 0;
+      for (int j = 0; j < nl; ++j) {
+        const ChainLayer& Lj = P.L[j];
+        const int nkb = Lj.kblocks[0] + Lj.kblocks[1];
+        const int nh = Lj.nh;
+        const uint32_t idesc = make_idesc(TC_BM, nh == 2 ? 128 : Lj.bn, 0, Lj.b_mn);
+        if (j > 0) {
+          mbar_wait(a_ready, (uint32_t)((j - 1) & 1));
+          tc_fence_after();
+        }
+        auto issue = [&](int h, int kb, int s, uint32_t accumulate) {
+          const uint32_t sB = smem_u32(ringB + (size_t)s * planes * stage_b);
+          const uint32_t sA = smem_u32(ringA + (size_t)((kb & 1) * planes) * TC_STAGE_A);
+          const uint32_t d = tmem_base + CH_ACC_COL + (uint32_t)(128 * h);
+          const int ksteps = j == 0 ? 4 : min(4, (Lj.K - kb * TC_BK + 15) / 16);
+          for (int k = 0; k < ksteps; ++k) {
+            const uint32_t b_off = Lj.b_mn ? k * 2048 : k * 32;
+            const uint64_t b_hi = make_desc(sB + b_off, Lj.b_mn ? 8192 : 16, 1024);
+            const uint64_t b_lo = make_desc(sB + stage_b + b_off, Lj.b_mn ? 8192 : 16, 1024);
+            if (j == 0) {
+              const uint64_t a_hi = make_desc(sA + k * 32, 16, 1024);
+              const uint64_t a_lo = make_desc(sA + TC_STAGE_A + k * 32, 16, 1024);
+              tc_mma(d, a_hi, b_hi, idesc, accumulate);
+              tc_mma(d, a_hi, b_lo, idesc, 1);
+              tc_mma(d, a_lo, b_hi, idesc, 1);
+            } else {
+              const uint32_t kcol = (uint32_t)(kb * 32 + k * 8);   // 2 bf16 per TMEM column
+              tc_mma_ts(d, tmem_base + CH_AHI_COL + kcol, b_hi, idesc, accumulate);
+              tc_mma_ts(d, tmem_base + CH_AHI_COL + kcol, b_lo, idesc, 1);
+              tc_mma_ts(d, tmem_base + CH_ALO_COL + kcol, b_hi, idesc, 1);
+            }
+            accumulate = 1;
+          }
+        };
+        if (j == 0) {
+          for (int kb = 0; kb < nkb; ++kb)
+            for (int h = 0; h < nh; ++h, ++it) {
+              const int s = it % CH_SPLIT_STAGES;
+              mbar_wait(&full[s], (uint32_t)((it / CH_SPLIT_STAGES) & 1));
+              tc_fence_after();
+              if (kb == 0 && h == 0) TC_STAMP(2);
+              issue(h, kb, s, kb > 0 ? 1u : 0u);
+              tc_commit(&empty[s]);
+            }
+          tc_commit(&acc_full[0]);
+          tc_commit(&acc_full[1]);
+          tc_commit(a_free);
+        } else {
+          for (int h = 0; h < nh; ++h) {
+            for (int kb = 0; kb < nkb; ++kb, ++it) {
+              const int s = it % CH_SPLIT_STAGES;
+              mbar_wait(&full[s], (uint32_t)((it / CH_SPLIT_STAGES) & 1));
+              tc_fence_after();
+              issue(h, kb, s, kb > 0 ? 1u : 0u);
+              tc_commit(&empty[s]);
+              // The epilogue of columns [0,128) overwrites TMEM A columns of k-blocks 0 and 1 with the next layer's
+              // operand: it may do so once the last MMAs that read them (second half, k-block 1) have completed.
+              if (h == nh - 1 && kb == (nkb > 1 ? 1 : 0)) tc_commit(a_free);
+            }
+            tc_commit(&acc_full[h]);   // columns [128 h, 128 h + 128) complete: their epilogue may start
+          }
+          if (nh == 1) tc_commit(&acc_full[1]);
+        }
+        TC_STAMP(8 + 3 * j);      // MMAs of layer j issued
+      }
+      TC_STAMP(3);
+    } else if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
       for (int j = 0; j < nl; ++j) {
@@ -265,7 +396,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_chain_kernel(const __grid_co
         }
         __syncwarp();
       }
-      mbar_wait(acc_full, (uint32_t)(j & 1));
+      mbar_wait(&acc_full[0], (uint32_t)(j & 1));
+      bool h1_ready = !SPLIT, a_writable = !SPLIT;   // split kernel: columns >= 128 / the TMEM A columns, see the MMA warp
       tc_fence_after();
       if (j == 0 && threadIdx.x == 64) TC_STAMP(4);
       if (threadIdx.x == 64) TC_STAMP(9 + 3 * j);   // accumulator of layer j complete (seen by the epilogue)
@@ -283,6 +415,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_chain_kernel(const __grid_co
       for (int ch = sub; ch < nch; ch += TC_EPI_WARPS / 4, ++k) {
         const int c0 = ch * 16;
         float v[16];
+        if (SPLIT && c0 >= 128 && !h1_ready) {
+          mbar_wait(&acc_full[1], (uint32_t)(j & 1));
+          tc_fence_after();
+          h1_ready = true;
+        }
         tc_ld16(lane_addr + CH_ACC_COL + (uint32_t)c0, v);   // v[i] = acc[row = lane][c0 + i]
         if (dact) {
           const int nxt = ch + TC_EPI_WARPS / 4;
@@ -392,6 +529,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_chain_kernel(const __grid_co
           }
         }
         if (feeds_next) {  // next layer's A operand: packed bf16 pairs along K, hi and lo planes
+          if (SPLIT && !a_writable) {
+            mbar_wait(a_free, (uint32_t)(j & 1));
+            tc_fence_after();
+            a_writable = true;
+          }
           tc_st8(lane_addr + CH_AHI_COL + (uint32_t)(c0 / 2), whi);
           if (planes == 2) tc_st8(lane_addr + CH_ALO_COL + (uint32_t)(c0 / 2), wlo);
         }

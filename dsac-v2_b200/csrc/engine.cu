@@ -171,6 +171,15 @@ struct dsact_handle {
     return cfg.act_dim <= 256;
   }
   int passes() const { return cfg.gemm_mode == DSACT_GEMM_BF16X3 ? 3 : 1; }
+  // split variant of the chain kernel (chain_tc.cuh): opt-in, bf16x3 only, every layer either <= 128 wide or exactly 256
+  bool chain_split() const {
+    static const bool want = getenv("DSACT_CHAIN_SPLIT") && getenv("DSACT_CHAIN_SPLIT")[0] == '1';
+    if (!want || passes() != 3 || !fused()) return false;
+    auto ok = [](int w) { const int bn = (w + 15) / 16 * 16; return bn <= 128 || bn == 256; };
+    for (int j = 0; j <= q.L + 1; ++j) if (!ok(q.s[j]) && j > 0) return false;
+    for (int j = 0; j <= pi.L + 1; ++j) if (!ok(pi.s[j]) && j > 0) return false;
+    return ok(cfg.act_dim);
+  }
   float* W() const { return reinterpret_cast<float*>(buf.workspace); }
   Img img(const ImgSlot& s, int rows) const {  // image handle with the live row count
     Img i;
@@ -542,8 +551,8 @@ struct ChainBuild {
   ChainGroup g;
   int grid = 0, stage_b = 16 * 128;
   double flops = 0.0;
-  bool ok = true;
-  explicit ChainBuild(int passes) { memset(&g, 0, sizeof(g)); g.passes = passes; }
+  bool ok = true, split = false;
+  explicit ChainBuild(int passes, bool split_ = false) : split(split_) { memset(&g, 0, sizeof(g)); g.passes = passes; }
   ChainPass& begin(const Img& a0, const Img& a1, int M) {
     ChainPass& P = g.p[g.n++];
     P.n_layers = 0; P.M = M; P.tile_start = grid;
@@ -555,11 +564,13 @@ struct ChainBuild {
   ChainLayer& layer(ChainPass& P, const Img& wimg, bool b_mn, int N, int K0, int K1, int kB1) {
     ChainLayer& L = P.L[P.n_layers++];
     L.N = N; L.bn = (N + 15) / 16 * 16; L.b_mn = b_mn ? 1 : 0;
+    L.nh = (split && L.bn == 256) ? 2 : 1;
     L.kblocks[0] = (K0 + TC_BK - 1) / TC_BK; L.kblocks[1] = (K1 + TC_BK - 1) / TC_BK;
     L.kB0[0] = 0; L.kB0[1] = kB1; L.K = K0;
-    ok = ok && make_map(&L.mapB, wimg, b_mn ? 64 : L.bn);
+    ok = ok && make_map(&L.mapB, wimg, b_mn ? 64 : (L.nh == 2 ? 128 : L.bn));   // split: one box = one 128-column half
     const int sb = b_mn ? (L.bn + 63) / 64 * 8192 : L.bn * 128;
     if (sb > stage_b) stage_b = sb;
+    if (split && L.nh == 1 && L.bn > 128) ok = false;   // (chain_split() excludes such widths)
     flops += 2.0 * P.M * N * ((double)K0 + K1);
     return L;
   }
@@ -574,14 +585,16 @@ static void launch_chain(const dsact_handle* h, ChainBuild& cb, int cls, Ctx& c)
   if (debug && !dbg) cudaMalloc(&dbg, sizeof(unsigned long long) * TC_DBG_SLOTS * 4096);
   if (debug && cb.grid <= 4096) { cudaMemsetAsync(dbg, 0, sizeof(unsigned long long) * TC_DBG_SLOTS * cb.grid, c.s); cb.g.dbg = dbg; }
   const int planes = cb.g.passes == 3 ? 2 : 1;
-  const int stages = planes == 2 ? 2 : 3;
-  const int smem = chain_smem_bytes(stages, planes, cb.stage_b);
+  const int stages = cb.split ? CH_SPLIT_STAGES : (planes == 2 ? 2 : 3);
+  const int smem = cb.split ? chain_smem_bytes_split(planes) : chain_smem_bytes(stages, planes, cb.stage_b);
   if (!g_chain_attr_done) {
     cudaFuncSetAttribute(tc_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     cudaFuncSetAttribute(tc_chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(tc_chain_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     g_chain_attr_done = true;
   }
-  if (planes == 2) launch_k(tc_chain_kernel<true>, cb.grid, TC_THREADS, smem, c, cb.g, stages, cb.stage_b);
+  if (cb.split) launch_k(tc_chain_kernel<true, true>, cb.grid, TC_THREADS, smem, c, cb.g, stages, (int)CH_SPLIT_STAGE_B);
+  else if (planes == 2) launch_k(tc_chain_kernel<true>, cb.grid, TC_THREADS, smem, c, cb.g, stages, cb.stage_b);
   else launch_k(tc_chain_kernel<false>, cb.grid, TC_THREADS, smem, c, cb.g, stages, cb.stage_b);
   c.done(cls, cb.flops);
   c.check();
@@ -781,7 +794,7 @@ static void enqueue_phase1(dsact_handle* h, const dsact_batch& bt, const dsact_n
   const bool fused = h->fused();
   const Img i_none;
   if (fused) {  // wave A as ONE launch: each CTA runs a 128-row block through every layer of its pass
-    ChainBuild cb(h->passes());
+    ChainBuild cb(h->passes(), h->chain_split());
     chain_fwd_pass(cb, h, pi, PIb[0], ar.i_wpi[0], t_obs.im, O, i_none, 0, 0, B, cf.act_pi, ar.zP, ar.i_hP, W + ar.logitsP);
     chain_fwd_pass(cb, h, pi, PIb[1], ar.i_wpi[1], t_obs2.im, O, i_none, 0, 0, B, cf.act_pi, nullptr, nullptr, W + ar.logitsT);
     for (int k = 0; k < 2; ++k)
@@ -847,7 +860,7 @@ static void enqueue_phase1(dsact_handle* h, const dsact_batch& bt, const dsact_n
   // wave B: Q1', Q2' on (s', a') and Q1, Q2 on (s, a~)
   const Ten t_new_act = ten(W + ar.new_act, ar.i_new_act), t_act2 = ten(W + ar.act2, ar.i_act2);
   if (fused) {
-    ChainBuild cb(h->passes());
+    ChainBuild cb(h->passes(), h->chain_split());
     for (int k = 0; k < 2; ++k)
       chain_fwd_pass(cb, h, q, Qb[2 + k], ar.i_wq[2 + k], t_obs2.im, O, t_act2.im, A, ar.kpad_q0, B, cf.act_q, nullptr, nullptr, W + ar.outQ[2 + k]);
     for (int k = 0; k < 2; ++k)
@@ -921,7 +934,7 @@ static void enqueue_phase2(dsact_handle* h, const dsact_batch& bt, int64_t globa
   Group gw;  // every weight-gradient problem of the two critics: independent once the dgrad chain has run
   const bool fused = h->fused();
   if (fused) {  // wave C dgrad as ONE launch: dz stays in tensor memory between layers
-    ChainBuild cb(h->passes());
+    ChainBuild cb(h->passes(), h->chain_split());
     for (int pp = 0; pp < 4; ++pp) {
       const int p = passes[pp], k = p & 1;
       chain_dgrad_pass(cb, h, q, ar.i_wq[k], h->img(ar.i_dOut[p], B), B, cf.act_q, ar.zQ[p], p < 2 ? Gq[k] : nullptr,
@@ -991,7 +1004,7 @@ static void enqueue_phase2(dsact_handle* h, const dsact_batch& bt, int64_t globa
   // wave D: policy backward
   Group gwp;
   if (fused) {
-    ChainBuild cb(h->passes());
+    ChainBuild cb(h->passes(), h->chain_split());
     chain_dgrad_pass(cb, h, pi, ar.i_wpi[0], h->img(ar.i_dlogits, B), B, cf.act_pi, ar.zP, Gpi, ar.i_dzP, nullptr, 0, 0);
     launch_chain(h, cb, CLS_GEMM_DGRAD, c);
   }
