@@ -16,6 +16,7 @@
 //   wgrad    dW = dy^T x  : A MN-major (dy image), B MN-major (x image); split over the batch, each split
 //                           stores its partial tile to a workspace slab (no atomics), reduced later.
 #pragma once
+#include <stdio.h>
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -70,12 +71,31 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+// Build with -DDSACT_MBAR_GUARD to turn a barrier that never completes (a protocol bug in a kernel under development)
+// into a trap after ~2 s instead of a hung GPU: DSACT_NVCC_FLAGS="-DDSACT_MBAR_GUARD" python -c "import __graft_entry__ ..."
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+#ifdef DSACT_MBAR_GUARD
+  unsigned long long t0;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+  for (;;) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, P1;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680) : "memory");
+    if (ok) return;
+    unsigned long long t1;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+    if (t1 - t0 > 2000000000ull) {
+      printf("mbar_wait timeout: block %d thread %d barrier smem+%u parity %u\n", (int)blockIdx.x, (int)threadIdx.x, smem_u32(bar), parity);
+      __trap();
+    }
+  }
+#else
   asm volatile(
       "{\n\t.reg .pred P1;\n\tWAIT_LOOP:\n\t"
       "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n\t"
       "@P1 bra WAIT_DONE;\n\tbra WAIT_LOOP;\n\tWAIT_DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity), "r"(0x989680)
       : "memory");
+#endif
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%1], %0;" ::"r"(bytes), "r"(smem_u32(bar)) : "memory");
