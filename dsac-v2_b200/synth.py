@@ -200,3 +200,24 @@ def cnn_reference_kwargs(cfg: dict, **over) -> dict:
               value_conv_type=cfg["conv_type"], policy_conv_type=cfg["conv_type"])
     kw.update(over)
     return kw
+
+
+# ---- other policy std types (reference networks/mlp.py:42-72; SURVEY.md §8f rank 4, oracle-level only) ----------------
+def make_weights_std(cfg: dict, std_type: str, seed: int = 0) -> dict:
+    """`make_weights` with the policy in the schema of `std_type`:
+    "mlp_separated": `policy.mean.{0,2,..}` and `policy.log_std.{0,2,..}` (two MLPs ending in act_dim outputs),
+    "parameter": `policy.mean.{0,2,..}` and the learnable row `policy.log_std` [1, act_dim] (= -0.5)."""
+    out = {k: v for k, v in make_weights(cfg, seed).items() if not k.startswith("policy")}
+    sizes = [cfg["obs_dim"]] + list(cfg["hidden"]) + [cfg["act_dim"]]
+    g = _rng(seed, 66, {"mlp_separated": 0, "parameter": 1}[std_type])
+    heads = ("mean", "log_std") if std_type == "mlp_separated" else ("mean",)
+    for head in heads:
+        for j in range(len(sizes) - 1):
+            bound = 1.0 / np.sqrt(sizes[j])
+            out[f"policy.{head}.{2 * j}.weight"] = g.uniform(-bound, bound, (sizes[j + 1], sizes[j])).astype(np.float32)
+            out[f"policy.{head}.{2 * j}.bias"] = g.uniform(-bound, bound, (sizes[j + 1],)).astype(np.float32)
+    if std_type == "parameter":
+        out["policy.log_std"] = np.full((1, cfg["act_dim"]), -0.5, dtype=np.float32)
+    for k in [k for k in out if k.startswith("policy.")]:
+        out["policy_target" + k[len("policy"):]] = out[k].copy()
+    return out

@@ -292,6 +292,79 @@ class OracleDSACT:
         return out
 
 
+class OracleDSACTStd(OracleDSACT):
+    """The same update with the policy's other `std_type`s (reference networks/mlp.py:42-100):
+    "mlp_separated" — two MLPs `mean` and `log_std`; "parameter" — one MLP `mean` and a learnable row `log_std` [1, A]
+    broadcast over the batch (:95-99).  Critics, losses, Adam and Polyak are inherited unchanged.
+
+    Parity status: PINNED on `tests/golden/tiny_std_separated.npz` / `tiny_std_parameter.npz`.  No CUDA path yet."""
+
+    def __init__(self, *args, std_type="mlp_separated", **hyper):
+        assert std_type in ("mlp_separated", "parameter")
+        self.std_type, self.names = std_type, {}
+        super().__init__(*args, **hyper)
+
+    def _load_weights(self, weights, nq, npi):
+        super_w = dict(weights)
+        # critics through the base schema; the policy by name, in the reference's named_parameters order:
+        # "mlp_separated": mean.*, log_std.* (attribute order); "parameter": mean.*, then log_std (nn.Parameter set last)
+        inner = {"q1": "q", "q2": "q"}
+
+        def grab_q(net):
+            return [torch.as_tensor(super_w[f"{net}.{inner[net.replace('_target', '')]}.{2 * j}.{leaf}"]).detach().clone().to(self.dtype)
+                    for j in range(nq) for leaf in ("weight", "bias")]
+
+        def grab_pi(net):
+            keys = [k for k in weights if k.startswith(net + ".")]
+            order = {"mean": 0, "log_std": 1}
+
+            def rank(k):
+                parts = k.split(".")
+                return (order[parts[1]], int(parts[2]) if len(parts) > 2 else 0, len(parts) > 3 and parts[3] == "bias")
+            keys.sort(key=rank)
+            self.names["policy"] = [k[len(net) + 1:] for k in keys]
+            return [torch.as_tensor(weights[k]).detach().clone().to(self.dtype) for k in keys]
+
+        self.p = {"q1": grab_q("q1"), "q2": grab_q("q2"), "policy": grab_pi("policy")}
+        self.t = {"q1": grab_q("q1_target"), "q2": grab_q("q2_target"), "policy": grab_pi("policy_target")}
+
+    def policy_logits(self, layers, obs):
+        w = dict(zip(self.names["policy"], layers))
+
+        def head(name):
+            ls, j = [], 0
+            while f"{name}.{2 * j}.weight" in w:
+                ls += [w[f"{name}.{2 * j}.weight"], w[f"{name}.{2 * j}.bias"]]
+                j += 1
+            return mlp_forward(ls, obs, self.act)
+
+        mean = head("mean")
+        log_std = head("log_std") if self.std_type == "mlp_separated" else w["log_std"] + torch.zeros_like(mean)
+        return mean, torch.clamp(log_std, self.min_log_std, self.max_log_std).exp()
+
+    def _named(self, net, group):
+        if net == "policy":
+            return list(zip(self.names["policy"], group))
+        return [(f"q.{2 * (i // 2)}.{'weight' if i % 2 == 0 else 'bias'}", w) for i, w in enumerate(group)]
+
+    def state_dict(self):
+        out = {"log_alpha": self.log_alpha.detach()}
+        for net in self.NETS:
+            for group, suffix in ((self.p, ""), (self.t, "_target")):
+                for name, w in self._named(net, group[net]):
+                    out[f"{net}{suffix}.{name}"] = w.detach()
+        return out
+
+    def grad_dict(self):
+        out = {}
+        for net in self.NETS:
+            for name, g in self._named(net, self.grads[net]):
+                out[f"{net}.{name}"] = g
+        if "log_alpha" in self.grads:
+            out["log_alpha"] = self.grads["log_alpha"][0]
+        return out
+
+
 class OracleDSACTCNN(OracleDSACT):
     """The same update with the reference's CNN approximators (BASELINE config 5): a private conv
     encoder per network (`CNN()`, networks/cnn.py:30-53, ReLU between convs) followed by two separate MLP heads `mean`
@@ -360,6 +433,13 @@ class OracleDSACTCNN(OracleDSACT):
         if "log_alpha" in self.grads:
             out["log_alpha"] = self.grads["log_alpha"][0]
         return out
+
+
+def std_from_config(cfg: dict, weights: dict, std_type: str, **hyper) -> OracleDSACTStd:
+    """Build from a `synth.CONFIGS` entry with weights of `synth.make_weights_std`."""
+    lim = [cfg["act_lim"]] * cfg["act_dim"]
+    return OracleDSACTStd(cfg["obs_dim"], cfg["act_dim"], cfg["hidden"], cfg["hidden"], lim, [-x for x in lim], weights,
+                          std_type=std_type, **hyper)
 
 
 def cnn_from_config(cfg: dict, weights: dict, **hyper) -> OracleDSACTCNN:

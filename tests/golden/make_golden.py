@@ -45,6 +45,9 @@ CASES = [
     ("humanoid_b4096", "humanoid", 4096, 6, (), {}),
     # fixed temperature + different delay / tau_b: exercises the non-default branches
     ("tiny_fixed_alpha", "tiny", 16, 12, (1, 12), {"auto_alpha": False, "alpha": 0.2, "delay_update": 3, "tau_b": 0.05}),
+    # the policy's other std types (networks/mlp.py:42-72)
+    ("tiny_std_separated", "tiny", 16, 10, (10,), {"policy_std_type": "mlp_separated"}),
+    ("tiny_std_parameter", "tiny", 16, 10, (10,), {"policy_std_type": "parameter"}),
     # CNN approximators (example_train/dsacv2_cnn_carracing_offasync.py: type_2 encoder, 3x96x96 observations); digests only
     ("cnn_carracing_b4", "carracing", 4, 6, (), {}),
 ] + [
@@ -118,7 +121,10 @@ def run_case(name, cfg_name, batch, steps, snaps, over):
     torch.manual_seed(0)
     alg = ref_dsac.DSAC_V2(**(synth.cnn_reference_kwargs(cfg, **over) if cnn else synth.reference_kwargs(cfg, **over)))
     sd = alg.networks.state_dict()
-    for k, v in (synth.make_cnn_weights(cfg) if cnn else synth.make_weights(cfg)).items():
+    std_type = over.get("policy_std_type", "mlp_shared")
+    weights = synth.make_cnn_weights(cfg) if cnn else \
+        (synth.make_weights(cfg) if std_type == "mlp_shared" else synth.make_weights_std(cfg, std_type))
+    for k, v in weights.items():
         assert tuple(sd[k].shape) == v.shape, k
         sd[k] = torch.from_numpy(v)
     alg.networks.load_state_dict(sd)

@@ -8,12 +8,14 @@ import pytest
 import torch
 
 from dsac_v2_b200 import synth
-from oracle.dsact_oracle import TB_KEYS, cnn_from_config, from_config
+from oracle.dsact_oracle import TB_KEYS, cnn_from_config, from_config, std_from_config
 
 CASES = ["tiny_b16", "ragged_b37", "tiny_fixed_alpha", "pendulum_b256", "halfcheetah_b512",
          "humanoid_b256", "humanoid_b4096",
          # the reference's other hidden activations (utils/common_utils.py:16-43)
          "tiny_relu", "tiny_tanh", "ragged_elu", "ragged_selu", "tiny_sigmoid",
+         # the policy's other std types (oracle-level groundwork for SURVEY.md 8f rank 4)
+         "tiny_std_separated", "tiny_std_parameter",
          # CNN approximators (BASELINE config 5; oracle-level groundwork for SURVEY.md 8f rank 1)
          "cnn_carracing_b4"]
 MAX_STEPS = {"humanoid_b256": 100, "pendulum_b256": 100}
@@ -36,7 +38,10 @@ def test_oracle_matches_reference(golden_dir, name):
     act = hyper.pop("value_hidden_activation", "gelu")
     assert hyper.pop("policy_hidden_activation", act) == act
     cnn = "conv_type" in cfg
-    if cnn:
+    std_type = hyper.pop("policy_std_type", "mlp_shared")
+    if std_type != "mlp_shared":
+        orc = std_from_config(cfg, synth.make_weights_std(cfg, std_type), std_type, hidden_activation=act, **hyper)
+    elif cnn:
         orc = cnn_from_config(cfg, synth.make_cnn_weights(cfg), hidden_activation=act, **hyper)
     else:
         orc = from_config(cfg, synth.make_weights(cfg), hidden_activation=act, **hyper)
