@@ -1,0 +1,34 @@
+"""Host-side pieces of the drop-in that need neither a GPU nor the CUDA library."""
+import numpy as np
+import pytest
+import torch
+
+from dsac_v2_b200 import _lib, dp
+
+
+class _Done:
+    def synchronize(self):
+        pass
+
+
+def test_lazy_tb_info_surfaces_data_parallel_timeouts():
+    """tb_info slot 14 is the exchange status of dsact_dp_step (include/dsact.h): non-zero must raise, not log."""
+    import dsac_v2
+    from dsac_v2_b200.engine import STAT_KEYS
+    ok = torch.arange(_lib.NUM_STATS, dtype=torch.float32)
+    ok[14] = 0.0
+    info = dsac_v2._LazyTbInfo(ok.clone(), _Done(), 1.5)
+    assert info[STAT_KEYS[0]] == 0.0 and len(info) == len(STAT_KEYS) + 1
+    bad = ok.clone()
+    bad[14] = 3.0    # rank 2 never arrived
+    with pytest.raises(_lib.DsactError, match="rank 2"):
+        dsac_v2._LazyTbInfo(bad, _Done(), 1.5)[STAT_KEYS[0]]
+
+
+@pytest.mark.parametrize("rows,world", [(37, 2), (4096, 8), (5, 8), (0, 3)])
+def test_shard_rows_partitions_the_minibatch(rows, world):
+    spans = [dp.shard_rows(rows, r, world) for r in range(world)]
+    assert spans[0][0] == 0 and spans[-1][1] == rows
+    assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))          # contiguous, in rank order
+    sizes = np.array([hi - lo for lo, hi in spans])
+    assert sizes.max() - sizes.min() <= 1 and sizes.sum() == rows
