@@ -128,7 +128,6 @@ class OffSerialTrainer:
 
     # ---- asynchronous sampler feed --------------------------------------
     def _sampler_loop(self):
-        torch.set_num_threads(1)
         while not self._stop.is_set():
             with self._mirror_lock:   # act with a consistent snapshot of the mirrored policy
                 samples, tb = self.sampler.sample()
