@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdsact.so")
+# DSACT_LIB: kernel-development aid (A/B of two builds on one GPU box); the product is libdsact.so beside this file
+LIB_PATH = os.environ.get("DSACT_LIB") or os.path.join(_HERE, "libdsact.so")
 
 ABI_VERSION = 1
 MAX_HIDDEN = 6
@@ -85,6 +86,9 @@ SYMBOLS = {
     "dsact_seed": (C.c_int, [C.c_void_p, C.c_uint64]),
     "dsact_set_carry": (C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_int64, C.c_int64, C.c_void_p]),
     "dsact_step": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.POINTER(Noise), C.c_int64, C.c_void_p]),
+    "dsact_step_host": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.POINTER(Noise), C.c_int64, C.c_void_p]),
+    "dsact_stage_host": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.POINTER(Batch), C.c_void_p]),
+    "dsact_stage_release": (C.c_int, [C.c_void_p, C.c_void_p]),
     "dsact_grad_phase1": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.POINTER(Noise), C.c_void_p]),
     "dsact_grad_phase2": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p]),
     "dsact_compute_grads": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.POINTER(Noise), C.c_void_p]),

@@ -9,7 +9,14 @@
 // activations never leave the SM unless the backward pass needs them (z for act', images for wgrad).
 // The weight tiles of layer j+1 are prefetched by the TMA warp while the epilogue of layer j runs.
 //
-// TMEM map (512 columns): [0,256) fp32 accumulator, [256,384) A hi (2 bf16 per column), [384,512) A lo.
+// TMEM map (512 columns), streamed variant (STREAM = true, the default): two 256-column buffers used alternately.
+// Layer j accumulates into buffer j & 1; its epilogue converts the accumulator IN PLACE into the next layer's A operand
+// (the 16 fp32 columns of a chunk become 8 columns of packed bf16 hi pairs + 8 columns of lo pairs: the same cells),
+// and layer j + 1, accumulating into the other buffer, issues the MMAs of k-block kb as soon as the four chunks of that
+// k-block have been written (one mbarrier per k-block, 16 warp arrivals): the tensor pipe trails the epilogue by one
+// k-block instead of waiting for the whole layer, so MMA time disappears behind epilogue time.
+// Serial variant (STREAM = false, DSACT_CHAIN_STREAM=0): [0,256) fp32 accumulator, [256,384) A hi, [384,512) A lo; the
+// MMAs of layer j + 1 start when the whole epilogue of layer j is done.
 // Roles: warp 0 TMA producer, warp 1 MMA issuer, warps 2..17 epilogue (lane quarter = warp % 4).
 #pragma once
 #include "gemm_tc.cuh"
@@ -26,7 +33,6 @@ struct ChainLayer {
   int kB0[2];                // offset of each segment along B's reduction dimension
   int K;                     // reduction length of layers >= 1 (= width of the previous layer)
   int N, bn;                 // outputs; tile width (multiple of 16, <= 256)
-  int nh;                    // split kernel: 2 = the layer runs as two 128-column halves (bn == 256), else 1
   int b_mn;
   int epi, act;              // EPI_BIAS_ACT | EPI_DACT | EPI_STORE
   const float* bias;
@@ -96,22 +102,10 @@ __host__ __device__ inline int chain_ringA_bytes(int stages, int planes) {
 }
 inline int chain_smem_bytes(int stages, int planes, int stage_b) {
   return stages * planes * stage_b + chain_ringA_bytes(stages, planes) + TC_EPI_WARPS * CH_ZIN1_WARP +
-         (2 * stages + 4 + 2 * TC_EPI_WARPS) * 8 + 1024;
+         (2 * stages + 8 + 2 * TC_EPI_WARPS) * 8 + 1024;
 }
 
-// Split variant (SPLIT = true, bf16x3 only; opt-in with DSACT_CHAIN_SPLIT=1 until it has been validated on hardware):
-// a 256-wide layer is issued as two 128-column halves.  The weight ring holds four half-tiles (16 KiB per plane) in
-// the order (half 0: k-blocks 0..), (half 1: k-blocks 0..), each half commits its own accumulator barrier, and the
-// epilogue warps start on columns [0,128) while the MMAs of columns [128,256) are still running: the tensor pipe and
-// the epilogue overlap inside one layer without any extra tensor memory.  Layer 0 (A from shared memory) keeps the
-// k-block-major order (both halves of a k-block share the A tile) and finishes both halves together.
-constexpr int CH_SPLIT_STAGES = 4, CH_SPLIT_STAGE_B = 16384;
-inline int chain_smem_bytes_split(int planes) {
-  return CH_SPLIT_STAGES * planes * CH_SPLIT_STAGE_B + chain_ringA_bytes(2, planes) + TC_EPI_WARPS * CH_ZIN1_WARP +
-         (2 * CH_SPLIT_STAGES + 6 + 2 * TC_EPI_WARPS) * 8 + 1024;
-}
-
-template <bool PLANES2, bool SPLIT = false>
+template <bool PLANES2, bool STREAM>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_chain_kernel(const __grid_constant__ ChainGroup g, int stages, int stage_b) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared address space (LDS/STS)
@@ -119,15 +113,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_chain_kernel(const __grid_co
   // [ B ring: stages x planes x stage_b ][ layer-0 A ring: stages x planes x 16 KiB, later the epilogue's transpose scratch ]
   uint8_t* ringB = smem;
   uint8_t* ringA = smem + (size_t)stages * planes * stage_b;
-  const int ringA_bytes = chain_ringA_bytes(SPLIT ? 2 : stages, planes);   // split: 4 weight half-stages, 2 A stages
+  const int ringA_bytes = chain_ringA_bytes(stages, planes);
   uint8_t* zin1 = ringA + ringA_bytes;                                   // [warps] second act' input buffers
   uint64_t* bars = reinterpret_cast<uint64_t*>(zin1 + TC_EPI_WARPS * CH_ZIN1_WARP);
   uint64_t* full = bars;               // [stages] TMA -> MMA
   uint64_t* empty = bars + stages;     // [stages] MMA -> TMA
-  uint64_t* acc_full = bars + 2 * stages;          // [2]: columns [0,128) / [128,256) in the split kernel; [0] otherwise
-  uint64_t* a_free = bars + 2 * stages + 2;        // split kernel: MMAs of columns [128,256) are past k-blocks 0 and 1 of A
-  uint64_t* a_ready = bars + 2 * stages + (SPLIT ? 3 : 1);
-  uint64_t* zbar = a_ready + 1;             // [warps][2] act' tile arrival
+  uint64_t* acc_full = bars + 2 * stages;          // MMA -> epilogue: accumulator of the layer complete
+  uint64_t* a_ready = bars + 2 * stages + 1;       // [4] epilogue -> MMA: the chunks of k-block kb of the next layer's A operand
+                                                   //     are in tensor memory (serial variant: [0] only, whole operand)
+  uint64_t* zbar = a_ready + 4;             // [warps][2] act' tile arrival
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(zbar + 2 * TC_EPI_WARPS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -143,9 +137,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_chain_kernel(const __grid_co
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    mbar_init(&acc_full[0], 1);
-    if (SPLIT) { mbar_init(&acc_full[1], 1); mbar_init(a_free, 1); }
-    mbar_init(a_ready, TC_EPI_WARPS);
+    mbar_init(acc_full, 1);
+    for (int i = 0; i < 4; ++i) mbar_init(&a_ready[i], TC_EPI_WARPS);
     for (int i = 0; i < 2 * TC_EPI_WARPS; ++i) mbar_init(&zbar[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -163,56 +156,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_chain_kernel(const __grid_co
 
   if (warp == 0) {
     // ===== TMA producer: runs ahead of the epilogues, bounded only by free ring slots =====
-    if (SPLIT && lane == 0) {
-      // half-stage sequence number `it`: stage = it % 4, phase = (it / 4) & 1, identical in the MMA warp
-      int it = 0;
-      int a_last[2] = {-1, -1};   // `it` of the last half-stage that read A ring slot 0 / 1 (layer 0 only)
-      for (int j = 0; j < nl; ++j) {
-        const ChainLayer& Lj = P.L[j];
-        const int nkb = Lj.kblocks[0] + Lj.kblocks[1];
-        const int nh = Lj.nh;
-        const int rows = nh == 2 ? 128 : Lj.bn;                     // columns of the layer held by one half-tile
-        const int b_boxes = Lj.b_mn ? (rows + 63) / 64 : 1;
-        const uint32_t b_bytes = Lj.b_mn ? (uint32_t)b_boxes * 8192 : (uint32_t)rows * 128;
-        auto load_b = [&](int h, int kB, int s) {
-          uint8_t* sB = ringB + (size_t)s * planes * stage_b;
-          for (int pl = 0; pl < planes; ++pl) {
-            if (Lj.b_mn) {
-              for (int i = 0; i < b_boxes; ++i) tma_load_3d(sB + pl * stage_b + i * 8192, &Lj.mapB, &full[s], 128 * h + 64 * i, kB, pl);
-            } else {
-              tma_load_3d(sB + pl * stage_b, &Lj.mapB, &full[s], kB, 128 * h, pl);
-            }
-          }
-        };
-        if (j == 0) {   // k-block major: the A tile of a k-block serves both halves
-          for (int kb = 0; kb < nkb; ++kb) {
-            const int seg = kb >= Lj.kblocks[0] ? 1 : 0;
-            const int kloc = (seg ? kb - Lj.kblocks[0] : kb) * TC_BK;
-            const int kB = Lj.kB0[seg] + kloc;
-            const int a_slot = kb & 1;
-            if (a_last[a_slot] >= 0) mbar_wait(&empty[a_last[a_slot] % CH_SPLIT_STAGES], (uint32_t)((a_last[a_slot] / CH_SPLIT_STAGES) & 1));
-            for (int h = 0; h < nh; ++h, ++it) {
-              const int s = it % CH_SPLIT_STAGES;
-              mbar_wait(&empty[s], (uint32_t)(((it / CH_SPLIT_STAGES) & 1) ^ 1));
-              mbar_expect_tx(&full[s], planes * (b_bytes + (h == 0 ? (uint32_t)TC_STAGE_A : 0u)));
-              if (h == 0)
-                for (int pl = 0; pl < planes; ++pl)
-                  tma_load_3d(ringA + (size_t)(a_slot * planes + pl) * TC_STAGE_A, &P.mapA[seg], &full[s], kloc, m0, pl);
-              load_b(h, kB, s);
-            }
-            a_last[a_slot] = it - 1;
-          }
-        } else {        // half major: all k-blocks of columns [0,128), then all of [128,256)
-          for (int h = 0; h < nh; ++h)
-            for (int kb = 0; kb < nkb; ++kb, ++it) {
-              const int s = it % CH_SPLIT_STAGES;
-              mbar_wait(&empty[s], (uint32_t)(((it / CH_SPLIT_STAGES) & 1) ^ 1));
-              mbar_expect_tx(&full[s], planes * b_bytes);
-              load_b(h, Lj.kB0[0] + kb * TC_BK, s);
-            }
-        }
-      }
-    } else if (lane == 0) {
+    if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
       for (int j = 0; j < nl; ++j) {
@@ -243,87 +187,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_chain_kernel(const __grid_co
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
-    if (SPLIT && lane == 0) {
-      int it = 0;
-      for (int j = 0; j < nl; ++j) {
-        const ChainLayer& Lj = P.L[j];
-        const int nkb = Lj.kblocks[0] + Lj.kblocks[1];
-        const int nh = Lj.nh;
-        const uint32_t idesc = make_idesc(TC_BM, nh == 2 ? 128 : Lj.bn, 0, Lj.b_mn);
-        if (j > 0) {
-          mbar_wait(a_ready, (uint32_t)((j - 1) & 1));
-          tc_fence_after();
-        }
-        auto issue = [&](int h, int kb, int s, uint32_t accumulate) {
-          const uint32_t sB = smem_u32(ringB + (size_t)s * planes * stage_b);
-          const uint32_t sA = smem_u32(ringA + (size_t)((kb & 1) * planes) * TC_STAGE_A);
-          const uint32_t d = tmem_base + CH_ACC_COL + (uint32_t)(128 * h);
-          const int ksteps = j == 0 ? 4 : min(4, (Lj.K - kb * TC_BK + 15) / 16);
-          for (int k = 0; k < ksteps; ++k) {
-            const uint32_t b_off = Lj.b_mn ? k * 2048 : k * 32;
-            const uint64_t b_hi = make_desc(sB + b_off, Lj.b_mn ? 8192 : 16, 1024);
-            const uint64_t b_lo = make_desc(sB + stage_b + b_off, Lj.b_mn ? 8192 : 16, 1024);
-            if (j == 0) {
-              const uint64_t a_hi = make_desc(sA + k * 32, 16, 1024);
-              const uint64_t a_lo = make_desc(sA + TC_STAGE_A + k * 32, 16, 1024);
-              tc_mma(d, a_hi, b_hi, idesc, accumulate);
-              tc_mma(d, a_hi, b_lo, idesc, 1);
-              tc_mma(d, a_lo, b_hi, idesc, 1);
-            } else {
-              const uint32_t kcol = (uint32_t)(kb * 32 + k * 8);   // 2 bf16 per TMEM column
-              tc_mma_ts(d, tmem_base + CH_AHI_COL + kcol, b_hi, idesc, accumulate);
-              tc_mma_ts(d, tmem_base + CH_AHI_COL + kcol, b_lo, idesc, 1);
-              tc_mma_ts(d, tmem_base + CH_ALO_COL + kcol, b_hi, idesc, 1);
-            }
-            accumulate = 1;
-          }
-        };
-        if (j == 0) {
-          for (int kb = 0; kb < nkb; ++kb)
-            for (int h = 0; h < nh; ++h, ++it) {
-              const int s = it % CH_SPLIT_STAGES;
-              mbar_wait(&full[s], (uint32_t)((it / CH_SPLIT_STAGES) & 1));
-              tc_fence_after();
-              if (kb == 0 && h == 0) TC_STAMP(2);
-              issue(h, kb, s, kb > 0 ? 1u : 0u);
-              tc_commit(&empty[s]);
-            }
-          tc_commit(&acc_full[0]);
-          tc_commit(&acc_full[1]);
-          tc_commit(a_free);
-        } else {
-          for (int h = 0; h < nh; ++h) {
-            for (int kb = 0; kb < nkb; ++kb, ++it) {
-              const int s = it % CH_SPLIT_STAGES;
-              mbar_wait(&full[s], (uint32_t)((it / CH_SPLIT_STAGES) & 1));
-              tc_fence_after();
-              issue(h, kb, s, kb > 0 ? 1u : 0u);
-              tc_commit(&empty[s]);
-              // The epilogue of columns [0,128) overwrites TMEM A columns of k-blocks 0 and 1 with the next layer's
-              // operand: it may do so once the last MMAs that read them (second half, k-block 1) have completed.
-              if (h == nh - 1 && kb == (nkb > 1 ? 1 : 0)) tc_commit(a_free);
-            }
-            tc_commit(&acc_full[h]);   // columns [128 h, 128 h + 128) complete: their epilogue may start
-          }
-          if (nh == 1) tc_commit(&acc_full[1]);
-        }
-        TC_STAMP(8 + 3 * j);      // MMAs of layer j issued
-      }
-      TC_STAMP(3);
-    } else if (lane == 0) {
+    if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
       for (int j = 0; j < nl; ++j) {
         const ChainLayer& Lj = P.L[j];
         const int nkb = Lj.kblocks[0] + Lj.kblocks[1];
         const uint32_t idesc = make_idesc(TC_BM, Lj.bn, 0, Lj.b_mn);
-        if (j > 0) {  // A of this layer = what the previous epilogue wrote to TMEM
-          mbar_wait(a_ready, (uint32_t)((j - 1) & 1));
+        // accumulator / A-operand columns of this layer (see the TMEM map at the top)
+        const uint32_t acc = tmem_base + (STREAM ? (uint32_t)((j & 1) * 256) : (uint32_t)CH_ACC_COL);
+        const uint32_t abuf = tmem_base + (uint32_t)(((j - 1) & 1) * 256);   // streamed: where layer j - 1 accumulated
+        if (!STREAM && j > 0) {  // A of this layer = what the previous epilogue wrote to TMEM
+          mbar_wait(&a_ready[0], (uint32_t)((j - 1) & 1));
           tc_fence_after();
         }
         uint32_t accumulate = 0;
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&full[stage], phase);
+          if (STREAM && j > 0) mbar_wait(&a_ready[kb], (uint32_t)((j - 1) & 1));   // chunks 4 kb .. 4 kb + 3 of the operand
           tc_fence_after();
           if (j == 0 && kb == 0) TC_STAMP(2);
           const uint32_t sB = smem_u32(ringB + (size_t)stage * planes * stage_b);
@@ -335,18 +216,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_chain_kernel(const __grid_co
             const uint64_t b_lo = make_desc(sB + stage_b + b_off, Lj.b_mn ? 8192 : 16, 1024);
             if (j == 0) {
               const uint64_t a_hi = make_desc(sA + k * 32, 16, 1024);
-              tc_mma(tmem_base + CH_ACC_COL, a_hi, b_hi, idesc, accumulate);
+              tc_mma(acc, a_hi, b_hi, idesc, accumulate);
               if (planes == 2) {
                 const uint64_t a_lo = make_desc(sA + TC_STAGE_A + k * 32, 16, 1024);
-                tc_mma(tmem_base + CH_ACC_COL, a_hi, b_lo, idesc, 1);
-                tc_mma(tmem_base + CH_ACC_COL, a_lo, b_hi, idesc, 1);
+                tc_mma(acc, a_hi, b_lo, idesc, 1);
+                tc_mma(acc, a_lo, b_hi, idesc, 1);
               }
             } else {
-              const uint32_t kcol = (uint32_t)(kb * 32 + k * 8);   // 2 bf16 per TMEM column
-              tc_mma_ts(tmem_base + CH_ACC_COL, tmem_base + CH_AHI_COL + kcol, b_hi, idesc, accumulate);
+              // 16 K elements = one epilogue chunk = 8 TMEM columns of packed bf16 pairs per plane
+              const uint32_t a_hi = STREAM ? abuf + (uint32_t)((kb * 4 + k) * 16) : tmem_base + CH_AHI_COL + (uint32_t)(kb * 32 + k * 8);
+              const uint32_t a_lo = STREAM ? a_hi + 8 : tmem_base + CH_ALO_COL + (uint32_t)(kb * 32 + k * 8);
+              tc_mma_ts(acc, a_hi, b_hi, idesc, accumulate);
               if (planes == 2) {
-                tc_mma_ts(tmem_base + CH_ACC_COL, tmem_base + CH_AHI_COL + kcol, b_lo, idesc, 1);
-                tc_mma_ts(tmem_base + CH_ACC_COL, tmem_base + CH_ALO_COL + kcol, b_hi, idesc, 1);
+                tc_mma_ts(acc, a_hi, b_lo, idesc, 1);
+                tc_mma_ts(acc, a_lo, b_hi, idesc, 1);
               }
             }
             accumulate = 1;
@@ -396,9 +279,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_chain_kernel(const __grid_co
         }
         __syncwarp();
       }
-      mbar_wait(&acc_full[0], (uint32_t)(j & 1));
-      bool h1_ready = !SPLIT, a_writable = !SPLIT;   // split kernel: columns >= 128 / the TMEM A columns, see the MMA warp
+      mbar_wait(acc_full, (uint32_t)(j & 1));
       tc_fence_after();
+      const uint32_t acc_addr = lane_addr + (STREAM ? (uint32_t)((j & 1) * 256) : (uint32_t)CH_ACC_COL);
       if (j == 0 && threadIdx.x == 64) TC_STAMP(4);
       if (threadIdx.x == 64) TC_STAMP(9 + 3 * j);   // accumulator of layer j complete (seen by the epilogue)
       const int epi = Lj.epi, act = Lj.act;
@@ -415,12 +298,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_chain_kernel(const __grid_co
       for (int ch = sub; ch < nch; ch += TC_EPI_WARPS / 4, ++k) {
         const int c0 = ch * 16;
         float v[16];
-        if (SPLIT && c0 >= 128 && !h1_ready) {
-          mbar_wait(&acc_full[1], (uint32_t)(j & 1));
-          tc_fence_after();
-          h1_ready = true;
-        }
-        tc_ld16(lane_addr + CH_ACC_COL + (uint32_t)c0, v);   // v[i] = acc[row = lane][c0 + i]
+        TC_CSTAMP(32);
+        tc_ld16(acc_addr + (uint32_t)c0, v);   // v[i] = acc[row = lane][c0 + i]
+        TC_CSTAMP(33);
         if (dact) {
           const int nxt = ch + TC_EPI_WARPS / 4;
           __syncwarp();  // every lane is done with the buffer the prefetch overwrites
@@ -435,7 +315,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_chain_kernel(const __grid_co
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const float4 d = zr[q ^ sw64];   // rows >= M and columns >= N arrive as zeros (TMA out-of-bounds fill)
-            v[4 * q] *= d.x; v[4 * q + 1] *= d.y; v[4 * q + 2] *= d.z; v[4 * q + 3] *= d.w;
+            upk2(mul2(pk2(v[4 * q], v[4 * q + 1]), pk2(d.x, d.y)), v[4 * q], v[4 * q + 1]);
+            upk2(mul2(pk2(v[4 * q + 2], v[4 * q + 3]), pk2(d.z, d.w)), v[4 * q + 2], v[4 * q + 3]);
           }
           if (Lj.colsum) {  // bias gradient: column sums over the warp's 32 rows by a reduce-scatter of the 16 columns
             float r[16];
@@ -473,7 +354,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_chain_kernel(const __grid_co
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               const float4 b = bp[q];
-              v[4 * q] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w;
+              upk2(add2(pk2(v[4 * q], v[4 * q + 1]), pk2(b.x, b.y)), v[4 * q], v[4 * q + 1]);
+              upk2(add2(pk2(v[4 * q + 2], v[4 * q + 3]), pk2(b.z, b.w)), v[4 * q + 2], v[4 * q + 3]);
             }
           }
           if (epi == EPI_BIAS_ACT) {
@@ -481,6 +363,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_chain_kernel(const __grid_co
             else act_fwdN<false, 16>(v, d, act, st_f32 + lane * 16);
           }
         }
+        TC_CSTAMP(34);
         if (c0 + 16 > Lj.N) {   // partial chunk: padding columns feed the next layer as zeros
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = (c0 + i < Lj.N) ? v[i] : 0.f;
@@ -500,6 +383,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_chain_kernel(const __grid_co
             split_pack2(v[2 * i], v[2 * i + 1], whi[i], wlo[i]);
           }
         }
+        TC_CSTAMP(35);
         if (st_z || Lj.img) {  // stage in shared memory (row layout), one lane issues the TMA stores (they clip at M and N)
           if (!scratch) {
             if (lane == 0) tma_store_wait_read();
@@ -528,22 +412,36 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_chain_kernel(const __grid_co
             tma_store_commit();
           }
         }
+        TC_CSTAMP(36);
         if (feeds_next) {  // next layer's A operand: packed bf16 pairs along K, hi and lo planes
-          if (SPLIT && !a_writable) {
-            mbar_wait(a_free, (uint32_t)(j & 1));
-            tc_fence_after();
-            a_writable = true;
+          if (STREAM) {    // in place: the chunk's 16 accumulator columns become 8 columns of hi pairs + 8 of lo pairs
+            tc_st8(acc_addr + (uint32_t)c0, whi);
+            if (planes == 2) tc_st8(acc_addr + (uint32_t)c0 + 8, wlo);
+          } else {
+            tc_st8(lane_addr + CH_AHI_COL + (uint32_t)(c0 / 2), whi);
+            if (planes == 2) tc_st8(lane_addr + CH_ALO_COL + (uint32_t)(c0 / 2), wlo);
           }
-          tc_st8(lane_addr + CH_AHI_COL + (uint32_t)(c0 / 2), whi);
-          if (planes == 2) tc_st8(lane_addr + CH_ALO_COL + (uint32_t)(c0 / 2), wlo);
         }
+        if (STREAM && feeds_next) {   // this warp's share of k-block k of the next layer's operand is in tensor memory
+          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&a_ready[k]);
+        }
+        TC_CSTAMP(37);
       }
+      if (g.dbg && j == 1 && threadIdx.x == 64) g.dbg[(size_t)blockIdx.x * TC_DBG_SLOTS + 38] = (unsigned long long)clock64();
       if (threadIdx.x == 64) TC_STAMP(10 + 3 * j);  // epilogue of layer j done (first epilogue warp)
       if (feeds_next) {
-        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(a_ready);
+        if (STREAM) {   // k-blocks in which this warp had no chunk (narrow layers): every barrier sees every warp once
+          for (; k < 4; ++k)
+            if (lane == 0) mbar_arrive(&a_ready[k]);
+        } else {
+          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&a_ready[0]);
+        }
       }
     }
     if (lane == 0) tma_store_wait_read();   // shared memory must stay valid until the last stores have read it

@@ -97,11 +97,12 @@ __global__ void dp_exchange_kernel(const DpComm c, float* __restrict__ state, in
 }
 
 // grads_out[i] = grads[i] + sum of the weight-gradient slabs (the local total, into the exchange buffer)
+// `tail`.enabled: the log_alpha element (index n - 1) is formed here from the logged sum (phase2_tail_kernel folded in)
 __global__ void dp_grad_fold_kernel(float* __restrict__ out, const float* __restrict__ grads, const float* __restrict__ slabs,
-                                    long long n, int nslabs, long long slab_stride) {
+                                    long long n, int nslabs, long long slab_stride, const float* __restrict__ state, const TailArgs tail) {
   pdl_sync();
   const bool vec = (slab_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(grads) & 15) == 0 && (reinterpret_cast<uintptr_t>(slabs) & 15) == 0;
-  const long long n4 = vec ? n / 4 : 0;
+  const long long n4 = vec ? (tail.enabled ? n - 1 : n) / 4 : 0;   // the log_alpha element always takes the scalar path
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     float4 s = reinterpret_cast<const float4*>(grads)[i];
     for (int k = 0; k < nslabs; ++k) {
@@ -113,6 +114,7 @@ __global__ void dp_grad_fold_kernel(float* __restrict__ out, const float* __rest
   for (long long i = n4 * 4 + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     float s = grads[i];
     for (int k = 0; k < nslabs; ++k) s += slabs[(size_t)k * slab_stride + i];
+    if (tail.enabled && i == n - 1) s = tail_grad_log_alpha(state, tail);
     out[i] = s;
   }
 }

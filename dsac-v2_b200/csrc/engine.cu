@@ -157,6 +157,15 @@ struct dsact_handle {
   void* dp_opened[DP_MAX_RANKS] = {}; // peers' buffers as opened here
   DpComm dp = {};
   bool dp_ready = false;
+  // host-minibatch staging (dsact_stage_host): two device sets + a private copy stream
+  float* stage_buf[2] = {nullptr, nullptr};
+  int64_t stage_floats = 0;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_stage_ready[2] = {nullptr, nullptr}, ev_stage_done[2] = {nullptr, nullptr};
+  bool stage_done_valid[2] = {false, false};
+  int stage_turn = 0, stage_held = -1;
+  bool tc_attr_done = false, chain_attr_done = false;   // cudaFuncSetAttribute is per device: tracked per handle
+  TcGroup tc_scratch;                                   // host-side lowering scratch of launch_tc (~5 KiB)
   std::vector<GraphEntry> graphs;
   uint64_t stamp;
   int64_t launches;
@@ -171,14 +180,10 @@ struct dsact_handle {
     return cfg.act_dim <= 256;
   }
   int passes() const { return cfg.gemm_mode == DSACT_GEMM_BF16X3 ? 3 : 1; }
-  // split variant of the chain kernel (chain_tc.cuh): opt-in, bf16x3 only, every layer either <= 128 wide or exactly 256
-  bool chain_split() const {
-    static const bool want = getenv("DSACT_CHAIN_SPLIT") && getenv("DSACT_CHAIN_SPLIT")[0] == '1';
-    if (!want || passes() != 3 || !fused()) return false;
-    auto ok = [](int w) { const int bn = (w + 15) / 16 * 16; return bn <= 128 || bn == 256; };
-    for (int j = 0; j <= q.L + 1; ++j) if (!ok(q.s[j]) && j > 0) return false;
-    for (int j = 0; j <= pi.L + 1; ++j) if (!ok(pi.s[j]) && j > 0) return false;
-    return ok(cfg.act_dim);
+  // streamed variant of the chain kernel (chain_tc.cuh): the default; DSACT_CHAIN_STREAM=0 selects the serial one
+  bool chain_stream() const {
+    static const bool off = getenv("DSACT_CHAIN_STREAM") && getenv("DSACT_CHAIN_STREAM")[0] == '0';
+    return !off;
   }
   float* W() const { return reinterpret_cast<float*>(buf.workspace); }
   Img img(const ImgSlot& s, int rows) const {  // image handle with the live row count
@@ -294,13 +299,11 @@ static void launch_simt(const dsact_handle* h, GemmGroup& g, int variant, Ctx& c
   else launch_variant<64, 64>(g, variant, grid, c);
 }
 
-static bool g_tc_attr_done = false;
-
 // Lower the group onto tcgen05: images instead of fp32 operands, TMA tensor maps, 128 x bn tiles.
 // `max_ctas` > 0: issue the group as several launches of at most that many CTAs (one CTA occupies an SM), which leaves
 // the remaining SMs to a concurrent branch of the step graph for the whole duration.
-static void launch_tc(const dsact_handle* h, Group& G, int variant, Ctx& c, int max_ctas = 0) {
-  static TcGroup t;  // ~5 KiB; host-side scratch (single trainer thread per process is the documented contract)
+static void launch_tc(dsact_handle* h, Group& G, int variant, Ctx& c, int max_ctas = 0) {
+  TcGroup& t = h->tc_scratch;
   memset(&t, 0, sizeof(t));
   t.n = G.n;
   t.passes = h->passes();
@@ -359,14 +362,14 @@ static void launch_tc(const dsact_handle* h, Group& G, int variant, Ctx& c, int 
   int stages = (200 * 1024) / (planes * (TC_STAGE_A + stage_b));
   if (stages > 8) stages = 8;
   const int smem = tc_smem_bytes(stages, planes, stage_b);
-  if (!g_tc_attr_done) {
+  if (!h->tc_attr_done) {
     cudaFuncSetAttribute(tc_gemm_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     cudaFuncSetAttribute(tc_gemm_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     cudaFuncSetAttribute(tc_gemm_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     cudaFuncSetAttribute(tc_gemm_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     cudaFuncSetAttribute(tc_gemm_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     cudaFuncSetAttribute(tc_gemm_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    g_tc_attr_done = true;
+    h->tc_attr_done = true;
   }
   const int total = grid;
   if (max_ctas > 0 && !debug && total > max_ctas) {  // equal slices, none above the bound
@@ -406,7 +409,7 @@ static void launch_tc(const dsact_handle* h, Group& G, int variant, Ctx& c, int 
   }
 }
 
-static void launch_group(const dsact_handle* h, Group& G, int variant, Ctx& c, int max_ctas = 0) {
+static void launch_group(dsact_handle* h, Group& G, int variant, Ctx& c, int max_ctas = 0) {
   if (G.n == 0) return;
   double flops = 0.0;
   for (int i = 0; i < G.n; ++i) flops += 2.0 * G.prob(i).M * G.prob(i).N * ((double)G.prob(i).K[0] + G.prob(i).K[1]);
@@ -511,9 +514,10 @@ struct ImgBatch {
     j.pitch = dst.pitch; j.fill_w = w1 > 0 ? dst1 + w1 : w0; j.plane = dst.plane;
   }
   void reserve(const dsact_handle* h, Ctx& c, int jobs) { if (g.n + jobs > IMG_MAXJ) launch(h, c); }   // flush when full
-  void launch(const dsact_handle* h, Ctx& c) {
+  // `pro` != null: the clears and the device noise ride in the same launch (step_prologue_kernel)
+  void launch(const dsact_handle* h, Ctx& c, PrologueArgs* pro = nullptr) {
     if (overflow) { c.err = cudaErrorInvalidValue; return; }
-    if (g.n == 0) return;
+    if (g.n == 0 && !pro) return;
     g.planes = h->passes() == 3 ? 2 : 1;
     int grid = 0;
     for (int i = 0; i < g.n; ++i) {
@@ -524,7 +528,12 @@ struct ImgBatch {
       if (blocks > 2 * h->num_sms) blocks = 2 * h->num_sms;
       grid += blocks;
     }
-    launch_k(image_kernel, grid, 256, 0, c, g);
+    if (pro) {
+      pro->img_blocks = grid;
+      launch_k(step_prologue_kernel, grid + pro->zero_blocks + pro->noise_blocks, 256, 0, c, g, *pro);
+    } else {
+      launch_k(image_kernel, grid, 256, 0, c, g);
+    }
     c.done();
     g.n = 0;
   }
@@ -551,8 +560,8 @@ struct ChainBuild {
   ChainGroup g;
   int grid = 0, stage_b = 16 * 128;
   double flops = 0.0;
-  bool ok = true, split = false;
-  explicit ChainBuild(int passes, bool split_ = false) : split(split_) { memset(&g, 0, sizeof(g)); g.passes = passes; }
+  bool ok = true, stream = true;
+  explicit ChainBuild(int passes, bool stream_ = true) : stream(stream_) { memset(&g, 0, sizeof(g)); g.passes = passes; }
   ChainPass& begin(const Img& a0, const Img& a1, int M) {
     ChainPass& P = g.p[g.n++];
     P.n_layers = 0; P.M = M; P.tile_start = grid;
@@ -564,20 +573,17 @@ struct ChainBuild {
   ChainLayer& layer(ChainPass& P, const Img& wimg, bool b_mn, int N, int K0, int K1, int kB1) {
     ChainLayer& L = P.L[P.n_layers++];
     L.N = N; L.bn = (N + 15) / 16 * 16; L.b_mn = b_mn ? 1 : 0;
-    L.nh = (split && L.bn == 256) ? 2 : 1;
     L.kblocks[0] = (K0 + TC_BK - 1) / TC_BK; L.kblocks[1] = (K1 + TC_BK - 1) / TC_BK;
     L.kB0[0] = 0; L.kB0[1] = kB1; L.K = K0;
-    ok = ok && make_map(&L.mapB, wimg, b_mn ? 64 : (L.nh == 2 ? 128 : L.bn));   // split: one box = one 128-column half
+    ok = ok && make_map(&L.mapB, wimg, b_mn ? 64 : L.bn);
     const int sb = b_mn ? (L.bn + 63) / 64 * 8192 : L.bn * 128;
     if (sb > stage_b) stage_b = sb;
-    if (split && L.nh == 1 && L.bn > 128) ok = false;   // (chain_split() excludes such widths)
     flops += 2.0 * P.M * N * ((double)K0 + K1);
     return L;
   }
 };
 
-static bool g_chain_attr_done = false;
-static void launch_chain(const dsact_handle* h, ChainBuild& cb, int cls, Ctx& c) {
+static void launch_chain(dsact_handle* h, ChainBuild& cb, int cls, Ctx& c) {
   if (cb.g.n == 0) return;
   if (!cb.ok) { c.err = cudaErrorInvalidValue; return; }
   static unsigned long long* dbg = nullptr;
@@ -585,17 +591,22 @@ static void launch_chain(const dsact_handle* h, ChainBuild& cb, int cls, Ctx& c)
   if (debug && !dbg) cudaMalloc(&dbg, sizeof(unsigned long long) * TC_DBG_SLOTS * 4096);
   if (debug && cb.grid <= 4096) { cudaMemsetAsync(dbg, 0, sizeof(unsigned long long) * TC_DBG_SLOTS * cb.grid, c.s); cb.g.dbg = dbg; }
   const int planes = cb.g.passes == 3 ? 2 : 1;
-  const int stages = cb.split ? CH_SPLIT_STAGES : (planes == 2 ? 2 : 3);
-  const int smem = cb.split ? chain_smem_bytes_split(planes) : chain_smem_bytes(stages, planes, cb.stage_b);
-  if (!g_chain_attr_done) {
-    cudaFuncSetAttribute(tc_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    cudaFuncSetAttribute(tc_chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  const int stages = planes == 2 ? 2 : 3;
+  const int smem = chain_smem_bytes(stages, planes, cb.stage_b);
+  if (!h->chain_attr_done) {
     cudaFuncSetAttribute(tc_chain_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    g_chain_attr_done = true;
+    cudaFuncSetAttribute(tc_chain_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(tc_chain_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(tc_chain_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    h->chain_attr_done = true;
   }
-  if (cb.split) launch_k(tc_chain_kernel<true, true>, cb.grid, TC_THREADS, smem, c, cb.g, stages, (int)CH_SPLIT_STAGE_B);
-  else if (planes == 2) launch_k(tc_chain_kernel<true>, cb.grid, TC_THREADS, smem, c, cb.g, stages, cb.stage_b);
-  else launch_k(tc_chain_kernel<false>, cb.grid, TC_THREADS, smem, c, cb.g, stages, cb.stage_b);
+  if (planes == 2) {
+    if (cb.stream) launch_k(tc_chain_kernel<true, true>, cb.grid, TC_THREADS, smem, c, cb.g, stages, cb.stage_b);
+    else launch_k(tc_chain_kernel<true, false>, cb.grid, TC_THREADS, smem, c, cb.g, stages, cb.stage_b);
+  } else {
+    if (cb.stream) launch_k(tc_chain_kernel<false, true>, cb.grid, TC_THREADS, smem, c, cb.g, stages, cb.stage_b);
+    else launch_k(tc_chain_kernel<false, false>, cb.grid, TC_THREADS, smem, c, cb.g, stages, cb.stage_b);
+  }
   c.done(cls, cb.flops);
   c.check();
   if (debug && cb.g.dbg) {
@@ -616,6 +627,10 @@ static void launch_chain(const dsact_handle* h, ChainBuild& cb, int cls, Ctx& c)
         fprintf(stderr, " L%d mma-issued %.1f acc-ready %.1f epi-done %.1f |", j, (d[8 + 3 * j] - d[0]) / 1e3, (d[9 + 3 * j] - d[0]) / 1e3,
                 (d[10 + 3 * j] - d[0]) / 1e3);
       fprintf(stderr, " end %.1f\n", (d[6] - d[0]) / 1e3);
+      if (d[32] && d[38])   // first chunk of layer 1, first epilogue warp (SM cycles): ld | math | split | stage+TMA | st+arrive ; whole layer
+        fprintf(stderr, "    L1 chunk0 cycles: ld %lld math %lld split %lld stage %lld st+arrive %lld | layer (4 chunks) %lld\n",
+                (long long)(d[33] - d[32]), (long long)(d[34] - d[33]), (long long)(d[35] - d[34]), (long long)(d[36] - d[35]),
+                (long long)(d[37] - d[36]), (long long)(d[38] - d[32]));
     }
   }
 }
@@ -697,11 +712,12 @@ static void enqueue_prologue(dsact_handle* h, const dsact_batch& bt, const dsact
   const float* Qb[4] = {P, P + q.n, T, T + q.n};        // q1, q2, q1', q2'
   const float* PIb[2] = {P + 2 * q.n, T + 2 * q.n};     // pi, pi'
 
-  {
-    const long long n = 2 * q.n + pi.n + 1;
-    int blocks = (int)((n / 4 + 255) / 256); if (blocks > 2 * h->num_sms) blocks = 2 * h->num_sms; if (blocks < 1) blocks = 1;
-    launch_k(begin_step_kernel, blocks, 256, 0, c, h->buf.state, h->buf.grads, n); c.done();
-  }
+  const long long n_grads = 2 * q.n + pi.n + 1;
+  int zero_blocks = (int)((n_grads / 4 + 255) / 256); if (zero_blocks > 2 * h->num_sms) zero_blocks = 2 * h->num_sms; if (zero_blocks < 1) zero_blocks = 1;
+  const bool want_noise = !nz && with_noise;
+  static const bool merge_off = getenv("DSACT_PROLOGUE_MERGE") && getenv("DSACT_PROLOGUE_MERGE")[0] == '0';
+  const bool merged = tc && !merge_off;   // tcgen05 modes: clears + images + noise as one launch
+  if (!merged) { launch_k(begin_step_kernel, zero_blocks, 256, 0, c, h->buf.state, h->buf.grads, n_grads); c.done(); }
 
   if (tc) {  // refresh the weight images (the caller may have written params/targets through its views) + inputs
     ImgBatch ib;
@@ -728,11 +744,25 @@ static void enqueue_prologue(dsact_handle* h, const dsact_batch& bt, const dsact
       ib.add(bt.obs2, O, h->img(ar.i_obs2, B), B, O);
       ib.add(bt.act, A, h->img(ar.i_act, B), B, A);
     }
-    ib.launch(h, c);
+    if (merged) {
+      PrologueArgs pa;
+      memset(&pa, 0, sizeof(pa));
+      pa.zero_blocks = zero_blocks;
+      pa.state = h->buf.state; pa.grads = h->buf.grads; pa.n_grads = n_grads;
+      if (want_noise) {
+        const int total = (B * A + 1) / 2 * 2 + (B + 1) / 2 * 2;
+        pa.noise_blocks = (total / 2 + 255) / 256; if (pa.noise_blocks < 1) pa.noise_blocks = 1;
+        pa.eps1 = W + ar.eps1; pa.eps2 = W + ar.eps2; pa.z3 = W + ar.z3; pa.z4 = W + ar.z4;
+        pa.B = B; pa.A = A; pa.seed = h->seed;
+      }
+      ib.launch(h, c, &pa);
+    } else {
+      ib.launch(h, c);
+    }
   }
 
   // device noise; the counter it reads is stepped by sample_kernel, once every reader of this step has run
-  if (!nz && with_noise) enqueue_noise(h, B, c);
+  if (want_noise && !merged) enqueue_noise(h, B, c);
   c.check();
 }
 
@@ -794,7 +824,7 @@ static void enqueue_phase1(dsact_handle* h, const dsact_batch& bt, const dsact_n
   const bool fused = h->fused();
   const Img i_none;
   if (fused) {  // wave A as ONE launch: each CTA runs a 128-row block through every layer of its pass
-    ChainBuild cb(h->passes(), h->chain_split());
+    ChainBuild cb(h->passes(), h->chain_stream());
     chain_fwd_pass(cb, h, pi, PIb[0], ar.i_wpi[0], t_obs.im, O, i_none, 0, 0, B, cf.act_pi, ar.zP, ar.i_hP, W + ar.logitsP);
     chain_fwd_pass(cb, h, pi, PIb[1], ar.i_wpi[1], t_obs2.im, O, i_none, 0, 0, B, cf.act_pi, nullptr, nullptr, W + ar.logitsT);
     for (int k = 0; k < 2; ++k)
@@ -860,7 +890,7 @@ static void enqueue_phase1(dsact_handle* h, const dsact_batch& bt, const dsact_n
   // wave B: Q1', Q2' on (s', a') and Q1, Q2 on (s, a~)
   const Ten t_new_act = ten(W + ar.new_act, ar.i_new_act), t_act2 = ten(W + ar.act2, ar.i_act2);
   if (fused) {
-    ChainBuild cb(h->passes(), h->chain_split());
+    ChainBuild cb(h->passes(), h->chain_stream());
     for (int k = 0; k < 2; ++k)
       chain_fwd_pass(cb, h, q, Qb[2 + k], ar.i_wq[2 + k], t_obs2.im, O, t_act2.im, A, ar.kpad_q0, B, cf.act_q, nullptr, nullptr, W + ar.outQ[2 + k]);
     for (int k = 0; k < 2; ++k)
@@ -892,7 +922,18 @@ static bool slabs_foldable(const dsact_handle* h) {
   return h->tc() && ((uintptr_t)(h->W() + h->ar.slabs) & 15) == 0 && ((uintptr_t)h->buf.grads & 15) == 0;
 }
 enum { REDUCE_INPLACE = 0, REDUCE_DEFER = 1, REDUCE_DP = 2 };   // where the weight-gradient slabs get folded
-static void enqueue_phase2(dsact_handle* h, const dsact_batch& bt, int64_t global_batch, Ctx& c, int reduce_mode = REDUCE_INPLACE) {
+static TailArgs tail_args(const dsact_handle* h, int64_t global_batch, int rows, bool enabled) {
+  const Net &q = h->q, &pi = h->pi;
+  TailArgs t;
+  t.sc.tau_b = (float)h->cfg.tau_b; t.sc.alpha_fixed = (float)h->cfg.alpha_fixed;
+  t.sc.inv_global_batch = (float)(1.0 / (double)global_batch);
+  t.sc.auto_alpha = h->cfg.auto_alpha; t.sc.log_alpha = h->buf.params + 2 * q.n + pi.n;
+  t.target_entropy = -(float)h->cfg.act_dim; t.rows = rows; t.enabled = enabled ? 1 : 0;
+  return t;
+}
+// `fold_tail`: the caller's next kernels (dp_grad_fold / apply) do the end-of-backward bookkeeping, no phase2_tail launch
+static void enqueue_phase2(dsact_handle* h, const dsact_batch& bt, int64_t global_batch, Ctx& c, int reduce_mode = REDUCE_INPLACE,
+                           bool fold_tail = false) {
   const bool defer_reduce = reduce_mode != REDUCE_INPLACE;
   const dsact_config& cf = h->cfg;
   const Net &q = h->q, &pi = h->pi;
@@ -930,17 +971,35 @@ static void enqueue_phase2(dsact_handle* h, const dsact_batch& bt, int64_t globa
   const int passes[4] = {0, 1, 4, 5};
   const Ten t_obs = ten(bt.obs, ar.i_obs), t_act = ten(bt.act, ar.i_act);
 
-  // wave C: critic passes 0,1 (dgrad + wgrad) and actor passes 4,5 (dgrad only), top layer down
-  Group gw;  // every weight-gradient problem of the two critics: independent once the dgrad chain has run
+  // wave C: critic passes 0,1 (dgrad + wgrad) and actor passes 4,5 (dgrad only), top layer down.
+  // The freeze trick of the reference (dsac_v2.py:166-181) makes the two backward passes independent.  Default: one
+  // 4-pass dgrad chain, then the critics' weight gradients as a side branch beside the policy backward.  Opt-in
+  // (DSACT_BWD_SPLIT=1): the critics' own backward (dgrad chain 0,1 -> their weight gradients) as a side branch beside
+  // the whole actor path (dgrad chain 4,5 -> policy_grad -> policy dgrad chain -> policy weight gradients) — measured
+  // 6 us SLOWER per step at B = 4096 (profiles/r2_ab_bwd_split.txt): two half-wave chain launches lose more than the
+  // earlier start of the policy path gains.
+  Group gw;  // every weight-gradient problem of the two critics
   const bool fused = h->fused();
-  if (fused) {  // wave C dgrad as ONE launch: dz stays in tensor memory between layers
-    ChainBuild cb(h->passes(), h->chain_split());
-    for (int pp = 0; pp < 4; ++pp) {
-      const int p = passes[pp], k = p & 1;
-      chain_dgrad_pass(cb, h, q, ar.i_wq[k], h->img(ar.i_dOut[p], B), B, cf.act_q, ar.zQ[p], p < 2 ? Gq[k] : nullptr,
-                       p < 2 ? ar.i_dzQ[p] : nullptr, p < 2 ? nullptr : W + ar.dAct[k], ar.kpad_q0, A);
-    }
-    launch_chain(h, cb, CLS_GEMM_DGRAD, c);
+  static const bool split_on = getenv("DSACT_BWD_SPLIT") && getenv("DSACT_BWD_SPLIT")[0] == '1';
+  const bool two_branches = fused && c.side != nullptr && split_on;
+  Ctx cs{c.side, 0, cudaSuccess};
+  cs.pdl = c.pdl;
+  if (two_branches) {
+    cudaEventRecord(h->ev_fork, c.s);
+    cudaStreamWaitEvent(c.side, h->ev_fork, 0);
+  }
+  if (fused) {  // dgrad as chain launches: dz stays in tensor memory between layers
+    auto chain_of = [&](int pp0, int pp1, Ctx& cx) {
+      ChainBuild cb(h->passes(), h->chain_stream());
+      for (int pp = pp0; pp < pp1; ++pp) {
+        const int p = passes[pp], k = p & 1;
+        chain_dgrad_pass(cb, h, q, ar.i_wq[k], h->img(ar.i_dOut[p], B), B, cf.act_q, ar.zQ[p], p < 2 ? Gq[k] : nullptr,
+                         p < 2 ? ar.i_dzQ[p] : nullptr, p < 2 ? nullptr : W + ar.dAct[k], ar.kpad_q0, A);
+      }
+      launch_chain(h, cb, CLS_GEMM_DGRAD, cx);
+    };
+    if (two_branches) { chain_of(0, 2, cs); chain_of(2, 4, c); }
+    else chain_of(0, 4, c);
   }
   for (int j = q.L; j >= 1; --j) {
     Group gd;
@@ -965,14 +1024,11 @@ static void enqueue_phase2(dsact_handle* h, const dsact_batch& bt, int64_t globa
         add_dgrad(gd, q, 0, weight(h, q, Pq[k], 0, ar.i_wq[k][0]), O, ar.kpad_q0, A, ten(W + ar.dzQ[4 + k][0], ar.i_dzQ[4 + k][0]),
                   ten(W + ar.dAct[k], none), nullptr, nullptr, B, 0);
     }
-    // the critics' weight gradients depend only on what has run so far; the policy backward (policy_grad -> dgrad chain
-    // of 32 CTAs -> its weight gradients) does not depend on them: run the two branches side by side inside the graph
-    bool forked = false;
-    if (c.side && fused) {
+    if (!two_branches && fused && c.side != nullptr) {   // one 4-pass chain on the main branch, the critics' weight gradients beside the policy backward
       cudaEventRecord(h->ev_fork, c.s);
       cudaStreamWaitEvent(c.side, h->ev_fork, 0);
-      Ctx cs{c.side, 0, cudaSuccess};
-      cs.pdl = c.pdl;
+    }
+    if (fused && c.side != nullptr) {
       // the policy backward chain needs ceil(B/128) whole SMs: keep them free of weight-gradient CTAs
       const int chain_ctas = (B + TC_BM - 1) / TC_BM;
       const int cap = h->num_sms - chain_ctas;
@@ -980,12 +1036,11 @@ static void enqueue_phase2(dsact_handle* h, const dsact_batch& bt, int64_t globa
       cudaEventRecord(h->ev_join, c.side);
       c.launches += cs.launches;
       if (cs.err != cudaSuccess && c.err == cudaSuccess) c.err = cs.err;
-      forked = true;
     } else {
       launch_group(h, gw, V_WGRAD, c);
     }
     launch_group(h, gd, V_DGRAD, c);
-    h->join_pending = forked;
+    h->join_pending = fused && c.side != nullptr;
   }
 
   {
@@ -1004,7 +1059,7 @@ static void enqueue_phase2(dsact_handle* h, const dsact_batch& bt, int64_t globa
   // wave D: policy backward
   Group gwp;
   if (fused) {
-    ChainBuild cb(h->passes(), h->chain_split());
+    ChainBuild cb(h->passes(), h->chain_stream());
     chain_dgrad_pass(cb, h, pi, ar.i_wpi[0], h->img(ar.i_dlogits, B), B, cf.act_pi, ar.zP, Gpi, ar.i_dzP, nullptr, 0, 0);
     launch_chain(h, cb, CLS_GEMM_DGRAD, c);
   }
@@ -1027,19 +1082,26 @@ static void enqueue_phase2(dsact_handle* h, const dsact_batch& bt, int64_t globa
     launch_k(grad_reduce_kernel, blocks, 256, 0, c, G_, W + ar.slabs, n, ar.nslabs, (long long)ar.slab_stride); c.done();
   }
   AdamHyper hy{cf.lr_q, cf.lr_pi, cf.lr_alpha, cf.adam_beta1, cf.adam_beta2};
-  launch_k(phase2_tail_kernel, 1, 32, 0, c, G_ + 2 * q.n + pi.n, h->buf.state, sc, -(float)cf.act_dim, B, hy, defer_reduce ? 1 : 0);
-  c.done();
+  if (!fold_tail) {
+    launch_k(phase2_tail_kernel, 1, 32, 0, c, G_ + 2 * q.n + pi.n, h->buf.state, sc, -(float)cf.act_dim, B, hy, defer_reduce ? 1 : 0);
+    c.done();
+  }
   if (reduce_mode == REDUCE_DP) {  // local total (bias gradients + slabs + log_alpha) -> this rank's block of the exchange buffer
     const long long n = 2 * q.n + pi.n + 1;
     int blocks = (int)((n / 4 + 255) / 256); if (blocks > 4 * h->num_sms) blocks = 4 * h->num_sms; if (blocks < 1) blocks = 1;
     launch_k(dp_grad_fold_kernel, blocks, 256, 0, c, h->dp_buf + DP_GRADS_OFF, (const float*)G_, (const float*)(tc ? W + ar.slabs : G_), n,
-             tc ? ar.nslabs : 0, (long long)(tc ? ar.slab_stride : 4));
+             tc ? ar.nslabs : 0, (long long)(tc ? ar.slab_stride : 4), (const float*)h->buf.state, tail_args(h, global_batch, B, fold_tail));
     c.done();
   }
   c.check();
 }
 
-static void enqueue_apply(dsact_handle* h, Ctx& c, bool reduce_slabs = false, bool dp = false) {
+static bool fold_tail_enabled() {   // DSACT_FOLD_TAIL=0: keep the separate phase2_tail launch (A/B aid)
+  static const bool off = getenv("DSACT_FOLD_TAIL") && getenv("DSACT_FOLD_TAIL")[0] == '0';
+  return !off;
+}
+// `tail` != null: this apply also does the end-of-backward bookkeeping of the step (see TailArgs)
+static void enqueue_apply(dsact_handle* h, Ctx& c, bool reduce_slabs = false, bool dp = false, const TailArgs* tail = nullptr) {
   const dsact_config& cf = h->cfg;
   ApplyArgs a;
   a.params = h->buf.params; a.targets = h->buf.targets; a.grads = h->buf.grads; a.m = h->buf.adam_m; a.v = h->buf.adam_v;
@@ -1048,6 +1110,8 @@ static void enqueue_apply(dsact_handle* h, Ctx& c, bool reduce_slabs = false, bo
   a.delay_update = cf.delay_update; a.auto_alpha = cf.auto_alpha;
   a.hy = AdamHyper{cf.lr_q, cf.lr_pi, cf.lr_alpha, cf.adam_beta1, cf.adam_beta2};
   a.scalars_ready = (reduce_slabs || dp) ? 1 : 0;   // single-call steps: the phase-2 tail of this very step computed them
+  memset(&a.tail, 0, sizeof(a.tail));
+  if (tail && tail->enabled) { a.tail = *tail; a.scalars_ready = 2; }   // folded tail: scalars precomputed by the previous apply if stamped
   a.dp_world = 0;
   for (int r = 0; r < 8; ++r) a.dp_grads[r] = nullptr;
   if (dp) {
@@ -1068,17 +1132,13 @@ static void enqueue_apply(dsact_handle* h, Ctx& c, bool reduce_slabs = false, bo
 static void enqueue_gather(dsact_handle* h, int B, const int64_t* idx, Ctx& c) {
   const Arena& ar = h->ar;
   float* W = h->W();
-  const int64_t* use = idx;
-  if (!idx) {
-    int64_t* dst = reinterpret_cast<int64_t*>(W + ar.idx);
-    int blocks = ((B + 1) / 2 + 255) / 256;
-    launch_k(index_kernel, blocks, 256, 0, c, dst, B, h->seed, h->buf.state); c.done();
-    use = dst;
-  }
+  // no index list: every warp of the gather draws its row's index itself (the sequence index_kernel defines) and records it
+  int64_t* draw = idx ? nullptr : reinterpret_cast<int64_t*>(W + ar.idx);
   int blocks = (B + 7) / 8; if (blocks > 8 * h->num_sms) blocks = 8 * h->num_sms;
-  launch_k(gather_kernel, blocks, 256, 0, c, h->rb.obs, h->rb.obs2, h->rb.act, h->rb.rew, h->rb.done, h->rb.logp, use,
+  launch_k(gather_kernel, blocks, 256, 0, c, h->rb.obs, h->rb.obs2, h->rb.act, h->rb.rew, h->rb.done, h->rb.logp, idx,
                                           W + ar.obs, W + ar.obs2, W + ar.act, W + ar.rew, W + ar.done, W + ar.logp, B,
-                                          h->cfg.obs_dim, h->cfg.act_dim, img_out(h, ar.i_obs), img_out(h, ar.i_obs2), img_out(h, ar.i_act));
+                                          h->cfg.obs_dim, h->cfg.act_dim, img_out(h, ar.i_obs), img_out(h, ar.i_obs2), img_out(h, ar.i_act),
+                                          draw, (unsigned long long)h->seed, (const float*)h->buf.state);
   c.done();
   c.check();
 }
@@ -1165,6 +1225,9 @@ static int check_noise(const dsact_noise* n) {
 static bool take_arena_images(dsact_handle* h, const dsact_batch& bt) {
   const bool yes = h->tc() && h->arena_imaged && bt.obs == h->W() + h->ar.obs && bt.obs2 == h->W() + h->ar.obs2 &&
                    bt.act == h->W() + h->ar.act;
+  // any other batch is imaged into the same shared slots by the call that asked: the arena's images are gone after it.
+  // (The arena views handed out by dsact_replay_sample are read-only for the same reason: edits are not re-imaged.)
+  if (!yes) h->arena_imaged = false;
   return yes;
 }
 
@@ -1267,6 +1330,12 @@ void dsact_destroy(dsact_handle* h) {
   cudaEventDestroy(h->ev_dp_join);
   for (int r = 0; r < DP_MAX_RANKS; ++r) if (h->dp_opened[r]) cudaIpcCloseMemHandle(h->dp_opened[r]);
   if (h->dp_buf) cudaFree(h->dp_buf);
+  for (int t = 0; t < 2; ++t) {
+    if (h->stage_buf[t]) cudaFree(h->stage_buf[t]);
+    if (h->ev_stage_ready[t]) cudaEventDestroy(h->ev_stage_ready[t]);
+    if (h->ev_stage_done[t]) cudaEventDestroy(h->ev_stage_done[t]);
+  }
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   delete h;
 }
 
@@ -1378,13 +1447,69 @@ int dsact_step(dsact_handle* h, const dsact_batch* batch, const dsact_noise* noi
   skey.size = imaged ? 1 : 0;
   rc = run(h, (cudaStream_t)stream, skey, [&](Ctx& c) {
     enqueue_phase1(h, bt, np, c, imaged);
-    enqueue_phase2(h, bt, bt.batch, c, REDUCE_DEFER);
-    enqueue_apply(h, c, true);
+    const TailArgs ta = tail_args(h, bt.batch, bt.batch, fold_tail_enabled());
+    enqueue_phase2(h, bt, bt.batch, c, REDUCE_DEFER, ta.enabled);
+    enqueue_apply(h, c, true, false, &ta);
   });
   if (rc) return rc;
   h->pending = bt; h->pending_batch = bt.batch;
   h->dev_iter = iteration + 1;
   return DSACT_OK;
+}
+
+// ---- host minibatches: staging on a private copy stream -------------------------------------------------------
+int dsact_stage_host(dsact_handle* h, const dsact_batch* host, dsact_batch* dev, void* stream) {
+  int rc = check_batch(h, host);
+  if (rc) return rc;
+  if (!dev) return fail(DSACT_EINVAL, "null out");
+  CUDA_TRY(cudaSetDevice(h->device));
+  const int64_t O = h->cfg.obs_dim, A = h->cfg.act_dim, Bm = h->cfg.max_batch;
+  const int64_t seg[5] = {round64(Bm * O), round64(Bm * A), round64(Bm), round64(Bm * O), round64(Bm)};   // obs act rew obs2 done
+  if (!h->copy_stream) {
+    h->stage_floats = seg[0] + seg[1] + seg[2] + seg[3] + seg[4];
+    CUDA_TRY(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    for (int t = 0; t < 2; ++t) {
+      CUDA_TRY(cudaMalloc(&h->stage_buf[t], sizeof(float) * (size_t)h->stage_floats));
+      CUDA_TRY(cudaEventCreateWithFlags(&h->ev_stage_ready[t], cudaEventDisableTiming));
+      CUDA_TRY(cudaEventCreateWithFlags(&h->ev_stage_done[t], cudaEventDisableTiming));
+    }
+  }
+  const int t = h->stage_turn;
+  const int64_t B = host->batch;
+  float* base = h->stage_buf[t];
+  float* d_obs = base; float* d_act = d_obs + seg[0]; float* d_rew = d_act + seg[1]; float* d_obs2 = d_rew + seg[2]; float* d_done = d_obs2 + seg[3];
+  if (h->stage_done_valid[t]) CUDA_TRY(cudaStreamWaitEvent(h->copy_stream, h->ev_stage_done[t], 0));   // last reader of this set
+  CUDA_TRY(cudaMemcpyAsync(d_obs, host->obs, sizeof(float) * B * O, cudaMemcpyHostToDevice, h->copy_stream));
+  CUDA_TRY(cudaMemcpyAsync(d_obs2, host->obs2, sizeof(float) * B * O, cudaMemcpyHostToDevice, h->copy_stream));
+  CUDA_TRY(cudaMemcpyAsync(d_act, host->act, sizeof(float) * B * A, cudaMemcpyHostToDevice, h->copy_stream));
+  CUDA_TRY(cudaMemcpyAsync(d_rew, host->rew, sizeof(float) * B, cudaMemcpyHostToDevice, h->copy_stream));
+  CUDA_TRY(cudaMemcpyAsync(d_done, host->done, sizeof(float) * B, cudaMemcpyHostToDevice, h->copy_stream));
+  CUDA_TRY(cudaEventRecord(h->ev_stage_ready[t], h->copy_stream));
+  CUDA_TRY(cudaStreamWaitEvent((cudaStream_t)stream, h->ev_stage_ready[t], 0));
+  dev->obs = d_obs; dev->act = d_act; dev->rew = d_rew; dev->obs2 = d_obs2; dev->done = d_done; dev->logp = nullptr;
+  dev->batch = host->batch;
+  h->stage_held = t;
+  h->stage_turn = t ^ 1;
+  return DSACT_OK;
+}
+
+int dsact_stage_release(dsact_handle* h, void* stream) {
+  if (!h) return fail(DSACT_EINVAL, "null handle");
+  if (h->stage_held < 0) return DSACT_OK;
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaEventRecord(h->ev_stage_done[h->stage_held], (cudaStream_t)stream));
+  h->stage_done_valid[h->stage_held] = true;
+  h->stage_held = -1;
+  return DSACT_OK;
+}
+
+int dsact_step_host(dsact_handle* h, const dsact_batch* host, const dsact_noise* noise, int64_t iteration, void* stream) {
+  dsact_batch dev;
+  int rc = dsact_stage_host(h, host, &dev, stream);
+  if (rc) return rc;
+  rc = dsact_step(h, &dev, noise, iteration, stream);
+  const int rc2 = dsact_stage_release(h, stream);
+  return rc ? rc : rc2;
 }
 
 int dsact_read_stats(dsact_handle* h, int64_t global_batch, float* host_out, void* stream) {
@@ -1487,8 +1612,9 @@ int dsact_replay_step(dsact_handle* h, int32_t batch, int64_t size, const int64_
     enqueue_gather(h, batch, idx, c);
     if (!idx && np) { launch_k(rng_advance_kernel, 1, 32, 0, c, h->buf.state); c.done(); }
     enqueue_phase1(h, bt, np, c, true, forked);  // device noise (np == null): phase1 advances the counter after the join
-    enqueue_phase2(h, bt, batch, c, REDUCE_DEFER);
-    enqueue_apply(h, c, true);
+    const TailArgs ta = tail_args(h, batch, batch, fold_tail_enabled());
+    enqueue_phase2(h, bt, batch, c, REDUCE_DEFER, ta.enabled);
+    enqueue_apply(h, c, true, false, &ta);
   });
   if (rc) return rc;
   h->pending = bt; h->pending_batch = batch;
@@ -1561,9 +1687,10 @@ int dsact_dp_step(dsact_handle* h, const dsact_batch* batch, const dsact_noise* 
   key.size = imaged ? 1 : 0;
   rc = run(h, (cudaStream_t)stream, key, [&](Ctx& c) {
     enqueue_phase1(h, bt, np, c, imaged, false, true);
-    enqueue_phase2(h, bt, global_batch, c, REDUCE_DP);
+    const TailArgs ta = tail_args(h, global_batch, bt.batch, fold_tail_enabled());
+    enqueue_phase2(h, bt, global_batch, c, REDUCE_DP, ta.enabled);
     enqueue_dp_exchange(h, 1, c);
-    enqueue_apply(h, c, false, true);
+    enqueue_apply(h, c, false, true, &ta);
   });
   if (rc) return rc;
   h->pending = bt; h->pending_batch = bt.batch;
@@ -1592,9 +1719,10 @@ int dsact_dp_replay_step(dsact_handle* h, int32_t batch, int64_t size, const int
     enqueue_gather(h, batch, idx, c);
     if (!idx && np) { launch_k(rng_advance_kernel, 1, 32, 0, c, h->buf.state); c.done(); }
     enqueue_phase1(h, bt, np, c, true, forked, true);
-    enqueue_phase2(h, bt, global_batch, c, REDUCE_DP);
+    const TailArgs ta = tail_args(h, global_batch, bt.batch, fold_tail_enabled());
+    enqueue_phase2(h, bt, global_batch, c, REDUCE_DP, ta.enabled);
     enqueue_dp_exchange(h, 1, c);
-    enqueue_apply(h, c, false, true);
+    enqueue_apply(h, c, false, true, &ta);
   });
   if (rc) return rc;
   h->pending = bt; h->pending_batch = batch;
@@ -1622,8 +1750,9 @@ int dsact_profile_step(dsact_handle* h, const dsact_batch* batch, const dsact_no
   CUDA_TRY(cudaEventCreate(&e0));
   CUDA_TRY(cudaEventRecord(e0, s));
   enqueue_phase1(h, bt, np, c);
-  enqueue_phase2(h, bt, bt.batch, c, REDUCE_DEFER);
-  enqueue_apply(h, c, true);
+  const TailArgs ta = tail_args(h, bt.batch, bt.batch, fold_tail_enabled());
+  enqueue_phase2(h, bt, bt.batch, c, REDUCE_DEFER, ta.enabled);
+  enqueue_apply(h, c, true, false, &ta);
   cudaError_t e = cudaStreamSynchronize(s);
   memset(out, 0, sizeof(*out));
   cudaEvent_t prev = e0;

@@ -23,6 +23,7 @@
 #include <stdint.h>
 
 #include "gemm_simt.cuh"  // activations, EPI_* enums
+#include "kernels.cuh"    // begin_step / noise bodies of the merged prologue launch
 
 namespace dsact {
 
@@ -168,8 +169,10 @@ __device__ __forceinline__ unsigned long long gtime() {
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
-#define TC_DBG_SLOTS 32
+#define TC_DBG_SLOTS 48
 #define TC_STAMP(slot) do { if (g.dbg) g.dbg[(size_t)blockIdx.x * TC_DBG_SLOTS + (slot)] = gtime(); } while (0)
+// SM-cycle stamps of one epilogue warp's first chunk of layer 1 (slots 32..39): where a chunk's time goes
+#define TC_CSTAMP(slot) do { if (g.dbg && j == 1 && k == 0 && threadIdx.x == 64) g.dbg[(size_t)blockIdx.x * TC_DBG_SLOTS + (slot)] = (unsigned long long)clock64(); } while (0)
 
 __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
   hi = __float2bfloat16_rn(x);
@@ -177,40 +180,88 @@ __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bflo
 }
 
 // ---- epilogue math ---------------------------------------------------------------------------------------
-// Branch-free Gaussian CDF: Phi(z) = 0.5 erfc(-z/sqrt2) with erfc(t) = 2^(-q(t)) for t = min(|z|/sqrt2, 4),
-// q = degree-8 minimax fit (abs error of erf 1.4e-7 in fp32, i.e. fp32 round-off level; fitted in this repo,
-// see DESIGN.md).  Half the instructions of erff() and no divergent branch.
+// Packed fp32 pairs (Blackwell FFMA2 / FMUL2 / FADD2: two fp32 lanes per issue slot).  The chain epilogue is bound by
+// instruction issue, so every multiply-add of the activation runs on pairs of neighbouring columns.
+struct f2 { unsigned long long v; };
+__device__ __forceinline__ f2 pk2(float lo, float hi) { f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void upk2(f2 a, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.v)); }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { f2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v)); return r; }
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) { f2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+__device__ __forceinline__ f2 add2(f2 a, f2 b) { f2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+__device__ __forceinline__ f2 bc2(float c) { return pk2(c, c); }
+
 __device__ __forceinline__ float ex2f(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-__device__ __forceinline__ float gauss_cdf(float z) {
-  const float t = fminf(fabsf(z) * 0.70710678118654752f, 4.0f);
-  float q = 4.5354528e-05f;              // coefficients of -log2(erfc(t)) / t
-  q = fmaf(q, t, -4.4547783e-04f);
-  q = fmaf(q, t, 1.4893662e-03f);
-  q = fmaf(q, t, 7.7470759e-04f);
-  q = fmaf(q, t, -2.8253708e-02f);
-  q = fmaf(q, t, 1.4848161e-01f);
-  q = fmaf(q, t, 9.1841640e-01f);
-  q = fmaf(q, t, 1.6279086e+00f);
-  const float half_u = 0.5f * ex2f(-q * t);   // 0.5 * erfc(t)
-  return z < 0.f ? half_u : 1.0f - half_u;
+__device__ __forceinline__ float rcpf(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
-__device__ __forceinline__ float gauss_pdf(float z) { return 0.3989422804014327f * ex2f(-0.72134752044448170f * z * z); }
+// Exact-erf GELU (nn.GELU(), reference networks/mlp.py:15-20) and its derivative for a pair of pre-activations:
+//   Phi(z) = 0.5 erfc(-z / sqrt 2),  erfc(x) = t P(t) exp(-x^2),  t = 1 / (1 + p x)  for x = |z| / sqrt 2 >= 0
+// (Abramowitz & Stegun 7.1.26, |error of erf| <= 1.5e-7; 3.0e-7 on Phi as evaluated here in fp32 — the bf16 split
+// products of this mode carry 1.5e-5).  exp(-x^2) = exp(-z^2 / 2) is also the Gaussian density up to a constant, so
+// one ex2 serves Phi and phi: 2 MUFU + 10 scalar + 13 packed instructions per PAIR of elements.
+template <bool WANT_D>
+__device__ __forceinline__ void gelu_pair(float& z0, float& z1, float& d0, float& d1) {
+  const f2 z = pk2(z0, z1);
+  const f2 az = pk2(fabsf(z0), fabsf(z1));
+  const f2 den = fma2(az, bc2(0.23164189f), bc2(1.0f));          // 1 + p |z| / sqrt 2, p = 0.3275911
+  float n0, n1;
+  upk2(den, n0, n1);
+  const f2 t = pk2(rcpf(n0), rcpf(n1));
+  const f2 se = mul2(mul2(z, bc2(-0.72134752044448170f)), z);     // -z^2 / 2 * log2 e
+  float s0, s1;
+  upk2(se, s0, s1);
+  const f2 e = pk2(ex2f(s0), ex2f(s1));                            // exp(-z^2 / 2)
+  f2 pl = fma2(bc2(0.5f * 1.061405429f), t, bc2(0.5f * -1.453152027f));
+  pl = fma2(pl, t, bc2(0.5f * 1.421413741f));
+  pl = fma2(pl, t, bc2(0.5f * -0.284496736f));
+  pl = fma2(pl, t, bc2(0.5f * 0.254829592f));
+  const f2 hu = mul2(mul2(pl, t), e);                              // 0.5 erfc(|z| / sqrt 2) = Phi(-|z|)
+  const f2 omh = fma2(hu, bc2(-1.0f), bc2(1.0f));
+  float h0, h1, o0, o1;
+  upk2(hu, h0, h1);
+  upk2(omh, o0, o1);
+  const f2 cdf = pk2(z0 < 0.f ? h0 : o0, z1 < 0.f ? h1 : o1);
+  const f2 a = mul2(z, cdf);
+  if (WANT_D) {
+    const f2 dd = fma2(mul2(z, bc2(0.3989422804014327f)), e, cdf);   // Phi + z phi
+    upk2(dd, d0, d1);
+  }
+  upk2(a, z0, z1);
+}
+// the same arithmetic on one element (per-layer kernel: its column-layout epilogue has no registers to spare for pairs)
+template <bool WANT_D>
+__device__ __forceinline__ void gelu_one(float& z0, float& d0) {
+  const float z = z0;
+  const float t = rcpf(fmaf(fabsf(z), 0.23164189f, 1.0f));
+  const float e = ex2f(z * -0.72134752044448170f * z);
+  float pl = fmaf(0.5f * 1.061405429f, t, 0.5f * -1.453152027f);
+  pl = fmaf(pl, t, 0.5f * 1.421413741f);
+  pl = fmaf(pl, t, 0.5f * -0.284496736f);
+  pl = fmaf(pl, t, 0.5f * 0.254829592f);
+  const float hu = pl * t * e;
+  const float cdf = z < 0.f ? hu : fmaf(hu, -1.0f, 1.0f);
+  z0 = z * cdf;
+  if (WANT_D) d0 = fmaf(z * 0.3989422804014327f, e, cdf);
+}
 
 // v[i] = act(z_i) with z_i = v[i] on entry; if D != nullptr also D[i] = act'(z_i).  The dispatch is hoisted out of
 // the unrolled loops (inlining the 7-way switch per element made the kernel ~600 KB of SASS and fetch bound):
 // GELU (the reference's default) and ReLU get unrolled bodies, the rest a compact loop over a private smem row.
-template <bool WANT_D, int NV>
+template <bool WANT_D, int NV, bool PACKED = true>
 __device__ __forceinline__ void act_fwdN(float (&v)[NV], float (&d)[NV], int act, float* row) {
   if (act == ACT_GELU) {
+    if (PACKED) {
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const float z = v[i], cdf = gauss_cdf(z);
-      v[i] = z * cdf;
-      if (WANT_D) d[i] = fmaf(z, gauss_pdf(z), cdf);
+      for (int i = 0; i < NV; i += 2) gelu_pair<WANT_D>(v[i], v[i + 1], d[i], d[i + 1]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) gelu_one<WANT_D>(v[i], d[i]);
     }
   } else if (act == ACT_RELU) {
 #pragma unroll
@@ -249,7 +300,10 @@ __device__ __forceinline__ uint32_t cvt_bf16x2(float lo_k, float hi_k) {
 }
 __device__ __forceinline__ void split_pack2(float x0, float x1, uint32_t& whi, uint32_t& wlo) {
   whi = cvt_bf16x2(x0, x1);
-  wlo = cvt_bf16x2(x0 - __uint_as_float(whi << 16), x1 - __uint_as_float(whi & 0xffff0000u));
+  const f2 r = fma2(pk2(__uint_as_float(whi << 16), __uint_as_float(whi & 0xffff0000u)), bc2(-1.0f), pk2(x0, x1));   // x - hi, both lanes
+  float r0, r1;
+  upk2(r, r0, r1);
+  wlo = cvt_bf16x2(r0, r1);
 }
 
 // What one epilogue chunk needs.  In the tcgen05 modes `Zout`/`Zin` carry act'(z) (computed where erf is already
@@ -289,7 +343,7 @@ __device__ __forceinline__ void epi_chunk(float (&v)[16], const EpiArgs& E, int 
       }
       if (E.epi == EPI_BIAS_ACT) {
         float dummy[16];
-        act_fwdN<false, 16>(v, dummy, E.act, tr + lane * TR_PITCH);
+        act_fwdN<false, 16, false>(v, dummy, E.act, tr + lane * TR_PITCH);
       }
     }
 #pragma unroll
@@ -314,13 +368,13 @@ __device__ __forceinline__ void epi_chunk(float (&v)[16], const EpiArgs& E, int 
       for (int r = 0; r < 16; ++r) a[r] += bias_n;
       if (E.epi == EPI_BIAS_ACT) {
         if (E.Zout) {
-          act_fwdN<true, 16>(a, d, E.act, tr + lane * TR_PITCH);
+          act_fwdN<true, 16, false>(a, d, E.act, tr + lane * TR_PITCH);
           float* zp = E.Zout + (size_t)(mbase + r0) * E.ldc + n;
 #pragma unroll
           for (int r = 0; r < 16; ++r)
             if (r < nrows) zp[(size_t)r * E.ldc] = d[r];
         } else {
-          act_fwdN<false, 16>(a, d, E.act, tr + lane * TR_PITCH);
+          act_fwdN<false, 16, false>(a, d, E.act, tr + lane * TR_PITCH);
         }
       }
     } else if (E.epi == EPI_DACT) {
@@ -561,18 +615,16 @@ struct ImgGroup {
   ImgJob j[IMG_MAXJ];
 };
 // One thread converts 8 consecutive columns of one row (one 16-byte store per plane).
-__global__ void image_kernel(const __grid_constant__ ImgGroup g) {
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+__device__ __forceinline__ void image_body(const ImgGroup& g, int block, int img_blocks) {
   int ji = 0;
 #pragma unroll
   for (int i = 1; i < IMG_MAXJ; ++i)
-    if (i < g.n && (int)blockIdx.x >= g.j[i].block_start) ji = i;
+    if (i < g.n && block >= g.j[i].block_start) ji = i;
   const ImgJob& J = g.j[ji];
   const int vec_per_row = J.pitch >> 3;
   const int total = J.rows * vec_per_row;
-  const int nblocks = (ji + 1 < g.n ? g.j[ji + 1].block_start : (int)gridDim.x) - J.block_start;
-  for (int i = (blockIdx.x - J.block_start) * blockDim.x + threadIdx.x; i < total; i += nblocks * blockDim.x) {
+  const int nblocks = (ji + 1 < g.n ? g.j[ji + 1].block_start : img_blocks) - J.block_start;
+  for (int i = (block - J.block_start) * blockDim.x + threadIdx.x; i < total; i += nblocks * blockDim.x) {
     const int r = i / vec_per_row, c0 = (i - r * vec_per_row) * 8;
     const float* src = J.src + (size_t)r * J.ld_src;
     uint32_t whi[4], wlo[4];
@@ -605,6 +657,31 @@ __global__ void image_kernel(const __grid_constant__ ImgGroup g) {
     *reinterpret_cast<uint4*>(dst) = make_uint4(whi[0], whi[1], whi[2], whi[3]);
     if (g.planes == 2) *reinterpret_cast<uint4*>(dst + J.plane) = make_uint4(wlo[0], wlo[1], wlo[2], wlo[3]);
   }
+}
+
+__global__ void image_kernel(const __grid_constant__ ImgGroup g) {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  image_body(g, (int)blockIdx.x, (int)gridDim.x);
+}
+
+// Start-of-step work that depends on nothing of the step itself, as ONE launch: weight (and caller-batch) images, the
+// accumulator / gradient clears (begin_step_kernel) and the device noise (noise_kernel), each on its own range of blocks.
+struct PrologueArgs {
+  int img_blocks, zero_blocks, noise_blocks;
+  float *state, *grads;
+  long long n_grads;
+  float *eps1, *eps2, *z3, *z4;
+  int B, A;
+  unsigned long long seed;
+};
+__global__ void step_prologue_kernel(const __grid_constant__ ImgGroup g, const __grid_constant__ PrologueArgs p) {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  const int b = (int)blockIdx.x;
+  if (b < p.img_blocks) image_body(g, b, p.img_blocks);
+  else if (b < p.img_blocks + p.zero_blocks) begin_step_body(p.state, p.grads, p.n_grads, b - p.img_blocks, p.zero_blocks);
+  else noise_body(p.eps1, p.eps2, p.z3, p.z4, p.B, p.A, p.seed, p.state, b - p.img_blocks - p.zero_blocks, p.noise_blocks);
 }
 
 // Sum the wgrad split slabs into the flat gradient buffer (which already holds the bias gradients).

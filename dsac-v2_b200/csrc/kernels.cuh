@@ -137,10 +137,9 @@ __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& n0, fl
 
 // Start of every step: clear the accumulators (and the std sums of phase1) and zero the flat gradient buffer
 // (bias gradients and column sums accumulate into it with atomics).
-__global__ void begin_step_kernel(float* __restrict__ state, float* __restrict__ grads, long long n) {
-  pdl_sync();
+__device__ __forceinline__ void begin_step_body(float* __restrict__ state, float* __restrict__ grads, long long n, int block, int nblocks) {
   const int t = threadIdx.x;
-  if (blockIdx.x == 0) {
+  if (block == 0) {
     if (t < 16) state[ST_ACC + t] = 0.f;
     else if (t < 32) state[ST_ACC + t] = __int_as_float(0x7f800000);
     if (t < 2) state[ST_STDSUM + t] = 0.f;
@@ -148,20 +147,24 @@ __global__ void begin_step_kernel(float* __restrict__ state, float* __restrict__
   }
   const bool vec = (reinterpret_cast<uintptr_t>(grads) & 15) == 0;
   const long long n4 = vec ? n / 4 : 0;
-  for (long long i = blockIdx.x * (long long)blockDim.x + t; i < n4; i += (long long)gridDim.x * blockDim.x)
+  for (long long i = block * (long long)blockDim.x + t; i < n4; i += (long long)nblocks * blockDim.x)
     reinterpret_cast<float4*>(grads)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (long long i = n4 * 4 + blockIdx.x * (long long)blockDim.x + t; i < n; i += (long long)gridDim.x * blockDim.x) grads[i] = 0.f;
+  for (long long i = n4 * 4 + block * (long long)blockDim.x + t; i < n; i += (long long)nblocks * blockDim.x) grads[i] = 0.f;
+}
+__global__ void begin_step_kernel(float* __restrict__ state, float* __restrict__ grads, long long n) {
+  pdl_sync();
+  begin_step_body(state, grads, n, (int)blockIdx.x, (int)gridDim.x);
 }
 
 // Device noise: eps1, eps2 [B,A] and z3, z4 [B] (SURVEY Appendix B keeps only the draws that matter).
-__global__ void noise_kernel(float* __restrict__ eps1, float* __restrict__ eps2, float* __restrict__ z3,
-                             float* __restrict__ z4, int B, int A, uint64_t seed, const float* __restrict__ state) {
-  pdl_sync();
+__device__ __forceinline__ void noise_body(float* __restrict__ eps1, float* __restrict__ eps2, float* __restrict__ z3,
+                                           float* __restrict__ z4, int B, int A, uint64_t seed, const float* __restrict__ state,
+                                           int block, int nblocks) {
   const uint32_t step = reinterpret_cast<const uint32_t*>(state)[ST_RNG_CTR];
   const int n_pairs_ea = (B * A + 1) / 2, n_pairs_z = (B + 1) / 2;
   const int total = 2 * n_pairs_ea + 2 * n_pairs_z;
   const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < (total + 1) / 2; i += gridDim.x * blockDim.x) {
+  for (int i = block * blockDim.x + threadIdx.x; i < (total + 1) / 2; i += nblocks * blockDim.x) {
     const uint4 r = philox4x32(make_uint4((uint32_t)i, step, 0x4e4f4953u, 0u), key);
     float n[4];
     box_muller(r.x, r.y, n[0], n[1]);
@@ -181,33 +184,47 @@ __global__ void noise_kernel(float* __restrict__ eps1, float* __restrict__ eps2,
   }
 }
 
-// Uniform replay indices in [0, size) (np.random.randint, training/replay_buffer.py:86).
-__global__ void index_kernel(int64_t* __restrict__ idx, int B, uint64_t seed, const float* __restrict__ state) {
+__global__ void noise_kernel(float* __restrict__ eps1, float* __restrict__ eps2, float* __restrict__ z3,
+                             float* __restrict__ z4, int B, int A, uint64_t seed, const float* __restrict__ state) {
   pdl_sync();
-  const uint32_t step = reinterpret_cast<const uint32_t*>(state)[ST_RNG_CTR];
-  const int64_t size = *reinterpret_cast<const int64_t*>(state + ST_RB_SIZE);
-  const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < (B + 1) / 2; i += gridDim.x * blockDim.x) {
-    const uint4 r = philox4x32(make_uint4((uint32_t)i, step, 0x49445853u, 0u), key);
-    const uint64_t a = ((uint64_t)r.x << 32) | r.y, b = ((uint64_t)r.z << 32) | r.w;
-    idx[2 * i] = (int64_t)__umul64hi(a, (uint64_t)size);  // floor(a / 2^64 * size)
-    if (2 * i + 1 < B) idx[2 * i + 1] = (int64_t)__umul64hi(b, (uint64_t)size);
-  }
+  noise_body(eps1, eps2, z3, z4, B, A, seed, state, (int)blockIdx.x, (int)gridDim.x);
 }
 
+// Uniform replay indices in [0, size) (np.random.randint, training/replay_buffer.py:86).
+// rows 2i and 2i+1 share one Philox block
+__device__ __forceinline__ int64_t replay_index(int row, uint32_t step, int64_t size, uint2 key) {
+  const uint4 r = philox4x32(make_uint4((uint32_t)(row >> 1), step, 0x49445853u, 0u), key);
+  const uint64_t a = (row & 1) ? (((uint64_t)r.z << 32) | r.w) : (((uint64_t)r.x << 32) | r.y);
+  return (int64_t)__umul64hi(a, (uint64_t)size);
+}
 // Replay gather (training/replay_buffer.py:87-90): one warp per sampled row, vectorised over obs columns.
 __global__ void gather_kernel(const float* __restrict__ r_obs, const float* __restrict__ r_obs2,
                               const float* __restrict__ r_act, const float* __restrict__ r_rew,
                               const float* __restrict__ r_done, const float* __restrict__ r_logp,
                               const int64_t* __restrict__ idx, float* __restrict__ obs, float* __restrict__ obs2,
                               float* __restrict__ act, float* __restrict__ rew, float* __restrict__ done,
-                              float* __restrict__ logp, int B, int O, int A, ImgOut i_obs, ImgOut i_obs2, ImgOut i_act) {
+                              float* __restrict__ logp, int B, int O, int A, ImgOut i_obs, ImgOut i_obs2, ImgOut i_act,
+                              int64_t* __restrict__ draw_idx, uint64_t seed, const float* __restrict__ state) {
   pdl_sync();
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   const bool v4 = (O & 3) == 0;
+  // draw_idx != null: no index list was given; every warp draws its row's index itself  and records it in draw_idx
+  uint32_t step = 0;
+  int64_t size = 1;
+  const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+  if (draw_idx) {
+    step = reinterpret_cast<const uint32_t*>(state)[ST_RNG_CTR];
+    size = *reinterpret_cast<const int64_t*>(state + ST_RB_SIZE);
+  }
   for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < B; row += gridDim.x * wpb) {
-    const int64_t src = idx[row];
+    int64_t src;
+    if (draw_idx) {
+      src = replay_index(row, step, size, key);
+      if (lane == 0) draw_idx[row] = src;
+    } else {
+      src = idx[row];
+    }
     const float* so = r_obs + src * O;
     const float* so2 = r_obs2 + src * O;
     float* dobs = obs + (size_t)row * O;
@@ -474,8 +491,22 @@ __device__ __forceinline__ void adam_scalars(const int* sti, const AdamHyper& a,
   out[3] = (float)(a.lr_alpha / bc1p);
   out[4] = (float)sqrt(1.0 - pow(a.b2, tp));
 }
+// The end-of-backward bookkeeping of a step (phase2_tail_kernel below) folded into the kernels that follow it in the
+// single-call steps: the log_alpha gradient is formed where the gradient element is consumed, the EMA / temperature
+// commit and the NEXT step's Adam scalars are written by the last block of apply_kernel.
+struct TailArgs {
+  StepScalars sc;
+  float target_entropy;
+  int rows;       // local shard size
+  int enabled;
+};
+__device__ __forceinline__ float tail_grad_log_alpha(const float* state, const TailArgs& t) {
+  return -(state[ST_ACC + ACC_LOGP] + (float)t.rows * t.target_entropy) * t.sc.inv_global_batch;
+}
+constexpr int ADAM_SC_MAGIC = 0x5ca1ab1e;   // state[ST_ADAM_SC + 7]: slots +0..4 hold the scalars for the counters in +5, +6
 struct ApplyArgs {
   float *params, *targets, *grads, *m, *v;
+  TailArgs tail;
   float* state;
   int64_t n_q2;      // 2*n_q  (critic span)
   int64_t n_all;     // 2*n_q + n_pi + 1
@@ -505,7 +536,11 @@ __global__ void apply_kernel(const __grid_constant__ ApplyArgs a) {
   __shared__ float sh[6];
   const int* sti = reinterpret_cast<const int*>(a.state);
   const bool delayed = (sti[ST_ITER] % a.delay_update) == 0;
-  if (a.scalars_ready) {
+  // scalars_ready: 1 = written by phase2_tail_kernel of this step; 2 = possibly precomputed by the previous apply (or
+  // set_carry): valid if stamped with the current counters; 0 = compute here
+  const bool stamped = a.scalars_ready == 2 && sti[ST_ADAM_SC + 7] == ADAM_SC_MAGIC && sti[ST_ADAM_SC + 5] == sti[ST_ADAM_Q] &&
+                       sti[ST_ADAM_SC + 6] == sti[ST_ADAM_PI];
+  if (a.scalars_ready == 1 || stamped) {
     if (threadIdx.x < 5) sh[threadIdx.x] = a.state[ST_ADAM_SC + threadIdx.x];
   } else if (threadIdx.x == 0) {
     adam_scalars(sti, a.hy, sh);
@@ -575,6 +610,10 @@ __global__ void apply_kernel(const __grid_constant__ ApplyArgs a) {
           for (int k = 0; k < a.nslabs; ++k) g[e] += a.slabs[(size_t)k * a.slab_stride + i];
           a.grads[i] = g[e];
         }
+        if (a.tail.enabled && i == a.n_all - 1) {   // log_alpha: dsac_v2.py:312-318 (data parallel: dp_grad_fold_kernel formed it)
+          if (a.dp_world == 0) { g[e] = tail_grad_log_alpha(a.state, a.tail); a.grads[i] = g[e]; }
+          a.state[ST_ALPHA_USED] = a.tail.sc.auto_alpha ? expf(w[e]) : a.tail.sc.alpha_fixed;   // temperature this step used
+        }
       }
     }
     bool touched = false;
@@ -616,10 +655,21 @@ __global__ void apply_kernel(const __grid_constant__ ApplyArgs a) {
     int* stw = reinterpret_cast<int*>(a.state);
     __threadfence();
     if (atomicAdd(stw + ST_TICKET, 1) == (int)gridDim.x - 1) {
+      if (a.tail.enabled) {   // commit of the mean_std EMA (every reader of this step used the carried values)
+        const float m0 = step_mean_std(a.state, a.tail.sc, 0), m1 = step_mean_std(a.state, a.tail.sc, 1);
+        a.state[ST_MEAN_STD1] = m0;
+        a.state[ST_MEAN_STD2] = m1;
+      }
       stw[ST_ADAM_Q] += 1;
       if (delayed) stw[ST_ADAM_PI] += 1;
       stw[ST_ITER] += 1;
       stw[ST_TICKET] = 0;
+      if (a.tail.enabled) {   // the next step's Adam scalars, stamped with the counters they belong to
+        adam_scalars(stw, a.hy, a.state + ST_ADAM_SC);
+        stw[ST_ADAM_SC + 5] = stw[ST_ADAM_Q];
+        stw[ST_ADAM_SC + 6] = stw[ST_ADAM_PI];
+        stw[ST_ADAM_SC + 7] = ADAM_SC_MAGIC;
+      }
     }
   }
 }

@@ -166,9 +166,10 @@ class _LazyTbInfo(Mapping):
     def _materialise(self):
         if self._vals is None:
             self._event.synchronize()
-            if float(self._slot[14]) != 0.0:   # include/dsact.h: tb_info slot 14 = 1 + rank of a peer that never arrived
-                raise _lib.DsactError(f"data-parallel exchange timed out waiting for rank {int(self._slot[14]) - 1}")
-            vals = {k: float(self._slot[i]) for i, k in enumerate(STAT_KEYS)}
+            err = float(self._slot[14])
+            if err != 0.0:   # include/dsact.h: tb_info slot 14 = 1 + rank of a peer that never arrived
+                raise _lib.DsactError(f"data-parallel exchange timed out waiting for rank {int(err) - 1}")
+            vals = dict(zip(STAT_KEYS, self._slot.tolist()))
             vals[tb_tags["alg_time"]] = self._alg_ms
             self._vals, self._slot = vals, None
         return self._vals

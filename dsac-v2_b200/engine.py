@@ -110,9 +110,8 @@ class Engine:
         self.replay = None
         self.dp_world = 0          # > 1 once dp_connect has mapped the peers
         self._seed = 0x5DEECE66D   # the library's default (csrc/engine.cu)
-        self._arena = None
-        self._copy_stream = None
-        self._staged_turn = None
+        self._staged = False
+        self._keep_host = [None, None]
         self._keep = None  # tensors referenced by the last enqueued call
 
     def _bind(self):
@@ -139,47 +138,46 @@ class Engine:
         return torch.cuda.current_stream(self.device).cuda_stream
 
     # ---- argument marshalling ------------------------------------------------
-    def _stage_in(self, data):
-        """Host minibatch -> one of two persistent device staging sets, copied on a side stream so that the
-        H2D transfer of call k+1 overlaps the kernels of call k (pinned sources; fixed destination pointers, so
-        captured graphs are replayed).  Not the gather arena: the library may keep bf16 images of the arena
-        minibatch between `replay_sample` and the step."""
-        B = data["obs"].shape[0]
+    def _host_batch(self, data) -> Batch:
+        """ctypes view of a HOST minibatch (contiguous fp32 CPU tensors; pinned ones copy at full PCIe rate)."""
+        t = {}
+        for k in ("obs", "act", "rew", "obs2", "done"):
+            v = data[k]
+            if v.dtype != torch.float32 or not v.is_contiguous():
+                v = v.to(torch.float32).contiguous()
+            t[k] = v
+        B = t["obs"].shape[0]
+        O, A = self.cfg.obs_dim, self.cfg.act_dim
         if B > self.cfg.max_batch:
             raise ValueError(f"batch {B} > max_batch {self.cfg.max_batch}")
-        if self._arena is None or self._arena[0] != B:
-            O, A = self.cfg.obs_dim, self.cfg.act_dim
-            z = lambda *s: torch.empty(*s, dtype=torch.float32, device=self.device)
-            sets = [{"obs": z(B, O), "obs2": z(B, O), "act": z(B, A), "rew": z(B), "done": z(B)} for _ in range(2)]
-            self._arena = (B, sets, [None, None], 0)
-            if self._copy_stream is None:
-                self._copy_stream = torch.cuda.Stream(device=self.device)
-        B_, sets, done_events, turn = self._arena
-        views = sets[turn]
-        main = torch.cuda.current_stream(self.device)
-        if done_events[turn] is not None:
-            self._copy_stream.wait_event(done_events[turn])   # the step that last read this set has finished
-        with torch.cuda.stream(self._copy_stream):
-            for k, v in views.items():
-                v.copy_(data[k].reshape(v.shape), non_blocking=True)
-            ready = torch.cuda.Event()
-            ready.record(self._copy_stream)
-        main.wait_event(ready)
-        self._staged_turn = turn
-        self._arena = (B_, sets, done_events, turn ^ 1)
-        return views
+        if t["obs"].shape != (B, O) or t["obs2"].shape != (B, O) or t["act"].shape != (B, A) \
+                or t["rew"].numel() != B or t["done"].numel() != B:
+            raise ValueError("minibatch shapes do not match the configured obs_dim/act_dim")
+        # the async copies read these tensors after the call returns: keep the last two sets alive
+        self._keep_host = (getattr(self, "_keep_host", None) or [None, None])[1:] + [t]
+        return Batch(t["obs"].data_ptr(), t["act"].data_ptr(), t["rew"].data_ptr(), t["obs2"].data_ptr(),
+                     t["done"].data_ptr(), B, None)
+
+    def _stage_in(self, data) -> Batch:
+        """Host minibatch -> one of the library's two device staging sets, copied on its private copy stream so that the
+        H2D transfer of call k+1 overlaps the kernels of call k (`dsact_stage_host`, include/dsact.h)."""
+        hb = self._host_batch(data)
+        dev = Batch()
+        check(self.lib.dsact_stage_host(self.h, C.byref(hb), C.byref(dev), self._stream()))
+        self._staged = True
+        return dev
 
     def _mark_staged_done(self):
-        """Record that the kernels reading the current staging set have been enqueued."""
-        if self._staged_turn is not None:
-            ev = torch.cuda.Event()
-            ev.record(torch.cuda.current_stream(self.device))
-            self._arena[2][self._staged_turn] = ev
-            self._staged_turn = None
+        """The kernels reading the current staging set have been enqueued: the set may be refilled after them."""
+        if getattr(self, "_staged", False):
+            check(self.lib.dsact_stage_release(self.h, self._stream()))
+            self._staged = False
 
     def _batch(self, data: Dict[str, torch.Tensor]) -> Batch:
         if data["obs"].device.type == "cpu":
-            data = self._stage_in(data)
+            b = self._stage_in(data)
+            self._keep = None
+            return b
         t = {k: _f32c(data[k], self.device) for k in ("obs", "act", "rew", "obs2", "done")}
         B = t["obs"].shape[0]
         O, A = self.cfg.obs_dim, self.cfg.act_dim
@@ -220,11 +218,16 @@ class Engine:
     def step(self, data, iteration: int, noise=None):
         """DSAC_V2.local_update (reference dsac_v2.py:102-105) on device tensors."""
         with torch.cuda.device(self.device):
-            b = self._batch(data)
-            n, keep = self._noise(noise, b.batch)
-            self._keep_noise = keep
-            check(self.lib.dsact_step(self.h, C.byref(b), n, int(iteration), self._stream()))
-            self._mark_staged_done()
+            if data["obs"].device.type == "cpu":   # the reference-facing call with a host minibatch: one C call
+                b = self._host_batch(data)
+                n, keep = self._noise(noise, b.batch)
+                self._keep_noise = keep
+                check(self.lib.dsact_step_host(self.h, C.byref(b), n, int(iteration), self._stream()))
+            else:
+                b = self._batch(data)
+                n, keep = self._noise(noise, b.batch)
+                self._keep_noise = keep
+                check(self.lib.dsact_step(self.h, C.byref(b), n, int(iteration), self._stream()))
         self.last_batch = b.batch
 
     def profile_step(self, data, iteration: int, noise=None) -> dict:
@@ -234,6 +237,7 @@ class Engine:
             b = self._batch(data)
             n, keep = self._noise(noise, b.batch)
             check(self.lib.dsact_profile_step(self.h, C.byref(b), n, int(iteration), self._stream(), C.byref(out)))
+            self._mark_staged_done()
         self.last_batch = b.batch
         names = ("other", "gemm_fwd", "gemm_dgrad", "gemm_wgrad")
         return {"total_ms": out.total_ms,

@@ -140,6 +140,17 @@ int dsact_set_carry(dsact_handle *h, float mean_std1, float mean_std2,
 int dsact_step(dsact_handle *h, const dsact_batch *batch, const dsact_noise *noise,
                int64_t iteration, void *stream);
 
+/* The same call with a HOST minibatch — what the reference's trainer hands to local_update (training/trainer.py:69,82:
+ * `replay_samples` are CPU tensors): `host` holds host pointers (pinned for full PCIe rate; pageable works).  The five
+ * arrays are copied into one of two internal device staging sets on a private copy stream (the copy of call k+1 runs
+ * under the kernels of call k), then dsact_step runs on that set.  dsact_stage_host / dsact_stage_release are the two
+ * halves for callers that want another entry point (dsact_dp_step, dsact_compute_grads ...) on a host minibatch:
+ * stage -> device pointers in `dev` (valid until the second next stage call) -> any step call(s) on `dev` ->
+ * release (marks the set reusable once the work enqueued on `stream` so far has finished). */
+int dsact_step_host(dsact_handle *h, const dsact_batch *host, const dsact_noise *noise, int64_t iteration, void *stream);
+int dsact_stage_host(dsact_handle *h, const dsact_batch *host, dsact_batch *dev, void *stream);
+int dsact_stage_release(dsact_handle *h, void *stream);
+
 /* split form = get_remote_update_info / remote_update (dsac_v2.py:107-138).
  * phase1: all forwards up to the per-critic sum of std over the local shard
  *         (state[DSACT_STATE_STDSUM..+1]); phase2: EMA, losses, all backward passes
