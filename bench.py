@@ -125,6 +125,16 @@ def ncu_traffic(mode):
         return None
 
 
+def cpu_ring_rows(cfg, want=1_000_000):
+    """Replay rows of the CPU arms: the benchmarked 1e6 when the host has the memory for it (3.1 GB for Humanoid)."""
+    try:
+        avail = os.sysconf("SC_AVPHYS_PAGES") * os.sysconf("SC_PAGE_SIZE")
+    except (ValueError, OSError):
+        avail = 0
+    need = want * 4 * (2 * cfg["obs_dim"] + cfg["act_dim"] + 2)
+    return want if avail > 4 * need else 100_000
+
+
 def oracle_setup(cfg, batch, ring_rows=100_000):
     from oracle.dsact_oracle import from_config
     torch.manual_seed(0)
@@ -166,8 +176,8 @@ def pick_threads(cfg, batch):
     return best
 
 
-def time_oracle(cfg, batch, warm, max_steps, budget_s):
-    step = oracle_setup(cfg, batch)
+def time_oracle(cfg, batch, warm, max_steps, budget_s, ring_rows=100_000):
+    step = oracle_setup(cfg, batch, ring_rows)
     for it in range(warm):
         step(it)
     t0, n = time.perf_counter(), 0
@@ -176,6 +186,111 @@ def time_oracle(cfg, batch, warm, max_steps, budget_s):
         n += 1
     dt = time.perf_counter() - t0
     return n / dt, n, dt
+
+
+def time_cuda_eager(cfg, batch, dev, steps=60, warm=5, ring_rows=200_000):
+    """The reference's arithmetic as eager PyTorch on THIS GPU: the oracle port with CUDA tensors issues the ATen ops the
+    reference's dsac_v2.py issues (torch.distributions object churn aside); replay ring, index draw and noise on the device.
+    Separates "what a B200 gives stock PyTorch" from what the hand-written kernels add."""
+    from oracle.dsact_oracle import from_config
+    orc = from_config(cfg, synth.make_weights(cfg), **synth.HYPER).to(dev)
+    O, A, lim = cfg["obs_dim"], cfg["act_dim"], cfg["act_lim"]
+    g = torch.Generator(device=dev).manual_seed(5)
+    ring = {"obs": torch.randn(ring_rows, O, device=dev, generator=g), "obs2": torch.randn(ring_rows, O, device=dev, generator=g),
+            "act": (torch.rand(ring_rows, A, device=dev, generator=g) * 2 - 1) * lim, "rew": torch.randn(ring_rows, device=dev, generator=g),
+            "done": (torch.rand(ring_rows, device=dev, generator=g) < 0.01).float()}
+
+    def step(it):
+        idx = torch.randint(0, ring_rows, (batch,), device=dev)
+        data = {k: v[idx] for k, v in ring.items()}
+        noise = [torch.randn(batch, A, device=dev), torch.randn(batch, A, device=dev)] + [torch.randn(batch, device=dev) for _ in range(6)]
+        return orc.update(data, noise, it)
+
+    for it in range(warm):
+        step(it)
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for it in range(steps):
+        step(warm + it)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    return 1000.0 * steps / e0.elapsed_time(e1)
+
+
+def h2d_gbs(eng, host_batch, nbytes, busy, reps=40):
+    """Host -> device bandwidth of the staging path itself (`dsact_stage_host`: five cudaMemcpyAsync calls of one pinned
+    minibatch on the library's copy stream), with no update behind the copies but WHILE the GPU runs device-resident
+    steps (`busy`): the ceiling of the end-to-end rate.  (An idle GPU drops its PCIe link speed and shows half of it.)"""
+    dev = eng.device
+    for _ in range(5):
+        busy()
+        eng._stage_in(host_batch); eng._mark_staged_done()
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        busy()
+        eng._stage_in(host_batch); eng._mark_staged_done()
+    torch.cuda.synchronize(dev)
+    return nbytes * reps / (time.perf_counter() - t0) / 1e9
+
+
+def check_replicas(alg, eng, cfg, B, rank, world, dev, dist, it0):
+    """N > 1 only.  (1) After the timed loops every rank's params / targets / Adam moments must be bit-identical (checksums
+    all-gathered).  (2) Three more data-parallel updates on host-generated shards with explicit noise; rank 0 then replays
+    the same three updates on ONE GPU over the concatenated minibatch, starting from a snapshot of the same state, and the
+    results must agree within the parity tolerance (the reduction order differs)."""
+    def checksum():
+        parts = [eng.params, eng.targets, eng.adam_m, eng.adam_v]
+        return torch.stack([p.double().sum() for p in parts] + [p.double().abs().sum() for p in parts])
+
+    cs = checksum()
+    gathered = [torch.zeros_like(cs) for _ in range(world)]
+    dist.all_gather(gathered, cs)
+    identical = all(bool(torch.equal(g, gathered[0])) for g in gathered)
+    snap = {k: getattr(eng, k).clone() for k in ("params", "targets", "adam_m", "adam_v", "state")}
+    GB = B * world
+    tbs = []
+    for s in range(3):
+        full, noise = synth.make_batch(cfg, GB, 900 + s), synth.make_noise(cfg, GB, 900 + s)
+        lo, hi = rank * B, (rank + 1) * B
+        shard = {k: torch.from_numpy(v[lo:hi]).to(dev) for k, v in full.items()}
+        nz = tuple(torch.from_numpy(noise[i][lo:hi]).to(dev) for i in (0, 1, 4, 5))
+        if getattr(alg, "_peer_dp", False):
+            eng.dp_step(shard, it0 + s, GB, nz)
+        else:
+            from dsac_v2_b200 import dp as dpmod
+            dpmod.data_parallel_gradients(eng, shard, nz, dist, B, GB)
+            eng.apply(it0 + s)
+        tbs.append(eng.read_stats(GB)["Loss/Critic loss-RL iter"])
+    cs2 = checksum()
+    dist.all_gather(gathered, cs2)
+    identical = identical and all(bool(torch.equal(g, gathered[0])) for g in gathered)
+    out = {"replicas_bit_identical": identical, "ranks": world}
+    if rank == 0:   # single-GPU replay of the same three updates on the concatenated minibatch
+        from dsac_v2_b200.engine import Engine
+        from dsac_v2_b200.engine import make_config
+        c = make_config(cfg["obs_dim"], cfg["act_dim"], cfg["hidden"], cfg["hidden"], max_batch=GB, gemm_mode=_lib_mode(eng))
+        one = Engine(c, dev, eng.act_high, eng.act_low)
+        for k, v in snap.items():
+            getattr(one, k).copy_(v)
+        ref = []
+        for s in range(3):
+            full, noise = synth.make_batch(cfg, GB, 900 + s), synth.make_noise(cfg, GB, 900 + s)
+            one.step({k: torch.from_numpy(v).to(dev) for k, v in full.items()}, it0 + s,
+                     tuple(torch.from_numpy(noise[i]).to(dev) for i in (0, 1, 4, 5)))
+            ref.append(one.read_stats()["Loss/Critic loss-RL iter"])
+        rel = max(abs(a - b) / max(abs(b), 1e-6) for a, b in zip(tbs, ref))
+        dw = float((one.params - eng.params).abs().max() / one.params.abs().max())
+        out.update({"critic_loss_dp": tbs, "critic_loss_one_gpu": ref, "max_rel_loss_diff": rel, "max_param_diff_rel": dw,
+                    "status": "ok" if identical and rel < 1e-4 and dw < 1e-4 else "MISMATCH"})
+        one.close()
+    return out
+
+
+def _lib_mode(eng):
+    from dsac_v2_b200 import _lib
+    return {v: k for k, v in _lib.GEMM_MODES.items()}[eng.cfg.gemm_mode]
 
 
 def cpu_model():
@@ -194,7 +309,8 @@ def run_reference(args, rank, world):
         return
     cfg = synth.CONFIGS[args.config]
     threads = pick_threads(cfg, args.batch)
-    step = oracle_setup(cfg, args.batch)
+    rows = cpu_ring_rows(cfg, args.replay_size)
+    step = oracle_setup(cfg, args.batch, rows)
     t0 = time.perf_counter()
     step(0)
     est = time.perf_counter() - t0
@@ -207,13 +323,13 @@ def run_reference(args, rank, world):
         step(warm + it)
     dt = time.perf_counter() - t0
     value = k / dt
-    sample = f"{k} full updates of batch {args.batch} (+ numpy replay gather from 1e5 rows), {warm} warm-up"
+    sample = f"{k} full updates of batch {args.batch} (+ numpy replay gather from a {rows}-row ring), {warm} warm-up"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": args.gpus,
         "steps": k, "warmup": warm, "ms_per_step": 1000 * dt / k, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"gym_humanoid-shaped synthetic, obs=376 act=17 MLP[256,256,256] batch={args.batch}, CPU torch",
-                   "global_batch": args.batch, "host": cpu_model()},
+                   "global_batch": args.batch, "host": cpu_model(), "replay_rows": rows},
         "cpu_baseline": {"value": value, "unit": "steps/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
@@ -234,6 +350,11 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
+    # host side of the end-to-end leg: sit on the GPU's NUMA node before any pinned allocation (hostnuma.py), and run
+    # torch's CPU ops with the reference's own thread count (utils/init_args.py:14 pins 4)
+    from dsac_v2_b200 import hostnuma
+    numa = hostnuma.bind_to_gpu_node(local)
+    torch.set_num_threads(4)
 
     import dsac_v2
     from training.replay_buffer import ReplayBuffer
@@ -333,6 +454,19 @@ def main():
         dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
     e2e_value = world * 1000.0 * args.steps / ms2.item()
     assert np.isfinite(sink)
+    h2d_bytes = 4 * B * (2 * O + A + 2)
+    h2d_rate = None
+    if world == 1:
+        def busy():
+            nonlocal it
+            dev_step(it); it += 1
+        h2d_rate = h2d_gbs(eng, ring[0], h2d_bytes, busy)
+
+    # ---- data-parallel replicas: bit-identical after the timed loops, and equal to one GPU on the concatenated batch ----
+    dp_check = None
+    if world > 1:
+        dp_check = check_replicas(alg, eng, cfg, B, rank, world, dev, dist, it)
+        it += 3
 
     # ---- roofline of the dominant kernel (grouped GEMM), per-launch events, eager -------------------
     peak_tf, peak_hbm, peak_src = peaks()
@@ -370,9 +504,17 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = pick_threads(cfg, B)
-        v, n, dt = time_oracle(cfg, B, warm=3, max_steps=2000, budget_s=12.0)
+        rows = cpu_ring_rows(cfg, args.replay_size)
+        v, n, dt = time_oracle(cfg, B, warm=3, max_steps=2000, budget_s=12.0, ring_rows=rows)
         cpu = {"value": v, "unit": "steps/s", "cores": threads, "kind": "port",
-               "sample": f"{n} full updates of batch {B} incl. numpy replay gather ({dt:.1f} s), {cpu_model()}"}
+               "sample": f"{n} full updates of batch {B} incl. numpy replay gather from a {rows}-row ring ({dt:.1f} s), {cpu_model()}"}
+        torch.set_num_threads(4)
+
+    eager = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v = time_cuda_eager(cfg, B, dev)
+        eager = {"value": v, "unit": "steps/s", "kind": "oracle port on CUDA tensors (stock eager PyTorch ops, same GPU)",
+                 "sample": f"60 updates of batch {B}, device ring 200000 rows, device randint/randn"}
 
     if rank == 0:
         out = {
@@ -385,13 +527,18 @@ def main():
                        "l2": f"inputs exceed L2: each step gathers {B} random rows from a {4 * args.replay_size * (2 * O + A + 3) / 1e9:.2f} GB ring",
                        "gemm_mode": args.gemm, "cuda_graph": True},
             "clocks": clocks.summary(),
-            "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": 4 * B * (2 * O + A + 2),
-                    "d2h_bytes_per_step": 64, "api": "DSAC_V2.local_update(host pinned dict, iteration) + tb_info read"},
+            "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": h2d_bytes,
+                    "d2h_bytes_per_step": 64, "api": "DSAC_V2.local_update(host pinned dict, iteration) + tb_info read "
+                                                     "(dsact_step_host: staging copies on the library's copy stream)",
+                    "h2d_gbs": h2d_rate, "h2d_gbs_used": e2e_value / world * h2d_bytes / 1e9,
+                    "host": {"numa": numa, "torch_threads": torch.get_num_threads()}},
+            "dp_check": dp_check,
             "gpu_launches": launches,
             "launches_per_step": launches_per_step,
             "tflops_algorithmic": FLOP_PER_SAMPLE * B * value / world / 1e12 if args.config == "humanoid" else None,
             "roofline": roof,
             "cpu_baseline": cpu,
+            "cuda_eager_baseline": eager,
         }
         print(json.dumps(out), flush=True)
     if world > 1:

@@ -41,6 +41,23 @@ class Config(C.Structure):
     ]
 
 
+MAX_CONV = 8
+
+
+class CnnConfig(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_int32), ("channels", C.c_int32), ("height", C.c_int32), ("width", C.c_int32),
+        ("act_dim", C.c_int32), ("n_conv", C.c_int32),
+        ("conv_kernel", C.c_int32 * MAX_CONV), ("conv_channels", C.c_int32 * MAX_CONV), ("conv_stride", C.c_int32 * MAX_CONV),
+        ("n_hidden", C.c_int32), ("hidden", C.c_int32 * MAX_HIDDEN), ("act_hidden", C.c_int32),
+        ("max_batch", C.c_int32), ("auto_alpha", C.c_int32), ("delay_update", C.c_int32),
+        ("gamma", C.c_double), ("tau", C.c_double), ("tau_b", C.c_double), ("alpha_fixed", C.c_double),
+        ("lr_q", C.c_double), ("lr_pi", C.c_double), ("lr_alpha", C.c_double),
+        ("min_log_std", C.c_double), ("max_log_std", C.c_double),
+        ("adam_beta1", C.c_double), ("adam_beta2", C.c_double), ("adam_eps", C.c_double),
+    ]
+
+
 class Layout(C.Structure):
     _fields_ = [("n_q", C.c_int64), ("n_pi", C.c_int64), ("n_params", C.c_int64), ("n_targets", C.c_int64),
                 ("workspace_bytes", C.c_int64), ("state_floats", C.c_int64), ("max_batch", C.c_int64)]
@@ -103,6 +120,17 @@ SYMBOLS = {
     "dsact_dp_step": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.POINTER(Noise), C.c_int64, C.c_int64, C.c_void_p]),
     "dsact_dp_replay_step": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.POINTER(Noise), C.c_int64, C.c_int64,
                                        C.c_void_p]),
+    "dsact_cnn_query_layout": (C.c_int, [C.POINTER(CnnConfig), C.POINTER(Layout)]),
+    "dsact_cnn_create": (C.c_int, [C.POINTER(CnnConfig), C.c_int, C.POINTER(C.c_void_p)]),
+    "dsact_cnn_destroy": (None, [C.c_void_p]),
+    "dsact_cnn_bind": (C.c_int, [C.c_void_p, C.POINTER(Buffers)]),
+    "dsact_cnn_set_carry": (C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_int64, C.c_int64, C.c_void_p]),
+    "dsact_cnn_replay_bind": (C.c_int, [C.c_void_p, C.POINTER(Replay)]),
+    "dsact_cnn_replay_add": (C.c_int, [C.c_void_p] + [C.c_void_p] * 6 + [C.c_int64, C.c_int64, C.c_void_p]),
+    "dsact_cnn_replay_sample": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.POINTER(Batch), C.c_void_p]),
+    "dsact_cnn_seed": (C.c_int, [C.c_void_p, C.c_uint64]),
+    "dsact_cnn_step": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.POINTER(Noise), C.c_int64, C.c_void_p]),
+    "dsact_cnn_read_stats": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "dsact_profile_step": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.POINTER(Noise), C.c_int64, C.c_void_p, C.POINTER(Profile)]),
     "dsact_launch_count": (C.c_int64, [C.c_void_p]),
     "dsact_last_call_launches": (C.c_int32, [C.c_void_p]),

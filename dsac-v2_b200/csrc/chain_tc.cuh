@@ -9,14 +9,12 @@
 // activations never leave the SM unless the backward pass needs them (z for act', images for wgrad).
 // The weight tiles of layer j+1 are prefetched by the TMA warp while the epilogue of layer j runs.
 //
-// TMEM map (512 columns), streamed variant (STREAM = true, the default): two 256-column buffers used alternately.
+// TMEM map (512 columns): two 256-column buffers used alternately.
 // Layer j accumulates into buffer j & 1; its epilogue converts the accumulator IN PLACE into the next layer's A operand
 // (the 16 fp32 columns of a chunk become 8 columns of packed bf16 hi pairs + 8 columns of lo pairs: the same cells),
 // and layer j + 1, accumulating into the other buffer, issues the MMAs of k-block kb as soon as the four chunks of that
 // k-block have been written (one mbarrier per k-block, 16 warp arrivals): the tensor pipe trails the epilogue by one
 // k-block instead of waiting for the whole layer, so MMA time disappears behind epilogue time.
-// Serial variant (STREAM = false, DSACT_CHAIN_STREAM=0): [0,256) fp32 accumulator, [256,384) A hi, [384,512) A lo; the
-// MMAs of layer j + 1 start when the whole epilogue of layer j is done.
 // Roles: warp 0 TMA producer, warp 1 MMA issuer, warps 2..17 epilogue (lane quarter = warp % 4).
 #pragma once
 #include "gemm_tc.cuh"
@@ -25,7 +23,6 @@ namespace dsact {
 
 constexpr int CH_MAX_LAYERS = DSACT_MAX_HIDDEN + 1;
 constexpr int CH_MAX_PASSES = 4;
-constexpr int CH_ACC_COL = 0, CH_AHI_COL = 256, CH_ALO_COL = 384;
 
 struct ChainLayer {
   CUtensorMap mapB;          // weight image; forward: K-major (box = bn rows), dgrad: MN-major (box = 64 x 64)
@@ -105,7 +102,7 @@ inline int chain_smem_bytes(int stages, int planes, int stage_b) {
          (2 * stages + 8 + 2 * TC_EPI_WARPS) * 8 + 1024;
 }
 
-template <bool PLANES2, bool STREAM>
+template <bool PLANES2>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_chain_kernel(const __grid_constant__ ChainGroup g, int stages, int stage_b) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared address space (LDS/STS)
@@ -120,7 +117,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_chain_kernel(const __grid_co
   uint64_t* empty = bars + stages;     // [stages] MMA -> TMA
   uint64_t* acc_full = bars + 2 * stages;          // MMA -> epilogue: accumulator of the layer complete
   uint64_t* a_ready = bars + 2 * stages + 1;       // [4] epilogue -> MMA: the chunks of k-block kb of the next layer's A operand
-                                                   //     are in tensor memory (serial variant: [0] only, whole operand)
+                                                   //     are in tensor memory
   uint64_t* zbar = a_ready + 4;             // [warps][2] act' tile arrival
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(zbar + 2 * TC_EPI_WARPS);
 
@@ -145,6 +142,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_chain_kernel(const __grid_co
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  if (warp == 2) {   // descriptor prefetch: every tensor map this CTA will use (they are kernel parameters: no dependency on
+                     // the preceding kernel), so that neither the first tile loads nor the epilogue's TMA stores wait for a fetch
+    for (int i = lane; i < 2 + 3 * nl; i += 32) {
+      const CUtensorMap* m = nullptr;
+      if (i == 0) m = &P.mapA[0];
+      else if (i == 1) { if (P.L[0].kblocks[1] > 0) m = &P.mapA[1]; }
+      else {
+        const ChainLayer& Lq = P.L[(i - 2) / 3];
+        const int which = (i - 2) % 3;
+        if (which == 0) m = &Lq.mapB;
+        else if (which == 1) { if (Lq.Zout || Lq.Zin) m = &Lq.mapZ; }
+        else if (Lq.img) m = &Lq.mapImg;
+      }
+      if (m) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -195,16 +208,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_chain_kernel(const __grid_co
         const int nkb = Lj.kblocks[0] + Lj.kblocks[1];
         const uint32_t idesc = make_idesc(TC_BM, Lj.bn, 0, Lj.b_mn);
         // accumulator / A-operand columns of this layer (see the TMEM map at the top)
-        const uint32_t acc = tmem_base + (STREAM ? (uint32_t)((j & 1) * 256) : (uint32_t)CH_ACC_COL);
+        const uint32_t acc = tmem_base + (uint32_t)((j & 1) * 256);
         const uint32_t abuf = tmem_base + (uint32_t)(((j - 1) & 1) * 256);   // streamed: where layer j - 1 accumulated
-        if (!STREAM && j > 0) {  // A of this layer = what the previous epilogue wrote to TMEM
-          mbar_wait(&a_ready[0], (uint32_t)((j - 1) & 1));
-          tc_fence_after();
-        }
         uint32_t accumulate = 0;
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&full[stage], phase);
-          if (STREAM && j > 0) mbar_wait(&a_ready[kb], (uint32_t)((j - 1) & 1));   // chunks 4 kb .. 4 kb + 3 of the operand
+          if (j > 0) mbar_wait(&a_ready[kb], (uint32_t)((j - 1) & 1));   // chunks 4 kb .. 4 kb + 3 of the operand
           tc_fence_after();
           if (j == 0 && kb == 0) TC_STAMP(2);
           const uint32_t sB = smem_u32(ringB + (size_t)stage * planes * stage_b);
@@ -224,8 +233,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_chain_kernel(const __grid_co
               }
             } else {
               // 16 K elements = one epilogue chunk = 8 TMEM columns of packed bf16 pairs per plane
-              const uint32_t a_hi = STREAM ? abuf + (uint32_t)((kb * 4 + k) * 16) : tmem_base + CH_AHI_COL + (uint32_t)(kb * 32 + k * 8);
-              const uint32_t a_lo = STREAM ? a_hi + 8 : tmem_base + CH_ALO_COL + (uint32_t)(kb * 32 + k * 8);
+              const uint32_t a_hi = abuf + (uint32_t)((kb * 4 + k) * 16), a_lo = a_hi + 8;
               tc_mma_ts(acc, a_hi, b_hi, idesc, accumulate);
               if (planes == 2) {
                 tc_mma_ts(acc, a_hi, b_lo, idesc, 1);
@@ -281,7 +289,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_chain_kernel(const __grid_co
       }
       mbar_wait(acc_full, (uint32_t)(j & 1));
       tc_fence_after();
-      const uint32_t acc_addr = lane_addr + (STREAM ? (uint32_t)((j & 1) * 256) : (uint32_t)CH_ACC_COL);
+      const uint32_t acc_addr = lane_addr + (uint32_t)((j & 1) * 256);
       if (j == 0 && threadIdx.x == 64) TC_STAMP(4);
       if (threadIdx.x == 64) TC_STAMP(9 + 3 * j);   // accumulator of layer j complete (seen by the epilogue)
       const int epi = Lj.epi, act = Lj.act;
@@ -414,15 +422,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_chain_kernel(const __grid_co
         }
         TC_CSTAMP(36);
         if (feeds_next) {  // next layer's A operand: packed bf16 pairs along K, hi and lo planes
-          if (STREAM) {    // in place: the chunk's 16 accumulator columns become 8 columns of hi pairs + 8 of lo pairs
-            tc_st8(acc_addr + (uint32_t)c0, whi);
-            if (planes == 2) tc_st8(acc_addr + (uint32_t)c0 + 8, wlo);
-          } else {
-            tc_st8(lane_addr + CH_AHI_COL + (uint32_t)(c0 / 2), whi);
-            if (planes == 2) tc_st8(lane_addr + CH_ALO_COL + (uint32_t)(c0 / 2), wlo);
-          }
+          // in place: the chunk's 16 accumulator columns become 8 columns of hi pairs + 8 of lo pairs
+          tc_st8(acc_addr + (uint32_t)c0, whi);
+          if (planes == 2) tc_st8(acc_addr + (uint32_t)c0 + 8, wlo);
         }
-        if (STREAM && feeds_next) {   // this warp's share of k-block k of the next layer's operand is in tensor memory
+        if (feeds_next) {   // this warp's share of k-block k of the next layer's operand is in tensor memory
           asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
           tc_fence_before();
           __syncwarp();
@@ -432,16 +436,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_chain_kernel(const __grid_co
       }
       if (g.dbg && j == 1 && threadIdx.x == 64) g.dbg[(size_t)blockIdx.x * TC_DBG_SLOTS + 38] = (unsigned long long)clock64();
       if (threadIdx.x == 64) TC_STAMP(10 + 3 * j);  // epilogue of layer j done (first epilogue warp)
-      if (feeds_next) {
-        if (STREAM) {   // k-blocks in which this warp had no chunk (narrow layers): every barrier sees every warp once
-          for (; k < 4; ++k)
-            if (lane == 0) mbar_arrive(&a_ready[k]);
-        } else {
-          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&a_ready[0]);
-        }
+      if (feeds_next) {   // k-blocks in which this warp had no chunk (narrow layers): every barrier sees every warp once
+        for (; k < 4; ++k)
+          if (lane == 0) mbar_arrive(&a_ready[k]);
       }
     }
     if (lane == 0) tma_store_wait_read();   // shared memory must stay valid until the last stores have read it

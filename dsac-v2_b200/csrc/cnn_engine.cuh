@@ -1,0 +1,572 @@
+// DSAC-T update with the reference's CNN approximators (BASELINE config 5; reference networks/cnn.py:30-53 conv stack,
+// :151-240 StochaPolicy, :383-461 ActionValueDistri).  Included at the end of engine.cu: it reuses the grouped fp32 GEMM
+// launcher, the loss / sample / policy-gradient kernels and apply_kernel of the MLP engine; what is new here is the conv
+// stack (conv.cuh) and the two-head wiring (separate `mean` and `log_std` MLPs per network, their outputs packed into the
+// [B,2] / [B,2A] arrays the loss kernels read, by strided GEMM outputs).
+//
+// One eager sequence of launches per step (no graph capture yet):
+//   conv forwards: pi(s), pi'(s'), Q1/Q2 features of s (shared by the (s,a) and (s,a~) passes), Q1'/Q2' features of s'
+//   heads: pi, pi' -> sample -> Q_k(s,a), Q'_k(s',a'), mean head of Q_k(s,a~) -> loss -> head backward (critics: both
+//   heads; actor path: mean head, input gradient only) -> policy_grad -> policy heads backward -> conv backward x3 -> Adam.
+#pragma once
+#include "conv.cuh"
+
+namespace dsact {
+__global__ void relu_mask_kernel(float* __restrict__ g, const float* __restrict__ a, long long n) {
+  pdl_sync();
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    if (!(a[i] > 0.f)) g[i] = 0.f;
+}
+__global__ void zero_kernel(float* __restrict__ p, long long n) {
+  pdl_sync();
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = 0.f;
+}
+}  // namespace dsact
+
+struct CnnGeom {   // one network: conv encoder + two identical head MLPs
+  int nconv;
+  int C[DSACT_MAX_CONV + 1], H[DSACT_MAX_CONV + 1], W[DSACT_MAX_CONV + 1];   // [0] = input image
+  int K[DSACT_MAX_CONV], S[DSACT_MAX_CONV];
+  int64_t cw[DSACT_MAX_CONV], cb[DSACT_MAX_CONV];
+  int F;                 // flattened feature size
+  Net head;              // s[0] = F (+ act_dim), hidden..., s[L+1] = outputs of ONE head
+  int64_t head_off[2];   // mean, log_std
+  int64_t n;
+  bool build(const dsact_cnn_config& c, int extra_in, int out) {
+    nconv = c.n_conv;
+    C[0] = c.channels; H[0] = c.height; W[0] = c.width;
+    n = 0;
+    for (int j = 0; j < nconv; ++j) {
+      K[j] = c.conv_kernel[j]; S[j] = c.conv_stride[j];
+      C[j + 1] = c.conv_channels[j];
+      H[j + 1] = (H[j] - K[j]) / S[j] + 1;
+      W[j + 1] = (W[j] - K[j]) / S[j] + 1;
+      if (H[j + 1] < 1 || W[j + 1] < 1) return false;
+      cw[j] = n; n += (int64_t)C[j + 1] * C[j] * K[j] * K[j];
+      cb[j] = n; n += C[j + 1];
+    }
+    F = C[nconv] * H[nconv] * W[nconv];
+    head.build(F + extra_in, c.hidden, c.n_hidden, out);
+    for (int hd = 0; hd < 2; ++hd) { head_off[hd] = n; n += head.n; }
+    return true;
+  }
+  ConvShape shape(int j, int B) const { return ConvShape{B, C[j], H[j], W[j], C[j + 1], K[j], S[j], H[j + 1], W[j + 1]}; }
+  int64_t act_elems(int j) const { return (int64_t)C[j] * H[j] * W[j]; }   // per sample, activation j (0 = image)
+};
+
+struct CnnHeadBuf { int64_t z[DSACT_MAX_HIDDEN], h[DSACT_MAX_HIDDEN], dz[DSACT_MAX_HIDDEN]; };
+
+struct dsact_cnn_handle {
+  dsact_cnn_config cfg;
+  int device, num_sms;
+  CnnGeom q, pi;
+  dsact_buffers buf;
+  bool bound = false;
+  uint64_t seed = 0x5DEECE66Dull;
+  int64_t dev_iter = -1, launches = 0;
+  // arena (floats from the workspace base)
+  int64_t convP[DSACT_MAX_CONV + 1], convT[DSACT_MAX_CONV + 1], convQ[4][DSACT_MAX_CONV + 1];   // activations 1..nconv
+  CnnHeadBuf hb[14];   // 0,1 pi mean/ls; 2,3 pi'; 4..7 Q1,Q2 (s,a) mean/ls; 8..11 Q1',Q2'; 12,13 mean head of Q1,Q2 on (s,a~)
+  int64_t logitsP, logitsT, dlogits, new_act, act2, logp_new, logp2, eps1, eps2, z3, z4, outQ[6], dOut[6], dAct[2];
+  int64_t dfeat[3], dfa[2];   // dL/dfeature of pi, Q1, Q2; dL/d(feature|act) scratch of the actor path
+  int64_t ga, gb;             // conv-backward ping-pong buffers (largest activation)
+  int64_t r_obs, r_obs2, r_act, r_rew, r_done, r_logp, r_idx;   // gathered replay minibatch
+  dsact_replay rb;
+  bool rb_bound = false;
+  int64_t dev_rb_size = -1;
+  int64_t total;
+  float* Wp() const { return reinterpret_cast<float*>(buf.workspace); }
+  void layout() {
+    const int64_t B = cfg.max_batch, A = cfg.act_dim;
+    int64_t off = 0;
+    auto take = [&](int64_t n) { int64_t o = off; off += round64(n); return o; };
+    auto conv_acts = [&](const CnnGeom& g, int64_t* a) { a[0] = -1; for (int j = 1; j <= g.nconv; ++j) a[j] = take(B * g.act_elems(j)); };
+    conv_acts(pi, convP); conv_acts(pi, convT);
+    for (int k = 0; k < 4; ++k) conv_acts(q, convQ[k]);
+    for (int p = 0; p < 14; ++p) {
+      const Net& net = p < 4 ? pi.head : q.head;
+      for (int j = 0; j < net.L; ++j) { hb[p].z[j] = take(B * net.s[j + 1]); hb[p].h[j] = take(B * net.s[j + 1]); hb[p].dz[j] = take(B * net.s[j + 1]); }
+    }
+    logitsP = take(B * 2 * A); logitsT = take(B * 2 * A); dlogits = take(B * 2 * A);
+    new_act = take(B * A); act2 = take(B * A); logp_new = take(B); logp2 = take(B);
+    eps1 = take(B * A); eps2 = take(B * A); z3 = take(B); z4 = take(B);
+    for (int p = 0; p < 6; ++p) { outQ[p] = take(B * 2); dOut[p] = take(B * 2); }
+    dAct[0] = take(B * A); dAct[1] = take(B * A);
+    dfeat[0] = take(B * pi.F); dfeat[1] = take(B * q.F); dfeat[2] = take(B * q.F);
+    dfa[0] = take(B * (q.F + A)); dfa[1] = take(B * (q.F + A));
+    int64_t big = 0;
+    for (int j = 1; j <= q.nconv; ++j) big = big > q.act_elems(j) ? big : q.act_elems(j);
+    for (int j = 1; j <= pi.nconv; ++j) big = big > pi.act_elems(j) ? big : pi.act_elems(j);
+    ga = take(B * big); gb = take(B * big);
+    const int64_t O = (int64_t)cfg.channels * cfg.height * cfg.width;
+    r_obs = take(B * O); r_obs2 = take(B * O); r_act = take(B * A); r_rew = take(B); r_done = take(B); r_logp = take(B); r_idx = take(2 * B);
+    total = off;
+  }
+};
+
+static int cnn_validate(const dsact_cnn_config* c) {
+  if (!c) return fail(DSACT_EINVAL, "null config");
+  if (c->abi_version != DSACT_ABI_VERSION) return fail(DSACT_EINVAL, "abi_version %d != %d", c->abi_version, DSACT_ABI_VERSION);
+  if (c->channels < 1 || c->height < 1 || c->width < 1 || c->act_dim < 1) return fail(DSACT_EINVAL, "bad observation / action shape");
+  if (c->n_conv < 1 || c->n_conv > DSACT_MAX_CONV) return fail(DSACT_EINVAL, "1..%d conv layers supported", DSACT_MAX_CONV);
+  for (int j = 0; j < c->n_conv; ++j)
+    if (c->conv_kernel[j] < 1 || c->conv_kernel[j] > 4 || c->conv_stride[j] < 1 || c->conv_channels[j] < 1)
+      return fail(DSACT_EINVAL, "conv layer %d: kernel sizes 1..4 are implemented (the reference's type_2 encoder)", j);
+  if (c->n_hidden < 1 || c->n_hidden > DSACT_MAX_HIDDEN) return fail(DSACT_EINVAL, "1..%d hidden layers per head", DSACT_MAX_HIDDEN);
+  if (c->act_hidden < 0 || c->act_hidden > DSACT_ACT_SELU) return fail(DSACT_EINVAL, "unknown activation");
+  if (c->max_batch < 1 || c->delay_update < 1) return fail(DSACT_EINVAL, "bad max_batch / delay_update");
+  CnnGeom g;
+  if (!g.build(*c, 0, 1)) return fail(DSACT_EINVAL, "the conv stack consumes the whole image");
+  return DSACT_OK;
+}
+
+// ---- head MLPs through the grouped fp32 GEMM -------------------------------------------------------------------------
+struct CnnHeadFwd {
+  const float* base;     // parameters of this head
+  const float* in0; int k0;
+  const float* in1; int k1;     // second input segment (the action) or null
+  CnnHeadBuf* hbuf;
+  bool keep_z;
+  float* out; int out_ld;       // head output column(s) inside a packed array
+};
+static void cnn_heads_forward(dsact_cnn_handle* h, const Net& net, std::vector<CnnHeadFwd>& P, int B, Ctx& c) {
+  float* W = h->Wp();
+  for (int j = 0; j <= net.L; ++j) {
+    size_t i0 = 0;
+    while (i0 < P.size()) {
+      GemmGroup G;
+      G.n = 0;
+      for (; i0 < P.size() && G.n < MAXG; ++i0) {
+        const CnnHeadFwd& f = P[i0];
+        GemmProb p = prob_zero();
+        const int in_dim = net.s[j];
+        if (j == 0) {
+          p.A[0] = f.in0; p.lda[0] = f.k0; p.K[0] = f.k0; p.B[0] = f.base + net.w[0]; p.ldb[0] = in_dim;
+          if (f.k1 > 0) { p.A[1] = f.in1; p.lda[1] = f.k1; p.K[1] = f.k1; p.B[1] = f.base + net.w[0] + f.k0; p.ldb[1] = in_dim; }
+        } else {
+          p.A[0] = W + f.hbuf->h[j - 1]; p.lda[0] = in_dim; p.K[0] = in_dim; p.B[0] = f.base + net.w[j]; p.ldb[0] = in_dim;
+        }
+        p.M = B; p.N = net.s[j + 1]; p.bias = f.base + net.b[j]; p.act = h->cfg.act_hidden;
+        if (j == net.L) { p.C = f.out; p.ldc = f.out_ld; p.epi = EPI_STORE; }
+        else { p.C = W + f.hbuf->h[j]; p.ldc = net.s[j + 1]; p.epi = EPI_BIAS_ACT; p.Zout = f.keep_z ? W + f.hbuf->z[j] : nullptr; }
+        G.p[G.n++] = p;
+      }
+      launch_simt(h->num_sms, G, V_FWD, c);
+      c.done();
+    }
+  }
+  c.check();
+}
+
+struct CnnHeadBwd {
+  const float* base;     // parameters of this head
+  float* gbase;          // its gradients, or null (actor path through a critic: input gradient only)
+  const float* in0; int k0; const float* in1; int k1;   // layer-0 inputs (for the weight gradient)
+  CnnHeadBuf* hbuf;
+  const float* dout; int dout_ld;   // dL/d(head output) inside a packed array
+  float* din;            // [B, k0 + k1] dL/d(layer-0 input), accumulated (+=), or null
+};
+static void cnn_heads_backward(dsact_cnn_handle* h, const Net& net, std::vector<CnnHeadBwd>& P, int B, Ctx& c) {
+  float* W = h->Wp();
+  for (int j = net.L; j >= 0; --j) {
+    GemmGroup gw, gd;
+    gw.n = gd.n = 0;
+    auto flush = [&](GemmGroup& G, int variant) { if (G.n) { launch_simt(h->num_sms, G, variant, c); c.done(); G.n = 0; } };
+    for (const CnnHeadBwd& f : P) {
+      const float* dY = j == net.L ? f.dout : W + f.hbuf->dz[j];
+      const int ldy = j == net.L ? f.dout_ld : net.s[j + 1];
+      if (f.gbase) {   // dW_j += dY^T X
+        auto wgrad = [&](const float* X, int ldx, int col0, int ncols) {
+          GemmProb p = prob_zero();
+          p.A[0] = dY; p.lda[0] = ldy; p.K[0] = B; p.B[0] = X; p.ldb[0] = ldx;
+          p.M = net.s[j + 1]; p.N = ncols; p.C = f.gbase + net.w[j] + col0; p.ldc = net.s[j]; p.epi = EPI_ATOMIC;
+          if (gw.n == MAXG) flush(gw, V_WGRAD);
+          gw.p[gw.n++] = p;
+        };
+        if (j == 0) { wgrad(f.in0, f.k0, 0, f.k0); if (f.k1 > 0) wgrad(f.in1, f.k1, f.k0, f.k1); }
+        else wgrad(W + f.hbuf->h[j - 1], net.s[j], 0, net.s[j]);
+      }
+      GemmProb p = prob_zero();   // dX = dY W_j (.) act'(z_{j-1})
+      p.A[0] = dY; p.lda[0] = ldy; p.K[0] = net.s[j + 1]; p.B[0] = f.base + net.w[j]; p.ldb[0] = net.s[j];
+      p.M = B; p.N = net.s[j];
+      if (j >= 1) {
+        p.C = W + f.hbuf->dz[j - 1]; p.ldc = net.s[j];
+        p.epi = EPI_DACT; p.Zin = W + f.hbuf->z[j - 1]; p.ldz = net.s[j]; p.act = h->cfg.act_hidden;
+        p.colsum = f.gbase ? f.gbase + net.b[j - 1] : nullptr;
+      } else {
+        if (!f.din) continue;
+        p.C = f.din; p.ldc = net.s[0]; p.epi = EPI_ATOMIC;   // several heads add into the same input gradient
+      }
+      if (gd.n == MAXG) flush(gd, V_DGRAD);
+      gd.p[gd.n++] = p;
+    }
+    flush(gw, V_WGRAD);
+    flush(gd, V_DGRAD);
+  }
+  c.check();
+}
+
+static void cnn_conv_forward(dsact_cnn_handle* h, const CnnGeom& g, const float* params, const float* img, const int64_t* acts, int B, Ctx& c) {
+  float* W = h->Wp();
+  const float* x = img;
+  for (int j = 0; j < g.nconv; ++j) {
+    const ConvShape s = g.shape(j, B);
+    dim3 grid((s.Hout * s.Wout + 127) / 128, s.Cout, B);
+    launch_k(conv_fwd_kernel, grid, 128, sizeof(float) * s.Cin * s.K * s.K, c, x, params + g.cw[j], params + g.cb[j], W + acts[j + 1], s);
+    c.done();
+    x = W + acts[j + 1];
+  }
+  c.check();
+}
+
+// backward through one encoder: `gtop` = dL/d(feature) [B, F] (consumed), grads += into gparams
+static void cnn_conv_backward(dsact_cnn_handle* h, const CnnGeom& g, const float* params, float* gparams, const float* img,
+                              const int64_t* acts, float* gtop, int B, Ctx& c) {
+  float* W = h->Wp();
+  float* gcur = gtop;
+  float* bufs[2] = {W + h->ga, W + h->gb};
+  int flip = 0;
+  for (int j = g.nconv - 1; j >= 0; --j) {
+    const ConvShape s = g.shape(j, B);
+    const long long n_out = (long long)B * g.act_elems(j + 1);
+    int blocks = (int)((n_out + 255) / 256); if (blocks > 8 * h->num_sms) blocks = 8 * h->num_sms;
+    launch_k(relu_mask_kernel, blocks, 256, 0, c, gcur, (const float*)(W + acts[j + 1]), n_out); c.done();   // dz_j = g_j (.) [a_j > 0]
+    const float* x = j == 0 ? img : W + acts[j];
+    launch_k(conv_wgrad_kernel, dim3(s.Cin, s.Cout), 256, 0, c, (const float*)gcur, x, gparams + g.cw[j], gparams + g.cb[j], s); c.done();
+    if (j > 0) {
+      float* gnext = bufs[flip]; flip ^= 1;
+      dim3 grid((s.Hin * s.Win + 127) / 128, s.Cin, B);
+      launch_k(conv_dgrad_kernel, grid, 128, 0, c, (const float*)gcur, params + g.cw[j], x, gnext, s, 0); c.done();
+      gcur = gnext;
+    }
+  }
+  c.check();
+}
+
+extern "C" {
+
+int dsact_cnn_query_layout(const dsact_cnn_config* cfg, dsact_layout* out) {
+  int rc = cnn_validate(cfg);
+  if (rc) return rc;
+  if (!out) return fail(DSACT_EINVAL, "null out");
+  dsact_cnn_handle h;
+  h.cfg = *cfg;
+  h.q.build(*cfg, cfg->act_dim, 1);
+  h.pi.build(*cfg, 0, cfg->act_dim);
+  h.layout();
+  out->n_q = h.q.n; out->n_pi = h.pi.n;
+  out->n_params = 2 * h.q.n + h.pi.n + 1;
+  out->n_targets = 2 * h.q.n + h.pi.n;
+  out->workspace_bytes = h.total * (int64_t)sizeof(float);
+  out->state_floats = ST_FLOATS;
+  out->max_batch = cfg->max_batch;
+  return DSACT_OK;
+}
+
+int dsact_cnn_create(const dsact_cnn_config* cfg, int device, dsact_cnn_handle** out) {
+  int rc = cnn_validate(cfg);
+  if (rc) return rc;
+  if (!out) return fail(DSACT_EINVAL, "null out");
+  CUDA_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return fail(DSACT_EARCH, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+  dsact_cnn_handle* h = new dsact_cnn_handle();
+  h->cfg = *cfg;
+  h->device = device;
+  h->num_sms = prop.multiProcessorCount;
+  h->q.build(*cfg, cfg->act_dim, 1);
+  h->pi.build(*cfg, 0, cfg->act_dim);
+  h->layout();
+  *out = h;
+  return DSACT_OK;
+}
+
+void dsact_cnn_destroy(dsact_cnn_handle* h) { delete h; }
+
+int dsact_cnn_bind(dsact_cnn_handle* h, const dsact_buffers* b) {
+  if (!h || !b) return fail(DSACT_EINVAL, "null argument");
+  if (!b->params || !b->targets || !b->grads || !b->adam_m || !b->adam_v || !b->act_high || !b->act_low || !b->state || !b->workspace)
+    return fail(DSACT_EINVAL, "null buffer pointer");
+  h->buf = *b;
+  h->bound = true;
+  h->dev_iter = -1;
+  return DSACT_OK;
+}
+
+int dsact_cnn_set_carry(dsact_cnn_handle* h, float m1, float m2, int64_t tq, int64_t tp, void* stream) {
+  if (!h || !h->bound) return fail(DSACT_ESTATE, "not bound");
+  CUDA_TRY(cudaSetDevice(h->device));
+  set_carry_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(h->buf.state, m1, m2, (int)tq, (int)tp);
+  CUDA_TRY(cudaGetLastError());
+  return DSACT_OK;
+}
+
+int dsact_cnn_seed(dsact_cnn_handle* h, uint64_t seed) {
+  if (!h) return fail(DSACT_EINVAL, "null handle");
+  h->seed = seed;
+  return DSACT_OK;
+}
+
+int dsact_cnn_read_stats(dsact_cnn_handle* h, int64_t global_batch, float* host_out, void* stream) {
+  if (!h || !h->bound) return fail(DSACT_ESTATE, "not bound");
+  if (!host_out || global_batch < 1) return fail(DSACT_EINVAL, "bad argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  finalize_stats_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(h->buf.state, (float)(1.0 / (double)global_batch),
+                                                            (float)(1.0 / ((double)global_batch * h->cfg.act_dim)));
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpyAsync(host_out, h->buf.state + ST_STATS, DSACT_NUM_STATS * sizeof(float), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  return DSACT_OK;
+}
+
+int dsact_cnn_replay_bind(dsact_cnn_handle* h, const dsact_replay* rb) {
+  if (!h || !rb) return fail(DSACT_EINVAL, "null argument");
+  if (!rb->obs || !rb->obs2 || !rb->act || !rb->rew || !rb->done || !rb->logp || rb->capacity < 1) return fail(DSACT_EINVAL, "bad replay buffers");
+  h->rb = *rb;
+  h->rb_bound = true;
+  h->dev_rb_size = -1;
+  return DSACT_OK;
+}
+
+int dsact_cnn_replay_add(dsact_cnn_handle* h, const float* obs, const float* obs2, const float* act, const float* rew,
+                         const float* done, const float* logp, int64_t n, int64_t ptr, void* stream) {
+  if (!h || !h->rb_bound) return fail(DSACT_ESTATE, "replay buffer not bound");
+  if (n < 0 || n > h->rb.capacity || ptr < 0 || ptr >= h->rb.capacity) return fail(DSACT_EINVAL, "bad n/ptr");
+  if (n == 0) return DSACT_OK;
+  if (!obs || !obs2 || !act || !rew || !done || !logp) return fail(DSACT_EINVAL, "null staging pointer");
+  CUDA_TRY(cudaSetDevice(h->device));
+  const int64_t first = (ptr + n <= h->rb.capacity) ? n : h->rb.capacity - ptr;
+  const int64_t O = (int64_t)h->cfg.channels * h->cfg.height * h->cfg.width, A = h->cfg.act_dim;
+  struct { float* dst; const float* src; int64_t w; } cols[6] = {
+      {h->rb.obs, obs, O}, {h->rb.obs2, obs2, O}, {h->rb.act, act, A}, {h->rb.rew, rew, 1}, {h->rb.done, done, 1}, {h->rb.logp, logp, 1}};
+  for (auto& c : cols) {
+    CUDA_TRY(cudaMemcpyAsync(c.dst + ptr * c.w, c.src, first * c.w * sizeof(float), cudaMemcpyDefault, (cudaStream_t)stream));
+    if (first < n)
+      CUDA_TRY(cudaMemcpyAsync(c.dst, c.src + first * c.w, (n - first) * c.w * sizeof(float), cudaMemcpyDefault, (cudaStream_t)stream));
+  }
+  return DSACT_OK;
+}
+
+int dsact_cnn_replay_sample(dsact_cnn_handle* h, int32_t batch, int64_t size, const int64_t* idx, dsact_batch* out, void* stream) {
+  if (!h || !h->bound || !h->rb_bound) return fail(DSACT_ESTATE, "not bound");
+  if (batch < 1 || batch > h->cfg.max_batch) return fail(DSACT_EINVAL, "batch outside [1, max_batch]");
+  if (size < 1 || size > h->rb.capacity) return fail(DSACT_EINVAL, "size %lld outside [1, capacity]", (long long)size);
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  if (h->dev_rb_size != size) { set_rb_size_kernel<<<1, 32, 0, s>>>(h->buf.state, size); CUDA_TRY(cudaGetLastError()); h->dev_rb_size = size; }
+  float* W = h->Wp();
+  const int O = h->cfg.channels * h->cfg.height * h->cfg.width, A = h->cfg.act_dim;
+  Ctx c{s, 0, cudaSuccess};
+  c.pdl = false;
+  int64_t* draw = idx ? nullptr : reinterpret_cast<int64_t*>(W + h->r_idx);
+  int blocks = (batch + 7) / 8; if (blocks > 8 * h->num_sms) blocks = 8 * h->num_sms;
+  const ImgOut none{nullptr, 0, 1, 0};
+  launch_k(gather_kernel, blocks, 256, 0, c, (const float*)h->rb.obs, (const float*)h->rb.obs2, (const float*)h->rb.act, (const float*)h->rb.rew,
+           (const float*)h->rb.done, (const float*)h->rb.logp, idx, W + h->r_obs, W + h->r_obs2, W + h->r_act, W + h->r_rew, W + h->r_done,
+           W + h->r_logp, (int)batch, O, A, none, none, none, draw, (unsigned long long)h->seed, (const float*)h->buf.state, 1);
+  c.done();
+  if (!idx) { launch_k(rng_advance_kernel, 1, 32, 0, c, h->buf.state); c.done(); }
+  if (c.err != cudaSuccess) return fail(DSACT_ECUDA, "kernel launch failed: %s", cudaGetErrorString(c.err));
+  h->launches += c.launches;
+  if (out) {
+    out->obs = W + h->r_obs; out->act = W + h->r_act; out->rew = W + h->r_rew; out->obs2 = W + h->r_obs2; out->done = W + h->r_done;
+    out->logp = W + h->r_logp; out->batch = batch;
+  }
+  return DSACT_OK;
+}
+
+int dsact_cnn_step(dsact_cnn_handle* h, const dsact_batch* batch, const dsact_noise* noise, int64_t iteration, void* stream) {
+  if (!h || !h->bound) return fail(DSACT_ESTATE, "dsact_cnn_bind has not been called");
+  if (!batch || !batch->obs || !batch->act || !batch->rew || !batch->obs2 || !batch->done) return fail(DSACT_EINVAL, "null batch pointer");
+  if (batch->batch < 1 || batch->batch > h->cfg.max_batch) return fail(DSACT_EINVAL, "batch %d outside [1, max_batch=%d]", batch->batch, h->cfg.max_batch);
+  int rc = check_noise(noise);
+  if (rc) return rc;
+  if (iteration < 0 || iteration > 0x7fffffff) return fail(DSACT_EINVAL, "iteration out of range");
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  if (h->dev_iter != iteration) { set_iter_kernel<<<1, 32, 0, s>>>(h->buf.state, (int)iteration); CUDA_TRY(cudaGetLastError()); }
+  const dsact_cnn_config& cf = h->cfg;
+  const CnnGeom &q = h->q, &pi = h->pi;
+  const int B = batch->batch, A = cf.act_dim;
+  float* W = h->Wp();
+  float* P = h->buf.params; float* T = h->buf.targets; float* G = h->buf.grads;
+  float* Pq[2] = {P, P + q.n}; float* Ppi = P + 2 * q.n;
+  float* Tq[2] = {T, T + q.n}; float* Tpi = T + 2 * q.n;
+  float* Gq[2] = {G, G + q.n}; float* Gpi = G + 2 * q.n;
+  Ctx c{s, 0, cudaSuccess};
+  c.pdl = false;
+  const long long n_all = 2 * q.n + pi.n + 1;
+  {
+    int blocks = (int)((n_all / 4 + 255) / 256); if (blocks > 2 * h->num_sms) blocks = 2 * h->num_sms; if (blocks < 1) blocks = 1;
+    launch_k(begin_step_kernel, blocks, 256, 0, c, h->buf.state, G, n_all); c.done();
+  }
+  const float *eps1, *eps2, *z3, *z4;
+  if (noise) { eps1 = noise->eps1; eps2 = noise->eps2; z3 = noise->z3; z4 = noise->z4; }
+  else {
+    const int total = (B * A + 1) / 2 * 2 + (B + 1) / 2 * 2;
+    int blocks = (total / 2 + 255) / 256; if (blocks < 1) blocks = 1;
+    launch_k(noise_kernel, blocks, 256, 0, c, W + h->eps1, W + h->eps2, W + h->z3, W + h->z4, B, A, h->seed, (const float*)h->buf.state); c.done();
+    eps1 = W + h->eps1; eps2 = W + h->eps2; z3 = W + h->z3; z4 = W + h->z4;
+  }
+
+  // ---- encoders: pi(s), pi'(s'), Q_k features of s, Q'_k features of s'
+  cnn_conv_forward(h, pi, Ppi, batch->obs, h->convP, B, c);
+  cnn_conv_forward(h, pi, Tpi, batch->obs2, h->convT, B, c);
+  for (int k = 0; k < 2; ++k) {
+    cnn_conv_forward(h, q, Pq[k], batch->obs, h->convQ[k], B, c);
+    cnn_conv_forward(h, q, Tq[k], batch->obs2, h->convQ[2 + k], B, c);
+  }
+  const float* featP = W + h->convP[pi.nconv];
+  const float* featT = W + h->convT[pi.nconv];
+  const float* featQ[4] = {W + h->convQ[0][q.nconv], W + h->convQ[1][q.nconv], W + h->convQ[2][q.nconv], W + h->convQ[3][q.nconv]};
+
+  // ---- policy heads: logits = (mean | log_std), the layout sample_kernel reads (networks/cnn.py:233-240)
+  {
+    std::vector<CnnHeadFwd> v;
+    for (int hd = 0; hd < 2; ++hd) {
+      v.push_back({Ppi + pi.head_off[hd], featP, pi.F, nullptr, 0, &h->hb[hd], true, W + h->logitsP + hd * A, 2 * A});
+      v.push_back({Tpi + pi.head_off[hd], featT, pi.F, nullptr, 0, &h->hb[2 + hd], false, W + h->logitsT + hd * A, 2 * A});
+    }
+    cnn_heads_forward(h, pi.head, v, B, c);
+  }
+  // ---- critics on (s, a): out = (mean, raw std) packed [B,2] (networks/cnn.py:454-461; softplus is applied by the loss kernels)
+  {
+    std::vector<CnnHeadFwd> v;
+    for (int k = 0; k < 2; ++k)
+      for (int hd = 0; hd < 2; ++hd)
+        v.push_back({Pq[k] + q.head_off[hd], featQ[k], q.F, batch->act, A, &h->hb[4 + 2 * k + hd], true, W + h->outQ[k] + hd, 2});
+    cnn_heads_forward(h, q.head, v, B, c);
+  }
+  {
+    SampleArgs a;
+    a.logits[0] = W + h->logitsP; a.logits[1] = W + h->logitsT;
+    a.eps[0] = eps1; a.eps[1] = eps2;
+    a.act[0] = W + h->new_act; a.act[1] = W + h->act2;
+    a.logp[0] = W + h->logp_new; a.logp[1] = W + h->logp2;
+    a.hi = h->buf.act_high; a.lo = h->buf.act_low; a.state = h->buf.state;
+    a.B = B; a.A = A; a.min_log_std = (float)cf.min_log_std; a.max_log_std = (float)cf.max_log_std;
+    a.img[0] = ImgOut{nullptr, 0, 1, 0}; a.img[1] = ImgOut{nullptr, 0, 1, 0};
+    a.out_q[0] = W + h->outQ[0]; a.out_q[1] = W + h->outQ[1];
+    a.advance_rng = noise ? 0 : 1;
+    int blocks = (B + 7) / 8; if (blocks > 4 * h->num_sms) blocks = 4 * h->num_sms;
+    launch_k(sample_kernel, dim3(blocks, 2), 256, 0, c, a); c.done();
+  }
+  // ---- targets on (s', a') and the mean heads of the critics on (s, a~)
+  {
+    std::vector<CnnHeadFwd> v;
+    for (int k = 0; k < 2; ++k)
+      for (int hd = 0; hd < 2; ++hd)
+        v.push_back({Tq[k] + q.head_off[hd], featQ[2 + k], q.F, W + h->act2, A, &h->hb[8 + 2 * k + hd], false, W + h->outQ[2 + k] + hd, 2});
+    for (int k = 0; k < 2; ++k)
+      v.push_back({Pq[k] + q.head_off[0], featQ[k], q.F, W + h->new_act, A, &h->hb[12 + k], true, W + h->outQ[4 + k], 2});
+    cnn_heads_forward(h, q.head, v, B, c);
+  }
+
+  // ---- losses and head-output gradients
+  const float invB = (float)(1.0 / (double)B);
+  StepScalars sc;
+  sc.tau_b = (float)cf.tau_b; sc.alpha_fixed = (float)cf.alpha_fixed; sc.inv_global_batch = invB;
+  sc.auto_alpha = cf.auto_alpha; sc.log_alpha = P + 2 * q.n + pi.n;
+  {
+    LossArgs a;
+    a.sc = sc;
+    a.rew = batch->rew; a.done = batch->done; a.z3 = z3; a.z4 = z4;
+    a.logp2 = W + h->logp2; a.logp_new = W + h->logp_new;
+    for (int k = 0; k < 2; ++k) {
+      a.out_q[k] = W + h->outQ[k]; a.out_qt[k] = W + h->outQ[2 + k]; a.out_qa[k] = W + h->outQ[4 + k];
+      a.d_out_q[k] = W + h->dOut[k]; a.d_out_qa[k] = W + h->dOut[4 + k];
+      a.gbias_q[k] = Gq[k] + q.head_off[0] + q.head.b[q.head.L];          // output bias of the mean head
+      a.gbias_q_raw[k] = Gq[k] + q.head_off[1] + q.head.b[q.head.L];      // ... and of the log_std head
+      a.img_q[k] = ImgOut{nullptr, 0, 1, 0}; a.img_qa[k] = ImgOut{nullptr, 0, 1, 0};
+    }
+    a.state = h->buf.state; a.B = B; a.gamma = (float)cf.gamma; a.inv_global_batch = invB;
+    int blocks = (B + 63) / 64; if (blocks > 4 * h->num_sms) blocks = 4 * h->num_sms;
+    launch_k(loss_kernel, blocks, 64, 0, c, a); c.done();
+  }
+  auto zero = [&](float* p, long long n) {
+    int blocks = (int)((n + 255) / 256); if (blocks > 4 * h->num_sms) blocks = 4 * h->num_sms; if (blocks < 1) blocks = 1;
+    launch_k(zero_kernel, blocks, 256, 0, c, p, n); c.done();
+  };
+  zero(W + h->dfeat[0], (long long)B * pi.F);
+  zero(W + h->dfeat[1], (long long)B * q.F);
+  zero(W + h->dfeat[2], (long long)B * q.F);
+  zero(W + h->dfa[0], (long long)B * (q.F + A));
+  zero(W + h->dfa[1], (long long)B * (q.F + A));
+  // ---- critic backward through both heads (feature gradient accumulated over the heads), actor path through the mean head
+  {
+    std::vector<CnnHeadBwd> v;
+    for (int k = 0; k < 2; ++k)
+      for (int hd = 0; hd < 2; ++hd)   // d(feature|act): only the feature part is used (replayed actions carry no gradient)
+        v.push_back({Pq[k] + q.head_off[hd], Gq[k] + q.head_off[hd], featQ[k], q.F, batch->act, A, &h->hb[4 + 2 * k + hd],
+                     W + h->dOut[k] + hd, 2, nullptr});
+    for (int k = 0; k < 2; ++k)
+      v.push_back({Pq[k] + q.head_off[0], nullptr, featQ[k], q.F, W + h->new_act, A, &h->hb[12 + k], W + h->dOut[4 + k], 2, W + h->dfa[k]});
+    cnn_heads_backward(h, q.head, v, B, c);
+  }
+  // feature gradients of the critics: the layer-0 input gradient of both heads, feature columns only.  The generic
+  // backward above skipped it for the critic passes (din = null): do it here with the feature-width problem
+  for (int k = 0; k < 2; ++k) {
+    GemmGroup gd;
+    gd.n = 0;
+    for (int hd = 0; hd < 2; ++hd) {
+      GemmProb p = prob_zero();
+      const Net& net = q.head;
+      p.A[0] = W + h->hb[4 + 2 * k + hd].dz[0]; p.lda[0] = net.s[1]; p.K[0] = net.s[1];
+      p.B[0] = Pq[k] + q.head_off[hd] + net.w[0]; p.ldb[0] = net.s[0];
+      p.M = B; p.N = q.F; p.C = W + h->dfeat[1 + k]; p.ldc = q.F; p.epi = EPI_ATOMIC;
+      gd.p[gd.n++] = p;
+    }
+    launch_simt(h->num_sms, gd, V_DGRAD, c); c.done();
+  }
+  // dL/da~ through critic k = the action columns of dfa[k]: compact them for policy_grad_kernel
+  for (int k = 0; k < 2; ++k) {
+    CUDA_TRY(cudaMemcpy2DAsync(W + h->dAct[k], sizeof(float) * A, W + h->dfa[k] + q.F, sizeof(float) * (q.F + A), sizeof(float) * A, B,
+                               cudaMemcpyDeviceToDevice, s));
+  }
+  {
+    PolicyGradArgs a;
+    a.logits = W + h->logitsP; a.eps = eps1; a.d_act1 = W + h->dAct[0]; a.d_act2 = W + h->dAct[1];
+    a.hi = h->buf.act_high; a.lo = h->buf.act_low;
+    a.d_logits = W + h->dlogits; a.state = h->buf.state;
+    a.gbias = Gpi + pi.head_off[0] + pi.head.b[pi.head.L];        // output bias of the mean head [A]
+    a.gbias_ls = Gpi + pi.head_off[1] + pi.head.b[pi.head.L];     // ... of the log_std head [A]
+    a.B = B; a.A = A; a.min_log_std = (float)cf.min_log_std; a.max_log_std = (float)cf.max_log_std;
+    a.inv_global_batch = invB;
+    a.img = ImgOut{nullptr, 0, 1, 0};
+    a.sc = sc;
+    int blocks = (B + 7) / 8; if (blocks > 8 * h->num_sms) blocks = 8 * h->num_sms; if (blocks < 1) blocks = 1;
+    launch_k(policy_grad_kernel, blocks, 256, sizeof(float) * 2 * A, c, a); c.done();
+  }
+  {
+    std::vector<CnnHeadBwd> v;
+    for (int hd = 0; hd < 2; ++hd)
+      v.push_back({Ppi + pi.head_off[hd], Gpi + pi.head_off[hd], featP, pi.F, nullptr, 0, &h->hb[hd], W + h->dlogits + hd * A, 2 * A,
+                   W + h->dfeat[0]});
+    cnn_heads_backward(h, pi.head, v, B, c);
+  }
+  // ---- encoders backward
+  cnn_conv_backward(h, pi, Ppi, Gpi, batch->obs, h->convP, W + h->dfeat[0], B, c);
+  for (int k = 0; k < 2; ++k) cnn_conv_backward(h, q, Pq[k], Gq[k], batch->obs, h->convQ[k], W + h->dfeat[1 + k], B, c);
+
+  // ---- end of backward bookkeeping + Adam / Polyak
+  AdamHyper hy{cf.lr_q, cf.lr_pi, cf.lr_alpha, cf.adam_beta1, cf.adam_beta2};
+  launch_k(phase2_tail_kernel, 1, 32, 0, c, G + 2 * q.n + pi.n, h->buf.state, sc, -(float)cf.act_dim, B, hy, 1); c.done();
+  {
+    ApplyArgs a;
+    memset(&a, 0, sizeof(a));
+    a.params = P; a.targets = T; a.grads = G; a.m = h->buf.adam_m; a.v = h->buf.adam_v; a.state = h->buf.state;
+    a.n_q2 = 2 * q.n; a.n_all = n_all;
+    a.delay_update = cf.delay_update; a.auto_alpha = cf.auto_alpha;
+    a.hy = hy; a.scalars_ready = 1;
+    a.eps = (float)cf.adam_eps; a.tau = (float)cf.tau;
+    a.omb1 = (float)(1.0 - cf.adam_beta1); a.b2f = (float)cf.adam_beta2; a.omb2 = (float)(1.0 - cf.adam_beta2);
+    int blocks = (int)(((n_all + 3) / 4 + 255) / 256); if (blocks > 8 * h->num_sms) blocks = 8 * h->num_sms;
+    launch_k(apply_kernel<0>, blocks, 256, 0, c, a); c.done();
+  }
+  if (c.err != cudaSuccess) return fail(DSACT_ECUDA, "kernel launch failed: %s", cudaGetErrorString(c.err));
+  h->launches += c.launches;
+  h->dev_iter = iteration + 1;
+  return DSACT_OK;
+}
+
+}  // extern "C"

@@ -7,11 +7,19 @@
 //   [0, 64)                       arrival flags (uint32 epochs): flag[kind * 16 + source_rank]
 //   [64, 64 + 2*2*R*32)           small payloads: small[kind][parity][source_rank][32]
 //   [DP_GRADS_OFF, + n_params)    this rank's local gradient sum of the running step
+//   [DP_GRADS_OFF + n_pad, + n_params)  the global gradient sum ("reduced" block; two-shot exchange only, see below)
 // kind 0 = after the forward passes (2 std sums, SUM), kind 1 = before Adam (16 logged sums SUM + 2 minima MIN; it is
 // also the "local gradients are complete" barrier).  Every rank pushes its payload into every peer's buffer, raises
 // its flag there (release, system scope) and polls only its own memory.  Reductions run in rank order on every rank,
 // so the replicas stay bit-identical.  Reuse is safe without further barriers: a rank overwrites its gradient block
 // in phase 2 of step t+1, i.e. after the kind-0 barrier of t+1, which every peer reaches only after its apply of t.
+//
+// Gradient exchange, two variants.  ONE-SHOT (world <= 2): apply_kernel reads every rank's block through NVLink and sums
+// in rank order — (N-1) x n floats cross the links per rank.  TWO-SHOT (world >= 3, dp_reduce_scatter_kernel): rank r
+// sums slice r of every rank's block in rank order (reads (N-1)/N x n), writes the sum into slice r of EVERY rank's
+// reduced block (writes (N-1)/N x n), raises its kind-2 flag everywhere; apply_kernel waits for all kind-2 flags and then
+// reads only local memory.  At N = 8 that is 2 x 2.46 MB per rank instead of 19.7 MB.  Sums run in rank order on the
+// one rank that owns the slice, so the replicas still hold bit-identical gradients.
 #pragma once
 #include <stdint.h>
 
@@ -117,6 +125,56 @@ __global__ void dp_grad_fold_kernel(float* __restrict__ out, const float* __rest
     if (tail.enabled && i == n - 1) s = tail_grad_log_alpha(state, tail);
     out[i] = s;
   }
+}
+
+// Two-shot exchange, first half + broadcast: this rank owns slice [lo, hi) (in float4 groups).  Launched after the
+// kind-1 exchange (every rank's block is complete).  The block that finishes last raises this rank's kind-2 flag at every
+// peer (release, system scope) after the slice has been written everywhere.
+struct DpSlice {
+  long long g_lo, g_hi;      // float4 groups of this rank's slice
+  long long red_off;         // floats from a rank's buffer base to its reduced block
+  int* ticket;               // zero-initialised int in this rank's buffer header
+};
+__global__ void __launch_bounds__(256) dp_reduce_scatter_kernel(const DpComm c, const DpSlice sl, const float* __restrict__ state) {
+  pdl_sync();
+  const uint32_t e = (uint32_t)reinterpret_cast<const int*>(state)[ST_DP_EPOCH];
+  for (long long gi = sl.g_lo + blockIdx.x * (long long)blockDim.x + threadIdx.x; gi < sl.g_hi; gi += (long long)gridDim.x * blockDim.x) {
+    float4 acc = ld_sys_f4(c.peer[0] + DP_GRADS_OFF + 4 * gi);
+    for (int r0 = 1; r0 < c.world; r0 += 4) {   // up to four peers' loads in flight, summed in rank order
+      float4 p[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+        if (r0 + r < c.world) p[r] = ld_sys_f4(c.peer[r0 + r] + DP_GRADS_OFF + 4 * gi);
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+        if (r0 + r < c.world) { acc.x += p[r].x; acc.y += p[r].y; acc.z += p[r].z; acc.w += p[r].w; }
+    }
+    for (int r = 0; r < c.world; ++r)
+      asm volatile("st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(c.peer[r] + sl.red_off + 4 * gi), "f"(acc.x), "f"(acc.y),
+                   "f"(acc.z), "f"(acc.w) : "memory");
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (atomicAdd(sl.ticket, 1) == (int)gridDim.x - 1) {
+      *sl.ticket = 0;
+      __threadfence_system();
+      for (int r = 0; r < c.world; ++r) st_release_sys(reinterpret_cast<uint32_t*>(c.peer[r]) + 2 * 16 + c.rank, e);
+    }
+  }
+}
+
+// apply_kernel's side of the two-shot exchange: one thread per block waits until every rank's kind-2 flag of this epoch
+// has arrived in this rank's own memory (the reduced block is then complete).  Returns false on timeout.
+__device__ __forceinline__ bool dp_wait_reduced(const float* own_buf, int world, uint32_t epoch, unsigned long long timeout_ns) {
+  const uint32_t* flags = reinterpret_cast<const uint32_t*>(own_buf) + 2 * 16;
+  const unsigned long long t0 = dp_time_ns();
+  for (int r = 0; r < world; ++r)
+    while ((int32_t)(ld_acquire_sys(flags + r) - epoch) < 0) {
+      if (dp_time_ns() - t0 > timeout_ns) return false;
+      __nanosleep(32);
+    }
+  return true;
 }
 
 }  // namespace dsact

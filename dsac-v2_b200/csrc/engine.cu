@@ -118,6 +118,7 @@ struct Arena {
       // batch split of the weight-gradient GEMMs: at most 4 slabs of >= 256 rows (about one wave of CTAs at B = 4096;
       // 8 slabs of 512 rows measured 5 % slower end to end: twice the partial tiles to write and to fold in apply)
       nslabs = (int)(B / 256); if (nslabs > 4) nslabs = 4; if (nslabs < 1) nslabs = 1;
+      if (getenv("DSACT_WG_SLABS")) { const int v = atoi(getenv("DSACT_WG_SLABS")); if (v >= 1 && v <= 16 && v * 128 <= B) nslabs = v; }   // tuning aid
       slab_stride = (2 * q.n + pi.n + 1 + 3) / 4 * 4;
       slabs = take((int64_t)nslabs * slab_stride);
     }
@@ -180,11 +181,6 @@ struct dsact_handle {
     return cfg.act_dim <= 256;
   }
   int passes() const { return cfg.gemm_mode == DSACT_GEMM_BF16X3 ? 3 : 1; }
-  // streamed variant of the chain kernel (chain_tc.cuh): the default; DSACT_CHAIN_STREAM=0 selects the serial one
-  bool chain_stream() const {
-    static const bool off = getenv("DSACT_CHAIN_STREAM") && getenv("DSACT_CHAIN_STREAM")[0] == '0';
-    return !off;
-  }
   float* W() const { return reinterpret_cast<float*>(buf.workspace); }
   Img img(const ImgSlot& s, int rows) const {  // image handle with the live row count
     Img i;
@@ -268,13 +264,13 @@ static void launch_variant(const GemmGroup& g, int variant, int grid, Ctx& c) {
   else launch_k(gemm_kernel<BM, BN, false, false>, grid, 256, 0, c, g);
 }
 
-static void launch_simt(const dsact_handle* h, GemmGroup& g, int variant, Ctx& c) {
+static void launch_simt(int num_sms, GemmGroup& g, int variant, Ctx& c) {
   auto count = [&](int T) {
     int total = 0;
     for (int i = 0; i < g.n; ++i) total += ((g.p[i].M + T - 1) / T) * ((g.p[i].N + T - 1) / T);
     return total;
   };
-  const bool big = variant != V_WGRAD && count(128) >= h->num_sms;
+  const bool big = variant != V_WGRAD && count(128) >= num_sms;
   const int T = big ? 128 : 64;
   const int base = count(T);
   int grid = 0;
@@ -285,7 +281,7 @@ static void launch_simt(const dsact_handle* h, GemmGroup& g, int variant, Ctx& c
     p.ksplit = 1;
     if (variant == V_WGRAD) {  // reduction over the batch: split it until ~2 CTAs per SM, >= 4 k-tiles each
       const int nt = (p.K[0] + KT - 1) / KT;
-      int want = (2 * h->num_sms + base - 1) / base;
+      int want = (2 * num_sms + base - 1) / base;
       int maxs = nt / 4 > 0 ? nt / 4 : 1;
       p.ksplit = want < maxs ? want : maxs;
       if (p.ksplit < 1) p.ksplit = 1;
@@ -315,6 +311,7 @@ static void launch_tc(dsact_handle* h, Group& G, int variant, Ctx& c, int max_ct
     int ctas = 0;
     for (int i = 0; i < G.n; ++i) ctas += ((G.prob(i).M + TC_BM - 1) / TC_BM) * ((G.prob(i).N + 127) / 128) * (G.wg_slab ? G.wg_nslabs : h->ar.nslabs);
     if (ctas * 2 <= h->num_sms) wg_bn = 64;
+    if (getenv("DSACT_WG_BN")) { const int v = atoi(getenv("DSACT_WG_BN")); if (v == 64 || v == 128 || v == 256) wg_bn = v; }   // tuning aid
   }
   for (int i = 0; i < G.n; ++i) {
     const GemmProb& s = G.prob(i);
@@ -418,13 +415,13 @@ static void launch_group(dsact_handle* h, Group& G, int variant, Ctx& c, int max
     c.done(CLS_GEMM_FWD + variant, flops);
   } else {
     G.g.n = G.n < MAXG ? G.n : MAXG;
-    launch_simt(h, G.g, variant, c);
+    launch_simt(h->num_sms, G.g, variant, c);
     c.done(CLS_GEMM_FWD + variant, flops);
     if (G.n > MAXG) {  // second launch for the overflow
       GemmGroup g2;
       g2.n = G.n - MAXG;
       for (int i = 0; i < g2.n; ++i) g2.p[i] = G.more[i];
-      launch_simt(h, g2, variant, c);
+      launch_simt(h->num_sms, g2, variant, c);
       c.done(CLS_GEMM_FWD + variant, 0.0);
     }
   }
@@ -560,8 +557,8 @@ struct ChainBuild {
   ChainGroup g;
   int grid = 0, stage_b = 16 * 128;
   double flops = 0.0;
-  bool ok = true, stream = true;
-  explicit ChainBuild(int passes, bool stream_ = true) : stream(stream_) { memset(&g, 0, sizeof(g)); g.passes = passes; }
+  bool ok = true;
+  explicit ChainBuild(int passes) { memset(&g, 0, sizeof(g)); g.passes = passes; }
   ChainPass& begin(const Img& a0, const Img& a1, int M) {
     ChainPass& P = g.p[g.n++];
     P.n_layers = 0; P.M = M; P.tile_start = grid;
@@ -594,19 +591,12 @@ static void launch_chain(dsact_handle* h, ChainBuild& cb, int cls, Ctx& c) {
   const int stages = planes == 2 ? 2 : 3;
   const int smem = chain_smem_bytes(stages, planes, cb.stage_b);
   if (!h->chain_attr_done) {
-    cudaFuncSetAttribute(tc_chain_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    cudaFuncSetAttribute(tc_chain_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    cudaFuncSetAttribute(tc_chain_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    cudaFuncSetAttribute(tc_chain_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(tc_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(tc_chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     h->chain_attr_done = true;
   }
-  if (planes == 2) {
-    if (cb.stream) launch_k(tc_chain_kernel<true, true>, cb.grid, TC_THREADS, smem, c, cb.g, stages, cb.stage_b);
-    else launch_k(tc_chain_kernel<true, false>, cb.grid, TC_THREADS, smem, c, cb.g, stages, cb.stage_b);
-  } else {
-    if (cb.stream) launch_k(tc_chain_kernel<false, true>, cb.grid, TC_THREADS, smem, c, cb.g, stages, cb.stage_b);
-    else launch_k(tc_chain_kernel<false, false>, cb.grid, TC_THREADS, smem, c, cb.g, stages, cb.stage_b);
-  }
+  if (planes == 2) launch_k(tc_chain_kernel<true>, cb.grid, TC_THREADS, smem, c, cb.g, stages, cb.stage_b);
+  else launch_k(tc_chain_kernel<false>, cb.grid, TC_THREADS, smem, c, cb.g, stages, cb.stage_b);
   c.done(cls, cb.flops);
   c.check();
   if (debug && cb.g.dbg) {
@@ -631,12 +621,15 @@ static void launch_chain(dsact_handle* h, ChainBuild& cb, int cls, Ctx& c) {
         fprintf(stderr, "    L1 chunk0 cycles: ld %lld math %lld split %lld stage %lld st+arrive %lld | layer (4 chunks) %lld\n",
                 (long long)(d[33] - d[32]), (long long)(d[34] - d[33]), (long long)(d[35] - d[34]), (long long)(d[36] - d[35]),
                 (long long)(d[37] - d[36]), (long long)(d[38] - d[32]));
+      if (d[39] && d[41])   // inside "stage": wait for the previous stores' reads | STS | proxy fence | TMA store issue
+        fprintf(stderr, "    L1 chunk0 stage cycles: wait_read %lld sts %lld fence %lld tma-issue %lld\n", (long long)(d[39] - d[35]),
+                (long long)(d[40] - d[39]), (long long)(d[41] - d[40]), (long long)(d[36] - d[41]));
     }
   }
 }
 
 // forward chain of one pass: out = head(act(...act(in W_0^T + b_0)...))
-static void chain_fwd_pass(ChainBuild& cb, const dsact_handle* h, const Net& net, const float* Wbase, const ImgSlot* wslots,
+static ChainPass& chain_fwd_pass(ChainBuild& cb, const dsact_handle* h, const Net& net, const float* Wbase, const ImgSlot* wslots,
                            const Img& in0, int k0, const Img& in1, int k1, int kB1, int B, int act,
                            const int64_t* zout_off, const ImgSlot* himg, float* out) {
   ChainPass& P = cb.begin(in0, in1, B);
@@ -658,10 +651,11 @@ static void chain_fwd_pass(ChainBuild& cb, const dsact_handle* h, const Net& net
       }
     }
   }
+  return P;
 }
 
 // dgrad chain of one pass: dz_{j-1} = (dz_j W_j) (.) act'(z_{j-1}) for j = L..1 (+ dAct = dz_0 W_0[:, act columns])
-static void chain_dgrad_pass(ChainBuild& cb, const dsact_handle* h, const Net& net, const ImgSlot* wslots, const Img& dout,
+static ChainPass& chain_dgrad_pass(ChainBuild& cb, const dsact_handle* h, const Net& net, const ImgSlot* wslots, const Img& dout,
                              int B, int act, const int64_t* zin_off, float* gbase /*bias grads of this net or null*/,
                              const ImgSlot* dzimg /*or null*/, float* dact_out, int act_col_img, int act_cols) {
   const Img none;
@@ -685,6 +679,7 @@ static void chain_dgrad_pass(ChainBuild& cb, const dsact_handle* h, const Net& n
     ChainLayer& L = cb.layer(P, wim, true, act_cols, net.s[1], 0, 0);
     L.epi = EPI_STORE; L.C = dact_out;
   }
+  return P;
 }
 
 // ---- enqueue: pieces of one update ---------------------------------------------
@@ -781,11 +776,34 @@ static bool fork_prologue(dsact_handle* h, const dsact_batch& bt, const dsact_no
   return true;
 }
 
+static unsigned long long dp_timeout_ns() {
+  static const unsigned long long t =
+      (unsigned long long)(getenv("DSACT_DP_TIMEOUT_MS") ? atoll(getenv("DSACT_DP_TIMEOUT_MS")) : 10000) * 1000000ull;
+  return t;
+}
+// two-shot gradient exchange (dp_peer.cuh) from 3 ranks up; DSACT_DP_TWO_SHOT=0/1 overrides
+static bool dp_two_shot(const dsact_handle* h) {
+  static const char* e = getenv("DSACT_DP_TWO_SHOT");
+  if (e && (e[0] == '0' || e[0] == '1')) return e[0] == '1';
+  return h->dp.world >= 3;
+}
+static long long dp_npad(const dsact_handle* h) { return (2 * h->q.n + h->pi.n + 1 + 3) / 4 * 4; }
+static void enqueue_dp_reduce_scatter(dsact_handle* h, Ctx& c) {
+  const long long groups = dp_npad(h) / 4, per = (groups + h->dp.world - 1) / h->dp.world;
+  DpSlice sl;
+  sl.g_lo = per * h->dp.rank;
+  sl.g_hi = sl.g_lo + per < groups ? sl.g_lo + per : groups;
+  if (sl.g_lo > groups) sl.g_lo = groups;
+  sl.red_off = DP_GRADS_OFF + dp_npad(h);
+  sl.ticket = reinterpret_cast<int*>(h->dp_buf) + 3 * 16;   // header word 48: block ticket of this kernel
+  int blocks = (int)((per + 255) / 256); if (blocks < 1) blocks = 1; if (blocks > 2 * h->num_sms) blocks = 2 * h->num_sms;
+  launch_k(dp_reduce_scatter_kernel, blocks, 256, 0, c, h->dp, sl, (const float*)h->buf.state);
+  c.done();
+}
+
 // One exchange of the peer-memory data-parallel path (dp_peer.cuh): kind 0 = critic-std sums, 1 = logged sums.
 static void enqueue_dp_exchange(dsact_handle* h, int kind, Ctx& c) {
-  static const unsigned long long timeout_ns =
-      (unsigned long long)(getenv("DSACT_DP_TIMEOUT_MS") ? atoll(getenv("DSACT_DP_TIMEOUT_MS")) : 10000) * 1000000ull;
-  launch_k(dp_exchange_kernel, 1, 32 * h->dp.world, 0, c, h->dp, h->buf.state, kind, timeout_ns);
+  launch_k(dp_exchange_kernel, 1, 32 * h->dp.world, 0, c, h->dp, h->buf.state, kind, dp_timeout_ns());
   c.done();
 }
 
@@ -824,7 +842,7 @@ static void enqueue_phase1(dsact_handle* h, const dsact_batch& bt, const dsact_n
   const bool fused = h->fused();
   const Img i_none;
   if (fused) {  // wave A as ONE launch: each CTA runs a 128-row block through every layer of its pass
-    ChainBuild cb(h->passes(), h->chain_stream());
+    ChainBuild cb(h->passes());
     chain_fwd_pass(cb, h, pi, PIb[0], ar.i_wpi[0], t_obs.im, O, i_none, 0, 0, B, cf.act_pi, ar.zP, ar.i_hP, W + ar.logitsP);
     chain_fwd_pass(cb, h, pi, PIb[1], ar.i_wpi[1], t_obs2.im, O, i_none, 0, 0, B, cf.act_pi, nullptr, nullptr, W + ar.logitsT);
     for (int k = 0; k < 2; ++k)
@@ -890,7 +908,7 @@ static void enqueue_phase1(dsact_handle* h, const dsact_batch& bt, const dsact_n
   // wave B: Q1', Q2' on (s', a') and Q1, Q2 on (s, a~)
   const Ten t_new_act = ten(W + ar.new_act, ar.i_new_act), t_act2 = ten(W + ar.act2, ar.i_act2);
   if (fused) {
-    ChainBuild cb(h->passes(), h->chain_stream());
+    ChainBuild cb(h->passes());
     for (int k = 0; k < 2; ++k)
       chain_fwd_pass(cb, h, q, Qb[2 + k], ar.i_wq[2 + k], t_obs2.im, O, t_act2.im, A, ar.kpad_q0, B, cf.act_q, nullptr, nullptr, W + ar.outQ[2 + k]);
     for (int k = 0; k < 2; ++k)
@@ -962,6 +980,7 @@ static void enqueue_phase2(dsact_handle* h, const dsact_batch& bt, int64_t globa
       a.out_q[k] = W + ar.outQ[k]; a.out_qt[k] = W + ar.outQ[2 + k]; a.out_qa[k] = W + ar.outQ[4 + k];
       a.d_out_q[k] = W + ar.dOut[k]; a.d_out_qa[k] = W + ar.dOut[4 + k];
       a.gbias_q[k] = Gq[k] + q.b[q.L];
+      a.gbias_q_raw[k] = nullptr;
     }
     a.state = h->buf.state; a.B = B; a.gamma = (float)cf.gamma; a.inv_global_batch = invB;
     for (int k = 0; k < 2; ++k) { a.img_q[k] = img_out(h, ar.i_dOut[k]); a.img_qa[k] = img_out(h, ar.i_dOut[4 + k]); }
@@ -990,7 +1009,7 @@ static void enqueue_phase2(dsact_handle* h, const dsact_batch& bt, int64_t globa
   }
   if (fused) {  // dgrad as chain launches: dz stays in tensor memory between layers
     auto chain_of = [&](int pp0, int pp1, Ctx& cx) {
-      ChainBuild cb(h->passes(), h->chain_stream());
+      ChainBuild cb(h->passes());
       for (int pp = pp0; pp < pp1; ++pp) {
         const int p = passes[pp], k = p & 1;
         chain_dgrad_pass(cb, h, q, ar.i_wq[k], h->img(ar.i_dOut[p], B), B, cf.act_q, ar.zQ[p], p < 2 ? Gq[k] : nullptr,
@@ -1047,7 +1066,7 @@ static void enqueue_phase2(dsact_handle* h, const dsact_batch& bt, int64_t globa
     PolicyGradArgs a;
     a.logits = W + ar.logitsP; a.eps = h->pending_eps1; a.d_act1 = W + ar.dAct[0]; a.d_act2 = W + ar.dAct[1];
     a.hi = h->buf.act_high; a.lo = h->buf.act_low;
-    a.d_logits = W + ar.dlogits; a.gbias = Gpi + pi.b[pi.L]; a.state = h->buf.state;
+    a.d_logits = W + ar.dlogits; a.gbias = Gpi + pi.b[pi.L]; a.gbias_ls = nullptr; a.state = h->buf.state;
     a.B = B; a.A = A; a.min_log_std = (float)cf.min_log_std; a.max_log_std = (float)cf.max_log_std;
     a.inv_global_batch = invB;
     a.img = img_out(h, ar.i_dlogits);
@@ -1059,7 +1078,7 @@ static void enqueue_phase2(dsact_handle* h, const dsact_batch& bt, int64_t globa
   // wave D: policy backward
   Group gwp;
   if (fused) {
-    ChainBuild cb(h->passes(), h->chain_stream());
+    ChainBuild cb(h->passes());
     chain_dgrad_pass(cb, h, pi, ar.i_wpi[0], h->img(ar.i_dlogits, B), B, cf.act_pi, ar.zP, Gpi, ar.i_dzP, nullptr, 0, 0);
     launch_chain(h, cb, CLS_GEMM_DGRAD, c);
   }
@@ -1113,8 +1132,13 @@ static void enqueue_apply(dsact_handle* h, Ctx& c, bool reduce_slabs = false, bo
   memset(&a.tail, 0, sizeof(a.tail));
   if (tail && tail->enabled) { a.tail = *tail; a.scalars_ready = 2; }   // folded tail: scalars precomputed by the previous apply if stamped
   a.dp_world = 0;
+  a.dp_own = nullptr; a.dp_wait_world = 0; a.dp_timeout_ns = dp_timeout_ns();
   for (int r = 0; r < 8; ++r) a.dp_grads[r] = nullptr;
-  if (dp) {
+  if (dp && dp_two_shot(h)) {   // the reduced block in this rank's own memory, once every rank's kind-2 flag is here
+    a.dp_world = 1;
+    a.dp_grads[0] = h->dp_buf + DP_GRADS_OFF + dp_npad(h);
+    a.dp_own = h->dp_buf; a.dp_wait_world = h->dp.world;
+  } else if (dp) {
     a.dp_world = h->dp.world;
     for (int r = 0; r < h->dp.world; ++r) a.dp_grads[r] = h->dp.peer[r] + DP_GRADS_OFF;
   }
@@ -1122,14 +1146,18 @@ static void enqueue_apply(dsact_handle* h, Ctx& c, bool reduce_slabs = false, bo
   a.omb1 = (float)(1.0 - cf.adam_beta1); a.b2f = (float)cf.adam_beta2; a.omb2 = (float)(1.0 - cf.adam_beta2);
   a.slabs = nullptr; a.nslabs = 0; a.slab_stride = 0;
   if (reduce_slabs && !dp && slabs_foldable(h)) { a.slabs = h->W() + h->ar.slabs; a.nslabs = h->ar.nslabs; a.slab_stride = h->ar.slab_stride; }
-  int blocks = (int)((a.n_all + 255) / 256);
+  int blocks = (int)(((a.n_all + 3) / 4 + 255) / 256);   // one 4-element group per thread
   if (blocks > 8 * h->num_sms) blocks = 8 * h->num_sms;
-  launch_k(apply_kernel, blocks, 256, 0, c, a);   // its last block also advances the step counters
+  // (its last block also advances the step counters)
+  if (a.dp_world > 0) launch_k(apply_kernel<2>, blocks, 256, 0, c, a);
+  else if (a.nslabs > 0) launch_k(apply_kernel<1>, blocks, 256, 0, c, a);
+  else launch_k(apply_kernel<0>, blocks, 256, 0, c, a);
   c.done();
   c.check();
 }
 
-static void enqueue_gather(dsact_handle* h, int B, const int64_t* idx, Ctx& c) {
+// `images_only`: the caller is a fused tcgen05 step, which reads obs / obs2 / act through their bf16 images alone
+static void enqueue_gather(dsact_handle* h, int B, const int64_t* idx, Ctx& c, bool images_only = false) {
   const Arena& ar = h->ar;
   float* W = h->W();
   // no index list: every warp of the gather draws its row's index itself (the sequence index_kernel defines) and records it
@@ -1138,7 +1166,7 @@ static void enqueue_gather(dsact_handle* h, int B, const int64_t* idx, Ctx& c) {
   launch_k(gather_kernel, blocks, 256, 0, c, h->rb.obs, h->rb.obs2, h->rb.act, h->rb.rew, h->rb.done, h->rb.logp, idx,
                                           W + ar.obs, W + ar.obs2, W + ar.act, W + ar.rew, W + ar.done, W + ar.logp, B,
                                           h->cfg.obs_dim, h->cfg.act_dim, img_out(h, ar.i_obs), img_out(h, ar.i_obs2), img_out(h, ar.i_act),
-                                          draw, (unsigned long long)h->seed, (const float*)h->buf.state);
+                                          draw, (unsigned long long)h->seed, (const float*)h->buf.state, images_only ? 0 : 1);
   c.done();
   c.check();
 }
@@ -1609,7 +1637,7 @@ int dsact_replay_step(dsact_handle* h, int32_t batch, int64_t size, const int64_
   key.idx = idx;
   rc = run(h, (cudaStream_t)stream, key, [&](Ctx& c) {
     const bool forked = fork_prologue(h, bt, np, c, true);   // weight images, noise, clears: beside the gather
-    enqueue_gather(h, batch, idx, c);
+    enqueue_gather(h, batch, idx, c, h->fused());
     if (!idx && np) { launch_k(rng_advance_kernel, 1, 32, 0, c, h->buf.state); c.done(); }
     enqueue_phase1(h, bt, np, c, true, forked);  // device noise (np == null): phase1 advances the counter after the join
     const TailArgs ta = tail_args(h, batch, batch, fold_tail_enabled());
@@ -1618,6 +1646,7 @@ int dsact_replay_step(dsact_handle* h, int32_t batch, int64_t size, const int64_
   });
   if (rc) return rc;
   h->pending = bt; h->pending_batch = batch;
+  h->arena_imaged = false;   // the arena's images (and, in the fused modes, only they) now belong to this step's gather
   h->dev_iter = iteration + 1;
   return DSACT_OK;
 }
@@ -1626,7 +1655,8 @@ int dsact_replay_step(dsact_handle* h, int32_t batch, int64_t size, const int64_
 int dsact_dp_export(dsact_handle* h, void* handle_out, int64_t* bytes_out) {
   if (!h || !handle_out) return fail(DSACT_EINVAL, "null argument");
   CUDA_TRY(cudaSetDevice(h->device));
-  const size_t bytes = sizeof(float) * (size_t)(DP_GRADS_OFF + (2 * h->q.n + h->pi.n + 1 + 3) / 4 * 4);
+  // header + this rank's gradient block + the reduced block of the two-shot exchange
+  const size_t bytes = sizeof(float) * (size_t)(DP_GRADS_OFF + 2 * ((2 * h->q.n + h->pi.n + 1 + 3) / 4 * 4));
   if (!h->dp_buf) {
     CUDA_TRY(cudaMalloc(&h->dp_buf, bytes));
     CUDA_TRY(cudaMemset(h->dp_buf, 0, bytes));
@@ -1690,6 +1720,7 @@ int dsact_dp_step(dsact_handle* h, const dsact_batch* batch, const dsact_noise* 
     const TailArgs ta = tail_args(h, global_batch, bt.batch, fold_tail_enabled());
     enqueue_phase2(h, bt, global_batch, c, REDUCE_DP, ta.enabled);
     enqueue_dp_exchange(h, 1, c);
+    if (dp_two_shot(h)) enqueue_dp_reduce_scatter(h, c);
     enqueue_apply(h, c, false, true, &ta);
   });
   if (rc) return rc;
@@ -1716,16 +1747,18 @@ int dsact_dp_replay_step(dsact_handle* h, int32_t batch, int64_t size, const int
   key.idx = idx;
   rc = run(h, (cudaStream_t)stream, key, [&](Ctx& c) {
     const bool forked = fork_prologue(h, bt, np, c, true);
-    enqueue_gather(h, batch, idx, c);
+    enqueue_gather(h, batch, idx, c, h->fused());
     if (!idx && np) { launch_k(rng_advance_kernel, 1, 32, 0, c, h->buf.state); c.done(); }
     enqueue_phase1(h, bt, np, c, true, forked, true);
     const TailArgs ta = tail_args(h, global_batch, bt.batch, fold_tail_enabled());
     enqueue_phase2(h, bt, global_batch, c, REDUCE_DP, ta.enabled);
     enqueue_dp_exchange(h, 1, c);
+    if (dp_two_shot(h)) enqueue_dp_reduce_scatter(h, c);
     enqueue_apply(h, c, false, true, &ta);
   });
   if (rc) return rc;
   h->pending = bt; h->pending_batch = batch;
+  h->arena_imaged = false;   // the arena's images (and, in the fused modes, only they) now belong to this step's gather
   h->dev_iter = iteration + 1;
   return DSACT_OK;
 }
@@ -1836,3 +1869,5 @@ int dsact_test_gemm(dsact_handle* h, int32_t variant, const float* A, int32_t ld
 }
 
 }  // extern "C"
+
+#include "cnn_engine.cuh"

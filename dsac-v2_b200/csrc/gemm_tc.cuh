@@ -475,6 +475,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
+  if (warp == 2 && lane < 3) {   // descriptor prefetch (kernel parameters: independent of the preceding kernel)
+    const CUtensorMap* m = lane == 0 ? &P.mapA[0] : (lane == 1 ? (P.kblocks[1] > 0 ? &P.mapA[1] : nullptr) : &P.mapB);
+    if (m) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();

@@ -204,7 +204,7 @@ __global__ void gather_kernel(const float* __restrict__ r_obs, const float* __re
                               const int64_t* __restrict__ idx, float* __restrict__ obs, float* __restrict__ obs2,
                               float* __restrict__ act, float* __restrict__ rew, float* __restrict__ done,
                               float* __restrict__ logp, int B, int O, int A, ImgOut i_obs, ImgOut i_obs2, ImgOut i_act,
-                              int64_t* __restrict__ draw_idx, uint64_t seed, const float* __restrict__ state) {
+                              int64_t* __restrict__ draw_idx, uint64_t seed, const float* __restrict__ state, int write_f32) {
   pdl_sync();
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
@@ -230,23 +230,38 @@ __global__ void gather_kernel(const float* __restrict__ r_obs, const float* __re
     float* dobs = obs + (size_t)row * O;
     float* dobs2 = obs2 + (size_t)row * O;
     if (v4) {
-      for (int c = lane; c < O / 4; c += 32) {
-        const float4 a = __ldg(reinterpret_cast<const float4*>(so) + c), b = __ldg(reinterpret_cast<const float4*>(so2) + c);
-        reinterpret_cast<float4*>(dobs)[c] = a;
-        reinterpret_cast<float4*>(dobs2)[c] = b;
-        img_put4(i_obs, row, 4 * c, a);
-        img_put4(i_obs2, row, 4 * c, b);
+      // three 16-byte columns of obs and of obs2 per lane and trip: six independent loads in flight per lane (the gather is
+      // bound by DRAM latency on 1.5 KB random rows, not by bandwidth)
+      for (int c0 = lane; c0 < O / 4; c0 += 96) {
+        float4 a[3], b[3];
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+          const int c = c0 + 32 * u;
+          if (c < O / 4) { a[u] = __ldg(reinterpret_cast<const float4*>(so) + c); b[u] = __ldg(reinterpret_cast<const float4*>(so2) + c); }
+        }
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+          const int c = c0 + 32 * u;
+          if (c < O / 4) {
+            if (write_f32) {   // (fused tcgen05 steps read only the images of obs / obs2 / act)
+              reinterpret_cast<float4*>(dobs)[c] = a[u];
+              reinterpret_cast<float4*>(dobs2)[c] = b[u];
+            }
+            img_put4(i_obs, row, 4 * c, a[u]);
+            img_put4(i_obs2, row, 4 * c, b[u]);
+          }
+        }
       }
     } else {
       for (int c = lane; c < O; c += 32) {
         const float a = __ldg(so + c), b = __ldg(so2 + c);
-        dobs[c] = a; dobs2[c] = b;
+        if (write_f32) { dobs[c] = a; dobs2[c] = b; }
         img_put(i_obs, row, c, a); img_put(i_obs2, row, c, b);
       }
     }
     for (int c = lane; c < A; c += 32) {
       const float a = __ldg(r_act + src * A + c);
-      act[(size_t)row * A + c] = a;
+      if (write_f32) act[(size_t)row * A + c] = a;
       img_put(i_act, row, c, a);
     }
     if (lane == 0) { rew[row] = __ldg(r_rew + src); done[row] = __ldg(r_done + src); logp[row] = __ldg(r_logp + src); }
@@ -271,6 +286,19 @@ struct SampleArgs {
                            // input of the mean_std EMA (dsac_v2.py:233-241)
   int advance_rng;         // device noise/indices were drawn with the current counter: step it (all readers are done)
 };
+// One action component of TanhGaussDistribution.rsample: the squashed, scaled action and its log-prob term.
+__device__ __forceinline__ void sample_elem(float mean, float ls, float eps, float hi, float lo, float min_ls, float max_ls,
+                                            float& act, float& lp, float& tanh_mean, float& sd_out) {
+  const float sd = expf(fminf(fmaxf(ls, min_ls), max_ls));
+  const float u = mean + sd * eps;
+  const float th = tanhf(u);
+  const float scale = 0.5f * (hi - lo), shift = 0.5f * (hi + lo);
+  act = scale * th + shift;
+  const float d = u - mean;
+  lp = -(d * d) / (2.f * sd * sd) - logf(sd) - HALF_LOG_2PI - logf(1.f + TG_EPS - th * th) - logf(scale);
+  tanh_mean = tanhf(mean);
+  sd_out = sd;
+}
 __global__ void sample_kernel(const __grid_constant__ SampleArgs a) {
   pdl_sync();
   __shared__ float red[2 * 32];
@@ -284,17 +312,13 @@ __global__ void sample_kernel(const __grid_constant__ SampleArgs a) {
   for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < a.B; row += gridDim.x * wpb) {
     float lp = 0.f;
     for (int j = lane; j < A; j += 32) {
-      const float mean = logits[(size_t)row * 2 * A + j];
-      const float ls = logits[(size_t)row * 2 * A + A + j];
-      const float sd = expf(fminf(fmaxf(ls, a.min_log_std), a.max_log_std));
-      const float u = mean + sd * eps[(size_t)row * A + j];
-      const float th = tanhf(u);
-      const float scale = 0.5f * (a.hi[j] - a.lo[j]), shift = 0.5f * (a.hi[j] + a.lo[j]);
-      a.act[which][(size_t)row * A + j] = scale * th + shift;
-      img_put(a.img[which], row, j, scale * th + shift);
-      const float d = u - mean;
-      lp += -(d * d) / (2.f * sd * sd) - logf(sd) - HALF_LOG_2PI - logf(1.f + TG_EPS - th * th) - logf(scale);
-      sums[0] += tanhf(mean);
+      float act, lpj, tm, sd;
+      sample_elem(logits[(size_t)row * 2 * A + j], logits[(size_t)row * 2 * A + A + j], eps[(size_t)row * A + j], a.hi[j], a.lo[j],
+                  a.min_log_std, a.max_log_std, act, lpj, tm, sd);
+      a.act[which][(size_t)row * A + j] = act;
+      img_put(a.img[which], row, j, act);
+      lp += lpj;
+      sums[0] += tm;
       sums[1] += sd;
     }
     lp = warp_sum(lp);
@@ -345,64 +369,86 @@ struct LossArgs {
   float* d_out_q[2];        // dL/d(mean, raw std) of Q_k(s,a)
   float* d_out_qa[2];       // dL/d(mean, raw std) of Q_k(s,a~)
   float* gbias_q[2];        // bias gradient of the critics' output layer [2] (+=)
+  float* gbias_q_raw[2];    // null: the raw-std component goes to gbias_q[k] + 1; else its own address (separate log_std head)
   float* state;
   int B;
   float gamma, inv_global_batch;
   ImgOut img_q[2], img_qa[2];
   StepScalars sc;
 };
+// Everything the loss needs of ONE sample (dsac_v2.py:218-318): gradients w.r.t. the critics' outputs on (s,a) and on
+// (s,a~), the per-sample loss terms and the logged values.  m[k] = mean_std of critic k, alpha = temperature in use.
+struct LossRow {
+  float g_mean[2], g_raw[2];   // dL/d(mean, raw std) of Q_k(s,a)
+  float g_pa[2];               // dL/d mean of Q_k(s,a~) (the raw-std component is zero)
+  float q[2], sd[2];           // Q_k(s,a) mean and softplus std
+  float loss_q, loss_pi, logp_new;
+};
+__device__ __forceinline__ LossRow loss_row(const LossArgs& a, int i, const float (&m)[2], float alpha) {
+  LossRow R;
+  const float invB = a.inv_global_batch;
+  const float q1n = a.out_qt[0][2 * i], s1n = softplus_f(a.out_qt[0][2 * i + 1]);
+  const float q2n = a.out_qt[1][2 * i], s2n = softplus_f(a.out_qt[1][2 * i + 1]);
+  const float zc3 = fminf(fmaxf(a.z3[i], -3.f), 3.f), zc4 = fminf(fmaxf(a.z4[i], -3.f), 3.f);
+  const float qn = fminf(q1n, q2n);
+  const float qn_s = q1n < q2n ? q1n + zc3 * s1n : q2n + zc4 * s2n;  // dsac_v2.py:252-253
+  const float nd = (1.f - a.done[i]) * a.gamma, lp2 = a.logp2[i], r = a.rew[i];
+  const float y = r + nd * (qn - alpha * lp2);      // dsac_v2.py:293-295
+  const float ys = r + nd * (qn_s - alpha * lp2);   // dsac_v2.py:296-298
+  R.loss_q = 0.f;
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const float q = a.out_q[k][2 * i], raw = a.out_q[k][2 * i + 1];
+    const float sd = softplus_f(raw);
+    const float b3 = 3.f * m[k];
+    const float yb = q + fminf(fmaxf(ys - q, -b3), b3);  // dsac_v2.py:299-301
+    const float w = fminf(fmaxf(m[k] * m[k] / (sd * sd + STD_BIAS), 0.1f), 10.f);  // dsac_v2.py:279-280
+    const float dq = q - y;
+    const float sterm = (sd * sd - huber_f(q - yb)) / (sd + STD_BIAS);
+    R.loss_q += w * (huber_f(dq) + sd * sterm);
+    R.g_mean[k] = w * fminf(fmaxf(dq, -HUBER_DELTA), HUBER_DELTA) * invB;
+    const float dsoft = raw > 20.f ? 1.f : 1.f / (1.f + expf(-raw));
+    R.g_raw[k] = w * sterm * invB * dsoft;
+    R.q[k] = q;
+    R.sd[k] = sd;
+  }
+  // actor: L_pi = mean(alpha*logp - min(q1pi, q2pi)), dsac_v2.py:304-310; ties split like torch.min
+  const float q1p = a.out_qa[0][2 * i], q2p = a.out_qa[1][2 * i];
+  R.logp_new = a.logp_new[i];
+  R.loss_pi = alpha * R.logp_new - fminf(q1p, q2p);
+  R.g_pa[0] = q1p < q2p ? -invB : (q1p == q2p ? -0.5f * invB : 0.f);
+  R.g_pa[1] = q2p < q1p ? -invB : (q1p == q2p ? -0.5f * invB : 0.f);
+  return R;
+}
 __global__ void loss_kernel(const __grid_constant__ LossArgs a) {
   pdl_sync();
   __shared__ float red[10 * 32];
   const float m[2] = {step_mean_std(a.state, a.sc, 0), step_mean_std(a.state, a.sc, 1)};
   const float alpha = step_alpha(a.sc);
-  const float invB = a.inv_global_batch;
   // sums: q1 q2 s1 s2 loss_pi loss_q logp | gb(q1 mean, q1 raw, q2 mean) ; q2 raw handled separately below
   float s[10] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   float gb_q2_raw = 0.f;
   float mn[2] = {__int_as_float(0x7f800000), __int_as_float(0x7f800000)};
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.B; i += gridDim.x * blockDim.x) {
-    const float q1n = a.out_qt[0][2 * i], s1n = softplus_f(a.out_qt[0][2 * i + 1]);
-    const float q2n = a.out_qt[1][2 * i], s2n = softplus_f(a.out_qt[1][2 * i + 1]);
-    const float zc3 = fminf(fmaxf(a.z3[i], -3.f), 3.f), zc4 = fminf(fmaxf(a.z4[i], -3.f), 3.f);
-    const float qn = fminf(q1n, q2n);
-    const float qn_s = q1n < q2n ? q1n + zc3 * s1n : q2n + zc4 * s2n;  // dsac_v2.py:252-253
-    const float nd = (1.f - a.done[i]) * a.gamma, lp2 = a.logp2[i], r = a.rew[i];
-    const float y = r + nd * (qn - alpha * lp2);      // dsac_v2.py:293-295
-    const float ys = r + nd * (qn_s - alpha * lp2);   // dsac_v2.py:296-298
+    const LossRow R = loss_row(a, i, m, alpha);
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
-      const float q = a.out_q[k][2 * i], raw = a.out_q[k][2 * i + 1];
-      const float sd = softplus_f(raw);
-      const float b3 = 3.f * m[k];
-      const float yb = q + fminf(fmaxf(ys - q, -b3), b3);  // dsac_v2.py:299-301
-      const float w = fminf(fmaxf(m[k] * m[k] / (sd * sd + STD_BIAS), 0.1f), 10.f);  // dsac_v2.py:279-280
-      const float dq = q - y;
-      const float sterm = (sd * sd - huber_f(q - yb)) / (sd + STD_BIAS);
-      s[ACC_LOSS_Q] += w * (huber_f(dq) + sd * sterm);
-      const float g_mean = w * fminf(fmaxf(dq, -HUBER_DELTA), HUBER_DELTA) * invB;
-      const float dsoft = raw > 20.f ? 1.f : 1.f / (1.f + expf(-raw));
-      const float g_raw = w * sterm * invB * dsoft;
-      a.d_out_q[k][2 * i] = g_mean;
-      a.d_out_q[k][2 * i + 1] = g_raw;
-      img_put(a.img_q[k], i, 0, g_mean);
-      img_put(a.img_q[k], i, 1, g_raw);
-      s[k] += q;
-      s[2 + k] += sd;
-      mn[k] = fminf(mn[k], sd);
-      if (k == 0) { s[7] += g_mean; s[8] += g_raw; } else { s[9] += g_mean; gb_q2_raw += g_raw; }
+      a.d_out_q[k][2 * i] = R.g_mean[k];
+      a.d_out_q[k][2 * i + 1] = R.g_raw[k];
+      img_put(a.img_q[k], i, 0, R.g_mean[k]);
+      img_put(a.img_q[k], i, 1, R.g_raw[k]);
+      s[k] += R.q[k];
+      s[2 + k] += R.sd[k];
+      mn[k] = fminf(mn[k], R.sd[k]);
+      if (k == 0) { s[7] += R.g_mean[k]; s[8] += R.g_raw[k]; } else { s[9] += R.g_mean[k]; gb_q2_raw += R.g_raw[k]; }
     }
-    // actor: L_pi = mean(alpha*logp - min(q1pi, q2pi)), dsac_v2.py:304-310; ties split like torch.min
-    const float q1p = a.out_qa[0][2 * i], q2p = a.out_qa[1][2 * i];
-    const float lpn = a.logp_new[i];
-    s[ACC_LOSS_PI] += alpha * lpn - fminf(q1p, q2p);
-    s[6] += lpn;
-    const float g1 = q1p < q2p ? -invB : (q1p == q2p ? -0.5f * invB : 0.f);
-    const float g2 = q2p < q1p ? -invB : (q1p == q2p ? -0.5f * invB : 0.f);
-    a.d_out_qa[0][2 * i] = g1; a.d_out_qa[0][2 * i + 1] = 0.f;
-    a.d_out_qa[1][2 * i] = g2; a.d_out_qa[1][2 * i + 1] = 0.f;
-    img_put(a.img_qa[0], i, 0, g1); img_put(a.img_qa[0], i, 1, 0.f);
-    img_put(a.img_qa[1], i, 0, g2); img_put(a.img_qa[1], i, 1, 0.f);
+    s[ACC_LOSS_Q] += R.loss_q;
+    s[ACC_LOSS_PI] += R.loss_pi;
+    s[6] += R.logp_new;
+    a.d_out_qa[0][2 * i] = R.g_pa[0]; a.d_out_qa[0][2 * i + 1] = 0.f;
+    a.d_out_qa[1][2 * i] = R.g_pa[1]; a.d_out_qa[1][2 * i + 1] = 0.f;
+    img_put(a.img_qa[0], i, 0, R.g_pa[0]); img_put(a.img_qa[0], i, 1, 0.f);
+    img_put(a.img_qa[1], i, 0, R.g_pa[1]); img_put(a.img_qa[1], i, 1, 0.f);
   }
   block_sum<10>(s, red);
   float one[1] = {gb_q2_raw};
@@ -419,8 +465,8 @@ __global__ void loss_kernel(const __grid_constant__ LossArgs a) {
     atomicAdd(acc + ACC_S1, s[2]); atomicAdd(acc + ACC_S2, s[3]);
     atomicAdd(acc + ACC_LOSS_PI, s[4]); atomicAdd(acc + ACC_LOSS_Q, s[5]);
     atomicAdd(acc + ACC_LOGP, s[6]);
-    atomicAdd(a.gbias_q[0], s[7]); atomicAdd(a.gbias_q[0] + 1, s[8]);
-    atomicAdd(a.gbias_q[1], s[9]); atomicAdd(a.gbias_q[1] + 1, one[0]);
+    atomicAdd(a.gbias_q[0], s[7]); atomicAdd(a.gbias_q_raw[0] ? a.gbias_q_raw[0] : a.gbias_q[0] + 1, s[8]);
+    atomicAdd(a.gbias_q[1], s[9]); atomicAdd(a.gbias_q_raw[1] ? a.gbias_q_raw[1] : a.gbias_q[1] + 1, one[0]);
   }
 }
 
@@ -431,13 +477,30 @@ struct PolicyGradArgs {
   const float *logits, *eps, *d_act1, *d_act2;  // d_act_k: dL/da~ through critic k  [B,A]
   const float *hi, *lo;
   float* d_logits;   // [B,2A]
-  float* gbias;      // [2A] (+=)
+  float* gbias;      // [2A] (+=), or [A] for the mean half when gbias_ls is given
+  float* gbias_ls;   // null, or [A]: bias gradient of a separate log_std head
   const float* state;
   int B, A;
   float min_log_std, max_log_std, inv_global_batch;
   ImgOut img;
   StepScalars sc;
 };
+// d(actor loss)/d(mean_j, log_std_j) of one row (chain rule through a~ = scale tanh(u) + shift and the log-prob)
+__device__ __forceinline__ void pgrad_elem(const PolicyGradArgs& a, int row, int j, float coef, float& gu, float& gls) {
+  const int A = a.A;
+  const float scale = 0.5f * (a.hi[j] - a.lo[j]);
+  const float mean = a.logits[(size_t)row * 2 * A + j];
+  const float ls = a.logits[(size_t)row * 2 * A + A + j];
+  const bool inside = ls >= a.min_log_std && ls <= a.max_log_std;
+  const float sd = expf(fminf(fmaxf(ls, a.min_log_std), a.max_log_std));
+  const float e = a.eps[(size_t)row * A + j];
+  const float th = tanhf(mean + sd * e);
+  const float om = 1.f - th * th;
+  const float da = a.d_act1[(size_t)row * A + j] + a.d_act2[(size_t)row * A + j];
+  gu = da * scale * om + coef * (2.f * th * om / (1.f + TG_EPS - th * th));
+  const float gsd = gu * e - coef / sd;
+  gls = inside ? gsd * sd : 0.f;
+}
 __global__ void policy_grad_kernel(const __grid_constant__ PolicyGradArgs a) {
   pdl_sync();
   extern __shared__ float gb[];   // [2A] block-local bias-gradient sums
@@ -447,20 +510,10 @@ __global__ void policy_grad_kernel(const __grid_constant__ PolicyGradArgs a) {
   __syncthreads();
   const float coef = step_alpha(a.sc) * a.inv_global_batch;  // dL/dlogp
   for (int j = lane; j < A; j += 32) {
-    const float scale = 0.5f * (a.hi[j] - a.lo[j]);
     float gb_mean = 0.f, gb_ls = 0.f;
     for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < a.B; row += gridDim.x * wpb) {
-      const float mean = a.logits[(size_t)row * 2 * A + j];
-      const float ls = a.logits[(size_t)row * 2 * A + A + j];
-      const bool inside = ls >= a.min_log_std && ls <= a.max_log_std;
-      const float sd = expf(fminf(fmaxf(ls, a.min_log_std), a.max_log_std));
-      const float e = a.eps[(size_t)row * A + j];
-      const float th = tanhf(mean + sd * e);
-      const float om = 1.f - th * th;
-      const float da = a.d_act1[(size_t)row * A + j] + a.d_act2[(size_t)row * A + j];
-      const float gu = da * scale * om + coef * (2.f * th * om / (1.f + TG_EPS - th * th));
-      const float gsd = gu * e - coef / sd;
-      const float gls = inside ? gsd * sd : 0.f;
+      float gu, gls;
+      pgrad_elem(a, row, j, coef, gu, gls);
       a.d_logits[(size_t)row * 2 * A + j] = gu;
       a.d_logits[(size_t)row * 2 * A + A + j] = gls;
       img_put(a.img, row, j, gu);
@@ -472,7 +525,7 @@ __global__ void policy_grad_kernel(const __grid_constant__ PolicyGradArgs a) {
     atomicAdd(&gb[A + j], gb_ls);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * A; i += blockDim.x) atomicAdd(a.gbias + i, gb[i]);
+  for (int i = threadIdx.x; i < 2 * A; i += blockDim.x) atomicAdd((a.gbias_ls && i >= A) ? a.gbias_ls + (i - A) : a.gbias + i, gb[i]);
 }
 
 // __update (dsac_v2.py:320-347): Adam on q1|q2 every step; on policy|log_alpha plus Polyak of all three
@@ -522,7 +575,13 @@ struct ApplyArgs {
   // peer-memory data parallelism (dp_peer.cuh): the global gradient is the rank-ordered sum of every rank's block
   const float* dp_grads[8];
   int dp_world;
+  // two-shot exchange (dp_peer.cuh): dp_world == 1, dp_grads[0] = this rank's reduced block; wait for `dp_wait_world`
+  // kind-2 flags in `dp_own` first
+  const float* dp_own;
+  int dp_wait_world;
+  unsigned long long dp_timeout_ns;
 };
+__device__ __forceinline__ bool dp_wait_reduced(const float* own_buf, int world, uint32_t epoch, unsigned long long timeout_ns);
 // torch.optim.Adam single-tensor step (amsgrad / weight decay off)
 __device__ __forceinline__ float adam_update(float w, float g, float& m, float& v, float step_size, float bc2_sqrt,
                                              float omb1, float b2, float omb2, float eps) {
@@ -531,7 +590,11 @@ __device__ __forceinline__ float adam_update(float w, float g, float& m, float& 
   const float denom = sqrtf(v) / bc2_sqrt + eps;
   return w - step_size * (m / denom);      // param.addcdiv_(exp_avg, denom, value=-lr/bias_correction1)
 }
-__global__ void apply_kernel(const __grid_constant__ ApplyArgs a) {
+// MODE 0: gradients as they are in `grads`; 1: + the weight-gradient split slabs; 2: rank-ordered sum of the peers' blocks.
+// Four blocks per SM (<= 64 registers): the pass is a single sweep of ~13 independent 16-byte streams per thread and is
+// bound by how many loads the SM keeps in flight (the 88-register version ran at 2 blocks per SM and 1 TB/s).
+template <int MODE>
+__global__ void __launch_bounds__(256, 4) apply_kernel(const __grid_constant__ ApplyArgs a) {
   pdl_sync();
   __shared__ float sh[6];
   const int* sti = reinterpret_cast<const int*>(a.state);
@@ -544,6 +607,10 @@ __global__ void apply_kernel(const __grid_constant__ ApplyArgs a) {
     if (threadIdx.x < 5) sh[threadIdx.x] = a.state[ST_ADAM_SC + threadIdx.x];
   } else if (threadIdx.x == 0) {
     adam_scalars(sti, a.hy, sh);
+  }
+  if (MODE == 2 && a.dp_wait_world > 0 && threadIdx.x == 32) {   // two-shot exchange: the reduced block is complete
+    if (!dp_wait_reduced(a.dp_own, a.dp_wait_world, (uint32_t)sti[ST_DP_EPOCH], a.dp_timeout_ns))
+      reinterpret_cast<int*>(a.state)[ST_DP_ERR] = 1 + a.dp_wait_world;   // (no single rank to name)
   }
   __syncthreads();
   const int64_t n_targets = a.n_all - 1;
@@ -564,29 +631,34 @@ __global__ void apply_kernel(const __grid_constant__ ApplyArgs a) {
         const float4 T4 = reinterpret_cast<const float4*>(a.targets)[gi];
         t[0] = T4.x; t[1] = T4.y; t[2] = T4.z; t[3] = T4.w;
       }
-      if (a.dp_world > 0) {
-        float4 p[8];
+      if (MODE == 2) {
+#pragma unroll 1
+        for (int r0 = 0; r0 < a.dp_world; r0 += 4) {   // four peers' loads in flight at a time, summed in rank order
+          float4 p[4];
 #pragma unroll
-        for (int r = 0; r < 8; ++r)
-          if (r < a.dp_world) {
-            asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];"
-                         : "=f"(p[r].x), "=f"(p[r].y), "=f"(p[r].z), "=f"(p[r].w) : "l"(a.dp_grads[r] + 4 * gi) : "memory");
-          }
-        g[0] = p[0].x; g[1] = p[0].y; g[2] = p[0].z; g[3] = p[0].w;
+          for (int r = 0; r < 4; ++r)
+            if (r0 + r < a.dp_world) {
+              asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];"
+                           : "=f"(p[r].x), "=f"(p[r].y), "=f"(p[r].z), "=f"(p[r].w) : "l"(a.dp_grads[r0 + r] + 4 * gi) : "memory");
+            }
 #pragma unroll
-        for (int r = 1; r < 8; ++r)
-          if (r < a.dp_world) { g[0] += p[r].x; g[1] += p[r].y; g[2] += p[r].z; g[3] += p[r].w; }
+          for (int r = 0; r < 4; ++r)
+            if (r0 + r < a.dp_world) {
+              if (r0 + r == 0) { g[0] = p[0].x; g[1] = p[0].y; g[2] = p[0].z; g[3] = p[0].w; }
+              else { g[0] += p[r].x; g[1] += p[r].y; g[2] += p[r].z; g[3] += p[r].w; }
+            }
+        }
         reinterpret_cast<float4*>(a.grads)[gi] = make_float4(g[0], g[1], g[2], g[3]);
-      } else if (a.nslabs > 0) {
-        float4 p[8];   // independent loads first (the arena never has more than 8 slabs), then the sum in slab order
+      } else if (MODE == 1) {
+#pragma unroll 1
+        for (int k0 = 0; k0 < a.nslabs; k0 += 4) {   // independent loads first, then the sum in slab order
+          float4 p[4];
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-          p[k] = k < a.nslabs ? __ldg(reinterpret_cast<const float4*>(a.slabs + (size_t)k * a.slab_stride) + gi) : make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int k = 0; k < 4; ++k)
+            p[k] = k0 + k < a.nslabs ? __ldg(reinterpret_cast<const float4*>(a.slabs + (size_t)(k0 + k) * a.slab_stride) + gi)
+                                     : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) { g[0] += p[k].x; g[1] += p[k].y; g[2] += p[k].z; g[3] += p[k].w; }
-        for (int k = 8; k < a.nslabs; ++k) {
-          const float4 q = __ldg(reinterpret_cast<const float4*>(a.slabs + (size_t)k * a.slab_stride) + gi);
-          g[0] += q.x; g[1] += q.y; g[2] += q.z; g[3] += q.w;
+          for (int k = 0; k < 4; ++k) { g[0] += p[k].x; g[1] += p[k].y; g[2] += p[k].z; g[3] += p[k].w; }
         }
         reinterpret_cast<float4*>(a.grads)[gi] = make_float4(g[0], g[1], g[2], g[3]);
       }
@@ -597,7 +669,7 @@ __global__ void apply_kernel(const __grid_constant__ ApplyArgs a) {
         const bool in = i < a.n_all;
         w[e] = in ? a.params[i] : 0.f; g[e] = in ? a.grads[i] : 0.f; m[e] = in ? a.m[i] : 0.f; v[e] = in ? a.v[i] : 0.f;
         t[e] = (in && i < n_targets) ? a.targets[i] : 0.f;
-        if (in && a.dp_world > 0) {
+        if (in && MODE == 2) {
           float acc = 0.f;
           for (int r = 0; r < a.dp_world; ++r) {
             float v;
@@ -606,12 +678,12 @@ __global__ void apply_kernel(const __grid_constant__ ApplyArgs a) {
           }
           g[e] = acc;
           a.grads[i] = acc;
-        } else if (in && a.nslabs > 0) {
+        } else if (in && MODE == 1) {
           for (int k = 0; k < a.nslabs; ++k) g[e] += a.slabs[(size_t)k * a.slab_stride + i];
           a.grads[i] = g[e];
         }
         if (a.tail.enabled && i == a.n_all - 1) {   // log_alpha: dsac_v2.py:312-318 (data parallel: dp_grad_fold_kernel formed it)
-          if (a.dp_world == 0) { g[e] = tail_grad_log_alpha(a.state, a.tail); a.grads[i] = g[e]; }
+          if (MODE != 2) { g[e] = tail_grad_log_alpha(a.state, a.tail); a.grads[i] = g[e]; }
           a.state[ST_ALPHA_USED] = a.tail.sc.auto_alpha ? expf(w[e]) : a.tail.sc.alpha_fixed;   // temperature this step used
         }
       }

@@ -28,12 +28,14 @@ from typing import Dict, Tuple
 import torch
 import torch.nn as nn
 
+import networks.cnn as _cnn
 import networks.mlp as _mlp
 from dsact_host import TB_TAGS as tb_tags
 from dsact_host import net_kwargs
 
 from dsac_v2_b200 import _lib, dp
 from dsac_v2_b200.engine import STAT_KEYS, Engine, make_config
+from dsac_v2_b200.engine_cnn import CnnEngine, make_cnn_config
 
 _TRAINABLE = ("q1", "q2", "policy")
 
@@ -46,7 +48,11 @@ class ApproxContainer(nn.Module):
         if kwargs.get("cnn_shared", False):
             raise NotImplementedError("cnn_shared feature nets are not part of the B200 update path")
         q_args, pi_args = net_kwargs("value", kwargs), net_kwargs("policy", kwargs)
-        q_cls, pi_cls = getattr(_mlp, q_args["name"], None), getattr(_mlp, pi_args["name"], None)
+        if q_args["apprfunc"] != pi_args["apprfunc"]:
+            raise NotImplementedError("value and policy approximators must be of the same type (both MLP or both CNN)")
+        self._cnn = q_args["apprfunc"] == "CNN"   # BASELINE config 5: conv encoder + separate mean / log_std heads
+        mod = _cnn if self._cnn else _mlp
+        q_cls, pi_cls = getattr(mod, q_args["name"], None), getattr(mod, pi_args["name"], None)
         if q_cls is None or pi_cls is None:
             raise NotImplementedError("This apprfunc is not properly defined")
         # construction order q1, q2, policy = the reference's consumption of torch's RNG (:31-39)
@@ -61,19 +67,31 @@ class ApproxContainer(nn.Module):
                 p.requires_grad = False
         self.log_alpha = nn.Parameter(torch.tensor(1, dtype=torch.float32))
 
-        self._cfg_args = dict(
-            obs_dim=q_args["obs_dim"], act_dim=q_args["act_dim"],
-            hidden_q=q_args["hidden_sizes"], hidden_pi=pi_args["hidden_sizes"],
-            act_q=q_args["hidden_activation"], act_pi=pi_args["hidden_activation"],
-            gamma=kwargs.get("gamma", 0.99), tau=kwargs.get("tau", 0.005), tau_b=kwargs.get("tau_b", None),
-            delay_update=kwargs.get("delay_update", 2), auto_alpha=kwargs.get("auto_alpha", True),
-            alpha=kwargs.get("alpha", 0.2), lr_q=kwargs["value_learning_rate"], lr_pi=kwargs["policy_learning_rate"],
-            lr_alpha=kwargs["alpha_learning_rate"], min_log_std=pi_args["min_log_std"], max_log_std=pi_args["max_log_std"],
-            gemm_mode=kwargs.get("dsact_gemm", "bf16x3"), use_graph=kwargs.get("dsact_graph", True))
+        common = dict(gamma=kwargs.get("gamma", 0.99), tau=kwargs.get("tau", 0.005), tau_b=kwargs.get("tau_b", None),
+                      delay_update=kwargs.get("delay_update", 2), auto_alpha=kwargs.get("auto_alpha", True),
+                      alpha=kwargs.get("alpha", 0.2), lr_q=kwargs["value_learning_rate"], lr_pi=kwargs["policy_learning_rate"],
+                      lr_alpha=kwargs["alpha_learning_rate"], min_log_std=pi_args["min_log_std"], max_log_std=pi_args["max_log_std"])
+        if self._cnn:
+            if q_args["conv_type"] != pi_args["conv_type"] or q_args["hidden_activation"] != pi_args["hidden_activation"]:
+                raise NotImplementedError("the CNN engine takes one conv_type / head activation for critics and policy")
+            t = _cnn.CONV_TYPES[q_args["conv_type"]]
+            self._cfg_args = dict(obs_shape=tuple(q_args["obs_dim"]), act_dim=q_args["act_dim"], kernels=t["kernels"],
+                                  channels=t["channels"], strides=t["strides"], hidden=t["heads"],
+                                  act_hidden=q_args["hidden_activation"], **common)
+        else:
+            self._cfg_args = dict(
+                obs_dim=q_args["obs_dim"], act_dim=q_args["act_dim"],
+                hidden_q=q_args["hidden_sizes"], hidden_pi=pi_args["hidden_sizes"],
+                act_q=q_args["hidden_activation"], act_pi=pi_args["hidden_activation"],
+                gemm_mode=kwargs.get("dsact_gemm", "bf16x3"), use_graph=kwargs.get("dsact_graph", True), **common)
         if q_args["output_activation"] != "linear" or pi_args["output_activation"] != "linear":
             raise NotImplementedError("the B200 engine implements linear output activations")
         self._max_batch = int(kwargs.get("dsact_max_batch", kwargs.get("replay_batch_size", 256)))
         self._engine = None
+        # seed of the device generator (noise + replay indices): the run's `seed` kwarg (reference utils/init_args.py
+        # seeds torch/numpy with it) mixed with the data-parallel rank, so that seeds and ranks draw independent streams
+        self._user_seed = kwargs.get("seed", None)
+        self._attachments = []   # objects holding a reference to the engine (ReplayBuffer): re-bound when the engine is rebuilt
         self._register_state_dict_hook(_detach_state_dict)
 
     def create_action_distributions(self, logits):
@@ -97,9 +115,14 @@ class ApproxContainer(nn.Module):
         eng = self._engine
         if eng is not None and eng.device != torch.device(device):
             self._engine = eng = None  # moved to another GPU: rebuild there
-        if eng is None:
+        if eng is None and self._cnn:
+            cfg = make_cnn_config(max_batch=self._max_batch, **self._cfg_args)
+            eng = self._engine = CnnEngine(cfg, device, self.policy.act_high_lim, self.policy.act_low_lim)
+            eng.seed(self.device_seed())
+        elif eng is None:
             cfg = make_config(max_batch=self._max_batch, **self._cfg_args)
             eng = self._engine = Engine(cfg, device, self.policy.act_high_lim, self.policy.act_low_lim)
+            eng.seed(self.device_seed())
         train, targ = self._flat_groups()
         with torch.no_grad():
             for flat, group in ((eng.params, train), (eng.targets, targ)):
@@ -113,12 +136,29 @@ class ApproxContainer(nn.Module):
                     off += n
                 assert off == flat.numel(), "flat layout does not match the module"
 
+    def device_seed(self) -> int:
+        """64-bit seed of the engine's Philox generator: splitmix64 of (user seed, data-parallel rank)."""
+        rank = 0
+        try:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                rank = dist.get_rank()
+        except Exception:   # noqa: BLE001
+            rank = 0
+        base = 0x5DEECE66D if self._user_seed is None else int(self._user_seed)
+        z = (base * 0x9E3779B97F4A7C15 + (rank + 1) * 0xBF58476D1CE4E5B9) & (2 ** 64 - 1)
+        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & (2 ** 64 - 1)
+        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & (2 ** 64 - 1)
+        return z ^ (z >> 31)
+
     def engine(self, batch: int = 0) -> Engine:
         """The bound engine; raises when the module is not on a CUDA device."""
         if self.log_alpha.device.type != "cuda" or self._engine is None:
             raise _lib.DsactError(
                 "DSAC_V2's update path runs only on the CUDA engine (libdsact.so, sm_100a); "
                 "move the networks to the GPU first (`alg.networks.cuda()`). There is no CPU fallback.")
+        if batch > self._max_batch and self._cnn:
+            raise ValueError(f"batch {batch} > dsact_max_batch / replay_batch_size {self._max_batch} (the CNN engine does not regrow)")
         if batch > self._max_batch:  # grow the activation arena, keep weights / Adam state / carry
             old = self._engine
             self._max_batch = int(batch)
@@ -127,10 +167,15 @@ class ApproxContainer(nn.Module):
             with torch.no_grad():
                 for name in ("params", "targets", "adam_m", "adam_v", "state"):
                     getattr(new, name).copy_(getattr(old, name))
+            new.seed(old._seed)            # a seed restored by load_full_state_dict survives the rebuild
             self._engine = new
             for p in self.parameters():  # force re-pointing
                 p.data = p.data.clone()
             self._attach(old.device)
+            for ref in list(self._attachments):   # replay rings move with their rows; peers reconnect on the next update
+                obj = ref()
+                if obj is not None:
+                    obj.rebind(old, new)
             old.close()
         return self._engine
 
@@ -206,7 +251,7 @@ class DSAC_V2:
         # "peer": exchanges inside the step's kernels over NVLink peer memory (falls back to NCCL if the ranks cannot
         # map each other's buffers); "nccl": torch.distributed all-reduces between three graph launches
         self.dp_transport = kwargs.get("dsact_dp_transport", "peer")
-        self._peer_dp = None
+        self._peer_dp, self._peer_eng = None, None
         self._slots, self._owners, self._cursor = None, [None] * self._RING, 0
 
     @property
@@ -300,8 +345,9 @@ class DSAC_V2:
         if world == 1:
             eng.step(data, iteration, self._noise(B))
             return self._stats(eng, B, t0)
-        if self._peer_dp is None:   # first data-parallel update: try to map the ranks' exchange buffers (collective)
-            self._peer_dp = self.dp_transport != "nccl" and dp.connect_peers(eng, dist)
+        if self._peer_dp is None or self._peer_eng is not eng:   # first data-parallel update (or the engine was rebuilt):
+            self._peer_dp = self.dp_transport != "nccl" and dp.connect_peers(eng, dist)   # map the exchange buffers (collective)
+            self._peer_eng = eng
         if self._peer_dp:           # one graph launch; exchanges inside the step's kernels over NVLink peer memory
             eng.dp_step(data, iteration, B * world, self._noise(B))
             return self._stats(eng, B * world, t0)

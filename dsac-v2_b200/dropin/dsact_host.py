@@ -124,20 +124,21 @@ def net_kwargs(kind: str, kwargs: dict) -> dict:
     """Per-network constructor arguments out of the flat kwargs dict; same keys and
     defaults as reference utils/common_utils.py:48-89 (MLP branch)."""
     func_type = kwargs[kind + "_func_type"]
-    if func_type != "MLP":
-        raise NotImplementedError(f"{kind}_func_type={func_type!r}: only MLP networks run on the B200 engine (CNN is next)")
+    if func_type not in ("MLP", "CNN"):
+        raise NotImplementedError(f"{kind}_func_type={func_type!r}: MLP and CNN networks run on the B200 engine (not CNN_SHARED)")
     if kwargs.get("action_type", "continu") != "continu":
         raise NotImplementedError("DSAC don't support discrete action space!")
     dist = kwargs.get("policy_act_distribution", "TanhGaussDistribution")
     cls = dist if isinstance(dist, type) else DISTRIBUTIONS.get(dist)
     if cls is None:
         raise NotImplementedError(f"unknown action distribution {dist!r}")
+    extra = dict(hidden_sizes=list(kwargs[kind + "_hidden_sizes"])) if func_type == "MLP" else dict(conv_type=kwargs[kind + "_conv_type"])
     return dict(
         apprfunc=func_type,
         name=kwargs[kind + "_func_name"],
         obs_dim=kwargs["obsv_dim"],
         act_dim=kwargs["action_dim"],
-        hidden_sizes=list(kwargs[kind + "_hidden_sizes"]),
+        **extra,
         hidden_activation=kwargs[kind + "_hidden_activation"],
         output_activation=kwargs[kind + "_output_activation"],
         min_log_std=kwargs.get(kind + "_min_log_std", -20.0),

@@ -23,8 +23,11 @@ class ReplayBuffer:
         self.obsv_dim = kwargs["obsv_dim"]
         self.act_dim = kwargs["action_dim"]
         self.max_size = int(kwargs["buffer_max_size"])
-        if not np.isscalar(self.obsv_dim) or not np.isscalar(self.act_dim):
-            raise NotImplementedError("image observations (CNN path) are not on the B200 replay path yet")
+        if not np.isscalar(self.act_dim):
+            raise NotImplementedError("the device ring buffer stores flat action vectors")
+        # image observations (CNN path, BASELINE config 5): rows hold the flattened [C*H*W] image
+        self.obs_shape = None if np.isscalar(self.obsv_dim) else tuple(int(x) for x in self.obsv_dim)
+        self.obs_elems = int(self.obsv_dim) if self.obs_shape is None else int(np.prod(self.obs_shape))
         if kwargs.get("additional_info"):
             raise NotImplementedError("additional_info fields are not supported by the device ring buffer")
         self.index_source = kwargs.get("dsact_index_source",
@@ -39,11 +42,13 @@ class ReplayBuffer:
     # ---- wiring -------------------------------------------------------------------
     def attach(self, engine):
         """Bind the ring storage to an engine (done by the trainer once the networks are on the GPU)."""
-        if engine.cfg.obs_dim != self.obsv_dim or engine.cfg.act_dim != self.act_dim:
+        eng_obs = getattr(engine, "obs_elems", None) or engine.cfg.obs_dim
+        if eng_obs != self.obs_elems or engine.cfg.act_dim != self.act_dim:
             raise ValueError("replay buffer and engine disagree on obs/act dimensions")
         self.engine = engine
         engine.bind_replay(self.max_size)
-        O, A, R = self.obsv_dim, self.act_dim, min(self._STAGE_ROWS, self.max_size)
+        O, A = self.obs_elems, self.act_dim
+        R = min(self._STAGE_ROWS if self.obs_shape is None else max(8, self._STAGE_ROWS * 400 // O), self.max_size)   # ~6 MB per staging set
         self._rows = R
         pin = lambda *s: torch.zeros(*s, dtype=torch.float32).pin_memory()
         self._stage = [dict(obs=pin(R, O), obs2=pin(R, O), act=pin(R, A), rew=pin(R), done=pin(R), logp=pin(R))
@@ -53,6 +58,17 @@ class ReplayBuffer:
         pending, self._pending = self._pending, []
         for row in pending:
             self._store_row(*row)
+
+    def rebind(self, old, new):
+        """The engine was rebuilt (larger activation arena): give the new one a ring and move the stored rows."""
+        if self.engine is not old:
+            return
+        self.flush()
+        torch.cuda.current_stream(old.device).synchronize()
+        new.bind_replay(self.max_size)
+        for k, v in old.replay.items():
+            new.replay[k].copy_(v)
+        self.engine = new
 
     def _require_engine(self):
         if self.engine is None:
@@ -64,7 +80,7 @@ class ReplayBuffer:
 
     def __get_RAM__(self):
         """MB of device memory holding valid transitions."""
-        row_bytes = 4 * (2 * self.obsv_dim + self.act_dim + 3)
+        row_bytes = 4 * (2 * self.obs_elems + self.act_dim + 3)
         return row_bytes * self.size / 1e6
 
     # ---- store ----------------------------------------------------------------------
@@ -74,8 +90,8 @@ class ReplayBuffer:
         if self._fill == 0 and self._events[self._cur] is not None:
             self._events[self._cur].synchronize()  # the async copy out of this staging buffer has finished
         s, i = self._np[self._cur], self._fill
-        s["obs"][i] = obs
-        s["obs2"][i] = next_obs
+        s["obs"][i] = obs.reshape(-1)
+        s["obs2"][i] = next_obs.reshape(-1)
         s["act"][i] = act
         s["rew"][i] = rew
         s["done"][i] = done

@@ -68,6 +68,8 @@ class OffSerialTrainer:
         engine = self.networks.engine(self.replay_batch_size)
         if hasattr(self.buffer, "attach"):
             self.buffer.attach(engine)
+            import weakref
+            self.networks._attachments.append(weakref.ref(self.buffer))   # follows the engine if it is rebuilt for a larger batch
 
         # CPU mirror of the behaviour policy for sampler and evaluator (they were handed
         # `alg.networks` itself in the reference, :24-26)
@@ -153,7 +155,9 @@ class OffSerialTrainer:
 
     # ---- full training state ------------------------------------------------------------------
     def save_trainstate(self, path):
-        torch.save({"alg": self.alg.full_state_dict(), "buffer": self.buffer.state_dict(), "iteration": self.iteration,
+        # "iteration" = the NEXT iteration to run: inside step() the state already holds this iteration's update
+        nxt = self.iteration + (1 if getattr(self, "_in_step", False) else 0)
+        torch.save({"alg": self.alg.full_state_dict(), "buffer": self.buffer.state_dict(), "iteration": nxt,
                     "best_tar": self.best_tar}, path)
 
     def load_trainstate(self, path):
@@ -165,6 +169,13 @@ class OffSerialTrainer:
 
     # ---- one iteration (reference :60-138) -----------------------------------------------
     def step(self):
+        self._in_step = True
+        try:
+            self._step()
+        finally:
+            self._in_step = False
+
+    def _step(self):
         sampler_tb_dict = {}
         if self.async_sampler:
             if self.iteration % self.mirror_interval == 0:

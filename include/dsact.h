@@ -212,6 +212,44 @@ int dsact_dp_step(dsact_handle *h, const dsact_batch *batch, const dsact_noise *
 int dsact_dp_replay_step(dsact_handle *h, int32_t batch, int64_t size, const int64_t *idx, const dsact_noise *noise,
                          int64_t global_batch, int64_t iteration, void *stream);
 
+/* ---- CNN approximators (BASELINE config 5, reference networks/cnn.py:30-53,151-240,383-461) --------------------------------
+ * The same update path when value_func_type / policy_func_type = "CNN": every network is a private conv encoder
+ * (Conv2d + ReLU per layer, no padding) followed by two separate MLP heads `mean` and `log_std` on the flattened
+ * feature (the critics append the action to it).  Flat layout per network, in state_dict order: conv.{0,2,..}.weight
+ * [Cout,Cin,k,k] / .bias, mean.{0,2,..}.weight / .bias, log_std.{0,2,..}.weight / .bias; params = [q1|q2|policy|log_alpha].
+ * First CUDA path of this configuration: fp32 direct convolutions + the fp32 grouped GEMMs for the heads, eager launches.
+ * dsact_cnn_step = DSAC_V2.local_update(data, iteration) with data["obs"] / ["obs2"] of shape [B, C, H, W] (contiguous). */
+#define DSACT_MAX_CONV 8
+typedef struct dsact_cnn_config {
+  int32_t abi_version;
+  int32_t channels, height, width;   /* obsv_dim = (C, H, W) */
+  int32_t act_dim;
+  int32_t n_conv;
+  int32_t conv_kernel[DSACT_MAX_CONV], conv_channels[DSACT_MAX_CONV], conv_stride[DSACT_MAX_CONV];
+  int32_t n_hidden;                  /* hidden layers of every head MLP (networks/cnn.py:204 mlp_hidden_layers) */
+  int32_t hidden[DSACT_MAX_HIDDEN];
+  int32_t act_hidden;                /* DSACT_ACT_* of the head MLPs (the conv stack is ReLU) */
+  int32_t max_batch, auto_alpha, delay_update;
+  double gamma, tau, tau_b, alpha_fixed, lr_q, lr_pi, lr_alpha, min_log_std, max_log_std;
+  double adam_beta1, adam_beta2, adam_eps;
+} dsact_cnn_config;
+typedef struct dsact_cnn_handle dsact_cnn_handle;
+int dsact_cnn_query_layout(const dsact_cnn_config *cfg, dsact_layout *out);
+int dsact_cnn_create(const dsact_cnn_config *cfg, int device, dsact_cnn_handle **out);
+void dsact_cnn_destroy(dsact_cnn_handle *h);
+int dsact_cnn_bind(dsact_cnn_handle *h, const dsact_buffers *bufs);
+int dsact_cnn_set_carry(dsact_cnn_handle *h, float mean_std1, float mean_std2, int64_t adam_steps_q, int64_t adam_steps_pi,
+                        void *stream);
+int dsact_cnn_seed(dsact_cnn_handle *h, uint64_t seed);
+int dsact_cnn_step(dsact_cnn_handle *h, const dsact_batch *batch, const dsact_noise *noise, int64_t iteration, void *stream);
+int dsact_cnn_read_stats(dsact_cnn_handle *h, int64_t global_batch, float *host_out, void *stream);
+/* device replay ring for image transitions: rows of obs / obs2 are the flattened [C*H*W] images (fp32, like the
+ * reference's CarRacing data, env_gym/gym_carracing_data.py:19-21); same semantics as dsact_replay_bind / _add / _sample */
+int dsact_cnn_replay_bind(dsact_cnn_handle *h, const dsact_replay *rb);
+int dsact_cnn_replay_add(dsact_cnn_handle *h, const float *obs, const float *obs2, const float *act, const float *rew,
+                         const float *done, const float *logp, int64_t n, int64_t ptr, void *stream);
+int dsact_cnn_replay_sample(dsact_cnn_handle *h, int32_t batch, int64_t size, const int64_t *idx, dsact_batch *out, void *stream);
+
 /* introspection for tests/bench: number of kernel launches (graph nodes included)
  * submitted by this handle so far, and by the most recent entry-point call */
 int64_t dsact_launch_count(const dsact_handle *h);

@@ -119,6 +119,20 @@ class OracleDSACT:
         self.steps = {"q1": 0, "q2": 0, "policy": 0, "log_alpha": 0}
         self.mean_std = [None, None]  # dsac_v2.py:88-89 (-1.0 sentinel)
         self.grads: Dict[str, List[torch.Tensor]] = {}
+        self.device = torch.device("cpu")
+
+    def to(self, device) -> "OracleDSACT":
+        """Move every tensor of the state to `device`.  The same ATen ops then run there: on a CUDA device this is what
+        the reference's eager PyTorch path does on that GPU (bench.py's `cuda_eager_baseline` leg); parity tests stay on CPU."""
+        self.device = torch.device(device)
+        mv = lambda w: w.detach().to(self.device).requires_grad_(w.requires_grad)
+        self.p = {k: [mv(w) for w in v] for k, v in self.p.items()}
+        self.t = {k: [mv(w) for w in v] for k, v in self.t.items()}
+        self.m = {k: [mv(w) for w in v] for k, v in self.m.items()}
+        self.v = {k: [mv(w) for w in v] for k, v in self.v.items()}
+        self.log_alpha, self.hi, self.lo = mv(self.log_alpha), mv(self.hi), mv(self.lo)
+        self.mean_std = [None if x is None else x.to(self.device) for x in self.mean_std]
+        return self
 
     def _load_weights(self, weights, nq, npi):
         """Parameter lists per network, in the reference's named_parameters order."""
@@ -170,7 +184,7 @@ class OracleDSACT:
         (SURVEY.md §8e): batch means become sums over the local rows divided by the global row
         count, and the two critic-std sums pass through the hook (an all-reduce) before the
         mean_std EMA.  With the defaults this is exactly the single-process update."""
-        c = lambda x: torch.as_tensor(x).to(self.dtype)
+        c = lambda x: torch.as_tensor(x).to(device=self.device, dtype=self.dtype)
         obs, act, rew, obs2, done = (c(batch[k]) for k in ("obs", "act", "rew", "obs2", "done"))
         eps1, eps2, _z1, _z2, z3, z4 = (c(n) for n in noise[:6])
         B = obs.shape[0]

@@ -42,7 +42,7 @@ CASES = [
     ("pendulum_b256", "pendulum", 256, 100, (), {}),
     ("halfcheetah_b512", "halfcheetah", 512, 40, (), {}),
     ("humanoid_b256", "humanoid", 256, 100, (), {}),
-    ("humanoid_b4096", "humanoid", 4096, 6, (), {}),
+    ("humanoid_b4096", "humanoid", 4096, 100, (), {}),   # the benchmarked configuration: the north_star gate is the first 100 losses
     # fixed temperature + different delay / tau_b: exercises the non-default branches
     ("tiny_fixed_alpha", "tiny", 16, 12, (1, 12), {"auto_alpha": False, "alpha": 0.2, "delay_update": 3, "tau_b": 0.05}),
     # the policy's other std types (networks/mlp.py:42-72)

@@ -1,6 +1,6 @@
-"""Data-parallel update on 2 GPUs == single-GPU update on the concatenated minibatch, for both transports:
+"""Data-parallel update on 2 / 4 / 8 GPUs (ragged shards) == single-GPU update on the concatenated minibatch, for both transports:
 "peer" (exchanges inside the step's kernels over NVLink peer memory, one graph per rank: dsact_dp_step) and "nccl"
-(torch.distributed all-reduces between the phase launches).  Needs >= 2 CUDA devices (`gpurun --gpus 2`)."""
+(torch.distributed all-reduces between the phase launches).  Needs >= 2 CUDA devices (`gpurun --gpus 2|4|8`); world sizes above the device count are skipped."""
 import os
 import sys
 
@@ -22,8 +22,8 @@ def _worker(rank, world, port, out_dir, gemm, transport):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     import dsac_v2
     from dsac_v2_b200 import dp, synth
-    cfg, B = synth.CONFIGS["halfcheetah"], 256
-    kw = synth.reference_kwargs(cfg, replay_batch_size=B // world, dsact_gemm=gemm)
+    cfg, B = synth.CONFIGS["halfcheetah"], GLOBAL_ROWS
+    kw = synth.reference_kwargs(cfg, replay_batch_size=(B + world - 1) // world, dsact_gemm=gemm)
     alg = dsac_v2.DSAC_V2(**kw)
     sd = alg.networks.state_dict()
     for k, v in synth.make_weights(cfg).items():
@@ -54,22 +54,28 @@ def _worker(rank, world, port, out_dir, gemm, transport):
     dist.destroy_process_group()
 
 
+GLOBAL_ROWS = 250   # not a multiple of 4 or 8: the ranks hold shards of different sizes (dp.shard_rows)
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
 @pytest.mark.parametrize("transport", ["peer", "nccl"])
 @pytest.mark.parametrize("gemm", ["fp32", "bf16x3"])
-def test_two_gpu_data_parallel_equals_single_gpu(tmp_path, gemm, transport):
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
-    port = 29600 + (os.getpid() + (7 if transport == "peer" else 0)) % 1000
-    mp.spawn(_worker, args=(2, port, str(tmp_path), gemm, transport), nprocs=2, join=True)
-    r0, r1 = np.load(tmp_path / "rank0.npz"), np.load(tmp_path / "rank1.npz")
-    np.testing.assert_array_equal(r0["params"], r1["params"])   # replicas stay bit-identical
-    np.testing.assert_array_equal(r0["targets"], r1["targets"])
-    np.testing.assert_array_equal(r0["grads"], r1["grads"])     # every rank holds the global gradient
+def test_data_parallel_equals_single_gpu(tmp_path, gemm, transport, world):
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    port = 29600 + (os.getpid() + 13 * world + (7 if transport == "peer" else 0)) % 1000
+    mp.spawn(_worker, args=(world, port, str(tmp_path), gemm, transport), nprocs=world, join=True)
+    ranks = [np.load(tmp_path / f"rank{r}.npz") for r in range(world)]
+    r0 = ranks[0]
+    for r in ranks[1:]:
+        np.testing.assert_array_equal(r0["params"], r["params"])   # replicas stay bit-identical
+        np.testing.assert_array_equal(r0["targets"], r["targets"])
+        np.testing.assert_array_equal(r0["grads"], r["grads"])     # every rank holds the global gradient
     # single GPU on the full minibatch
     sys.path.insert(0, os.path.join(REPO, "dsac-v2_b200", "dropin"))
     from dsac_v2_b200 import synth
     from dsac_v2_b200.engine import Engine, make_config
-    cfg, B = synth.CONFIGS["halfcheetah"], 256
+    cfg, B = synth.CONFIGS["halfcheetah"], GLOBAL_ROWS
     lim = torch.full((cfg["act_dim"],), cfg["act_lim"])
     eng = Engine(make_config(cfg["obs_dim"], cfg["act_dim"], cfg["hidden"], cfg["hidden"], max_batch=B, gemm_mode=gemm),
                  torch.device("cuda", 0), lim, -lim)

@@ -289,3 +289,61 @@ def test_async_sampler_feeds_buffer_while_training(tmp_path):
     assert sampler.get_total_sample_number() >= buf.size - 0
     assert np.isfinite(trainer.last_tb["Loss/Critic loss-RL iter"])
     assert os.path.exists(tmp_path / "apprfunc" / "trainstate_200.pkl")
+
+
+def test_trainer_checkpoint_resumes_at_the_next_iteration(tmp_path):
+    """A trainer restored from an in-step trainstate continues with the NEXT iteration: the interrupted run and the
+    uninterrupted one produce the same critic losses and the same final weights (no repeated update)."""
+    from training.replay_buffer import ReplayBuffer
+    from training.trainer import create_trainer
+    cfg = synth.CONFIGS["tiny"]
+
+    def make(folder, **extra):
+        np.random.seed(3); torch.manual_seed(3)
+        alg, kw = build_alg(cfg, 32, seed=11)
+        kw = dict(kw, buffer_max_size=2000, additional_info={}, buffer_name="replay_buffer", buffer_warm_size=100,
+                  max_iteration=16, log_save_interval=1000, apprfunc_save_interval=8, eval_interval=1000,
+                  save_folder=str(folder), ini_network_dir=None, use_gpu=True, dsact_tensorboard=False,
+                  dsact_full_checkpoint=True, sample_interval=1000, **extra)   # no new transitions after the warm-up
+        sampler, evaluator = _StubEnvSampler(kw, cfg), _StubEvaluator()
+        buf = ReplayBuffer(**kw)
+        rec = []
+        inner = alg.local_update
+
+        def local_update(data, it):
+            tb = inner(data, it)
+            rec.append((it, tb["Loss/Critic loss-RL iter"]))
+            return tb
+
+        alg.local_update = local_update
+        return create_trainer(alg, sampler, buf, evaluator, **kw), alg, rec
+
+    full, alg_full, rec_full = make(tmp_path / "full")
+    full.train()
+    assert [it for it, _ in rec_full] == list(range(16))
+    ck = tmp_path / "full" / "apprfunc" / "trainstate_8.pkl"      # written inside iteration 8, after its update
+    assert torch.load(ck, weights_only=False)["iteration"] == 9
+    resumed, alg_res, rec_res = make(tmp_path / "resumed", dsact_resume_dir=str(ck))
+    assert resumed.iteration == 9
+    resumed.train()
+    assert [it for it, _ in rec_res] == list(range(9, 16))
+    np.testing.assert_allclose([v for _, v in rec_res], [v for _, v in rec_full[9:]], rtol=2e-5)
+    for (k, va), vb in zip(alg_full.networks.state_dict().items(), alg_res.networks.state_dict().values()):
+        torch.testing.assert_close(va, vb, rtol=2e-5, atol=1e-7, msg=k)
+
+
+def test_device_generator_is_seeded_from_the_run_seed():
+    """Two seeds draw different device noise and replay indices; the same seed reproduces them."""
+    cfg, B = synth.CONFIGS["tiny"], 64
+    outs = []
+    for seed in (1, 2, 1):
+        alg, kw = build_alg(cfg, B, seed=seed)
+        alg.networks.cuda()
+        eng = alg.networks.engine()
+        data = {k: torch.from_numpy(v).cuda() for k, v in synth.make_batch(cfg, B, 0).items()}
+        alg.local_update(data, 0)
+        torch.cuda.synchronize()
+        off = 2 * ((B * cfg["obs_dim"] + 63) // 64 * 64) + (B * cfg["act_dim"] + 63) // 64 * 64 + 3 * ((B + 63) // 64 * 64) + (2 * B + 63) // 64 * 64
+        outs.append(eng._ws_view[off:off + B * cfg["act_dim"]].clone())
+    assert not torch.equal(outs[0], outs[1])
+    assert torch.equal(outs[0], outs[2])

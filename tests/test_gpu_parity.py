@@ -195,6 +195,35 @@ def test_bf16x3_tensor_core_path_matches_reference_golden(golden_dir, name):
     eng.close()
 
 
+@pytest.mark.parametrize("mode", ["bf16x3", "fp32"])
+@pytest.mark.parametrize("cfg_name,batch,steps", [("humanoid", 65536, 2), ("halfcheetah", 8192, 3)])
+def test_large_batches_match_oracle(cfg_name, batch, steps, mode):
+    """The largest configurations of BASELINE.json (config 4's 65536-row sweep point; config 3's 8192 rows per GPU):
+    multi-wave chain launches and the bounded weight-gradient launches, against the pinned oracle on the same inputs."""
+    from oracle.dsact_oracle import TB_KEYS, from_config
+    cfg = synth.CONFIGS[cfg_name]
+    eng = make_engine(cfg, batch, use_graph=True, gemm_mode=mode)
+    orc = from_config(cfg, synth.make_weights(cfg), **synth.HYPER)
+    torch.set_num_threads(min(16, os.cpu_count() or 4))
+    try:
+        for it in range(steps):
+            hb, hn = synth.make_batch(cfg, batch, it), synth.make_noise(cfg, batch, it)
+            ref = orc.update(hb, hn, it)
+            b = {k: torch.from_numpy(v).cuda() for k, v in hb.items()}
+            n = tuple(torch.from_numpy(hn[i]).cuda() for i in (0, 1, 4, 5))
+            eng.step(b, it, n)
+            got = stats_vec(eng)
+            np.testing.assert_allclose(got, [ref[k] for k in TB_KEYS], rtol=RTOL, atol=1e-5, err_msg=f"{cfg_name} B={batch} step {it}")
+    finally:
+        torch.set_num_threads(4)
+    w, sd = eng.export_weights(), orc.state_dict()
+    for k, v in sd.items():   # digests: |.|-sum and the first elements of every tensor
+        a, r = w[k].double().reshape(-1), v.double().reshape(-1)
+        np.testing.assert_allclose(a.abs().sum().item(), r.abs().sum().item(), rtol=RTOL, err_msg=k)
+        np.testing.assert_allclose(a[:8].numpy(), r[:8].numpy(), rtol=RTOL, atol=1e-6, err_msg=k)
+    eng.close()
+
+
 def test_bf16x3_gradients_match_reference_golden(golden_dir):
     z, cfg, batch, steps, over = load(golden_dir, "ragged_b37")
     eng = make_engine(cfg, batch, over, use_graph=False, gemm_mode="bf16x3")

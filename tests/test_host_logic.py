@@ -32,3 +32,22 @@ def test_shard_rows_partitions_the_minibatch(rows, world):
     assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))          # contiguous, in rank order
     sizes = np.array([hi - lo for lo, hi in spans])
     assert sizes.max() - sizes.min() <= 1 and sizes.sum() == rows
+
+
+def test_device_seed_mixes_run_seed_and_rank(monkeypatch):
+    """every run used the same Philox key.  The engine seed is now a mix of the `seed` kwarg and the
+    data-parallel rank: distinct seeds and distinct ranks give distinct 64-bit keys, the same pair reproduces."""
+    import dsac_v2
+    import torch.distributed as dist
+    from dsac_v2_b200 import synth
+    kw = synth.reference_kwargs(synth.CONFIGS["tiny"])
+    seeds = {}
+    for seed in (None, 0, 1, 12345):
+        net = dsac_v2.ApproxContainer(**dict(kw, seed=seed))
+        for rank in (0, 1, 7):
+            monkeypatch.setattr(dist, "is_initialized", lambda: True)
+            monkeypatch.setattr(dist, "get_rank", lambda r=rank: r)
+            s = net.device_seed()
+            assert 0 <= s < 2 ** 64 and s == net.device_seed()
+            seeds[(seed, rank)] = s
+    assert len(set(seeds.values())) == len(seeds)

@@ -112,6 +112,8 @@ def main():
 
     loop("default affinity, read every step")
     loop("default affinity, no stats read", read=False)
+    torch.set_num_threads(4)
+    loop("torch threads=4 (the reference's setting, utils/init_args.py:14)")
     torch.set_num_threads(1)
     loop("torch threads=1")
     gpu_node = sh(f"cat /sys/bus/pci/devices/{bdf}/numa_node")

@@ -10,6 +10,7 @@ REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, REPO)
 import torch  # noqa: E402
 
+from bench import ClockSampler  # noqa: E402  (nvidia-smi clocks / throttle reasons during the timed region)
 from dsac_v2_b200 import synth  # noqa: E402
 from dsac_v2_b200.engine import Engine, make_config  # noqa: E402
 
@@ -35,16 +36,21 @@ for mode in a.modes.split(","):
         for _ in range(5):
             eng.replay_step(B, a.replay_size, it); it += 1
         torch.cuda.synchronize()
-        n = max(5, min(300, int(2e6 / B)))
+        est = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        est[0].record()
+        eng.replay_step(B, a.replay_size, it); it += 1
+        est[1].record(); torch.cuda.synchronize()
+        n = max(20, min(4000, int(1300.0 / max(est[0].elapsed_time(est[1]), 1e-3))))   # >= 1.3 s: a few clock samples per row
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(n):
-            eng.replay_step(B, a.replay_size, it); it += 1
-        e1.record(); torch.cuda.synchronize()
+        with ClockSampler(0) as clocks:
+            e0.record()
+            for _ in range(n):
+                eng.replay_step(B, a.replay_size, it); it += 1
+            e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / n
         row = {"mode": mode, "batch": B, "ms_per_step": round(ms, 4), "steps_per_s": round(1000 / ms, 1),
                "samples_per_s": round(B * 1000 / ms), "tflops_algorithmic": round(FLOP * B / ms / 1e9, 2),
-               "finite": bool(torch.isfinite(eng.params).all())}
+               "steps": n, "finite": bool(torch.isfinite(eng.params).all()), "clocks": clocks.summary()}
         print(json.dumps(row), flush=True)
         out.append(row)
         eng.close(); del eng
