@@ -116,7 +116,9 @@ class ClockSampler:
 def ncu_traffic(mode):
     """Average dram bytes (read + write) per GEMM-class launch from the committed `ncu --set full` summary of this
     mode (profiles/), or None if no capture is committed for it."""
-    path = os.path.join(REPO, "profiles", f"r1_{mode}_tc_full.txt")
+    path = os.path.join(REPO, "profiles", f"r2_{mode}_tc_full.txt")
+    if not os.path.exists(path):
+        path = os.path.join(REPO, "profiles", f"r1_{mode}_tc_full.txt")
     try:
         rows = [l.split(" | ") for l in open(path) if l.startswith("void ")]
         mb = [float(r[3]) + float(r[4]) for r in rows]
@@ -347,7 +349,16 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # NCCL prints its version banner on stdout when the communicator is created: keep stdout for the ONE JSON line
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.all_reduce(torch.zeros(1, device=torch.device("cuda", local)))
+            torch.cuda.synchronize()
+        finally:
+            os.dup2(saved, 1)
+            os.close(saved)
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     # host side of the end-to-end leg: sit on the GPU's NUMA node before any pinned allocation (hostnuma.py), and run

@@ -211,8 +211,14 @@ static void cnn_conv_forward(dsact_cnn_handle* h, const CnnGeom& g, const float*
   const float* x = img;
   for (int j = 0; j < g.nconv; ++j) {
     const ConvShape s = g.shape(j, B);
-    dim3 grid((s.Hout * s.Wout + 127) / 128, s.Cout, B);
-    launch_k(conv_fwd_kernel, grid, 128, sizeof(float) * s.Cin * s.K * s.K, c, x, params + g.cw[j], params + g.cb[j], W + acts[j + 1], s);
+    const size_t smem8 = sizeof(float) * 8 * s.Cin * s.K * s.K;
+    if (s.Cout % 8 == 0 && smem8 <= 48 * 1024) {   // eight output channels per thread
+      dim3 grid((s.Hout * s.Wout + 127) / 128, s.Cout / 8, B);
+      launch_k(conv_fwd8_kernel, grid, 128, smem8, c, x, params + g.cw[j], params + g.cb[j], W + acts[j + 1], s);
+    } else {
+      dim3 grid((s.Hout * s.Wout + 127) / 128, s.Cout, B);
+      launch_k(conv_fwd_kernel, grid, 128, sizeof(float) * s.Cin * s.K * s.K, c, x, params + g.cw[j], params + g.cb[j], W + acts[j + 1], s);
+    }
     c.done();
     x = W + acts[j + 1];
   }

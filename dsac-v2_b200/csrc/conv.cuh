@@ -44,6 +44,42 @@ __global__ void conv_fwd_kernel(const float* __restrict__ x, const float* __rest
   y[((size_t)b * s.Cout + co) * s.Hout * s.Wout + p] = fmaxf(acc, 0.f);
 }
 
+// The same with 8 output channels per thread: the input patch is read once for eight accumulators (the one-channel form
+// is bound by its loads).  grid: (ceil(Hout*Wout / 128), Cout / 8, B); block 128; dynamic smem 8 * Cin * K * K floats.
+__global__ void conv_fwd8_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                                 float* __restrict__ y, const ConvShape s) {
+  pdl_sync();
+  extern __shared__ float wsm[];   // [Cin*K*K][8]: the eight weights of one tap are adjacent (two 16-byte broadcasts)
+  const int co0 = blockIdx.y * 8, b = blockIdx.z;
+  const int nw = s.Cin * s.K * s.K;
+  for (int i = threadIdx.x; i < 8 * nw; i += blockDim.x) {
+    const int c = i / nw, tap = i - c * nw;
+    wsm[tap * 8 + c] = w[(size_t)(co0 + c) * nw + tap];
+  }
+  __syncthreads();
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= s.Hout * s.Wout) return;
+  const int oy = p / s.Wout, ox = p - oy * s.Wout;
+  const float* xb = x + (size_t)b * s.Cin * s.Hin * s.Win;
+  float acc[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) acc[c] = bias[co0 + c];
+  for (int ci = 0; ci < s.Cin; ++ci) {
+    const float* xc = xb + (size_t)ci * s.Hin * s.Win + (size_t)(oy * s.S) * s.Win + ox * s.S;
+    const float* wc = wsm + (size_t)ci * s.K * s.K * 8;
+    for (int ky = 0; ky < s.K; ++ky)
+      for (int kx = 0; kx < s.K; ++kx) {
+        const float v = xc[ky * s.Win + kx];
+        const float4 w0 = *reinterpret_cast<const float4*>(wc + (ky * s.K + kx) * 8);
+        const float4 w1 = *reinterpret_cast<const float4*>(wc + (ky * s.K + kx) * 8 + 4);
+        acc[0] = fmaf(v, w0.x, acc[0]); acc[1] = fmaf(v, w0.y, acc[1]); acc[2] = fmaf(v, w0.z, acc[2]); acc[3] = fmaf(v, w0.w, acc[3]);
+        acc[4] = fmaf(v, w1.x, acc[4]); acc[5] = fmaf(v, w1.y, acc[5]); acc[6] = fmaf(v, w1.z, acc[6]); acc[7] = fmaf(v, w1.w, acc[7]);
+      }
+  }
+#pragma unroll
+  for (int c = 0; c < 8; ++c) y[((size_t)b * s.Cout + co0 + c) * s.Hout * s.Wout + p] = fmaxf(acc[c], 0.f);
+}
+
 // dL/dx (pre-mask) then masked by x > 0 when `mask_by_x` (x is the ReLU output of the layer below; the first layer's
 // input is the image: no mask, and its dx is not needed at all).  grid: (ceil(Hin*Win / 128), Cin, B); block 128
 __global__ void conv_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ w, const float* __restrict__ x,

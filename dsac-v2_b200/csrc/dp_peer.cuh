@@ -14,8 +14,8 @@
 // so the replicas stay bit-identical.  Reuse is safe without further barriers: a rank overwrites its gradient block
 // in phase 2 of step t+1, i.e. after the kind-0 barrier of t+1, which every peer reaches only after its apply of t.
 //
-// Gradient exchange, two variants.  ONE-SHOT (world <= 2): apply_kernel reads every rank's block through NVLink and sums
-// in rank order — (N-1) x n floats cross the links per rank.  TWO-SHOT (world >= 3, dp_reduce_scatter_kernel): rank r
+// Gradient exchange, two variants.  ONE-SHOT (world < 6): apply_kernel reads every rank's block through NVLink and sums
+// in rank order — (N-1) x n floats cross the links per rank.  TWO-SHOT (world >= 6, dp_reduce_scatter_kernel): rank r
 // sums slice r of every rank's block in rank order (reads (N-1)/N x n), writes the sum into slice r of EVERY rank's
 // reduced block (writes (N-1)/N x n), raises its kind-2 flag everywhere; apply_kernel waits for all kind-2 flags and then
 // reads only local memory.  At N = 8 that is 2 x 2.46 MB per rank instead of 19.7 MB.  Sums run in rank order on the

@@ -781,11 +781,12 @@ static unsigned long long dp_timeout_ns() {
       (unsigned long long)(getenv("DSACT_DP_TIMEOUT_MS") ? atoll(getenv("DSACT_DP_TIMEOUT_MS")) : 10000) * 1000000ull;
   return t;
 }
-// two-shot gradient exchange (dp_peer.cuh) from 3 ranks up; DSACT_DP_TWO_SHOT=0/1 overrides
+// two-shot gradient exchange (dp_peer.cuh) from 6 ranks up (measured, profiles/r2_scaling_8gpu_box.txt: one-shot is 5 % faster
+// at 4 ranks, two-shot 0.6 % faster at 8); DSACT_DP_TWO_SHOT=0/1 overrides
 static bool dp_two_shot(const dsact_handle* h) {
   static const char* e = getenv("DSACT_DP_TWO_SHOT");
   if (e && (e[0] == '0' || e[0] == '1')) return e[0] == '1';
-  return h->dp.world >= 3;
+  return h->dp.world >= 6;
 }
 static long long dp_npad(const dsact_handle* h) { return (2 * h->q.n + h->pi.n + 1 + 3) / 4 * 4; }
 static void enqueue_dp_reduce_scatter(dsact_handle* h, Ctx& c) {

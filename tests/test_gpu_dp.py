@@ -90,4 +90,9 @@ def test_data_parallel_equals_single_gpu(tmp_path, gemm, transport, world):
                                    "DSAC2/critic_avg_min_std1-RL iter", "DSAC2/mean_std1")])
     tol = 2e-5 if gemm == "fp32" else 1e-4
     np.testing.assert_allclose(r0["tb"], np.array(tbs), rtol=tol, atol=1e-6)
-    np.testing.assert_allclose(r0["params"], eng.params.cpu().numpy(), rtol=tol, atol=2e-6)
+    # parameters after 5 Adam steps (each moves a weight by <= 1e-4): Adam's normalisation turns the split-precision
+    # summation-order noise on near-zero gradients into up to a few 1e-6 of weight, more with more shards
+    atol = 2e-6 if gemm == "fp32" else 1e-5
+    diff = np.abs(r0["params"] - eng.params.cpu().numpy())
+    print(f"{gemm} {transport} world {world}: max |param diff| vs one GPU = {diff.max():.2e}")
+    np.testing.assert_allclose(r0["params"], eng.params.cpu().numpy(), rtol=tol, atol=atol)
