@@ -17,14 +17,25 @@ __global__ void relu_mask_kernel(float* __restrict__ g, const float* __restrict_
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     if (!(a[i] > 0.f)) g[i] = 0.f;
 }
+// logits[b][col0 + j] = row[j]: the learnable log_std row of policy std_type "parameter" broadcast over the batch
+// (reference networks/mlp.py:95-96)
+__global__ void bcast_row_kernel(float* __restrict__ out, int ld, int col0, const float* __restrict__ row, int B, int A) {
+  pdl_sync();
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < (long long)B * A; i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / A), j = (int)(i - (long long)b * A);
+    out[(size_t)b * ld + col0 + j] = row[j];
+  }
+}
 __global__ void zero_kernel(float* __restrict__ p, long long n) {
   pdl_sync();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = 0.f;
 }
 }  // namespace dsact
 
-struct CnnGeom {   // one network: conv encoder + two identical head MLPs
+struct CnnGeom {   // one network: conv encoder (possibly empty) + 1 or 2 identical head MLPs (+ a learnable log_std row)
   int nconv;
+  int nheads;            // 2: separate mean / log_std (std) heads; 1: one head (both outputs, or the mean with a log_std row)
+  int64_t ls_row;        // offset of the learnable log_std row [out] (policy std_type "parameter"), or -1
   int C[DSACT_MAX_CONV + 1], H[DSACT_MAX_CONV + 1], W[DSACT_MAX_CONV + 1];   // [0] = input image
   int K[DSACT_MAX_CONV], S[DSACT_MAX_CONV];
   int64_t cw[DSACT_MAX_CONV], cb[DSACT_MAX_CONV];
@@ -32,8 +43,8 @@ struct CnnGeom {   // one network: conv encoder + two identical head MLPs
   Net head;              // s[0] = F (+ act_dim), hidden..., s[L+1] = outputs of ONE head
   int64_t head_off[2];   // mean, log_std
   int64_t n;
-  bool build(const dsact_cnn_config& c, int extra_in, int out) {
-    nconv = c.n_conv;
+  bool build(const dsact_cnn_config& c, int extra_in, int out, int heads, bool std_row) {
+    nconv = c.n_conv; nheads = heads; ls_row = -1;
     C[0] = c.channels; H[0] = c.height; W[0] = c.width;
     n = 0;
     for (int j = 0; j < nconv; ++j) {
@@ -47,12 +58,16 @@ struct CnnGeom {   // one network: conv encoder + two identical head MLPs
     }
     F = C[nconv] * H[nconv] * W[nconv];
     head.build(F + extra_in, c.hidden, c.n_hidden, out);
-    for (int hd = 0; hd < 2; ++hd) { head_off[hd] = n; n += head.n; }
+    if (std_row) { ls_row = n; n += out; }   // nn.Module.parameters() yields a module's own parameters before its children's
+    head_off[1] = -1;
+    for (int hd = 0; hd < nheads; ++hd) { head_off[hd] = n; n += head.n; }
     return true;
   }
   ConvShape shape(int j, int B) const { return ConvShape{B, C[j], H[j], W[j], C[j + 1], K[j], S[j], H[j + 1], W[j + 1]}; }
   int64_t act_elems(int j) const { return (int64_t)C[j] * H[j] * W[j]; }   // per sample, activation j (0 = image)
 };
+
+constexpr int CNN_DGRAD_SMEM = 96 * 1024;   // opt-in dynamic shared memory of conv_dgrad8_kernel
 
 struct CnnHeadBuf { int64_t z[DSACT_MAX_HIDDEN], h[DSACT_MAX_HIDDEN], dz[DSACT_MAX_HIDDEN]; };
 
@@ -104,11 +119,22 @@ struct dsact_cnn_handle {
   }
 };
 
+// critics: two heads of one output (networks/cnn.py) or one head of two (networks/mlp.py:113-127); policy: mean and
+// log_std heads (networks/cnn.py, mlp.py std_type "mlp_separated") or a mean head + learnable row (std_type "parameter")
+static void cnn_build_nets(dsact_cnn_handle* h) {
+  const dsact_cnn_config& c = h->cfg;
+  const bool q1 = c.q_heads == 1, row = c.pi_std == 1;
+  h->q.build(c, c.act_dim, q1 ? 2 : 1, q1 ? 1 : 2, false);
+  h->pi.build(c, 0, c.act_dim, row ? 1 : 2, row);
+}
+
 static int cnn_validate(const dsact_cnn_config* c) {
   if (!c) return fail(DSACT_EINVAL, "null config");
   if (c->abi_version != DSACT_ABI_VERSION) return fail(DSACT_EINVAL, "abi_version %d != %d", c->abi_version, DSACT_ABI_VERSION);
   if (c->channels < 1 || c->height < 1 || c->width < 1 || c->act_dim < 1) return fail(DSACT_EINVAL, "bad observation / action shape");
-  if (c->n_conv < 1 || c->n_conv > DSACT_MAX_CONV) return fail(DSACT_EINVAL, "1..%d conv layers supported", DSACT_MAX_CONV);
+  if (c->n_conv < 0 || c->n_conv > DSACT_MAX_CONV) return fail(DSACT_EINVAL, "0..%d conv layers supported", DSACT_MAX_CONV);
+  if (c->q_heads != 1 && c->q_heads != 2) return fail(DSACT_EINVAL, "q_heads must be 1 (one head, two outputs) or 2 (mean and std heads)");
+  if (c->pi_std != 0 && c->pi_std != 1) return fail(DSACT_EINVAL, "pi_std must be 0 (log_std head) or 1 (learnable row)");
   for (int j = 0; j < c->n_conv; ++j)
     if (c->conv_kernel[j] < 1 || c->conv_kernel[j] > 4 || c->conv_stride[j] < 1 || c->conv_channels[j] < 1)
       return fail(DSACT_EINVAL, "conv layer %d: kernel sizes 1..4 are implemented (the reference's type_2 encoder)", j);
@@ -116,7 +142,7 @@ static int cnn_validate(const dsact_cnn_config* c) {
   if (c->act_hidden < 0 || c->act_hidden > DSACT_ACT_SELU) return fail(DSACT_EINVAL, "unknown activation");
   if (c->max_batch < 1 || c->delay_update < 1) return fail(DSACT_EINVAL, "bad max_batch / delay_update");
   CnnGeom g;
-  if (!g.build(*c, 0, 1)) return fail(DSACT_EINVAL, "the conv stack consumes the whole image");
+  if (!g.build(*c, 0, 1, 2, false)) return fail(DSACT_EINVAL, "the conv stack consumes the whole image");
   return DSACT_OK;
 }
 
@@ -206,17 +232,43 @@ static void cnn_heads_backward(dsact_cnn_handle* h, const Net& net, std::vector<
   c.check();
 }
 
+template <int R>
+static void launch_conv_fwd8(const ConvShape& s, long long rows, size_t smem, Ctx& c, const float* x, const float* w, const float* b, float* y) {
+  const dim3 grid((unsigned)((rows + 128 * R - 1) / (128 * R)), s.Cout / 8);
+  switch (s.K) {
+    case 1: launch_k(conv_fwd8_kernel<1, R>, grid, 128, smem, c, x, w, b, y, s); break;
+    case 2: launch_k(conv_fwd8_kernel<2, R>, grid, 128, smem, c, x, w, b, y, s); break;
+    case 3: launch_k(conv_fwd8_kernel<3, R>, grid, 128, smem, c, x, w, b, y, s); break;
+    default: launch_k(conv_fwd8_kernel<4, R>, grid, 128, smem, c, x, w, b, y, s); break;
+  }
+}
+
+// a layer whose window is its whole input is a linear layer over the flattened [Cin*K*K] sample (its NCHW order)
+static bool conv_is_linear(const ConvShape& s) { return s.Hin == s.K && s.Win == s.K; }
+
 static void cnn_conv_forward(dsact_cnn_handle* h, const CnnGeom& g, const float* params, const float* img, const int64_t* acts, int B, Ctx& c) {
   float* W = h->Wp();
   const float* x = img;
   for (int j = 0; j < g.nconv; ++j) {
     const ConvShape s = g.shape(j, B);
+    const long long rows = (long long)B * s.Hout * s.Wout;
     const size_t smem8 = sizeof(float) * 8 * s.Cin * s.K * s.K;
-    if (s.Cout % 8 == 0 && smem8 <= 48 * 1024) {   // eight output channels per thread
-      dim3 grid((s.Hout * s.Wout + 127) / 128, s.Cout / 8, B);
-      launch_k(conv_fwd8_kernel, grid, 128, smem8, c, x, params + g.cw[j], params + g.cb[j], W + acts[j + 1], s);
+    if (conv_is_linear(s)) {
+      GemmGroup G; G.n = 0;
+      GemmProb p = prob_zero();
+      const int kin = s.Cin * s.K * s.K;
+      p.A[0] = x; p.lda[0] = kin; p.K[0] = kin; p.B[0] = params + g.cw[j]; p.ldb[0] = kin;
+      p.M = B; p.N = s.Cout; p.C = W + acts[j + 1]; p.ldc = s.Cout; p.bias = params + g.cb[j]; p.act = ACT_RELU; p.epi = EPI_BIAS_ACT;
+      G.p[G.n++] = p;
+      launch_simt(h->num_sms, G, V_FWD, c);
+    } else if (s.Cout % 8 == 0 && smem8 <= 48 * 1024) {   // eight output channels per thread, 1 / 2 / 4 positions
+      const long long wave = 2LL * h->num_sms * 128;
+      const float *w = params + g.cw[j], *b = params + g.cb[j];
+      if (rows >= 4 * wave) launch_conv_fwd8<4>(s, rows, smem8, c, x, w, b, W + acts[j + 1]);
+      else if (rows >= 2 * wave) launch_conv_fwd8<2>(s, rows, smem8, c, x, w, b, W + acts[j + 1]);
+      else launch_conv_fwd8<1>(s, rows, smem8, c, x, w, b, W + acts[j + 1]);
     } else {
-      dim3 grid((s.Hout * s.Wout + 127) / 128, s.Cout, B);
+      dim3 grid((unsigned)((rows + 127) / 128), s.Cout);
       launch_k(conv_fwd_kernel, grid, 128, sizeof(float) * s.Cin * s.K * s.K, c, x, params + g.cw[j], params + g.cb[j], W + acts[j + 1], s);
     }
     c.done();
@@ -225,24 +277,74 @@ static void cnn_conv_forward(dsact_cnn_handle* h, const CnnGeom& g, const float*
   c.check();
 }
 
-// backward through one encoder: `gtop` = dL/d(feature) [B, F] (consumed), grads += into gparams
+template <int COB>
+static void launch_conv_wgrad(const ConvShape& s, int slabs, Ctx& c, const float* dy, const float* x, float* dw, float* db) {
+  const dim3 grid(s.Cin, s.Cout / COB, slabs);
+  switch (s.K) {
+    case 1: launch_k(conv_wgrad_kernel<1, COB>, grid, 256, 0, c, dy, x, dw, db, s); break;
+    case 2: launch_k(conv_wgrad_kernel<2, COB>, grid, 256, 0, c, dy, x, dw, db, s); break;
+    case 3: launch_k(conv_wgrad_kernel<3, COB>, grid, 256, 0, c, dy, x, dw, db, s); break;
+    default: launch_k(conv_wgrad_kernel<4, COB>, grid, 256, 0, c, dy, x, dw, db, s); break;
+  }
+}
+
+// backward through one encoder: `gtop` = dL/d(feature) [B, F] (consumed); gparams was cleared by begin_step_kernel
 static void cnn_conv_backward(dsact_cnn_handle* h, const CnnGeom& g, const float* params, float* gparams, const float* img,
                               const int64_t* acts, float* gtop, int B, Ctx& c) {
   float* W = h->Wp();
   float* gcur = gtop;
   float* bufs[2] = {W + h->ga, W + h->gb};
   int flip = 0;
+  {   // dz of the top layer = g (.) [feature > 0]; the layers below are masked by the dgrad kernel that produces them
+    const long long n_out = (long long)B * g.act_elems(g.nconv);
+    int blocks = (int)((n_out + 255) / 256); if (blocks > 8 * h->num_sms) blocks = 8 * h->num_sms;
+    launch_k(relu_mask_kernel, blocks, 256, 0, c, gcur, (const float*)(W + acts[g.nconv]), n_out); c.done();
+  }
   for (int j = g.nconv - 1; j >= 0; --j) {
     const ConvShape s = g.shape(j, B);
-    const long long n_out = (long long)B * g.act_elems(j + 1);
-    int blocks = (int)((n_out + 255) / 256); if (blocks > 8 * h->num_sms) blocks = 8 * h->num_sms;
-    launch_k(relu_mask_kernel, blocks, 256, 0, c, gcur, (const float*)(W + acts[j + 1]), n_out); c.done();   // dz_j = g_j (.) [a_j > 0]
     const float* x = j == 0 ? img : W + acts[j];
-    launch_k(conv_wgrad_kernel, dim3(s.Cin, s.Cout), 256, 0, c, (const float*)gcur, x, gparams + g.cw[j], gparams + g.cb[j], s); c.done();
+    const long long rows = (long long)B * s.Hout * s.Wout;
+    if (conv_is_linear(s)) {   // dW = dz^T x through the GEMM
+      GemmGroup gw; gw.n = 0;
+      GemmProb p = prob_zero();
+      const int kin = s.Cin * s.K * s.K;
+      p.A[0] = gcur; p.lda[0] = s.Cout; p.K[0] = B; p.B[0] = x; p.ldb[0] = kin;
+      p.M = s.Cout; p.N = kin; p.C = gparams + g.cw[j]; p.ldc = kin; p.epi = EPI_ATOMIC;
+      gw.p[gw.n++] = p;
+      launch_simt(h->num_sms, gw, V_WGRAD, c); c.done();
+      launch_k(colsum_rows_kernel, (s.Cout + 31) / 32, dim3(32, 8), 0, c, (const float*)gcur, B, s.Cout, gparams + g.cb[j]); c.done();
+    } else {
+      // slabs: >= 32 rows per thread, enough blocks for ~4 per SM
+      const int base = s.Cin * (s.Cout % 8 == 0 && s.K <= 3 ? s.Cout / 8 : s.Cout % 4 == 0 ? s.Cout / 4 : s.Cout);
+      long long slabs = (4LL * h->num_sms + base - 1) / base;
+      const long long cap = (rows + 256 * 32 - 1) / (256 * 32);
+      if (slabs > cap) slabs = cap;
+      if (slabs < 1) slabs = 1;
+      if (s.Cout % 8 == 0 && s.K <= 3) launch_conv_wgrad<8>(s, (int)slabs, c, gcur, x, gparams + g.cw[j], gparams + g.cb[j]);
+      else if (s.Cout % 4 == 0) launch_conv_wgrad<4>(s, (int)slabs, c, gcur, x, gparams + g.cw[j], gparams + g.cb[j]);
+      else launch_conv_wgrad<1>(s, (int)slabs, c, gcur, x, gparams + g.cw[j], gparams + g.cb[j]);
+      c.done();
+    }
     if (j > 0) {
       float* gnext = bufs[flip]; flip ^= 1;
-      dim3 grid((s.Hin * s.Win + 127) / 128, s.Cin, B);
-      launch_k(conv_dgrad_kernel, grid, 128, 0, c, (const float*)gcur, params + g.cw[j], x, gnext, s, 0); c.done();
+      const long long rin = (long long)B * s.Hin * s.Win;
+      const size_t smem8 = sizeof(float) * 8 * s.Cout * s.K * s.K;
+      if (conv_is_linear(s)) {   // dx = dz W (.) [x > 0]
+        GemmGroup G; G.n = 0;
+        GemmProb p = prob_zero();
+        const int kin = s.Cin * s.K * s.K;
+        p.A[0] = gcur; p.lda[0] = s.Cout; p.K[0] = s.Cout; p.B[0] = params + g.cw[j]; p.ldb[0] = kin;
+        p.M = B; p.N = kin; p.C = gnext; p.ldc = kin; p.epi = EPI_DACT; p.Zin = x; p.ldz = kin; p.act = ACT_RELU;
+        G.p[G.n++] = p;
+        launch_simt(h->num_sms, G, V_DGRAD, c);
+      } else if (s.Cin % 8 == 0 && smem8 <= (size_t)CNN_DGRAD_SMEM) {
+        dim3 grid((unsigned)((rin + 127) / 128), s.Cin / 8);
+        launch_k(conv_dgrad8_kernel, grid, 128, smem8, c, (const float*)gcur, params + g.cw[j], x, gnext, s, 1);
+      } else {
+        dim3 grid((unsigned)((rin + 127) / 128), s.Cin);
+        launch_k(conv_dgrad_kernel, grid, 128, 0, c, (const float*)gcur, params + g.cw[j], x, gnext, s, 1);
+      }
+      c.done();
       gcur = gnext;
     }
   }
@@ -257,8 +359,7 @@ int dsact_cnn_query_layout(const dsact_cnn_config* cfg, dsact_layout* out) {
   if (!out) return fail(DSACT_EINVAL, "null out");
   dsact_cnn_handle h;
   h.cfg = *cfg;
-  h.q.build(*cfg, cfg->act_dim, 1);
-  h.pi.build(*cfg, 0, cfg->act_dim);
+  cnn_build_nets(&h);
   h.layout();
   out->n_q = h.q.n; out->n_pi = h.pi.n;
   out->n_params = 2 * h.q.n + h.pi.n + 1;
@@ -277,12 +378,12 @@ int dsact_cnn_create(const dsact_cnn_config* cfg, int device, dsact_cnn_handle**
   cudaDeviceProp prop;
   CUDA_TRY(cudaGetDeviceProperties(&prop, device));
   if (prop.major != 10) return fail(DSACT_EARCH, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+  CUDA_TRY(cudaFuncSetAttribute(conv_dgrad8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CNN_DGRAD_SMEM));
   dsact_cnn_handle* h = new dsact_cnn_handle();
   h->cfg = *cfg;
   h->device = device;
   h->num_sms = prop.multiProcessorCount;
-  h->q.build(*cfg, cfg->act_dim, 1);
-  h->pi.build(*cfg, 0, cfg->act_dim);
+  cnn_build_nets(h);
   h->layout();
   *out = h;
   return DSACT_OK;
@@ -422,24 +523,32 @@ int dsact_cnn_step(dsact_cnn_handle* h, const dsact_batch* batch, const dsact_no
     cnn_conv_forward(h, q, Pq[k], batch->obs, h->convQ[k], B, c);
     cnn_conv_forward(h, q, Tq[k], batch->obs2, h->convQ[2 + k], B, c);
   }
-  const float* featP = W + h->convP[pi.nconv];
-  const float* featT = W + h->convT[pi.nconv];
-  const float* featQ[4] = {W + h->convQ[0][q.nconv], W + h->convQ[1][q.nconv], W + h->convQ[2][q.nconv], W + h->convQ[3][q.nconv]};
+  // without a conv stack (the MLP approximators with separate heads) the feature is the observation itself
+  const bool enc = pi.nconv > 0;
+  const float* featP = enc ? W + h->convP[pi.nconv] : batch->obs;
+  const float* featT = enc ? W + h->convT[pi.nconv] : batch->obs2;
+  const float* featQ[4] = {enc ? W + h->convQ[0][q.nconv] : batch->obs, enc ? W + h->convQ[1][q.nconv] : batch->obs,
+                           enc ? W + h->convQ[2][q.nconv] : batch->obs2, enc ? W + h->convQ[3][q.nconv] : batch->obs2};
 
   // ---- policy heads: logits = (mean | log_std), the layout sample_kernel reads (networks/cnn.py:233-240)
   {
     std::vector<CnnHeadFwd> v;
-    for (int hd = 0; hd < 2; ++hd) {
+    for (int hd = 0; hd < pi.nheads; ++hd) {
       v.push_back({Ppi + pi.head_off[hd], featP, pi.F, nullptr, 0, &h->hb[hd], true, W + h->logitsP + hd * A, 2 * A});
       v.push_back({Tpi + pi.head_off[hd], featT, pi.F, nullptr, 0, &h->hb[2 + hd], false, W + h->logitsT + hd * A, 2 * A});
     }
     cnn_heads_forward(h, pi.head, v, B, c);
+    if (pi.ls_row >= 0) {   // std_type "parameter": log_std columns = the learnable row
+      int blocks = (B * A + 255) / 256; if (blocks > 4 * h->num_sms) blocks = 4 * h->num_sms;
+      launch_k(bcast_row_kernel, blocks, 256, 0, c, W + h->logitsP, 2 * A, A, (const float*)(Ppi + pi.ls_row), B, A); c.done();
+      launch_k(bcast_row_kernel, blocks, 256, 0, c, W + h->logitsT, 2 * A, A, (const float*)(Tpi + pi.ls_row), B, A); c.done();
+    }
   }
   // ---- critics on (s, a): out = (mean, raw std) packed [B,2] (networks/cnn.py:454-461; softplus is applied by the loss kernels)
   {
     std::vector<CnnHeadFwd> v;
     for (int k = 0; k < 2; ++k)
-      for (int hd = 0; hd < 2; ++hd)
+      for (int hd = 0; hd < q.nheads; ++hd)
         v.push_back({Pq[k] + q.head_off[hd], featQ[k], q.F, batch->act, A, &h->hb[4 + 2 * k + hd], true, W + h->outQ[k] + hd, 2});
     cnn_heads_forward(h, q.head, v, B, c);
   }
@@ -461,7 +570,7 @@ int dsact_cnn_step(dsact_cnn_handle* h, const dsact_batch* batch, const dsact_no
   {
     std::vector<CnnHeadFwd> v;
     for (int k = 0; k < 2; ++k)
-      for (int hd = 0; hd < 2; ++hd)
+      for (int hd = 0; hd < q.nheads; ++hd)
         v.push_back({Tq[k] + q.head_off[hd], featQ[2 + k], q.F, W + h->act2, A, &h->hb[8 + 2 * k + hd], false, W + h->outQ[2 + k] + hd, 2});
     for (int k = 0; k < 2; ++k)
       v.push_back({Pq[k] + q.head_off[0], featQ[k], q.F, W + h->new_act, A, &h->hb[12 + k], true, W + h->outQ[4 + k], 2});
@@ -482,7 +591,7 @@ int dsact_cnn_step(dsact_cnn_handle* h, const dsact_batch* batch, const dsact_no
       a.out_q[k] = W + h->outQ[k]; a.out_qt[k] = W + h->outQ[2 + k]; a.out_qa[k] = W + h->outQ[4 + k];
       a.d_out_q[k] = W + h->dOut[k]; a.d_out_qa[k] = W + h->dOut[4 + k];
       a.gbias_q[k] = Gq[k] + q.head_off[0] + q.head.b[q.head.L];          // output bias of the mean head
-      a.gbias_q_raw[k] = Gq[k] + q.head_off[1] + q.head.b[q.head.L];      // ... and of the log_std head
+      a.gbias_q_raw[k] = q.nheads == 2 ? Gq[k] + q.head_off[1] + q.head.b[q.head.L] : nullptr;   // ... of the std head (one head: the next element)
       a.img_q[k] = ImgOut{nullptr, 0, 1, 0}; a.img_qa[k] = ImgOut{nullptr, 0, 1, 0};
     }
     a.state = h->buf.state; a.B = B; a.gamma = (float)cf.gamma; a.inv_global_batch = invB;
@@ -502,7 +611,7 @@ int dsact_cnn_step(dsact_cnn_handle* h, const dsact_batch* batch, const dsact_no
   {
     std::vector<CnnHeadBwd> v;
     for (int k = 0; k < 2; ++k)
-      for (int hd = 0; hd < 2; ++hd)   // d(feature|act): only the feature part is used (replayed actions carry no gradient)
+      for (int hd = 0; hd < q.nheads; ++hd)   // d(feature|act): only the feature part is used (replayed actions carry no gradient)
         v.push_back({Pq[k] + q.head_off[hd], Gq[k] + q.head_off[hd], featQ[k], q.F, batch->act, A, &h->hb[4 + 2 * k + hd],
                      W + h->dOut[k] + hd, 2, nullptr});
     for (int k = 0; k < 2; ++k)
@@ -511,10 +620,10 @@ int dsact_cnn_step(dsact_cnn_handle* h, const dsact_batch* batch, const dsact_no
   }
   // feature gradients of the critics: the layer-0 input gradient of both heads, feature columns only.  The generic
   // backward above skipped it for the critic passes (din = null): do it here with the feature-width problem
-  for (int k = 0; k < 2; ++k) {
+  for (int k = 0; k < 2 && enc; ++k) {
     GemmGroup gd;
     gd.n = 0;
-    for (int hd = 0; hd < 2; ++hd) {
+    for (int hd = 0; hd < q.nheads; ++hd) {
       GemmProb p = prob_zero();
       const Net& net = q.head;
       p.A[0] = W + h->hb[4 + 2 * k + hd].dz[0]; p.lda[0] = net.s[1]; p.K[0] = net.s[1];
@@ -535,7 +644,7 @@ int dsact_cnn_step(dsact_cnn_handle* h, const dsact_batch* batch, const dsact_no
     a.hi = h->buf.act_high; a.lo = h->buf.act_low;
     a.d_logits = W + h->dlogits; a.state = h->buf.state;
     a.gbias = Gpi + pi.head_off[0] + pi.head.b[pi.head.L];        // output bias of the mean head [A]
-    a.gbias_ls = Gpi + pi.head_off[1] + pi.head.b[pi.head.L];     // ... of the log_std head [A]
+    a.gbias_ls = pi.ls_row >= 0 ? Gpi + pi.ls_row : Gpi + pi.head_off[1] + pi.head.b[pi.head.L];   // ... of the log_std head / row [A]
     a.B = B; a.A = A; a.min_log_std = (float)cf.min_log_std; a.max_log_std = (float)cf.max_log_std;
     a.inv_global_batch = invB;
     a.img = ImgOut{nullptr, 0, 1, 0};
@@ -545,14 +654,16 @@ int dsact_cnn_step(dsact_cnn_handle* h, const dsact_batch* batch, const dsact_no
   }
   {
     std::vector<CnnHeadBwd> v;
-    for (int hd = 0; hd < 2; ++hd)
+    for (int hd = 0; hd < pi.nheads; ++hd)
       v.push_back({Ppi + pi.head_off[hd], Gpi + pi.head_off[hd], featP, pi.F, nullptr, 0, &h->hb[hd], W + h->dlogits + hd * A, 2 * A,
-                   W + h->dfeat[0]});
+                   enc ? W + h->dfeat[0] : nullptr});
     cnn_heads_backward(h, pi.head, v, B, c);
   }
   // ---- encoders backward
-  cnn_conv_backward(h, pi, Ppi, Gpi, batch->obs, h->convP, W + h->dfeat[0], B, c);
-  for (int k = 0; k < 2; ++k) cnn_conv_backward(h, q, Pq[k], Gq[k], batch->obs, h->convQ[k], W + h->dfeat[1 + k], B, c);
+  if (enc) {
+    cnn_conv_backward(h, pi, Ppi, Gpi, batch->obs, h->convP, W + h->dfeat[0], B, c);
+    for (int k = 0; k < 2; ++k) cnn_conv_backward(h, q, Pq[k], Gq[k], batch->obs, h->convQ[k], W + h->dfeat[1 + k], B, c);
+  }
 
   // ---- end of backward bookkeeping + Adam / Polyak
   AdamHyper hy{cf.lr_q, cf.lr_pi, cf.lr_alpha, cf.adam_beta1, cf.adam_beta2};

@@ -35,7 +35,7 @@ from dsact_host import net_kwargs
 
 from dsac_v2_b200 import _lib, dp
 from dsac_v2_b200.engine import STAT_KEYS, Engine, make_config
-from dsac_v2_b200.engine_cnn import CnnEngine, make_cnn_config
+from dsac_v2_b200.engine_cnn import CnnEngine, make_cnn_config, make_heads_config
 
 _TRAINABLE = ("q1", "q2", "policy")
 
@@ -51,6 +51,7 @@ class ApproxContainer(nn.Module):
         if q_args["apprfunc"] != pi_args["apprfunc"]:
             raise NotImplementedError("value and policy approximators must be of the same type (both MLP or both CNN)")
         self._cnn = q_args["apprfunc"] == "CNN"   # BASELINE config 5: conv encoder + separate mean / log_std heads
+        self._heads_std = None
         mod = _cnn if self._cnn else _mlp
         q_cls, pi_cls = getattr(mod, q_args["name"], None), getattr(mod, pi_args["name"], None)
         if q_cls is None or pi_cls is None:
@@ -78,6 +79,14 @@ class ApproxContainer(nn.Module):
             self._cfg_args = dict(obs_shape=tuple(q_args["obs_dim"]), act_dim=q_args["act_dim"], kernels=t["kernels"],
                                   channels=t["channels"], strides=t["strides"], hidden=t["heads"],
                                   act_hidden=q_args["hidden_activation"], **common)
+        elif pi_args["std_type"] != "mlp_shared":
+            # separate mean / log_std (reference networks/mlp.py:43-72): the head-wise fp32 engine without an encoder
+            if q_args["hidden_sizes"] != pi_args["hidden_sizes"] or q_args["hidden_activation"] != pi_args["hidden_activation"]:
+                raise NotImplementedError("policy std_type != 'mlp_shared': critics and policy take one hidden_sizes / activation")
+            self._cnn = True     # same engine class and entry points as the CNN approximators
+            self._heads_std = pi_args["std_type"]
+            self._cfg_args = dict(obs_dim=q_args["obs_dim"], act_dim=q_args["act_dim"], hidden=q_args["hidden_sizes"],
+                                  std_type=pi_args["std_type"], act_hidden=q_args["hidden_activation"], **common)
         else:
             self._cfg_args = dict(
                 obs_dim=q_args["obs_dim"], act_dim=q_args["act_dim"],
@@ -116,7 +125,8 @@ class ApproxContainer(nn.Module):
         if eng is not None and eng.device != torch.device(device):
             self._engine = eng = None  # moved to another GPU: rebuild there
         if eng is None and self._cnn:
-            cfg = make_cnn_config(max_batch=self._max_batch, **self._cfg_args)
+            make = make_heads_config if self._heads_std else make_cnn_config
+            cfg = make(max_batch=self._max_batch, **self._cfg_args)
             eng = self._engine = CnnEngine(cfg, device, self.policy.act_high_lim, self.policy.act_low_lim)
             eng.seed(self.device_seed())
         elif eng is None:

@@ -43,11 +43,18 @@ class StochaPolicy(nn.Module, ActionDistributionMixin):
     def __init__(self, **kwargs):
         super().__init__()
         self.std_type = kwargs["std_type"]
-        if self.std_type != "mlp_shared":
-            raise NotImplementedError(f"policy std_type={self.std_type!r}: the B200 engine implements 'mlp_shared'")
         obs_dim, act_dim = kwargs["obs_dim"], kwargs["act_dim"]
-        self.policy = build_mlp([obs_dim, *kwargs["hidden_sizes"], 2 * act_dim],
-                                kwargs["hidden_activation"], kwargs["output_activation"])
+        net = lambda out: build_mlp([obs_dim, *kwargs["hidden_sizes"], out], kwargs["hidden_activation"], kwargs["output_activation"])
+        if self.std_type == "mlp_shared":          # one MLP, 2 * act_dim outputs (reference :56-62)
+            self.policy = net(2 * act_dim)
+        elif self.std_type == "mlp_separated":     # two MLPs (reference :43-54); creation order = the reference's RNG consumption
+            self.mean = net(act_dim)
+            self.log_std = net(act_dim)
+        elif self.std_type == "parameter":         # mean MLP + learnable row (reference :64-71)
+            self.mean = net(act_dim)
+            self.log_std = nn.Parameter(-0.5 * torch.ones(1, act_dim))
+        else:
+            raise NotImplementedError(f"policy std_type={self.std_type!r}")
         self.min_log_std = kwargs["min_log_std"]
         self.max_log_std = kwargs["max_log_std"]
         self.register_buffer("act_high_lim", torch.from_numpy(kwargs["act_high_lim"]))
@@ -55,7 +62,13 @@ class StochaPolicy(nn.Module, ActionDistributionMixin):
         self.action_distribution_cls = kwargs["action_distribution_cls"]
 
     def forward(self, obs):
-        mean, log_std = self.policy(obs).chunk(2, dim=-1)
+        if self.std_type == "mlp_shared":
+            mean, log_std = self.policy(obs).chunk(2, dim=-1)
+        elif self.std_type == "mlp_separated":
+            mean, log_std = self.mean(obs), self.log_std(obs)
+        else:
+            mean = self.mean(obs)
+            log_std = self.log_std + torch.zeros_like(mean)
         std = log_std.clamp(self.min_log_std, self.max_log_std).exp()
         return torch.cat((mean, std), dim=-1)
 

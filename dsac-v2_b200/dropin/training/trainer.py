@@ -13,7 +13,9 @@ training/trainer.py:15-158), reorganised around the GPU-resident engine:
 Optional (kwargs, all off by default = the reference's serial semantics):
 * `dsact_async_sampler=True` — the CPU env loop runs in a background thread and feeds the replay buffer
   asynchronously (north_star: "the off_sampler env loop stays on CPU and feeds the buffer asynchronously"); the
-  trainer drains what has been collected at each iteration instead of waiting for `sample_batch_size` env steps;
+  trainer drains what has been collected at each iteration instead of waiting for `sample_batch_size` env steps,
+  and publishes the policy without blocking (`publish_policy`: one async D2H copy; the sampler thread picks the
+  snapshot up between two `sample()` calls);
 * `dsact_full_checkpoint=True` — next to every `apprfunc_{it}.pkl` write `trainstate_{it}.pkl` (Adam moments,
   mean_std EMA, counters, generator state, replay ring); `dsact_resume_dir=<file>` restores it.
 """
@@ -96,6 +98,7 @@ class OffSerialTrainer:
 
         self.async_sampler = bool(kwargs.get("dsact_async_sampler", False))
         self._mirror_lock = threading.Lock()
+        self._pub_lock, self._pub_event, self._pub_seq, self._applied_seq = threading.Lock(), None, 0, 0
         self._feed, self._stop, self._thread = queue.Queue(maxsize=64), threading.Event(), None
         if self.async_sampler:
             self._thread = threading.Thread(target=self._sampler_loop, name="dsact-sampler", daemon=True)
@@ -113,25 +116,54 @@ class OffSerialTrainer:
         """Copy the current policy weights GPU -> pinned host -> the CPU module sampler/evaluator use."""
         lo, hi = self._policy_span
         eng = self.networks.engine()
-        self._policy_host.copy_(eng.params[lo:hi], non_blocking=True)
-        torch.cuda.current_stream(eng.device).synchronize()
-        off = 0
-        lock = getattr(self, "_mirror_lock", None)
+        lock = getattr(self, "_mirror_lock", None)   # absent during construction (no sampler thread yet)
         if lock:
-            lock.acquire()
+            lock.acquire()                           # waits for a running sample() of the sampler thread
         try:
+            with getattr(self, "_pub_lock", threading.Lock()):
+                self._policy_host.copy_(eng.params[lo:hi], non_blocking=True)
+                torch.cuda.current_stream(eng.device).synchronize()
+                off = 0
+                with torch.no_grad():
+                    for p in self.cpu_networks.policy.parameters():
+                        p.copy_(self._policy_host[off:off + p.numel()].view(p.shape))
+                        off += p.numel()
+                if hasattr(self, "_pub_seq"):
+                    self._applied_seq = self._pub_seq    # anything published earlier is older than this snapshot
+        finally:
+            if lock:
+                lock.release()
+
+    def publish_policy(self):
+        """Asynchronous mode: enqueue the GPU -> pinned host copy of the current policy and return; the sampler thread
+        moves the snapshot into its CPU module between two `sample()` calls.  The trainer neither synchronises the
+        stream nor waits for a running `sample()`."""
+        lo, hi = self._policy_span
+        eng = self.networks.engine()
+        with self._pub_lock:   # held by the sampler thread only while it copies host -> module
+            self._policy_host.copy_(eng.params[lo:hi], non_blocking=True)
+            if self._pub_event is None:
+                self._pub_event = torch.cuda.Event()
+            self._pub_event.record(torch.cuda.current_stream(eng.device))
+            self._pub_seq += 1
+
+    def _apply_published(self):
+        with self._pub_lock:
+            if self._pub_seq == self._applied_seq:
+                return
+            self._pub_event.synchronize()
+            off = 0
             with torch.no_grad():
                 for p in self.cpu_networks.policy.parameters():
                     p.copy_(self._policy_host[off:off + p.numel()].view(p.shape))
                     off += p.numel()
-        finally:
-            if lock:
-                lock.release()
+            self._applied_seq = self._pub_seq
 
     # ---- asynchronous sampler feed (SURVEY §8f rank 2) --------------------------------------
     def _sampler_loop(self):
         while not self._stop.is_set():
             with self._mirror_lock:   # act with a consistent snapshot of the mirrored policy
+                self._apply_published()
                 samples, tb = self.sampler.sample()
             try:
                 self._feed.put((samples, tb), timeout=1.0)
@@ -179,7 +211,7 @@ class OffSerialTrainer:
         sampler_tb_dict = {}
         if self.async_sampler:
             if self.iteration % self.mirror_interval == 0:
-                self.refresh_policy_mirror()
+                self.publish_policy()
             sampler_tb_dict = self._drain_feed()
         elif self.iteration % self.sample_interval == 0:
             if self.iteration % self.mirror_interval == 0:

@@ -17,7 +17,9 @@ from .engine import STAT_KEYS
 def make_cnn_config(obs_shape: Sequence[int], act_dim: int, kernels: Sequence[int], channels: Sequence[int],
                     strides: Sequence[int], hidden: Sequence[int], *, max_batch: int, act_hidden: str = "gelu", gamma=0.99,
                     tau=0.005, tau_b=None, delay_update=2, auto_alpha=True, alpha=0.2, lr_q=1e-4, lr_pi=1e-4, lr_alpha=3e-4,
-                    min_log_std=-20.0, max_log_std=0.5) -> CnnConfig:
+                    min_log_std=-20.0, max_log_std=0.5, q_heads: int = 2, pi_std: str = "head") -> CnnConfig:
+    """`q_heads` / `pi_std` select the head wiring: (2, "head") = networks/cnn.py; with no conv layers and
+    obs_shape = (obs_dim, 1, 1): (1, "head") = networks/mlp.py with policy std_type "mlp_separated", (1, "row") = "parameter"."""
     if len(kernels) > _lib.MAX_CONV or len(hidden) > _lib.MAX_HIDDEN:
         raise ValueError("too many layers")
     c = CnnConfig()
@@ -35,7 +37,15 @@ def make_cnn_config(obs_shape: Sequence[int], act_dim: int, kernels: Sequence[in
     c.lr_q, c.lr_pi, c.lr_alpha = float(lr_q), float(lr_pi), float(lr_alpha)
     c.min_log_std, c.max_log_std = float(min_log_std), float(max_log_std)
     c.adam_beta1, c.adam_beta2, c.adam_eps = 0.9, 0.999, 1e-8
+    c.q_heads, c.pi_std = int(q_heads), {"head": 0, "row": 1}[pi_std]
     return c
+
+
+def make_heads_config(obs_dim: int, act_dim: int, hidden: Sequence[int], std_type: str, **kw) -> CnnConfig:
+    """The MLP approximators whose policy keeps mean and log_std apart (reference networks/mlp.py:43-72, std_type
+    "mlp_separated" / "parameter"): no encoder, one two-output head per critic."""
+    return make_cnn_config((int(obs_dim), 1, 1), act_dim, (), (), (), hidden, q_heads=1,
+                           pi_std={"mlp_separated": "head", "parameter": "row"}[std_type], **kw)
 
 
 class CnnEngine:
@@ -98,19 +108,32 @@ class CnnEngine:
             cin, hh, ww = co, (hh - k) // st + 1, (ww - k) // st + 1
         feat = cin * hh * ww
         hidden = [c.hidden[j] for j in range(c.n_hidden)]
+
+        def leaf(net, name, shape):
+            nonlocal off
+            n = 1
+            for d in shape:
+                n *= int(d)
+            out.append((f"{net}.{name}", f"{net}_target.{name}", off, n, shape))
+            off += n
+
+        def mlp(net, head, sizes):
+            for j in range(len(sizes) - 1):
+                leaf(net, f"{head}.{2 * j}.weight", (sizes[j + 1], sizes[j]))
+                leaf(net, f"{head}.{2 * j}.bias", (sizes[j + 1],))
+
         for net, extra, width in (("q1", c.act_dim, 1), ("q2", c.act_dim, 1), ("policy", 0, c.act_dim)):
             for name, wshape, bshape in shapes:
-                for leaf, shape in (("weight", wshape), ("bias", bshape)):
-                    n = int(torch.tensor(shape).prod())
-                    out.append((f"{net}.{name}.{leaf}", f"{net}_target.{name}.{leaf}", off, n, shape))
-                    off += n
-            sizes = [feat + extra] + hidden + [width]
-            for head in ("mean", "log_std"):
-                for j in range(len(sizes) - 1):
-                    for leaf, shape in (("weight", (sizes[j + 1], sizes[j])), ("bias", (sizes[j + 1],))):
-                        n = int(torch.tensor(shape).prod())
-                        out.append((f"{net}.{head}.{2 * j}.{leaf}", f"{net}_target.{head}.{2 * j}.{leaf}", off, n, shape))
-                        off += n
+                leaf(net, f"{name}.weight", wshape)
+                leaf(net, f"{name}.bias", bshape)
+            if net != "policy" and c.q_heads == 1:          # networks/mlp.py ActionValueDistri: self.q
+                mlp(net, "q", [feat + extra] + hidden + [2])
+            elif net == "policy" and c.pi_std == 1:         # the module's own parameter precedes its children's
+                leaf(net, "log_std", (1, width))
+                mlp(net, "mean", [feat] + hidden + [width])
+            else:
+                for head in ("mean", "log_std"):
+                    mlp(net, head, [feat + extra] + hidden + [width])
         return out, off
 
     def load_weights(self, weights: dict):
@@ -140,7 +163,7 @@ class CnnEngine:
             t = {k: data[k].to(device=self.device, dtype=torch.float32).contiguous() for k in ("obs", "act", "rew", "obs2", "done")}
             B = t["obs"].shape[0]
             c = self.cfg
-            if tuple(t["obs"].shape[1:]) != (c.channels, c.height, c.width) or t["act"].shape != (B, c.act_dim):
+            if t["obs"][0].numel() != self.obs_elems or t["obs2"].shape != t["obs"].shape or t["act"].shape != (B, c.act_dim):
                 raise ValueError("minibatch shapes do not match the configured observation / action shape")
             b = Batch(t["obs"].data_ptr(), t["act"].data_ptr(), t["rew"].data_ptr(), t["obs2"].data_ptr(), t["done"].data_ptr(), B, None)
             n = None
@@ -188,7 +211,7 @@ class CnnEngine:
             off = (ptr - base) // 4
             return self._ws_view[off:off + n].view(shape)
 
-        img = (B, c.channels, c.height, c.width)
+        img = (B, c.channels, c.height, c.width) if c.n_conv else (B, self.obs_elems)
         return {"obs": view(out.obs, B * self.obs_elems, img), "obs2": view(out.obs2, B * self.obs_elems, img),
                 "act": view(out.act, B * A, (B, A)), "rew": view(out.rew, B, (B,)), "done": view(out.done, B, (B,)),
                 "logp": view(out.logp, B, (B,))}

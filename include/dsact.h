@@ -224,12 +224,16 @@ typedef struct dsact_cnn_config {
   int32_t abi_version;
   int32_t channels, height, width;   /* obsv_dim = (C, H, W) */
   int32_t act_dim;
-  int32_t n_conv;
+  int32_t n_conv;                    /* 0: no encoder, the observation (channels = obs_dim, height = width = 1) feeds the heads */
   int32_t conv_kernel[DSACT_MAX_CONV], conv_channels[DSACT_MAX_CONV], conv_stride[DSACT_MAX_CONV];
   int32_t n_hidden;                  /* hidden layers of every head MLP (networks/cnn.py:204 mlp_hidden_layers) */
   int32_t hidden[DSACT_MAX_HIDDEN];
   int32_t act_hidden;                /* DSACT_ACT_* of the head MLPs (the conv stack is ReLU) */
   int32_t max_batch, auto_alpha, delay_update;
+  int32_t q_heads;                   /* 2: separate mean and std heads (networks/cnn.py:383-461); 1: one head with both outputs
+                                        (networks/mlp.py:113-127, with n_conv = 0) */
+  int32_t pi_std;                    /* 0: log_std from its own head (networks/cnn.py, mlp.py std_type "mlp_separated");
+                                        1: learnable row [1, act_dim] (mlp.py std_type "parameter"), laid out BEFORE the mean head */
   double gamma, tau, tau_b, alpha_fixed, lr_q, lr_pi, lr_alpha, min_log_std, max_log_std;
   double adam_beta1, adam_beta2, adam_eps;
 } dsact_cnn_config;
