@@ -19,6 +19,7 @@ NUM_STATS = 16
 
 ACTIVATIONS = {"linear": 0, "relu": 1, "gelu": 2, "tanh": 3, "sigmoid": 4, "elu": 5, "selu": 6}
 GEMM_MODES = {"fp32": 0, "bf16x3": 1, "bf16": 2}
+ACT_DISTS = {"TanhGaussDistribution": 0, "GaussDistribution": 1}   # utils/act_distribution_cls.py
 
 # state slots, include/dsact.h
 STATE_STDSUM = 4
@@ -33,7 +34,7 @@ class Config(C.Structure):
         ("hidden_q", C.c_int32 * MAX_HIDDEN), ("hidden_pi", C.c_int32 * MAX_HIDDEN),
         ("act_q", C.c_int32), ("act_pi", C.c_int32), ("max_batch", C.c_int32),
         ("auto_alpha", C.c_int32), ("delay_update", C.c_int32), ("gemm_mode", C.c_int32),
-        ("use_graph", C.c_int32),
+        ("use_graph", C.c_int32), ("act_dist", C.c_int32),
         ("gamma", C.c_double), ("tau", C.c_double), ("tau_b", C.c_double), ("alpha_fixed", C.c_double),
         ("lr_q", C.c_double), ("lr_pi", C.c_double), ("lr_alpha", C.c_double),
         ("min_log_std", C.c_double), ("max_log_std", C.c_double),
@@ -51,7 +52,7 @@ class CnnConfig(C.Structure):
         ("conv_kernel", C.c_int32 * MAX_CONV), ("conv_channels", C.c_int32 * MAX_CONV), ("conv_stride", C.c_int32 * MAX_CONV),
         ("n_hidden", C.c_int32), ("hidden", C.c_int32 * MAX_HIDDEN), ("act_hidden", C.c_int32),
         ("max_batch", C.c_int32), ("auto_alpha", C.c_int32), ("delay_update", C.c_int32),
-        ("q_heads", C.c_int32), ("pi_std", C.c_int32),
+        ("q_heads", C.c_int32), ("act_dist", C.c_int32), ("pi_std", C.c_int32),
         ("gamma", C.c_double), ("tau", C.c_double), ("tau_b", C.c_double), ("alpha_fixed", C.c_double),
         ("lr_q", C.c_double), ("lr_pi", C.c_double), ("lr_alpha", C.c_double),
         ("min_log_std", C.c_double), ("max_log_std", C.c_double),

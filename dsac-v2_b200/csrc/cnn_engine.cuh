@@ -135,9 +135,10 @@ static int cnn_validate(const dsact_cnn_config* c) {
   if (c->n_conv < 0 || c->n_conv > DSACT_MAX_CONV) return fail(DSACT_EINVAL, "0..%d conv layers supported", DSACT_MAX_CONV);
   if (c->q_heads != 1 && c->q_heads != 2) return fail(DSACT_EINVAL, "q_heads must be 1 (one head, two outputs) or 2 (mean and std heads)");
   if (c->pi_std != 0 && c->pi_std != 1) return fail(DSACT_EINVAL, "pi_std must be 0 (log_std head) or 1 (learnable row)");
+  if (c->act_dist != 0 && c->act_dist != 1) return fail(DSACT_EINVAL, "act_dist must be 0 (TanhGaussDistribution) or 1 (GaussDistribution)");
   for (int j = 0; j < c->n_conv; ++j)
-    if (c->conv_kernel[j] < 1 || c->conv_kernel[j] > 4 || c->conv_stride[j] < 1 || c->conv_channels[j] < 1)
-      return fail(DSACT_EINVAL, "conv layer %d: kernel sizes 1..4 are implemented (the reference's type_2 encoder)", j);
+    if (c->conv_kernel[j] < 1 || (c->conv_kernel[j] > 4 && c->conv_kernel[j] != 8) || c->conv_stride[j] < 1 || c->conv_channels[j] < 1)
+      return fail(DSACT_EINVAL, "conv layer %d: kernel sizes 1..4 and 8 are implemented (the reference's type_1 / type_2 encoders)", j);
   if (c->n_hidden < 1 || c->n_hidden > DSACT_MAX_HIDDEN) return fail(DSACT_EINVAL, "1..%d hidden layers per head", DSACT_MAX_HIDDEN);
   if (c->act_hidden < 0 || c->act_hidden > DSACT_ACT_SELU) return fail(DSACT_EINVAL, "unknown activation");
   if (c->max_batch < 1 || c->delay_update < 1) return fail(DSACT_EINVAL, "bad max_batch / delay_update");
@@ -239,7 +240,10 @@ static void launch_conv_fwd8(const ConvShape& s, long long rows, size_t smem, Ct
     case 1: launch_k(conv_fwd8_kernel<1, R>, grid, 128, smem, c, x, w, b, y, s); break;
     case 2: launch_k(conv_fwd8_kernel<2, R>, grid, 128, smem, c, x, w, b, y, s); break;
     case 3: launch_k(conv_fwd8_kernel<3, R>, grid, 128, smem, c, x, w, b, y, s); break;
-    default: launch_k(conv_fwd8_kernel<4, R>, grid, 128, smem, c, x, w, b, y, s); break;
+    case 4: launch_k(conv_fwd8_kernel<4, R>, grid, 128, smem, c, x, w, b, y, s); break;
+    default:   // 8x8 window (type_1's first layer): one position per thread (64 taps in registers)
+      if constexpr (R == 1) launch_k(conv_fwd8_kernel<8, 1>, grid, 128, smem, c, x, w, b, y, s);
+      break;
   }
 }
 
@@ -264,7 +268,8 @@ static void cnn_conv_forward(dsact_cnn_handle* h, const CnnGeom& g, const float*
     } else if (s.Cout % 8 == 0 && smem8 <= 48 * 1024) {   // eight output channels per thread, 1 / 2 / 4 positions
       const long long wave = 2LL * h->num_sms * 128;
       const float *w = params + g.cw[j], *b = params + g.cb[j];
-      if (rows >= 4 * wave) launch_conv_fwd8<4>(s, rows, smem8, c, x, w, b, W + acts[j + 1]);
+      if (s.K > 4) launch_conv_fwd8<1>(s, rows, smem8, c, x, w, b, W + acts[j + 1]);
+      else if (rows >= 4 * wave) launch_conv_fwd8<4>(s, rows, smem8, c, x, w, b, W + acts[j + 1]);
       else if (rows >= 2 * wave) launch_conv_fwd8<2>(s, rows, smem8, c, x, w, b, W + acts[j + 1]);
       else launch_conv_fwd8<1>(s, rows, smem8, c, x, w, b, W + acts[j + 1]);
     } else {
@@ -284,7 +289,8 @@ static void launch_conv_wgrad(const ConvShape& s, int slabs, Ctx& c, const float
     case 1: launch_k(conv_wgrad_kernel<1, COB>, grid, 256, 0, c, dy, x, dw, db, s); break;
     case 2: launch_k(conv_wgrad_kernel<2, COB>, grid, 256, 0, c, dy, x, dw, db, s); break;
     case 3: launch_k(conv_wgrad_kernel<3, COB>, grid, 256, 0, c, dy, x, dw, db, s); break;
-    default: launch_k(conv_wgrad_kernel<4, COB>, grid, 256, 0, c, dy, x, dw, db, s); break;
+    case 4: if constexpr (COB <= 4) launch_k(conv_wgrad_kernel<4, COB>, grid, 256, 0, c, dy, x, dw, db, s); break;
+    default: if constexpr (COB == 1) launch_k(conv_wgrad_kernel<8, 1>, grid, 256, 0, c, dy, x, dw, db, s); break;   // 64 taps x 1 channel
   }
 }
 
@@ -315,13 +321,14 @@ static void cnn_conv_backward(dsact_cnn_handle* h, const CnnGeom& g, const float
       launch_k(colsum_rows_kernel, (s.Cout + 31) / 32, dim3(32, 8), 0, c, (const float*)gcur, B, s.Cout, gparams + g.cb[j]); c.done();
     } else {
       // slabs: >= 32 rows per thread, enough blocks for ~4 per SM
-      const int base = s.Cin * (s.Cout % 8 == 0 && s.K <= 3 ? s.Cout / 8 : s.Cout % 4 == 0 ? s.Cout / 4 : s.Cout);
+      const int cob = s.K > 4 ? 1 : (s.Cout % 8 == 0 && s.K <= 3) ? 8 : s.Cout % 4 == 0 ? 4 : 1;   // K*K*cob accumulators per thread
+      const int base = s.Cin * (s.Cout / cob);
       long long slabs = (4LL * h->num_sms + base - 1) / base;
       const long long cap = (rows + 256 * 32 - 1) / (256 * 32);
       if (slabs > cap) slabs = cap;
       if (slabs < 1) slabs = 1;
-      if (s.Cout % 8 == 0 && s.K <= 3) launch_conv_wgrad<8>(s, (int)slabs, c, gcur, x, gparams + g.cw[j], gparams + g.cb[j]);
-      else if (s.Cout % 4 == 0) launch_conv_wgrad<4>(s, (int)slabs, c, gcur, x, gparams + g.cw[j], gparams + g.cb[j]);
+      if (cob == 8) launch_conv_wgrad<8>(s, (int)slabs, c, gcur, x, gparams + g.cw[j], gparams + g.cb[j]);
+      else if (cob == 4) launch_conv_wgrad<4>(s, (int)slabs, c, gcur, x, gparams + g.cw[j], gparams + g.cb[j]);
       else launch_conv_wgrad<1>(s, (int)slabs, c, gcur, x, gparams + g.cw[j], gparams + g.cb[j]);
       c.done();
     }
@@ -559,7 +566,7 @@ int dsact_cnn_step(dsact_cnn_handle* h, const dsact_batch* batch, const dsact_no
     a.act[0] = W + h->new_act; a.act[1] = W + h->act2;
     a.logp[0] = W + h->logp_new; a.logp[1] = W + h->logp2;
     a.hi = h->buf.act_high; a.lo = h->buf.act_low; a.state = h->buf.state;
-    a.B = B; a.A = A; a.min_log_std = (float)cf.min_log_std; a.max_log_std = (float)cf.max_log_std;
+    a.B = B; a.A = A; a.min_log_std = (float)cf.min_log_std; a.max_log_std = (float)cf.max_log_std; a.gauss = cf.act_dist;
     a.img[0] = ImgOut{nullptr, 0, 1, 0}; a.img[1] = ImgOut{nullptr, 0, 1, 0};
     a.out_q[0] = W + h->outQ[0]; a.out_q[1] = W + h->outQ[1];
     a.advance_rng = noise ? 0 : 1;
@@ -645,7 +652,7 @@ int dsact_cnn_step(dsact_cnn_handle* h, const dsact_batch* batch, const dsact_no
     a.d_logits = W + h->dlogits; a.state = h->buf.state;
     a.gbias = Gpi + pi.head_off[0] + pi.head.b[pi.head.L];        // output bias of the mean head [A]
     a.gbias_ls = pi.ls_row >= 0 ? Gpi + pi.ls_row : Gpi + pi.head_off[1] + pi.head.b[pi.head.L];   // ... of the log_std head / row [A]
-    a.B = B; a.A = A; a.min_log_std = (float)cf.min_log_std; a.max_log_std = (float)cf.max_log_std;
+    a.B = B; a.A = A; a.min_log_std = (float)cf.min_log_std; a.max_log_std = (float)cf.max_log_std; a.gauss = cf.act_dist;
     a.inv_global_batch = invB;
     a.img = ImgOut{nullptr, 0, 1, 0};
     a.sc = sc;

@@ -882,7 +882,7 @@ static void enqueue_phase1(dsact_handle* h, const dsact_batch& bt, const dsact_n
     a.act[0] = W + ar.new_act; a.act[1] = W + ar.act2;
     a.logp[0] = W + ar.logp_new; a.logp[1] = W + ar.logp2;
     a.hi = h->buf.act_high; a.lo = h->buf.act_low; a.state = h->buf.state;
-    a.B = B; a.A = A; a.min_log_std = (float)cf.min_log_std; a.max_log_std = (float)cf.max_log_std;
+    a.B = B; a.A = A; a.min_log_std = (float)cf.min_log_std; a.max_log_std = (float)cf.max_log_std; a.gauss = cf.act_dist;
     a.img[0] = img_out(h, ar.i_new_act); a.img[1] = img_out(h, ar.i_act2);
     a.out_q[0] = W + ar.outQ[0]; a.out_q[1] = W + ar.outQ[1];
     a.advance_rng = nz ? 0 : 1;
@@ -1068,7 +1068,7 @@ static void enqueue_phase2(dsact_handle* h, const dsact_batch& bt, int64_t globa
     a.logits = W + ar.logitsP; a.eps = h->pending_eps1; a.d_act1 = W + ar.dAct[0]; a.d_act2 = W + ar.dAct[1];
     a.hi = h->buf.act_high; a.lo = h->buf.act_low;
     a.d_logits = W + ar.dlogits; a.gbias = Gpi + pi.b[pi.L]; a.gbias_ls = nullptr; a.state = h->buf.state;
-    a.B = B; a.A = A; a.min_log_std = (float)cf.min_log_std; a.max_log_std = (float)cf.max_log_std;
+    a.B = B; a.A = A; a.min_log_std = (float)cf.min_log_std; a.max_log_std = (float)cf.max_log_std; a.gauss = cf.act_dist;
     a.inv_global_batch = invB;
     a.img = img_out(h, ar.i_dlogits);
     a.sc = sc;
@@ -1289,6 +1289,7 @@ static int validate(const dsact_config* c) {
   if (c->max_batch < 1) return fail(DSACT_EINVAL, "max_batch must be positive");
   if (c->delay_update < 1) return fail(DSACT_EINVAL, "delay_update must be >= 1");
   if (c->gemm_mode < DSACT_GEMM_FP32 || c->gemm_mode > DSACT_GEMM_BF16) return fail(DSACT_EINVAL, "unknown gemm_mode %d", c->gemm_mode);
+  if (c->act_dist != 0 && c->act_dist != 1) return fail(DSACT_EINVAL, "act_dist must be 0 (TanhGaussDistribution) or 1 (GaussDistribution)");
   return DSACT_OK;
 }
 

@@ -285,12 +285,22 @@ struct SampleArgs {
   const float* out_q[2];   // Q_k(s,a) [B,2]: the blockIdx.y = 1 half also sums softplus(raw std) into ST_STDSUM, the
                            // input of the mean_std EMA (dsac_v2.py:233-241)
   int advance_rng;         // device noise/indices were drawn with the current counter: step it (all readers are done)
+  int gauss;               // 1: GaussDistribution (utils/act_distribution_cls.py:82-116): no squashing, no action limits
 };
-// One action component of TanhGaussDistribution.rsample: the squashed, scaled action and its log-prob term.
+// One action component of TanhGaussDistribution.rsample: the squashed, scaled action and its log-prob term
+// (gauss: GaussDistribution.rsample, the raw Gaussian sample and Normal.log_prob).
 __device__ __forceinline__ void sample_elem(float mean, float ls, float eps, float hi, float lo, float min_ls, float max_ls,
-                                            float& act, float& lp, float& tanh_mean, float& sd_out) {
+                                            float& act, float& lp, float& tanh_mean, float& sd_out, bool gauss = false) {
   const float sd = expf(fminf(fmaxf(ls, min_ls), max_ls));
   const float u = mean + sd * eps;
+  if (gauss) {
+    const float d = u - mean;
+    act = u;
+    lp = -(d * d) / (2.f * sd * sd) - logf(sd) - HALF_LOG_2PI;
+    tanh_mean = tanhf(mean);
+    sd_out = sd;
+    return;
+  }
   const float th = tanhf(u);
   const float scale = 0.5f * (hi - lo), shift = 0.5f * (hi + lo);
   act = scale * th + shift;
@@ -314,7 +324,7 @@ __global__ void sample_kernel(const __grid_constant__ SampleArgs a) {
     for (int j = lane; j < A; j += 32) {
       float act, lpj, tm, sd;
       sample_elem(logits[(size_t)row * 2 * A + j], logits[(size_t)row * 2 * A + A + j], eps[(size_t)row * A + j], a.hi[j], a.lo[j],
-                  a.min_log_std, a.max_log_std, act, lpj, tm, sd);
+                  a.min_log_std, a.max_log_std, act, lpj, tm, sd, a.gauss != 0);
       a.act[which][(size_t)row * A + j] = act;
       img_put(a.img[which], row, j, act);
       lp += lpj;
@@ -484,6 +494,7 @@ struct PolicyGradArgs {
   float min_log_std, max_log_std, inv_global_batch;
   ImgOut img;
   StepScalars sc;
+  int gauss;         // 1: GaussDistribution (a~ = u, log-prob of the Normal only)
 };
 // d(actor loss)/d(mean_j, log_std_j) of one row (chain rule through a~ = scale tanh(u) + shift and the log-prob)
 __device__ __forceinline__ void pgrad_elem(const PolicyGradArgs& a, int row, int j, float coef, float& gu, float& gls) {
@@ -494,9 +505,14 @@ __device__ __forceinline__ void pgrad_elem(const PolicyGradArgs& a, int row, int
   const bool inside = ls >= a.min_log_std && ls <= a.max_log_std;
   const float sd = expf(fminf(fmaxf(ls, a.min_log_std), a.max_log_std));
   const float e = a.eps[(size_t)row * A + j];
+  const float da = a.d_act1[(size_t)row * A + j] + a.d_act2[(size_t)row * A + j];
+  if (a.gauss) {   // a~ = u; d logp / d mean = 0, d logp / d sd = -1/sd
+    gu = da;
+    gls = inside ? (gu * e - coef / sd) * sd : 0.f;
+    return;
+  }
   const float th = tanhf(mean + sd * e);
   const float om = 1.f - th * th;
-  const float da = a.d_act1[(size_t)row * A + j] + a.d_act2[(size_t)row * A + j];
   gu = da * scale * om + coef * (2.f * th * om / (1.f + TG_EPS - th * th));
   const float gsd = gu * e - coef / sd;
   gls = inside ? gsd * sd : 0.f;

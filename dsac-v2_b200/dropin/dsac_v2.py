@@ -68,10 +68,13 @@ class ApproxContainer(nn.Module):
                 p.requires_grad = False
         self.log_alpha = nn.Parameter(torch.tensor(1, dtype=torch.float32))
 
+        if pi_args["action_distribution_cls"].__name__ not in _lib.ACT_DISTS:
+            raise NotImplementedError("the B200 engine implements TanhGaussDistribution and GaussDistribution")
         common = dict(gamma=kwargs.get("gamma", 0.99), tau=kwargs.get("tau", 0.005), tau_b=kwargs.get("tau_b", None),
                       delay_update=kwargs.get("delay_update", 2), auto_alpha=kwargs.get("auto_alpha", True),
                       alpha=kwargs.get("alpha", 0.2), lr_q=kwargs["value_learning_rate"], lr_pi=kwargs["policy_learning_rate"],
-                      lr_alpha=kwargs["alpha_learning_rate"], min_log_std=pi_args["min_log_std"], max_log_std=pi_args["max_log_std"])
+                      lr_alpha=kwargs["alpha_learning_rate"], min_log_std=pi_args["min_log_std"], max_log_std=pi_args["max_log_std"],
+                      act_dist=pi_args["action_distribution_cls"].__name__)
         if self._cnn:
             if q_args["conv_type"] != pi_args["conv_type"] or q_args["hidden_activation"] != pi_args["hidden_activation"]:
                 raise NotImplementedError("the CNN engine takes one conv_type / head activation for critics and policy")

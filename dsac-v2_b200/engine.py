@@ -35,7 +35,7 @@ STAT_KEYS = [
 def make_config(obs_dim: int, act_dim: int, hidden_q: Sequence[int], hidden_pi: Sequence[int], *, max_batch: int,
                 act_q: str = "gelu", act_pi: str = "gelu", gamma=0.99, tau=0.005, tau_b=None, delay_update=2,
                 auto_alpha=True, alpha=0.2, lr_q=1e-4, lr_pi=1e-4, lr_alpha=3e-4, min_log_std=-20.0,
-                max_log_std=0.5, gemm_mode="fp32", use_graph=True) -> Config:
+                max_log_std=0.5, gemm_mode="fp32", use_graph=True, act_dist="TanhGaussDistribution") -> Config:
     if len(hidden_q) > _lib.MAX_HIDDEN or len(hidden_pi) > _lib.MAX_HIDDEN:
         raise ValueError(f"at most {_lib.MAX_HIDDEN} hidden layers")
     for name in (act_q, act_pi):
@@ -53,6 +53,7 @@ def make_config(obs_dim: int, act_dim: int, hidden_q: Sequence[int], hidden_pi: 
     c.max_batch = int(max_batch)
     c.auto_alpha, c.delay_update = int(bool(auto_alpha)), int(delay_update)
     c.gemm_mode, c.use_graph = _lib.GEMM_MODES[gemm_mode], int(bool(use_graph))
+    c.act_dist = _lib.ACT_DISTS[act_dist]
     c.gamma, c.tau = float(gamma), float(tau)
     c.tau_b = float(tau if tau_b is None else tau_b)
     c.alpha_fixed = float(alpha)

@@ -17,7 +17,8 @@ from .engine import STAT_KEYS
 def make_cnn_config(obs_shape: Sequence[int], act_dim: int, kernels: Sequence[int], channels: Sequence[int],
                     strides: Sequence[int], hidden: Sequence[int], *, max_batch: int, act_hidden: str = "gelu", gamma=0.99,
                     tau=0.005, tau_b=None, delay_update=2, auto_alpha=True, alpha=0.2, lr_q=1e-4, lr_pi=1e-4, lr_alpha=3e-4,
-                    min_log_std=-20.0, max_log_std=0.5, q_heads: int = 2, pi_std: str = "head") -> CnnConfig:
+                    min_log_std=-20.0, max_log_std=0.5, q_heads: int = 2, pi_std: str = "head",
+                    act_dist: str = "TanhGaussDistribution") -> CnnConfig:
     """`q_heads` / `pi_std` select the head wiring: (2, "head") = networks/cnn.py; with no conv layers and
     obs_shape = (obs_dim, 1, 1): (1, "head") = networks/mlp.py with policy std_type "mlp_separated", (1, "row") = "parameter"."""
     if len(kernels) > _lib.MAX_CONV or len(hidden) > _lib.MAX_HIDDEN:
@@ -38,6 +39,7 @@ def make_cnn_config(obs_shape: Sequence[int], act_dim: int, kernels: Sequence[in
     c.min_log_std, c.max_log_std = float(min_log_std), float(max_log_std)
     c.adam_beta1, c.adam_beta2, c.adam_eps = 0.9, 0.999, 1e-8
     c.q_heads, c.pi_std = int(q_heads), {"head": 0, "row": 1}[pi_std]
+    c.act_dist = _lib.ACT_DISTS[act_dist]
     return c
 
 

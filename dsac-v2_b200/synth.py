@@ -31,11 +31,17 @@ CONFIGS = {
 # heads.  Oracle-level only so far (oracle/dsact_oracle.py:OracleDSACTCNN, tests/golden/cnn_carracing_b4.npz).
 CNN_CONFIGS = {
     "carracing": dict(obs_dim=(3, 96, 96), act_dim=3, act_lim=1.0, conv_type="type_2"),
+    # the reference's other encoder (networks/cnn.py:173-186: 8x8/4, 4x4/2, 3x3/1, heads 512-256) on a smaller image
+    "small_t1": dict(obs_dim=(2, 44, 44), act_dim=2, act_lim=1.0, conv_type="type_1"),
+    "odd": dict(obs_dim=(3, 13, 11), act_dim=2, act_lim=1.0, conv_type="test_odd"),
 }
 # reference networks/cnn.py:201-216 (type_2) and :163-170 (type_1): kernel sizes, channels, strides, head widths
 CONV_TYPES = {
     "type_1": dict(kernels=(8, 4, 3), channels=(32, 64, 64), strides=(4, 2, 1), heads=(512, 256)),
     "type_2": dict(kernels=(4, 3, 3, 3, 3, 3), channels=(8, 16, 32, 64, 128, 256), strides=(2, 2, 2, 2, 1, 1), heads=(256, 256, 256)),
+    # not a reference type: channel counts that are no multiples of 4 / 8 and 2x2 / 1x1 windows, for the one-channel-per-thread
+    # kernels of conv.cuh (tests only; checked against the oracle)
+    "test_odd": dict(kernels=(3, 2, 1), channels=(6, 10, 12), strides=(2, 1, 1), heads=(24,)),
 }
 
 HYPER = dict(

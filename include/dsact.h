@@ -74,6 +74,8 @@ typedef struct dsact_config {
   int32_t delay_update;          /* dsac_v2.py:87 */
   int32_t gemm_mode;             /* DSACT_GEMM_* */
   int32_t use_graph;             /* replay captured CUDA graphs for repeated identical calls */
+  int32_t act_dist;              /* policy_act_distribution: 0 TanhGaussDistribution, 1 GaussDistribution
+                                    (utils/act_distribution_cls.py:20-79, 82-116) */
   /* scalars are doubles because the reference holds them as Python floats and forms
    * 1-beta, lr/(1-beta^t) ... in double before they touch an fp32 tensor */
   double gamma, tau, tau_b;       /* dsac_v2.py:82,83,90 */
@@ -232,6 +234,7 @@ typedef struct dsact_cnn_config {
   int32_t max_batch, auto_alpha, delay_update;
   int32_t q_heads;                   /* 2: separate mean and std heads (networks/cnn.py:383-461); 1: one head with both outputs
                                         (networks/mlp.py:113-127, with n_conv = 0) */
+  int32_t act_dist;                  /* 0 TanhGaussDistribution, 1 GaussDistribution (as in dsact_config) */
   int32_t pi_std;                    /* 0: log_std from its own head (networks/cnn.py, mlp.py std_type "mlp_separated");
                                         1: learnable row [1, act_dim] (mlp.py std_type "parameter"), laid out BEFORE the mean head */
   double gamma, tau, tau_b, alpha_fixed, lr_q, lr_pi, lr_alpha, min_log_std, max_log_std;

@@ -91,10 +91,12 @@ class OracleDSACT:
                  delay_update=2, auto_alpha=True, alpha=0.2, value_learning_rate=1e-4,
                  policy_learning_rate=1e-4, alpha_learning_rate=3e-4,
                  policy_min_log_std=-20.0, policy_max_log_std=0.5, hidden_activation="gelu",
-                 dtype=torch.float32, **_ignored):
+                 policy_act_distribution="TanhGaussDistribution", dtype=torch.float32, **_ignored):
         self.O, self.A = int(obs_dim), int(act_dim)
         self.dtype = dtype
         self.act = hidden_activation
+        assert policy_act_distribution in ("TanhGaussDistribution", "GaussDistribution")
+        self.gauss_only = policy_act_distribution == "GaussDistribution"   # utils/act_distribution_cls.py:82-116
         self.gamma, self.tau = float(gamma), float(tau)
         self.tau_b = float(tau if tau_b is None else tau_b)  # dsac_v2.py:90
         self.delay_update = int(delay_update)
@@ -163,11 +165,14 @@ class OracleDSACT:
         return out[..., 0], F.softplus(out[..., 1])
 
     def tanh_gauss_rsample(self, mean, std, eps):
-        """TanhGaussDistribution.rsample (utils/act_distribution_cls.py:44-54)."""
+        """TanhGaussDistribution.rsample (utils/act_distribution_cls.py:44-54); GaussDistribution.rsample (:97-100) when
+        the policy's action distribution is the plain Gaussian (no squashing, no limits in the update)."""
         u = mean + std * eps
+        gauss = (-((u - mean) ** 2) / (2 * std ** 2) - std.log() - math.log(math.sqrt(2 * math.pi))).sum(-1)
+        if self.gauss_only:
+            return u, gauss
         t = torch.tanh(u)
         scale, shift = (self.hi - self.lo) / 2, (self.hi + self.lo) / 2
-        gauss = (-((u - mean) ** 2) / (2 * std ** 2) - std.log() - math.log(math.sqrt(2 * math.pi))).sum(-1)
         logp = gauss - torch.log(1 + EPS - t.pow(2)).sum(-1) - torch.log(scale).sum(-1)
         return scale * t + shift, logp
 

@@ -48,8 +48,11 @@ CASES = [
     # the policy's other std types (networks/mlp.py:42-72)
     ("tiny_std_separated", "tiny", 16, 10, (10,), {"policy_std_type": "mlp_separated"}),
     ("tiny_std_parameter", "tiny", 16, 10, (10,), {"policy_std_type": "parameter"}),
+    # the plain Gaussian action distribution (utils/act_distribution_cls.py:82-116)
+    ("tiny_gauss", "tiny", 16, 10, (1, 2, 10), {"policy_act_distribution": "GaussDistribution"}),
     # CNN approximators (example_train/dsacv2_cnn_carracing_offasync.py: type_2 encoder, 3x96x96 observations); digests only
     ("cnn_carracing_b4", "carracing", 4, 6, (), {}),
+    ("cnn_type1_b5", "small_t1", 5, 4, (), {}),   # type_1 encoder (8x8 stride 4 first layer)
 ] + [
     # the reference's other hidden activations (utils/common_utils.py:16-43), same one in critics and policy
     (f"{cfg}_{act}", cfg, batch, 10, (10,), {"value_hidden_activation": act, "policy_hidden_activation": act})

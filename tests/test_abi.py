@@ -24,8 +24,8 @@ def test_header_symbols_are_exported_and_bound():
 
 
 def test_struct_sizes_match_header_layout():
-    # 5 + 12 + 7 int32 = 24 int32 (96 B, 8-aligned) + 12 doubles
-    assert C.sizeof(_lib.Config) == 96 + 12 * 8
+    # 5 + 12 + 8 int32 = 25 int32 (100 B, padded to 104 for the doubles) + 12 doubles
+    assert C.sizeof(_lib.Config) == 104 + 12 * 8
     assert C.sizeof(_lib.Batch) == 5 * 8 + 8 + 8
     assert C.sizeof(_lib.Buffers) == 9 * 8
 

@@ -35,9 +35,10 @@ def feed(cfg, batch, it):
     return b, tuple(torch.from_numpy(n[i]).cuda() for i in (0, 1, 4, 5))
 
 
-def test_cnn_update_matches_reference_golden(golden_dir):
+@pytest.mark.parametrize("name", ["cnn_carracing_b4", "cnn_type1_b5"])
+def test_cnn_update_matches_reference_golden(golden_dir, name):
     from dsac_v2_b200.engine import STAT_KEYS
-    z = np.load(os.path.join(golden_dir, "cnn_carracing_b4.npz"))
+    z = np.load(os.path.join(golden_dir, name + ".npz"))
     cfg_name, batch, steps, over = z["meta"]
     cfg, batch, steps = synth.CNN_CONFIGS[str(cfg_name)], int(batch), int(steps)
     assert dict(ast.literal_eval(str(over))) == {}
@@ -58,12 +59,13 @@ def test_cnn_update_matches_reference_golden(golden_dir):
     eng.close()
 
 
-@pytest.mark.parametrize("batch", [3, 32])
-def test_cnn_update_matches_oracle(batch):
-    """Another batch size (ragged against every tile size), full post-update state and the gradients of the last step."""
+@pytest.mark.parametrize("cfg_name,batch", [("carracing", 3), ("carracing", 32), ("small_t1", 7), ("odd", 9), ("odd", 200)])
+def test_cnn_update_matches_oracle(cfg_name, batch):
+    """Other batch sizes (ragged against every tile size) and encoders — type_1 (8x8 first layer) and a stack whose channel
+    counts force the one-channel-per-thread kernels —, full post-update state and the gradients of the last step."""
     from dsac_v2_b200.engine import STAT_KEYS
     from oracle.dsact_oracle import TB_KEYS, cnn_from_config
-    cfg = synth.CNN_CONFIGS["carracing"]
+    cfg = synth.CNN_CONFIGS[cfg_name]
     eng = make_engine(cfg, batch)
     orc = cnn_from_config(cfg, synth.make_cnn_weights(cfg), **synth.HYPER)
     assert STAT_KEYS == TB_KEYS

@@ -26,6 +26,8 @@ def make_engine(cfg, batch, over=None, **kw):
     from dsac_v2_b200.engine import Engine, make_config
     hyper = dict(synth.HYPER)
     hyper.update(over or {})
+    if "policy_act_distribution" in hyper:   # golden of the plain Gaussian action distribution
+        kw.setdefault("act_dist", hyper.pop("policy_act_distribution"))
     if "value_hidden_activation" in hyper:   # goldens of the reference's other activations
         kw.setdefault("act_q", hyper.pop("value_hidden_activation"))
         kw.setdefault("act_pi", hyper.pop("policy_hidden_activation"))
@@ -53,7 +55,7 @@ def stats_vec(eng):
 
 
 CASES = ["tiny_b16", "ragged_b37", "tiny_fixed_alpha", "pendulum_b256", "halfcheetah_b512", "humanoid_b256",
-         "humanoid_b4096", "tiny_relu", "tiny_tanh", "ragged_elu", "ragged_selu", "tiny_sigmoid"]
+         "humanoid_b4096", "tiny_relu", "tiny_tanh", "ragged_elu", "ragged_selu", "tiny_sigmoid", "tiny_gauss"]
 
 
 @pytest.mark.parametrize("use_graph", [False, True])
@@ -168,7 +170,7 @@ def test_device_noise_statistics():
 # ---- tcgen05 paths -------------------------------------------------------------------------------------
 TC_CASES = ["tiny_b16", "ragged_b37", "halfcheetah_b512", "humanoid_b256", "humanoid_b4096",
             # the generic-activation branch of the fused chain epilogue (GELU and ReLU have their own)
-            "tiny_relu", "tiny_tanh", "ragged_elu", "ragged_selu", "tiny_sigmoid"]
+            "tiny_relu", "tiny_tanh", "ragged_elu", "ragged_selu", "tiny_sigmoid", "tiny_gauss"]
 
 
 @pytest.mark.parametrize("name", TC_CASES)

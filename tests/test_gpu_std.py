@@ -120,3 +120,31 @@ def test_std_type_dropin_local_update(golden_dir, std_type):
     import copy
     out = copy.deepcopy(alg.networks.policy).cpu()(obs)
     assert out.shape == (B, 2 * cfg["act_dim"]) and torch.isfinite(out).all()
+
+
+def test_gauss_distribution_dropin(golden_dir):
+    """`policy_act_distribution="GaussDistribution"` (reference utils/act_distribution_cls.py:82-116) through the drop-in:
+    the engine samples without squashing; tb_info follows the reference golden (the engine-level parity of this case, fp32
+    and bf16x3, is in test_gpu_parity.py)."""
+    import dsac_v2
+    from dsac_v2_b200.engine import STAT_KEYS
+    z = np.load(os.path.join(golden_dir, "tiny_gauss.npz"))
+    cfg, B = synth.CONFIGS["tiny"], int(z["meta"][1])
+    kw = synth.reference_kwargs(cfg, policy_act_distribution="GaussDistribution", replay_batch_size=B, dsact_gemm="fp32")
+    alg = dsac_v2.DSAC_V2(**kw)
+    sd = alg.networks.state_dict()
+    for k, v in synth.make_weights(cfg).items():
+        sd[k] = torch.from_numpy(v)
+    alg.networks.load_state_dict(sd)
+    alg.networks.cuda()
+    eng = alg.networks.engine(B)
+    assert eng.cfg.act_dist == 1
+    for it in range(3):
+        b = {k: torch.from_numpy(v).cuda() for k, v in synth.make_batch(cfg, B, it).items()}
+        n = synth.make_noise(cfg, B, it)
+        eng.step(b, it, tuple(torch.from_numpy(n[i]).cuda() for i in (0, 1, 4, 5)))
+        s = eng.read_stats()
+        np.testing.assert_allclose([s[k] for k in STAT_KEYS], z["tb"][it], rtol=RTOL, atol=1e-6)
+    # the host-side distribution the sampler acts with is the plain Gaussian too
+    dist = alg.networks.create_action_distributions(torch.zeros(2, 2 * cfg["act_dim"]).add_(0.5))
+    assert type(dist).__name__ == "GaussDistribution"

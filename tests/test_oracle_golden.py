@@ -13,11 +13,11 @@ from oracle.dsact_oracle import TB_KEYS, cnn_from_config, from_config, std_from_
 CASES = ["tiny_b16", "ragged_b37", "tiny_fixed_alpha", "pendulum_b256", "halfcheetah_b512",
          "humanoid_b256", "humanoid_b4096",
          # the reference's other hidden activations (utils/common_utils.py:16-43)
-         "tiny_relu", "tiny_tanh", "ragged_elu", "ragged_selu", "tiny_sigmoid",
+         "tiny_relu", "tiny_tanh", "ragged_elu", "ragged_selu", "tiny_sigmoid", "tiny_gauss",
          # the policy's other std types (oracle-level groundwork for SURVEY.md 8f rank 4)
          "tiny_std_separated", "tiny_std_parameter",
          # CNN approximators (BASELINE config 5; oracle-level groundwork for SURVEY.md 8f rank 1)
-         "cnn_carracing_b4"]
+         "cnn_carracing_b4", "cnn_type1_b5"]
 MAX_STEPS = {"humanoid_b256": 100, "pendulum_b256": 100}
 
 
