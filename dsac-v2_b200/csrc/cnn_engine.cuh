@@ -684,6 +684,7 @@ int dsact_cnn_step(dsact_cnn_handle* h, const dsact_batch* batch, const dsact_no
     a.hy = hy; a.scalars_ready = 1;
     a.eps = (float)cf.adam_eps; a.tau = (float)cf.tau;
     a.omb1 = (float)(1.0 - cf.adam_beta1); a.b2f = (float)cf.adam_beta2; a.omb2 = (float)(1.0 - cf.adam_beta2);
+    a.g_lo = 0; a.g_hi = (n_all + 3) / 4; a.finish = 1;
     int blocks = (int)(((n_all + 3) / 4 + 255) / 256); if (blocks > 8 * h->num_sms) blocks = 8 * h->num_sms;
     launch_k(apply_kernel<0>, blocks, 256, 0, c, a); c.done();
   }

@@ -147,6 +147,7 @@ struct dsact_handle {
   const float *pending_eps1, *pending_z3, *pending_z4;  // noise phase1 used (phase2 needs it again)
   int64_t dev_rb_size;       // what state[ST_RB_SIZE] holds
   bool join_pending = false; // a forked branch of the current enqueue has not been joined yet
+  bool apply_early = false;  // phase 2 of the current enqueue already ran the critics' part of the update
   bool arena_imaged;         // the last dsact_replay_sample left bf16 images of obs/obs2/act beside the arena batch
   cudaStream_t cap_stream;   // capture-only stream
   cudaStream_t side_stream;  // second branch inside a step (critic weight gradients || policy backward chain)
@@ -951,8 +952,11 @@ static TailArgs tail_args(const dsact_handle* h, int64_t global_batch, int rows,
   return t;
 }
 // `fold_tail`: the caller's next kernels (dp_grad_fold / apply) do the end-of-backward bookkeeping, no phase2_tail launch
+static void enqueue_apply(dsact_handle* h, Ctx& c, bool reduce_slabs, bool dp, const TailArgs* tail, int part);
+// `early_apply` (single-GPU fused steps with the folded tail): update the critics on the side branch as soon as their
+// weight gradients are complete, beside the policy backward; the caller's enqueue_apply then does the rest.
 static void enqueue_phase2(dsact_handle* h, const dsact_batch& bt, int64_t global_batch, Ctx& c, int reduce_mode = REDUCE_INPLACE,
-                           bool fold_tail = false) {
+                           bool fold_tail = false, const TailArgs* early_apply = nullptr) {
   const bool defer_reduce = reduce_mode != REDUCE_INPLACE;
   const dsact_config& cf = h->cfg;
   const Net &q = h->q, &pi = h->pi;
@@ -1053,6 +1057,10 @@ static void enqueue_phase2(dsact_handle* h, const dsact_batch& bt, int64_t globa
       const int chain_ctas = (B + TC_BM - 1) / TC_BM;
       const int cap = h->num_sms - chain_ctas;
       launch_group(h, gw, V_WGRAD, cs, cap >= h->num_sms / 2 ? cap : 0);
+      if (early_apply) {   // Adam + Polyak of both critics beside the policy backward: every critic gradient is final here
+        enqueue_apply(h, cs, true, false, early_apply, 1);
+        h->apply_early = true;
+      }
       cudaEventRecord(h->ev_join, c.side);
       c.launches += cs.launches;
       if (cs.err != cudaSuccess && c.err == cudaSuccess) c.err = cs.err;
@@ -1121,8 +1129,15 @@ static bool fold_tail_enabled() {   // DSACT_FOLD_TAIL=0: keep the separate phas
   return !off;
 }
 // `tail` != null: this apply also does the end-of-backward bookkeeping of the step (see TailArgs)
-static void enqueue_apply(dsact_handle* h, Ctx& c, bool reduce_slabs = false, bool dp = false, const TailArgs* tail = nullptr) {
+// `part`: 0 = the whole flat buffer; 1 = the critics' span only, without closing the step (launched beside the policy
+// backward, see enqueue_phase2); 2 = everything after that span + the end-of-step bookkeeping
+static bool apply_split_enabled() {   // DSACT_APPLY_SPLIT=0: one apply launch after the whole backward (A/B aid)
+  static const bool off = getenv("DSACT_APPLY_SPLIT") && getenv("DSACT_APPLY_SPLIT")[0] == '0';
+  return !off;
+}
+static void enqueue_apply(dsact_handle* h, Ctx& c, bool reduce_slabs = false, bool dp = false, const TailArgs* tail = nullptr, int part = 0) {
   const dsact_config& cf = h->cfg;
+  if (part == 0 && h->apply_early) { part = 2; h->apply_early = false; }   // phase 2 already updated the critics
   ApplyArgs a;
   a.params = h->buf.params; a.targets = h->buf.targets; a.grads = h->buf.grads; a.m = h->buf.adam_m; a.v = h->buf.adam_v;
   a.state = h->buf.state;
@@ -1147,8 +1162,11 @@ static void enqueue_apply(dsact_handle* h, Ctx& c, bool reduce_slabs = false, bo
   a.omb1 = (float)(1.0 - cf.adam_beta1); a.b2f = (float)cf.adam_beta2; a.omb2 = (float)(1.0 - cf.adam_beta2);
   a.slabs = nullptr; a.nslabs = 0; a.slab_stride = 0;
   if (reduce_slabs && !dp && slabs_foldable(h)) { a.slabs = h->W() + h->ar.slabs; a.nslabs = h->ar.nslabs; a.slab_stride = h->ar.slab_stride; }
-  int blocks = (int)(((a.n_all + 3) / 4 + 255) / 256);   // one 4-element group per thread
+  const int64_t g_all = (a.n_all + 3) / 4, g_q = a.n_q2 / 4;   // a group straddling the critic / policy boundary goes with part 2
+  a.g_lo = part == 2 ? g_q : 0; a.g_hi = part == 1 ? g_q : g_all; a.finish = part == 1 ? 0 : 1;
+  int blocks = (int)((a.g_hi - a.g_lo + 255) / 256);   // one 4-element group per thread
   if (blocks > 8 * h->num_sms) blocks = 8 * h->num_sms;
+  if (blocks < 1) blocks = 1;
   // (its last block also advances the step counters)
   if (a.dp_world > 0) launch_k(apply_kernel<2>, blocks, 256, 0, c, a);
   else if (a.nslabs > 0) launch_k(apply_kernel<1>, blocks, 256, 0, c, a);
@@ -1478,7 +1496,8 @@ int dsact_step(dsact_handle* h, const dsact_batch* batch, const dsact_noise* noi
   rc = run(h, (cudaStream_t)stream, skey, [&](Ctx& c) {
     enqueue_phase1(h, bt, np, c, imaged);
     const TailArgs ta = tail_args(h, bt.batch, bt.batch, fold_tail_enabled());
-    enqueue_phase2(h, bt, bt.batch, c, REDUCE_DEFER, ta.enabled);
+    const bool early = ta.enabled && h->fused() && slabs_foldable(h) && apply_split_enabled();
+    enqueue_phase2(h, bt, bt.batch, c, REDUCE_DEFER, ta.enabled, early ? &ta : nullptr);
     enqueue_apply(h, c, true, false, &ta);
   });
   if (rc) return rc;
@@ -1643,7 +1662,8 @@ int dsact_replay_step(dsact_handle* h, int32_t batch, int64_t size, const int64_
     if (!idx && np) { launch_k(rng_advance_kernel, 1, 32, 0, c, h->buf.state); c.done(); }
     enqueue_phase1(h, bt, np, c, true, forked);  // device noise (np == null): phase1 advances the counter after the join
     const TailArgs ta = tail_args(h, batch, batch, fold_tail_enabled());
-    enqueue_phase2(h, bt, batch, c, REDUCE_DEFER, ta.enabled);
+    const bool early = ta.enabled && h->fused() && slabs_foldable(h) && apply_split_enabled();
+    enqueue_phase2(h, bt, batch, c, REDUCE_DEFER, ta.enabled, early ? &ta : nullptr);
     enqueue_apply(h, c, true, false, &ta);
   });
   if (rc) return rc;

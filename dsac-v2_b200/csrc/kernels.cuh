@@ -596,6 +596,11 @@ struct ApplyArgs {
   const float* dp_own;
   int dp_wait_world;
   unsigned long long dp_timeout_ns;
+  // 4-element groups [g_lo, g_hi) of the flat buffers this launch updates; `finish`: its last block closes the step
+  // (counters, EMA commit, next Adam scalars).  A step may update the critics' span early, beside the policy backward,
+  // with finish = 0, and the rest afterwards with finish = 1.
+  int64_t g_lo, g_hi;
+  int finish;
 };
 __device__ __forceinline__ bool dp_wait_reduced(const float* own_buf, int world, uint32_t epoch, unsigned long long timeout_ns);
 // torch.optim.Adam single-tensor step (amsgrad / weight decay off)
@@ -633,8 +638,7 @@ __global__ void __launch_bounds__(256, 4) apply_kernel(const __grid_constant__ A
   const float polyak = 1.f - a.tau;
   // 4 consecutive elements per thread (float4 traffic); a group is uniform unless it straddles the critic/policy
   // boundary or holds log_alpha, so the per-element logic below stays cheap
-  const int64_t ngroups = (a.n_all + 3) / 4;
-  for (int64_t gi = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; gi < ngroups; gi += (int64_t)gridDim.x * blockDim.x) {
+  for (int64_t gi = a.g_lo + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; gi < a.g_hi; gi += (int64_t)gridDim.x * blockDim.x) {
     const int64_t i0 = gi * 4;
     const bool full = i0 + 3 < n_targets;
     float w[4], g[4], m[4], v[4], t[4];
@@ -738,6 +742,7 @@ __global__ void __launch_bounds__(256, 4) apply_kernel(const __grid_constant__ A
     }
   }
   // the block that finishes last advances the counters every block read at its start
+  if (!a.finish) return;
   __syncthreads();
   if (threadIdx.x == 0) {
     int* stw = reinterpret_cast<int*>(a.state);
