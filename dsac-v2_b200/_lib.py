@@ -52,11 +52,11 @@ class CnnConfig(C.Structure):
         ("conv_kernel", C.c_int32 * MAX_CONV), ("conv_channels", C.c_int32 * MAX_CONV), ("conv_stride", C.c_int32 * MAX_CONV),
         ("n_hidden", C.c_int32), ("hidden", C.c_int32 * MAX_HIDDEN), ("act_hidden", C.c_int32),
         ("max_batch", C.c_int32), ("auto_alpha", C.c_int32), ("delay_update", C.c_int32),
-        ("q_heads", C.c_int32), ("act_dist", C.c_int32), ("pi_std", C.c_int32),
+        ("q_heads", C.c_int32), ("act_dist", C.c_int32), ("pi_std", C.c_int32), ("algo", C.c_int32), ("v1_bound", C.c_int32),
         ("gamma", C.c_double), ("tau", C.c_double), ("tau_b", C.c_double), ("alpha_fixed", C.c_double),
         ("lr_q", C.c_double), ("lr_pi", C.c_double), ("lr_alpha", C.c_double),
         ("min_log_std", C.c_double), ("max_log_std", C.c_double),
-        ("adam_beta1", C.c_double), ("adam_beta2", C.c_double), ("adam_eps", C.c_double),
+        ("adam_beta1", C.c_double), ("adam_beta2", C.c_double), ("adam_eps", C.c_double), ("td_bound", C.c_double),
     ]
 
 

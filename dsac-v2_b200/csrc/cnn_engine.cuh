@@ -123,9 +123,9 @@ struct dsact_cnn_handle {
 // log_std heads (networks/cnn.py, mlp.py std_type "mlp_separated") or a mean head + learnable row (std_type "parameter")
 static void cnn_build_nets(dsact_cnn_handle* h) {
   const dsact_cnn_config& c = h->cfg;
-  const bool q1 = c.q_heads == 1, row = c.pi_std == 1;
+  const bool q1 = c.q_heads == 1, row = c.pi_std == 1, shared = c.pi_std == 2;
   h->q.build(c, c.act_dim, q1 ? 2 : 1, q1 ? 1 : 2, false);
-  h->pi.build(c, 0, c.act_dim, row ? 1 : 2, row);
+  h->pi.build(c, 0, shared ? 2 * c.act_dim : c.act_dim, (row || shared) ? 1 : 2, row);
 }
 
 static int cnn_validate(const dsact_cnn_config* c) {
@@ -134,7 +134,9 @@ static int cnn_validate(const dsact_cnn_config* c) {
   if (c->channels < 1 || c->height < 1 || c->width < 1 || c->act_dim < 1) return fail(DSACT_EINVAL, "bad observation / action shape");
   if (c->n_conv < 0 || c->n_conv > DSACT_MAX_CONV) return fail(DSACT_EINVAL, "0..%d conv layers supported", DSACT_MAX_CONV);
   if (c->q_heads != 1 && c->q_heads != 2) return fail(DSACT_EINVAL, "q_heads must be 1 (one head, two outputs) or 2 (mean and std heads)");
-  if (c->pi_std != 0 && c->pi_std != 1) return fail(DSACT_EINVAL, "pi_std must be 0 (log_std head) or 1 (learnable row)");
+  if (c->pi_std < 0 || c->pi_std > 2) return fail(DSACT_EINVAL, "pi_std must be 0 (log_std head), 1 (learnable row) or 2 (one head, 2*act_dim outputs)");
+  if (c->algo != 0 && c->algo != 1) return fail(DSACT_EINVAL, "algo must be 0 (DSAC_V2 / DSAC-T) or 1 (DSAC_V1)");
+  if (c->algo == 1 && !(c->td_bound > 0.0)) return fail(DSACT_EINVAL, "DSAC_V1 needs TD_bound > 0");
   if (c->act_dist != 0 && c->act_dist != 1) return fail(DSACT_EINVAL, "act_dist must be 0 (TanhGaussDistribution) or 1 (GaussDistribution)");
   for (int j = 0; j < c->n_conv; ++j)
     if (c->conv_kernel[j] < 1 || (c->conv_kernel[j] > 4 && c->conv_kernel[j] != 8) || c->conv_stride[j] < 1 || c->conv_channels[j] < 1)
@@ -358,6 +360,8 @@ static void cnn_conv_backward(dsact_cnn_handle* h, const CnnGeom& g, const float
   c.check();
 }
 
+#include "v1_step.cuh"
+
 extern "C" {
 
 int dsact_cnn_query_layout(const dsact_cnn_config* cfg, dsact_layout* out) {
@@ -368,9 +372,10 @@ int dsact_cnn_query_layout(const dsact_cnn_config* cfg, dsact_layout* out) {
   h.cfg = *cfg;
   cnn_build_nets(&h);
   h.layout();
+  const int ncrit = cfg->algo == 1 ? 1 : 2;   // DSAC_V1 has one critic
   out->n_q = h.q.n; out->n_pi = h.pi.n;
-  out->n_params = 2 * h.q.n + h.pi.n + 1;
-  out->n_targets = 2 * h.q.n + h.pi.n;
+  out->n_params = ncrit * h.q.n + h.pi.n + 1;
+  out->n_targets = ncrit * h.q.n + h.pi.n;
   out->workspace_bytes = h.total * (int64_t)sizeof(float);
   out->state_floats = ST_FLOATS;
   out->max_batch = cfg->max_batch;
@@ -426,8 +431,9 @@ int dsact_cnn_read_stats(dsact_cnn_handle* h, int64_t global_batch, float* host_
   if (!h || !h->bound) return fail(DSACT_ESTATE, "not bound");
   if (!host_out || global_batch < 1) return fail(DSACT_EINVAL, "bad argument");
   CUDA_TRY(cudaSetDevice(h->device));
-  finalize_stats_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(h->buf.state, (float)(1.0 / (double)global_batch),
-                                                            (float)(1.0 / ((double)global_batch * h->cfg.act_dim)));
+  // DSAC_V1 logs one entry of the logits row per sample (dsac_v1.py:142-143), DSAC-T the mean over all action dimensions
+  const double pol = h->cfg.algo == 1 ? (double)global_batch : (double)global_batch * h->cfg.act_dim;
+  finalize_stats_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(h->buf.state, (float)(1.0 / (double)global_batch), (float)(1.0 / pol));
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaMemcpyAsync(host_out, h->buf.state + ST_STATS, DSACT_NUM_STATS * sizeof(float), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
   return DSACT_OK;
@@ -500,6 +506,7 @@ int dsact_cnn_step(dsact_cnn_handle* h, const dsact_batch* batch, const dsact_no
   cudaStream_t s = (cudaStream_t)stream;
   if (h->dev_iter != iteration) { set_iter_kernel<<<1, 32, 0, s>>>(h->buf.state, (int)iteration); CUDA_TRY(cudaGetLastError()); }
   const dsact_cnn_config& cf = h->cfg;
+  if (cf.algo == 1) return cnn_step_v1(h, batch, noise, iteration, s);
   const CnnGeom &q = h->q, &pi = h->pi;
   const int B = batch->batch, A = cf.act_dim;
   float* W = h->Wp();
@@ -651,7 +658,7 @@ int dsact_cnn_step(dsact_cnn_handle* h, const dsact_batch* batch, const dsact_no
     a.hi = h->buf.act_high; a.lo = h->buf.act_low;
     a.d_logits = W + h->dlogits; a.state = h->buf.state;
     a.gbias = Gpi + pi.head_off[0] + pi.head.b[pi.head.L];        // output bias of the mean head [A]
-    a.gbias_ls = pi.ls_row >= 0 ? Gpi + pi.ls_row : Gpi + pi.head_off[1] + pi.head.b[pi.head.L];   // ... of the log_std head / row [A]
+    a.gbias_ls = pi.ls_row >= 0 ? Gpi + pi.ls_row : (pi.nheads == 2 ? Gpi + pi.head_off[1] + pi.head.b[pi.head.L] : nullptr);   // log_std head / row [A]
     a.B = B; a.A = A; a.min_log_std = (float)cf.min_log_std; a.max_log_std = (float)cf.max_log_std; a.gauss = cf.act_dist;
     a.inv_global_batch = invB;
     a.img = ImgOut{nullptr, 0, 1, 0};

@@ -286,6 +286,8 @@ struct SampleArgs {
                            // input of the mean_std EMA (dsac_v2.py:233-241)
   int advance_rng;         // device noise/indices were drawn with the current counter: step it (all readers are done)
   int gauss;               // 1: GaussDistribution (utils/act_distribution_cls.py:82-116): no squashing, no action limits
+  int v1_stats = 0;        // 1: DSAC_V1's logged policy_mean / policy_std (dsac_v1.py:142-143): tanh(logits[..., 0]) and
+                           // logits[..., 1] of cat(mean, std), i.e. the first mean and the SECOND entry of the 2A-wide row
 };
 // One action component of TanhGaussDistribution.rsample: the squashed, scaled action and its log-prob term
 // (gauss: GaussDistribution.rsample, the raw Gaussian sample and Normal.log_prob).
@@ -328,8 +330,11 @@ __global__ void sample_kernel(const __grid_constant__ SampleArgs a) {
       a.act[which][(size_t)row * A + j] = act;
       img_put(a.img[which], row, j, act);
       lp += lpj;
-      sums[0] += tm;
-      sums[1] += sd;
+      if (!a.v1_stats) { sums[0] += tm; sums[1] += sd; }
+      else {
+        if (j == 0) sums[0] += tm;
+        if (A == 1 ? j == 0 : j == 1) sums[1] += A == 1 ? sd : logits[(size_t)row * 2 * A + j];
+      }
     }
     lp = warp_sum(lp);
     if (lane == 0) a.logp[which][row] = lp;

@@ -18,7 +18,8 @@ def make_cnn_config(obs_shape: Sequence[int], act_dim: int, kernels: Sequence[in
                     strides: Sequence[int], hidden: Sequence[int], *, max_batch: int, act_hidden: str = "gelu", gamma=0.99,
                     tau=0.005, tau_b=None, delay_update=2, auto_alpha=True, alpha=0.2, lr_q=1e-4, lr_pi=1e-4, lr_alpha=3e-4,
                     min_log_std=-20.0, max_log_std=0.5, q_heads: int = 2, pi_std: str = "head",
-                    act_dist: str = "TanhGaussDistribution") -> CnnConfig:
+                    act_dist: str = "TanhGaussDistribution", algo: str = "DSAC_V2", bound: bool = True,
+                    td_bound: float = 20.0) -> CnnConfig:
     """`q_heads` / `pi_std` select the head wiring: (2, "head") = networks/cnn.py; with no conv layers and
     obs_shape = (obs_dim, 1, 1): (1, "head") = networks/mlp.py with policy std_type "mlp_separated", (1, "row") = "parameter"."""
     if len(kernels) > _lib.MAX_CONV or len(hidden) > _lib.MAX_HIDDEN:
@@ -38,16 +39,18 @@ def make_cnn_config(obs_shape: Sequence[int], act_dim: int, kernels: Sequence[in
     c.lr_q, c.lr_pi, c.lr_alpha = float(lr_q), float(lr_pi), float(lr_alpha)
     c.min_log_std, c.max_log_std = float(min_log_std), float(max_log_std)
     c.adam_beta1, c.adam_beta2, c.adam_eps = 0.9, 0.999, 1e-8
-    c.q_heads, c.pi_std = int(q_heads), {"head": 0, "row": 1}[pi_std]
+    c.q_heads, c.pi_std = int(q_heads), {"head": 0, "row": 1, "shared": 2}[pi_std]
+    c.algo, c.v1_bound, c.td_bound = {"DSAC_V2": 0, "DSAC_V1": 1}[algo], int(bool(bound)), float(td_bound)
     c.act_dist = _lib.ACT_DISTS[act_dist]
     return c
 
 
 def make_heads_config(obs_dim: int, act_dim: int, hidden: Sequence[int], std_type: str, **kw) -> CnnConfig:
-    """The MLP approximators whose policy keeps mean and log_std apart (reference networks/mlp.py:43-72, std_type
-    "mlp_separated" / "parameter"): no encoder, one two-output head per critic."""
+    """The MLP approximators on the head-wise fp32 engine: no encoder, one two-output head per critic, the policy with any
+    of the reference's std types (networks/mlp.py:43-72).  DSAC-T with "mlp_shared" normally runs on `engine.Engine`
+    (tcgen05); this entry is for "mlp_separated" / "parameter" and for `algo="DSAC_V1"`."""
     return make_cnn_config((int(obs_dim), 1, 1), act_dim, (), (), (), hidden, q_heads=1,
-                           pi_std={"mlp_separated": "head", "parameter": "row"}[std_type], **kw)
+                           pi_std={"mlp_separated": "head", "parameter": "row", "mlp_shared": "shared"}[std_type], **kw)
 
 
 class CnnEngine:
@@ -124,12 +127,15 @@ class CnnEngine:
                 leaf(net, f"{head}.{2 * j}.weight", (sizes[j + 1], sizes[j]))
                 leaf(net, f"{head}.{2 * j}.bias", (sizes[j + 1],))
 
-        for net, extra, width in (("q1", c.act_dim, 1), ("q2", c.act_dim, 1), ("policy", 0, c.act_dim)):
+        critics = ("q",) if c.algo == 1 else ("q1", "q2")   # dsac_v1.ApproxContainer holds ONE critic named `q`
+        for net, extra, width in tuple((n, c.act_dim, 1) for n in critics) + (("policy", 0, c.act_dim),):
             for name, wshape, bshape in shapes:
                 leaf(net, f"{name}.weight", wshape)
                 leaf(net, f"{name}.bias", bshape)
             if net != "policy" and c.q_heads == 1:          # networks/mlp.py ActionValueDistri: self.q
                 mlp(net, "q", [feat + extra] + hidden + [2])
+            elif net == "policy" and c.pi_std == 2:         # networks/mlp.py std_type "mlp_shared": self.policy, 2A outputs
+                mlp(net, "policy", [feat] + hidden + [2 * width])
             elif net == "policy" and c.pi_std == 1:         # the module's own parameter precedes its children's
                 leaf(net, "log_std", (1, width))
                 mlp(net, "mean", [feat] + hidden + [width])

@@ -227,3 +227,16 @@ def make_weights_std(cfg: dict, std_type: str, seed: int = 0) -> dict:
     for k in [k for k in out if k.startswith("policy.")]:
         out["policy_target" + k[len("policy"):]] = out[k].copy()
     return out
+
+
+# ---- DSAC_V1 (reference dsac_v1.py) --------------------------------------------------------------
+def make_weights_v1(cfg: dict, seed: int = 0) -> dict:
+    """`make_weights` in the schema of `dsac_v1.ApproxContainer` (:17-52): one critic `q.q.*`, `policy.policy.*`, targets."""
+    w = make_weights(cfg, seed)
+    out = {}
+    for k, v in w.items():
+        if k.startswith("q1"):
+            out["q" + k[2:]] = v.copy()
+        elif k.startswith("policy"):
+            out[k] = v.copy()
+    return out

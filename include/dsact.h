@@ -236,9 +236,14 @@ typedef struct dsact_cnn_config {
                                         (networks/mlp.py:113-127, with n_conv = 0) */
   int32_t act_dist;                  /* 0 TanhGaussDistribution, 1 GaussDistribution (as in dsact_config) */
   int32_t pi_std;                    /* 0: log_std from its own head (networks/cnn.py, mlp.py std_type "mlp_separated");
-                                        1: learnable row [1, act_dim] (mlp.py std_type "parameter"), laid out BEFORE the mean head */
+                                        1: learnable row [1, act_dim] (mlp.py std_type "parameter"), laid out BEFORE the mean head;
+                                        2: ONE head with 2 * act_dim outputs (mlp.py std_type "mlp_shared") */
+  int32_t algo;                      /* 0: DSAC_V2 / DSAC-T (dsac_v2.py); 1: DSAC_V1 (dsac_v1.py:56-273): ONE critic, flat layout
+                                        [q | policy | log_alpha], fixed TD bound */
+  int32_t v1_bound;                  /* DSAC_V1 `bound` (dsac_v1.py:80): 1 = bounded loss (:219-229), 0 = Gaussian NLL (:231) */
   double gamma, tau, tau_b, alpha_fixed, lr_q, lr_pi, lr_alpha, min_log_std, max_log_std;
   double adam_beta1, adam_beta2, adam_eps;
+  double td_bound;                   /* DSAC_V1 `TD_bound` (dsac_v1.py:79, default 20) */
 } dsact_cnn_config;
 typedef struct dsact_cnn_handle dsact_cnn_handle;
 int dsact_cnn_query_layout(const dsact_cnn_config *cfg, dsact_layout *out);

@@ -474,3 +474,125 @@ def from_config(cfg: dict, weights: dict, **hyper) -> OracleDSACT:
     lim = [cfg["act_lim"]] * cfg["act_dim"]
     return OracleDSACT(cfg["obs_dim"], cfg["act_dim"], cfg["hidden"], cfg["hidden"], lim,
                        [-x for x in lim], weights, **hyper)
+
+
+# ---- DSAC_V1 (reference dsac_v1.py): one critic, fixed TD bound ---------------------------------
+V1_TB_KEYS = [
+    "DSAC/critic_avg_q-RL iter",
+    "DSAC/critic_avg_std-RL iter",
+    "Loss/Actor loss-RL iter",
+    "DSAC/policy_mean-RL iter",
+    "DSAC/policy_std-RL iter",
+    "DSAC/entropy-RL iter",
+    "DSAC/alpha-RL iter",
+]
+V1_STD_BIAS = 0.1  # dsac_v1.py:224
+
+
+class OracleDSACV1(OracleDSACT):
+    """State + one-update arithmetic of the reference's older algorithm (`dsac_v1.ApproxContainer` :17-52, `DSAC_V1` :56-273):
+    networks q, q_target, policy, policy_target (the same MLP classes as DSAC-T, std_type mlp_shared) + log_alpha."""
+
+    NETS = ("q", "policy")
+
+    def __init__(self, *args, TD_bound=20.0, bound=True, **hyper):
+        self.TD_bound, self.bound = float(TD_bound), bool(bound)
+        super().__init__(*args, **hyper)
+        self.lr = {"q": self.lr["q1"], "policy": self.lr["policy"], "log_alpha": self.lr["log_alpha"]}
+        self.steps = {"q": 0, "policy": 0, "log_alpha": 0}
+
+    def _load_weights(self, weights, nq, npi):
+        inner = {"q": "q", "policy": "policy"}
+
+        def grab(net, n_layers):
+            out = []
+            for j in range(n_layers):
+                for leaf in ("weight", "bias"):
+                    w = weights[f"{net}.{inner[net.replace('_target', '')]}.{2 * j}.{leaf}"]
+                    out.append(torch.as_tensor(w).detach().clone().to(self.dtype))
+            return out
+
+        self.p = {"q": grab("q", nq), "policy": grab("policy", npi)}
+        self.t = {"q": grab("q_target", nq), "policy": grab("policy_target", npi)}
+
+    def compute_gradients(self, batch, noise, **_unused) -> Dict[str, float]:
+        """__compute_gradient (dsac_v1.py:137-183).  `noise` = (eps1, eps2, z_q, z_next, z_pi): the normal draws in the
+        reference's order; only z_next enters the arithmetic (the other two samples are computed and dropped there)."""
+        c = lambda x: torch.as_tensor(x).to(device=self.device, dtype=self.dtype)
+        obs, act, rew, obs2, done = (c(batch[k]) for k in ("obs", "act", "rew", "obs2", "done"))
+        eps1, eps2, z_next = c(noise[0]), c(noise[1]), c(noise[3])
+        P, T = self.p, self.t
+        alpha = self.alpha()
+        mean, std = self.policy_logits(P["policy"], obs)
+        logits = torch.cat((mean, std), dim=-1)
+        new_act, new_logp = self.tanh_gauss_rsample(mean, std, eps1)
+        # __compute_loss_q (dsac_v1.py:195-233)
+        with torch.no_grad():
+            mean2, std2 = self.policy_logits(T["policy"], obs2)
+            act2, logp2 = self.tanh_gauss_rsample(mean2, std2, eps2)
+            qn, sn = self.q_dist(T["q"], obs2, act2)
+            qn_s = qn + torch.clamp(z_next, -3, 3) * sn                      # __q_evaluate :185-193
+        q, s = self.q_dist(P["q"], obs, act)
+        with torch.no_grad():                                                # __compute_target_q :235-241
+            target = rew + (1 - done) * self.gamma * (qn_s - alpha * logp2)
+            target_bound = q.detach() + torch.clamp(target - q.detach(), -self.TD_bound, self.TD_bound)
+        if self.bound:
+            sd = torch.clamp(s, min=0.0).detach()
+            loss_q = torch.mean(-(target - q).detach() / (sd.pow(2) + V1_STD_BIAS) * q
+                                - ((q.detach() - target_bound).pow(2) - sd.pow(2)) / (sd.pow(3) + V1_STD_BIAS) * s)
+        else:
+            loss_q = -torch.distributions.Normal(q, s).log_prob(target).mean()
+        self.grads = {"q": list(torch.autograd.grad(loss_q, P["q"]))}
+        # __compute_loss_policy (:243-248); the critic is frozen (:155-163)
+        qp, _ = self.q_dist([w.detach() for w in P["q"]], obs, new_act)
+        loss_pi = (alpha * new_logp - qp).mean()
+        self.grads["policy"] = list(torch.autograd.grad(loss_pi, P["policy"]))
+        entropy = -new_logp.detach().mean()
+        if self.auto_alpha:                                                  # __compute_loss_alpha :250-256
+            loss_alpha = -self.log_alpha * (new_logp.detach() + self.target_entropy).mean()
+            self.grads["log_alpha"] = list(torch.autograd.grad(loss_alpha, [self.log_alpha]))
+        # tb_info (:172-181); policy_mean / policy_std index the LOGITS at [..., 0] and [..., 1] (:142-143)
+        vals = [q.detach().mean(), s.detach().mean(), loss_pi.detach(), torch.tanh(logits[..., 0]).mean().detach(),
+                logits[..., 1].mean().detach(), entropy, alpha]
+        return {k: float(v) for k, v in zip(V1_TB_KEYS, vals)}
+
+    def apply(self, iteration: int) -> None:
+        """__update (dsac_v1.py:258-273)."""
+        self._adam("q", self.p["q"], self.grads["q"])
+        if iteration % self.delay_update == 0:
+            self._adam("policy", self.p["policy"], self.grads["policy"])
+            if self.auto_alpha:
+                self._adam("log_alpha", [self.log_alpha], self.grads["log_alpha"])
+            with torch.no_grad():
+                polyak = 1 - self.tau
+                for net in self.NETS:
+                    for w, wt in zip(self.p[net], self.t[net]):
+                        wt.mul_(polyak)
+                        wt.add_((1 - polyak) * w)
+
+    def state_dict(self) -> Dict[str, torch.Tensor]:
+        inner = {"q": "q", "policy": "policy"}
+        out = {"log_alpha": self.log_alpha.detach()}
+        for net in self.NETS:
+            for group, suffix in ((self.p, ""), (self.t, "_target")):
+                for i, w in enumerate(group[net]):
+                    leaf = "weight" if i % 2 == 0 else "bias"
+                    out[f"{net}{suffix}.{inner[net]}.{2 * (i // 2)}.{leaf}"] = w.detach()
+        return out
+
+    def grad_dict(self) -> Dict[str, torch.Tensor]:
+        inner = {"q": "q", "policy": "policy"}
+        out = {}
+        for net in self.NETS:
+            for i, g in enumerate(self.grads[net]):
+                leaf = "weight" if i % 2 == 0 else "bias"
+                out[f"{net}.{inner[net]}.{2 * (i // 2)}.{leaf}"] = g
+        if "log_alpha" in self.grads:
+            out["log_alpha"] = self.grads["log_alpha"][0]
+        return out
+
+
+def v1_from_config(cfg: dict, weights: dict, **hyper) -> OracleDSACV1:
+    """Build from a `synth.CONFIGS` entry with weights of `synth.make_weights_v1`."""
+    lim = [cfg["act_lim"]] * cfg["act_dim"]
+    return OracleDSACV1(cfg["obs_dim"], cfg["act_dim"], cfg["hidden"], cfg["hidden"], lim, [-x for x in lim], weights, **hyper)

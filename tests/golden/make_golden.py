@@ -32,6 +32,7 @@ sys.path.insert(0, os.path.join(HERE, "gymstub"))
 import torch  # noqa: E402
 import utils  # noqa: E402,F401  (reference utils/__init__ puts utils/ on sys.path)
 import dsac_v2 as ref_dsac  # noqa: E402
+import dsac_v1 as ref_dsac_v1  # noqa: E402
 
 assert os.path.realpath(ref_dsac.__file__).startswith(os.path.realpath(REF)), ref_dsac.__file__
 
@@ -53,6 +54,10 @@ CASES = [
     # CNN approximators (example_train/dsacv2_cnn_carracing_offasync.py: type_2 encoder, 3x96x96 observations); digests only
     ("cnn_carracing_b4", "carracing", 4, 6, (), {}),
     ("cnn_type1_b5", "small_t1", 5, 4, (), {}),   # type_1 encoder (8x8 stride 4 first layer)
+    # the older algorithm (dsac_v1.py): bounded loss with the default TD bound, a tight bound that clips, the Gaussian NLL
+    ("v1_tiny_b16", "tiny", 16, 12, (1, 2, 12), {"algorithm": "DSAC_V1"}),
+    ("v1_ragged_tight", "ragged", 37, 8, (8,), {"algorithm": "DSAC_V1", "TD_bound": 0.5, "delay_update": 3}),
+    ("v1_tiny_nll", "tiny", 16, 8, (8,), {"algorithm": "DSAC_V1", "bound": False}),
 ] + [
     # the reference's other hidden activations (utils/common_utils.py:16-43), same one in critics and policy
     (f"{cfg}_{act}", cfg, batch, 10, (10,), {"value_hidden_activation": act, "policy_hidden_activation": act})
@@ -60,6 +65,8 @@ CASES = [
                             ("tiny", 8, "sigmoid"))
 ]
 
+V1_TB_KEYS = ["DSAC/critic_avg_q-RL iter", "DSAC/critic_avg_std-RL iter", "Loss/Actor loss-RL iter", "DSAC/policy_mean-RL iter",
+              "DSAC/policy_std-RL iter", "DSAC/entropy-RL iter", "DSAC/alpha-RL iter"]   # dsac_v1.py:172-181
 TB_KEYS = [
     "DSAC2/critic_avg_q1-RL iter",
     "DSAC2/critic_avg_q2-RL iter",
@@ -122,10 +129,13 @@ def run_case(name, cfg_name, batch, steps, snaps, over):
     cnn = cfg_name in synth.CNN_CONFIGS   # BASELINE config 5: conv encoder + separate heads (networks/cnn.py)
     cfg = synth.CNN_CONFIGS[cfg_name] if cnn else synth.CONFIGS[cfg_name]
     torch.manual_seed(0)
-    alg = ref_dsac.DSAC_V2(**(synth.cnn_reference_kwargs(cfg, **over) if cnn else synth.reference_kwargs(cfg, **over)))
+    v1 = over.get("algorithm") == "DSAC_V1"
+    tb_keys = V1_TB_KEYS if v1 else TB_KEYS
+    kw = synth.cnn_reference_kwargs(cfg, **over) if cnn else synth.reference_kwargs(cfg, **over)
+    alg = ref_dsac_v1.DSAC_V1(**kw) if v1 else ref_dsac.DSAC_V2(**kw)
     sd = alg.networks.state_dict()
     std_type = over.get("policy_std_type", "mlp_shared")
-    weights = synth.make_cnn_weights(cfg) if cnn else \
+    weights = synth.make_cnn_weights(cfg) if cnn else synth.make_weights_v1(cfg) if v1 else \
         (synth.make_weights(cfg) if std_type == "mlp_shared" else synth.make_weights_std(cfg, std_type))
     for k, v in weights.items():
         assert tuple(sd[k].shape) == v.shape, k
@@ -136,14 +146,14 @@ def run_case(name, cfg_name, batch, steps, snaps, over):
 
     feed = NoiseFeed()
     feed.install()
-    out = {"tb": np.zeros((steps, len(TB_KEYS)))}
+    out = {"tb": np.zeros((steps, len(tb_keys)))}
     try:
         for it in range(steps):
             data = {k: torch.from_numpy(v) for k, v in (synth.make_cnn_batch if cnn else synth.make_batch)(cfg, batch, it).items()}
-            feed.queue = synth.make_noise(cfg, batch, it)
+            feed.queue = synth.make_noise(cfg, batch, it)[:5 if v1 else 8]   # DSAC_V1 draws eps1, eps2 and three z's
             tb = alg.local_update(data, it)
             assert not feed.queue
-            out["tb"][it] = [float(tb[k]) for k in TB_KEYS]
+            out["tb"][it] = [float(tb[k]) for k in tb_keys]
             params = dict(alg.networks.named_parameters())
             if it + 1 in DIGEST_STEPS and it + 1 <= steps:
                 out[f"pdigest_{it + 1}"] = np.stack([digest(params[k]) for k in names])
@@ -160,10 +170,11 @@ def run_case(name, cfg_name, batch, steps, snaps, over):
         feed.remove()
     out["param_names"] = np.array(names)
     out["trainable_names"] = np.array(trainable)
-    out["tb_keys"] = np.array(TB_KEYS)
+    out["tb_keys"] = np.array(tb_keys)
     out["meta"] = np.array([cfg_name, str(batch), str(steps), repr(sorted(over.items()))])
     np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
-    print(f"{name}: {steps} steps, critic loss {out['tb'][0, 7]:.6f} -> {out['tb'][-1, 7]:.6f}, "
+    col = 2 if v1 else 7   # actor loss (DSAC_V1 does not log the critic loss) / critic loss
+    print(f"{name}: {steps} steps, loss {out['tb'][0, col]:.6f} -> {out['tb'][-1, col]:.6f}, "
           f"{os.path.getsize(os.path.join(HERE, name + '.npz')) / 1024:.0f} KiB")
 
 

@@ -8,7 +8,7 @@ import pytest
 import torch
 
 from dsac_v2_b200 import synth
-from oracle.dsact_oracle import TB_KEYS, cnn_from_config, from_config, std_from_config
+from oracle.dsact_oracle import TB_KEYS, V1_TB_KEYS, cnn_from_config, from_config, std_from_config, v1_from_config
 
 CASES = ["tiny_b16", "ragged_b37", "tiny_fixed_alpha", "pendulum_b256", "halfcheetah_b512",
          "humanoid_b256", "humanoid_b4096",
@@ -17,7 +17,7 @@ CASES = ["tiny_b16", "ragged_b37", "tiny_fixed_alpha", "pendulum_b256", "halfche
          # the policy's other std types (oracle-level groundwork for SURVEY.md 8f rank 4)
          "tiny_std_separated", "tiny_std_parameter",
          # CNN approximators (BASELINE config 5; oracle-level groundwork for SURVEY.md 8f rank 1)
-         "cnn_carracing_b4", "cnn_type1_b5"]
+         "cnn_carracing_b4", "cnn_type1_b5", "v1_tiny_b16", "v1_ragged_tight", "v1_tiny_nll"]
 MAX_STEPS = {"humanoid_b256": 100, "pendulum_b256": 100}
 
 
@@ -32,14 +32,19 @@ def load(golden_dir, name):
 def test_oracle_matches_reference(golden_dir, name):
     torch.set_num_threads(4)
     z, cfg, batch, steps, over = load(golden_dir, name)
-    assert list(z["tb_keys"]) == TB_KEYS
+    v1 = over.get("algorithm") == "DSAC_V1"   # the older algorithm (dsac_v1.py): its own oracle class and tb_info keys
+    tb_keys = V1_TB_KEYS if v1 else TB_KEYS
+    assert list(z["tb_keys"]) == tb_keys
     hyper = dict(synth.HYPER)
     hyper.update(over)
+    hyper.pop("algorithm", None)
     act = hyper.pop("value_hidden_activation", "gelu")
     assert hyper.pop("policy_hidden_activation", act) == act
     cnn = "conv_type" in cfg
     std_type = hyper.pop("policy_std_type", "mlp_shared")
-    if std_type != "mlp_shared":
+    if v1:
+        orc = v1_from_config(cfg, synth.make_weights_v1(cfg), hidden_activation=act, **hyper)
+    elif std_type != "mlp_shared":
         orc = std_from_config(cfg, synth.make_weights_std(cfg, std_type), std_type, hidden_activation=act, **hyper)
     elif cnn:
         orc = cnn_from_config(cfg, synth.make_cnn_weights(cfg), hidden_activation=act, **hyper)
@@ -50,7 +55,7 @@ def test_oracle_matches_reference(golden_dir, name):
     trainable = [str(n) for n in z["trainable_names"]]
     for it in range(steps):
         tb = orc.update(make_batch(cfg, batch, it), synth.make_noise(cfg, batch, it), it)
-        got = np.array([tb[k] for k in TB_KEYS])
+        got = np.array([tb[k] for k in tb_keys])
         # same ATen ops in the same order: expect (near) bitwise agreement
         np.testing.assert_allclose(got, z["tb"][it], rtol=2e-6, atol=1e-7, err_msg=f"{name} step {it}")
         sd = orc.state_dict()
