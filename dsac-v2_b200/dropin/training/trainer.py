@@ -108,9 +108,12 @@ class OffSerialTrainer:
 
     # ---- policy mirror ----------------------------------------------------------------
     def _find_policy_span(self):
-        n_q = sum(p.numel() for p in self.networks.q1.parameters())
+        """[lo, hi) of the policy inside the engine's flat parameter buffer: after the critics (q1, q2 of DSAC-T; the
+        single q of DSAC_V1), before log_alpha."""
+        critics = [n for n in ("q1", "q2", "q") if hasattr(self.networks, n)]
+        lo = sum(p.numel() for n in critics for p in getattr(self.networks, n).parameters())
         n_pi = sum(p.numel() for p in self.networks.policy.parameters())
-        return 2 * n_q, 2 * n_q + n_pi
+        return lo, lo + n_pi
 
     def refresh_policy_mirror(self):
         """Copy the current policy weights GPU -> pinned host -> the CPU module sampler/evaluator use."""

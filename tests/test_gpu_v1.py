@@ -119,3 +119,58 @@ def test_v1_dropin_local_update(golden_dir):
     assert set(V1_TB_KEYS) <= set(tb) and all(np.isfinite(tb[k]) for k in V1_TB_KEYS)
     with pytest.raises(NotImplementedError):
         alg.get_remote_update_info({}, 0)
+
+
+@pytest.mark.parametrize("variant", ["DSAC_V1", "mlp_separated", "parameter"])
+def test_trainer_loop_on_the_head_wise_engine(tmp_path, variant):
+    """The drop-in `OffSerialTrainer` (device replay ring, policy mirror for the CPU sampler) around the head-wise engine:
+    DSAC_V1 and DSAC-T with the policy's other std types."""
+    import dsac_v1
+    import dsac_v2
+    from training.replay_buffer import ReplayBuffer
+    from training.trainer import create_trainer
+    cfg = synth.CONFIGS["tiny"]
+    mod, over = (dsac_v1, {"algorithm": "DSAC_V1"}) if variant == "DSAC_V1" else (dsac_v2, {"policy_std_type": variant})
+    kw = synth.reference_kwargs(cfg, replay_batch_size=32, **over)
+    kw = dict(kw, buffer_max_size=1000, additional_info={}, buffer_name="replay_buffer", buffer_warm_size=100, max_iteration=12,
+              log_save_interval=5, apprfunc_save_interval=10, eval_interval=6, save_folder=str(tmp_path), ini_network_dir=None,
+              use_gpu=True, dsact_tensorboard=False)
+    alg = (mod.DSAC_V1 if variant == "DSAC_V1" else mod.DSAC_V2)(**kw)
+
+    class Sampler:
+        def __init__(self):
+            self.networks = mod.ApproxContainer(**kw)
+            self.n, self.g = 0, np.random.default_rng(0)
+            self.obs = self.g.standard_normal(cfg["obs_dim"]).astype(np.float32)
+
+        def sample(self):
+            out = []
+            for _ in range(20):
+                logits = self.networks.policy(torch.from_numpy(self.obs[None]))
+                act, logp = self.networks.create_action_distributions(logits).sample()
+                nxt = (0.9 * self.obs + 0.1 * self.g.standard_normal(cfg["obs_dim"])).astype(np.float32)
+                out.append((self.obs.copy(), {}, act.detach()[0].numpy(), float(-np.abs(nxt).mean()), nxt.copy(), False, logp.detach()[0].numpy(), {}))
+                self.obs = nxt
+            self.n += 20
+            return out, {}
+
+        def get_total_sample_number(self):
+            return self.n
+
+    class Evaluator:
+        networks, calls = None, 0
+
+        def run_evaluation(self, it):
+            self.calls += 1
+            return 0.0
+
+    sampler, evaluator = Sampler(), Evaluator()
+    trainer = create_trainer(alg, sampler, ReplayBuffer(**kw), evaluator, **kw)
+    first = next(iter(alg.networks.policy.parameters())).detach().clone()
+    trainer.train()
+    assert trainer.iteration == 12 and evaluator.calls == 2
+    now = next(iter(alg.networks.policy.parameters())).detach()
+    assert not torch.equal(first, now)
+    trainer.refresh_policy_mirror()   # the CPU mirror the sampler acts with tracks the trained GPU policy
+    torch.testing.assert_close(next(iter(sampler.networks.policy.parameters())).detach(), now.cpu(), rtol=0, atol=0)
+    assert all(np.isfinite(float(v)) for v in trainer.last_tb.values())

@@ -15,4 +15,4 @@ python tools/sweep.py --modes bf16x3,fp32 --batches 256,4096,65536 > gpurun_out/
 python tools/bench_cnn.py --cpu > gpurun_out/bench_cnn.json 2> gpurun_out/bench_cnn.err
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_cnn.csv \
   python tools/bench_cnn.py --steps 1 --warmup 1 > gpurun_out/ncu3.log 2>&1
-tail -2 gpurun_out/ncu1.log gpurun_out/ncu2.log gpurun_out/ncu3.log
+tail -n 2 gpurun_out/ncu1.log gpurun_out/ncu2.log gpurun_out/ncu3.log
