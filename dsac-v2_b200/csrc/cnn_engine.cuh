@@ -4,6 +4,10 @@
 // stack (conv.cuh) and the two-head wiring (separate `mean` and `log_std` MLPs per network, their outputs packed into the
 // [B,2] / [B,2A] arrays the loss kernels read, by strided GEMM outputs).
 //
+// The same wiring without an encoder (n_conv = 0), with one two-output head per critic (q_heads = 1), with the policy as one
+// head / two heads / mean head + learnable log_std row (pi_std) serves the MLP approximators whose variants the tcgen05
+// engine does not implement (policy std_type mlp_separated / parameter), and DSAC_V1 (v1_step.cuh).
+//
 // One eager sequence of launches per step (no graph capture yet):
 //   conv forwards: pi(s), pi'(s'), Q1/Q2 features of s (shared by the (s,a) and (s,a~) passes), Q1'/Q2' features of s'
 //   heads: pi, pi' -> sample -> Q_k(s,a), Q'_k(s',a'), mean head of Q_k(s,a~) -> loss -> head backward (critics: both

@@ -784,20 +784,32 @@ static unsigned long long dp_timeout_ns() {
 }
 // two-shot gradient exchange (dp_peer.cuh) from 6 ranks up (measured, profiles/r2_scaling_8gpu_box.txt: one-shot is 5 % faster
 // at 4 ranks, two-shot 0.6 % faster at 8); DSACT_DP_TWO_SHOT=0/1 overrides
+// DSACT_DP_SPLIT=1: the critics' part of the gradient exchange and of the update on the side branch, beside the policy
+// backward (SURVEY.md 8e's overlap).  Validated (replicas bit-identical, tests green in both exchange variants) but not
+// faster: 2 ranks one-shot 8637 / 8498 vs 8517 / 8505 steps/s, two-shot 7853 vs 8210 (profiles/r2_ab_dp_split.txt) — the
+// data-parallel overhead is barrier skew and launch count, which a second exchange adds to.  Default: one exchange.
+static bool dp_split_enabled() {
+  static const bool on = getenv("DSACT_DP_SPLIT") && getenv("DSACT_DP_SPLIT")[0] == '1';
+  return on;
+}
 static bool dp_two_shot(const dsact_handle* h) {
   static const char* e = getenv("DSACT_DP_TWO_SHOT");
   if (e && (e[0] == '0' || e[0] == '1')) return e[0] == '1';
   return h->dp.world >= 6;
 }
 static long long dp_npad(const dsact_handle* h) { return (2 * h->q.n + h->pi.n + 1 + 3) / 4 * 4; }
-static void enqueue_dp_reduce_scatter(dsact_handle* h, Ctx& c) {
-  const long long groups = dp_npad(h) / 4, per = (groups + h->dp.world - 1) / h->dp.world;
+// `part`: 0 = the whole buffer, 1 = the critics' groups [0, n_q2 / 4) (kind-4 flags), 2 = the rest (kind-2 flags)
+static void enqueue_dp_reduce_scatter(dsact_handle* h, Ctx& c, int part = 0) {
+  const long long g_all = dp_npad(h) / 4, g_q = (2 * h->q.n) / 4;
+  const long long G0 = part == 2 ? g_q : 0, G1 = part == 1 ? g_q : g_all;
+  const long long groups = G1 - G0, per = (groups + h->dp.world - 1) / h->dp.world;
   DpSlice sl;
-  sl.g_lo = per * h->dp.rank;
-  sl.g_hi = sl.g_lo + per < groups ? sl.g_lo + per : groups;
-  if (sl.g_lo > groups) sl.g_lo = groups;
+  sl.g_lo = G0 + per * h->dp.rank;
+  sl.g_hi = sl.g_lo + per < G1 ? sl.g_lo + per : G1;
+  if (sl.g_lo > G1) sl.g_lo = G1;
   sl.red_off = DP_GRADS_OFF + dp_npad(h);
-  sl.ticket = reinterpret_cast<int*>(h->dp_buf) + 3 * 16;   // header word 48: block ticket of this kernel
+  sl.ticket = reinterpret_cast<int*>(h->dp_buf) + DP_TICKET + (part == 1 ? 1 : 0);   // block ticket of this launch
+  sl.flag_kind = part == 1 ? 4 : 2;
   int blocks = (int)((per + 255) / 256); if (blocks < 1) blocks = 1; if (blocks > 2 * h->num_sms) blocks = 2 * h->num_sms;
   launch_k(dp_reduce_scatter_kernel, blocks, 256, 0, c, h->dp, sl, (const float*)h->buf.state);
   c.done();
@@ -956,7 +968,7 @@ static void enqueue_apply(dsact_handle* h, Ctx& c, bool reduce_slabs, bool dp, c
 // `early_apply` (single-GPU fused steps with the folded tail): update the critics on the side branch as soon as their
 // weight gradients are complete, beside the policy backward; the caller's enqueue_apply then does the rest.
 static void enqueue_phase2(dsact_handle* h, const dsact_batch& bt, int64_t global_batch, Ctx& c, int reduce_mode = REDUCE_INPLACE,
-                           bool fold_tail = false, const TailArgs* early_apply = nullptr) {
+                           bool fold_tail = false, const TailArgs* early_apply = nullptr, bool dp_early = false) {
   const bool defer_reduce = reduce_mode != REDUCE_INPLACE;
   const dsact_config& cf = h->cfg;
   const Net &q = h->q, &pi = h->pi;
@@ -1057,7 +1069,18 @@ static void enqueue_phase2(dsact_handle* h, const dsact_batch& bt, int64_t globa
       const int chain_ctas = (B + TC_BM - 1) / TC_BM;
       const int cap = h->num_sms - chain_ctas;
       launch_group(h, gw, V_WGRAD, cs, cap >= h->num_sms / 2 ? cap : 0);
-      if (early_apply) {   // Adam + Polyak of both critics beside the policy backward: every critic gradient is final here
+      if (early_apply && dp_early) {   // data parallel: the critics' blocks are exchanged and applied here, beside the policy backward
+        const long long nq = (2 * q.n) / 4 * 4;   // whole float4 groups of the critics' span
+        int blocks = (int)((nq / 4 + 255) / 256); if (blocks > 4 * h->num_sms) blocks = 4 * h->num_sms; if (blocks < 1) blocks = 1;
+        TailArgs none; memset(&none, 0, sizeof(none));
+        launch_k(dp_grad_fold_kernel, blocks, 256, 0, cs, h->dp_buf + DP_GRADS_OFF, (const float*)G_, (const float*)(W + ar.slabs), nq,
+                 ar.nslabs, (long long)ar.slab_stride, (const float*)h->buf.state, none);
+        cs.done();
+        enqueue_dp_exchange(h, 3, cs);
+        if (dp_two_shot(h)) enqueue_dp_reduce_scatter(h, cs, 1);
+        enqueue_apply(h, cs, false, true, early_apply, 1);
+        h->apply_early = true;
+      } else if (early_apply) {   // Adam + Polyak of both critics beside the policy backward: every critic gradient is final here
         enqueue_apply(h, cs, true, false, early_apply, 1);
         h->apply_early = true;
       }
@@ -1115,9 +1138,10 @@ static void enqueue_phase2(dsact_handle* h, const dsact_batch& bt, int64_t globa
     c.done();
   }
   if (reduce_mode == REDUCE_DP) {  // local total (bias gradients + slabs + log_alpha) -> this rank's block of the exchange buffer
-    const long long n = 2 * q.n + pi.n + 1;
+    const long long lo = h->apply_early ? (2 * q.n) / 4 * 4 : 0;   // the critics' groups went out on the side branch
+    const long long n = 2 * q.n + pi.n + 1 - lo;
     int blocks = (int)((n / 4 + 255) / 256); if (blocks > 4 * h->num_sms) blocks = 4 * h->num_sms; if (blocks < 1) blocks = 1;
-    launch_k(dp_grad_fold_kernel, blocks, 256, 0, c, h->dp_buf + DP_GRADS_OFF, (const float*)G_, (const float*)(tc ? W + ar.slabs : G_), n,
+    launch_k(dp_grad_fold_kernel, blocks, 256, 0, c, h->dp_buf + DP_GRADS_OFF + lo, (const float*)G_ + lo, (const float*)(tc ? W + ar.slabs : G_) + lo, n,
              tc ? ar.nslabs : 0, (long long)(tc ? ar.slab_stride : 4), (const float*)h->buf.state, tail_args(h, global_batch, B, fold_tail));
     c.done();
   }
@@ -1150,7 +1174,8 @@ static void enqueue_apply(dsact_handle* h, Ctx& c, bool reduce_slabs = false, bo
   a.dp_world = 0;
   a.dp_own = nullptr; a.dp_wait_world = 0; a.dp_timeout_ns = dp_timeout_ns();
   for (int r = 0; r < 8; ++r) a.dp_grads[r] = nullptr;
-  if (dp && dp_two_shot(h)) {   // the reduced block in this rank's own memory, once every rank's kind-2 flag is here
+  a.dp_wait_kind = part == 1 ? 4 : 2;
+  if (dp && dp_two_shot(h)) {   // the reduced block in this rank's own memory, once every rank's kind-2 (kind-4) flag is here
     a.dp_world = 1;
     a.dp_grads[0] = h->dp_buf + DP_GRADS_OFF + dp_npad(h);
     a.dp_own = h->dp_buf; a.dp_wait_world = h->dp.world;
@@ -1740,9 +1765,11 @@ int dsact_dp_step(dsact_handle* h, const dsact_batch* batch, const dsact_noise* 
   rc = run(h, (cudaStream_t)stream, key, [&](Ctx& c) {
     enqueue_phase1(h, bt, np, c, imaged, false, true);
     const TailArgs ta = tail_args(h, global_batch, bt.batch, fold_tail_enabled());
-    enqueue_phase2(h, bt, global_batch, c, REDUCE_DP, ta.enabled);
+    const bool early = ta.enabled && h->fused() && slabs_foldable(h) && dp_split_enabled();
+    enqueue_phase2(h, bt, global_batch, c, REDUCE_DP, ta.enabled, early ? &ta : nullptr, true);
+    const bool split = h->apply_early;   // the critics' part went out (and was applied) beside the policy backward
     enqueue_dp_exchange(h, 1, c);
-    if (dp_two_shot(h)) enqueue_dp_reduce_scatter(h, c);
+    if (dp_two_shot(h)) enqueue_dp_reduce_scatter(h, c, split ? 2 : 0);
     enqueue_apply(h, c, false, true, &ta);
   });
   if (rc) return rc;
@@ -1773,9 +1800,11 @@ int dsact_dp_replay_step(dsact_handle* h, int32_t batch, int64_t size, const int
     if (!idx && np) { launch_k(rng_advance_kernel, 1, 32, 0, c, h->buf.state); c.done(); }
     enqueue_phase1(h, bt, np, c, true, forked, true);
     const TailArgs ta = tail_args(h, global_batch, bt.batch, fold_tail_enabled());
-    enqueue_phase2(h, bt, global_batch, c, REDUCE_DP, ta.enabled);
+    const bool early = ta.enabled && h->fused() && slabs_foldable(h) && dp_split_enabled();
+    enqueue_phase2(h, bt, global_batch, c, REDUCE_DP, ta.enabled, early ? &ta : nullptr, true);
+    const bool split = h->apply_early;
     enqueue_dp_exchange(h, 1, c);
-    if (dp_two_shot(h)) enqueue_dp_reduce_scatter(h, c);
+    if (dp_two_shot(h)) enqueue_dp_reduce_scatter(h, c, split ? 2 : 0);
     enqueue_apply(h, c, false, true, &ta);
   });
   if (rc) return rc;

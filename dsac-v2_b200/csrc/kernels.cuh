@@ -600,6 +600,7 @@ struct ApplyArgs {
   // kind-2 flags in `dp_own` first
   const float* dp_own;
   int dp_wait_world;
+  int dp_wait_kind;   // 2, or 4 for the critics' part
   unsigned long long dp_timeout_ns;
   // 4-element groups [g_lo, g_hi) of the flat buffers this launch updates; `finish`: its last block closes the step
   // (counters, EMA commit, next Adam scalars).  A step may update the critics' span early, beside the policy backward,
@@ -607,7 +608,7 @@ struct ApplyArgs {
   int64_t g_lo, g_hi;
   int finish;
 };
-__device__ __forceinline__ bool dp_wait_reduced(const float* own_buf, int world, uint32_t epoch, unsigned long long timeout_ns);
+__device__ __forceinline__ bool dp_wait_reduced(const float* own_buf, int world, uint32_t epoch, unsigned long long timeout_ns, int kind);
 // torch.optim.Adam single-tensor step (amsgrad / weight decay off)
 __device__ __forceinline__ float adam_update(float w, float g, float& m, float& v, float step_size, float bc2_sqrt,
                                              float omb1, float b2, float omb2, float eps) {
@@ -635,7 +636,7 @@ __global__ void __launch_bounds__(256, 4) apply_kernel(const __grid_constant__ A
     adam_scalars(sti, a.hy, sh);
   }
   if (MODE == 2 && a.dp_wait_world > 0 && threadIdx.x == 32) {   // two-shot exchange: the reduced block is complete
-    if (!dp_wait_reduced(a.dp_own, a.dp_wait_world, (uint32_t)sti[ST_DP_EPOCH], a.dp_timeout_ns))
+    if (!dp_wait_reduced(a.dp_own, a.dp_wait_world, (uint32_t)sti[ST_DP_EPOCH], a.dp_timeout_ns, a.dp_wait_kind))
       reinterpret_cast<int*>(a.state)[ST_DP_ERR] = 1 + a.dp_wait_world;   // (no single rank to name)
   }
   __syncthreads();

@@ -219,8 +219,12 @@ int dsact_dp_replay_step(dsact_handle *h, int32_t batch, int64_t size, const int
  * (Conv2d + ReLU per layer, no padding) followed by two separate MLP heads `mean` and `log_std` on the flattened
  * feature (the critics append the action to it).  Flat layout per network, in state_dict order: conv.{0,2,..}.weight
  * [Cout,Cin,k,k] / .bias, mean.{0,2,..}.weight / .bias, log_std.{0,2,..}.weight / .bias; params = [q1|q2|policy|log_alpha].
- * First CUDA path of this configuration: fp32 direct convolutions + the fp32 grouped GEMMs for the heads, eager launches.
- * dsact_cnn_step = DSAC_V2.local_update(data, iteration) with data["obs"] / ["obs2"] of shape [B, C, H, W] (contiguous). */
+ * fp32 direct convolutions + the fp32 grouped GEMMs for the heads, eager launches.
+ * dsact_cnn_step = DSAC_V2.local_update(data, iteration) with data["obs"] / ["obs2"] of shape [B, C, H, W] (contiguous).
+ * The same head-wise engine also carries the variants of the reference that keep network outputs in separate heads or
+ * need another loss, all in fp32: no encoder (n_conv = 0: the observation vector feeds the heads), one two-output head per
+ * critic (q_heads = 1, networks/mlp.py), the policy's std types (pi_std), the plain Gaussian action distribution
+ * (act_dist) and DSAC_V1 (algo = 1: ONE critic, flat layout [q | policy | log_alpha], dsac_v1.py). */
 #define DSACT_MAX_CONV 8
 typedef struct dsact_cnn_config {
   int32_t abi_version;
