@@ -695,6 +695,10 @@ static void enqueue_noise(dsact_handle* h, int B, Ctx& c) {
   launch_k(noise_kernel, blocks, 256, 0, c, W + ar.eps1, W + ar.eps2, W + ar.z3, W + ar.z4, B, A, h->seed, h->buf.state);
   c.done();
 }
+static bool prologue_merged() {   // DSACT_PROLOGUE_MERGE=0: separate clear / image / noise launches (A/B aid)
+  static const bool off = getenv("DSACT_PROLOGUE_MERGE") && getenv("DSACT_PROLOGUE_MERGE")[0] == '0';
+  return !off;
+}
 static void enqueue_prologue(dsact_handle* h, const dsact_batch& bt, const dsact_noise* nz, Ctx& c, bool inputs_imaged,
                              bool with_noise = true) {
   const dsact_config& cf = h->cfg;
@@ -711,8 +715,7 @@ static void enqueue_prologue(dsact_handle* h, const dsact_batch& bt, const dsact
   const long long n_grads = 2 * q.n + pi.n + 1;
   int zero_blocks = (int)((n_grads / 4 + 255) / 256); if (zero_blocks > 2 * h->num_sms) zero_blocks = 2 * h->num_sms; if (zero_blocks < 1) zero_blocks = 1;
   const bool want_noise = !nz && with_noise;
-  static const bool merge_off = getenv("DSACT_PROLOGUE_MERGE") && getenv("DSACT_PROLOGUE_MERGE")[0] == '0';
-  const bool merged = tc && !merge_off;   // tcgen05 modes: clears + images + noise as one launch
+  const bool merged = tc && prologue_merged();   // tcgen05 modes: clears + images + noise as one launch
   if (!merged) { launch_k(begin_step_kernel, zero_blocks, 256, 0, c, h->buf.state, h->buf.grads, n_grads); c.done(); }
 
   if (tc) {  // refresh the weight images (the caller may have written params/targets through its views) + inputs
@@ -745,6 +748,7 @@ static void enqueue_prologue(dsact_handle* h, const dsact_batch& bt, const dsact
       memset(&pa, 0, sizeof(pa));
       pa.zero_blocks = zero_blocks;
       pa.state = h->buf.state; pa.grads = h->buf.grads; pa.n_grads = n_grads;
+      pa.hy = AdamHyper{cf.lr_q, cf.lr_pi, cf.lr_alpha, cf.adam_beta1, cf.adam_beta2};
       if (want_noise) {
         const int total = (B * A + 1) / 2 * 2 + (B + 1) / 2 * 2;
         pa.noise_blocks = (total / 2 + 255) / 256; if (pa.noise_blocks < 1) pa.noise_blocks = 1;
@@ -1189,6 +1193,7 @@ static void enqueue_apply(dsact_handle* h, Ctx& c, bool reduce_slabs = false, bo
   if (reduce_slabs && !dp && slabs_foldable(h)) { a.slabs = h->W() + h->ar.slabs; a.nslabs = h->ar.nslabs; a.slab_stride = h->ar.slab_stride; }
   const int64_t g_all = (a.n_all + 3) / 4, g_q = a.n_q2 / 4;   // a group straddling the critic / policy boundary goes with part 2
   a.g_lo = part == 2 ? g_q : 0; a.g_hi = part == 1 ? g_q : g_all; a.finish = part == 1 ? 0 : 1;
+  a.next_scalars = (h->tc() && prologue_merged()) ? 0 : 1;   // the merged prologue of every step forms them itself
   int blocks = (int)((a.g_hi - a.g_lo + 255) / 256);   // one 4-element group per thread
   if (blocks > 8 * h->num_sms) blocks = 8 * h->num_sms;
   if (blocks < 1) blocks = 1;

@@ -678,13 +678,17 @@ struct PrologueArgs {
   float *eps1, *eps2, *z3, *z4;
   int B, A;
   unsigned long long seed;
+  AdamHyper hy;   // this step's Adam scalars are formed here (last block of the clear range), see adam_scalars_stamp
 };
 __global__ void step_prologue_kernel(const __grid_constant__ ImgGroup g, const __grid_constant__ PrologueArgs p) {
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int b = (int)blockIdx.x;
   if (b < p.img_blocks) image_body(g, b, p.img_blocks);
-  else if (b < p.img_blocks + p.zero_blocks) begin_step_body(p.state, p.grads, p.n_grads, b - p.img_blocks, p.zero_blocks);
+  else if (b < p.img_blocks + p.zero_blocks) {
+    if (b == p.img_blocks + p.zero_blocks - 1) adam_scalars_stamp(p.state, p.hy);
+    begin_step_body(p.state, p.grads, p.n_grads, b - p.img_blocks, p.zero_blocks);
+  }
   else noise_body(p.eps1, p.eps2, p.z3, p.z4, p.B, p.A, p.seed, p.state, b - p.img_blocks - p.zero_blocks, p.noise_blocks);
 }
 

@@ -565,6 +565,23 @@ __device__ __forceinline__ void adam_scalars(const int* sti, const AdamHyper& a,
   out[3] = (float)(a.lr_alpha / bc1p);
   out[4] = (float)sqrt(1.0 - pow(a.b2, tp));
 }
+constexpr int ADAM_SC_MAGIC = 0x5ca1ab1e;   // state[ST_ADAM_SC + 7]: slots +0..4 hold the scalars for the counters in +5, +6
+// The same five scalars by four lanes of one warp (one double-precision pow each: a single thread needs ~5 us for them),
+// stamped with the counters they belong to.  Called by the step prologue: off the critical path, the counters are final
+// there (the previous step's apply advanced them), and apply_kernel finds the stamp.
+__device__ __forceinline__ void adam_scalars_stamp(float* state, const AdamHyper& a) {
+  const int t = threadIdx.x;
+  int* sti = reinterpret_cast<int*>(state);
+  if (t < 4) {
+    const double step = ((t & 1) ? sti[ST_ADAM_PI] : sti[ST_ADAM_Q]) + 1;
+    const double pw = pow(t < 2 ? a.b1 : a.b2, step);
+    if (t == 0) state[ST_ADAM_SC + 0] = (float)(a.lr_q / (1.0 - pw));
+    else if (t == 1) { state[ST_ADAM_SC + 2] = (float)(a.lr_pi / (1.0 - pw)); state[ST_ADAM_SC + 3] = (float)(a.lr_alpha / (1.0 - pw)); }
+    else if (t == 2) state[ST_ADAM_SC + 1] = (float)sqrt(1.0 - pw);
+    else state[ST_ADAM_SC + 4] = (float)sqrt(1.0 - pw);
+    if (t == 0) { sti[ST_ADAM_SC + 5] = sti[ST_ADAM_Q]; sti[ST_ADAM_SC + 6] = sti[ST_ADAM_PI]; sti[ST_ADAM_SC + 7] = ADAM_SC_MAGIC; }
+  }
+}
 // The end-of-backward bookkeeping of a step (phase2_tail_kernel below) folded into the kernels that follow it in the
 // single-call steps: the log_alpha gradient is formed where the gradient element is consumed, the EMA / temperature
 // commit and the NEXT step's Adam scalars are written by the last block of apply_kernel.
@@ -577,7 +594,6 @@ struct TailArgs {
 __device__ __forceinline__ float tail_grad_log_alpha(const float* state, const TailArgs& t) {
   return -(state[ST_ACC + ACC_LOGP] + (float)t.rows * t.target_entropy) * t.sc.inv_global_batch;
 }
-constexpr int ADAM_SC_MAGIC = 0x5ca1ab1e;   // state[ST_ADAM_SC + 7]: slots +0..4 hold the scalars for the counters in +5, +6
 struct ApplyArgs {
   float *params, *targets, *grads, *m, *v;
   TailArgs tail;
@@ -607,6 +623,7 @@ struct ApplyArgs {
   // with finish = 0, and the rest afterwards with finish = 1.
   int64_t g_lo, g_hi;
   int finish;
+  int next_scalars;   // the finishing block also precomputes the NEXT step's Adam scalars (steps whose prologue does not)
 };
 __device__ __forceinline__ bool dp_wait_reduced(const float* own_buf, int world, uint32_t epoch, unsigned long long timeout_ns, int kind);
 // torch.optim.Adam single-tensor step (amsgrad / weight decay off)
@@ -763,7 +780,7 @@ __global__ void __launch_bounds__(256, 4) apply_kernel(const __grid_constant__ A
       if (delayed) stw[ST_ADAM_PI] += 1;
       stw[ST_ITER] += 1;
       stw[ST_TICKET] = 0;
-      if (a.tail.enabled) {   // the next step's Adam scalars, stamped with the counters they belong to
+      if (a.tail.enabled && a.next_scalars) {   // the next step's Adam scalars, stamped with the counters they belong to
         adam_scalars(stw, a.hy, a.state + ST_ADAM_SC);
         stw[ST_ADAM_SC + 5] = stw[ST_ADAM_Q];
         stw[ST_ADAM_SC + 6] = stw[ST_ADAM_PI];
