@@ -190,6 +190,23 @@ def time_oracle(cfg, batch, warm, max_steps, budget_s, ring_rows=100_000):
     return n / dt, n, dt
 
 
+def time_cnn_cpu_port(cfg, batch, host_batch, updates=3):
+    """CPU arm of tools/bench_cnn.py (BASELINE config 5): the oracle port of the CNN update on the host cores."""
+    import torch
+    from dsac_v2_b200 import synth
+    from oracle.dsact_oracle import cnn_from_config
+    torch.set_num_threads(min(32, os.cpu_count() or 4))
+    orc = cnn_from_config(cfg, synth.make_cnn_weights(cfg), **synth.HYPER)
+    nz = synth.make_noise(cfg, batch, 0)
+    orc.update(host_batch, nz, 0)
+    t0 = time.perf_counter()
+    for n in range(updates):
+        orc.update(host_batch, nz, n + 1)
+    dt = (time.perf_counter() - t0) / updates
+    return {"value": 1.0 / dt, "unit": "steps/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{updates} updates of batch {batch}, {cpu_model()}"}
+
+
 def time_cuda_eager(cfg, batch, dev, steps=60, warm=5, ring_rows=200_000):
     """The reference's arithmetic as eager PyTorch on THIS GPU: the oracle port with CUDA tensors issues the ATen ops the
     reference's dsac_v2.py issues (torch.distributions object churn aside); replay ring, index draw and noise on the device.

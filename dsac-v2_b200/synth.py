@@ -28,7 +28,7 @@ CONFIGS = {
 }
 
 # BASELINE.json config 5 (gym_carracingraw): conv encoder `type_2` + separate mean / log_std
-# heads.  Oracle-level only so far (oracle/dsact_oracle.py:OracleDSACTCNN, tests/golden/cnn_carracing_b4.npz).
+# heads (csrc/cnn_engine.cuh; oracle/dsact_oracle.py:OracleDSACTCNN, tests/golden/cnn_carracing_b4.npz).
 CNN_CONFIGS = {
     "carracing": dict(obs_dim=(3, 96, 96), act_dim=3, act_lim=1.0, conv_type="type_2"),
     # the reference's other encoder (networks/cnn.py:173-186: 8x8/4, 4x4/2, 3x3/1, heads 512-256) on a smaller image
@@ -208,7 +208,7 @@ def cnn_reference_kwargs(cfg: dict, **over) -> dict:
     return kw
 
 
-# ---- other policy std types (reference networks/mlp.py:42-72; SURVEY.md §8f rank 4, oracle-level only) ----------------
+# ---- other policy std types (reference networks/mlp.py:42-72) ---------------------------------
 def make_weights_std(cfg: dict, std_type: str, seed: int = 0) -> dict:
     """`make_weights` with the policy in the schema of `std_type`:
     "mlp_separated": `policy.mean.{0,2,..}` and `policy.log_std.{0,2,..}` (two MLPs ending in act_dim outputs),

@@ -55,18 +55,7 @@ out = {"metric": "DSAC-T gradient-steps/sec, CNN encoder (carracing type_2, 3x96
        "unit": "steps/s", "ms_per_step": ms, "steps": a.steps, "warmup": a.warmup, "dtype": "f32", "data": "synthetic",
        "config": {"workload": "gym_carracing shapes, conv(4,3,3,3,3,3)/(8..256) + mean/log_std heads [256,256,256], fp32 direct convolutions",
                   "batch": B}, "finite": bool(all(v == v for v in stats.values())), "clocks": clocks.summary()}
-if a.cpu:
-    from oracle.dsact_oracle import cnn_from_config
-    torch.set_num_threads(min(32, os.cpu_count() or 4))
-    orc = cnn_from_config(cfg, synth.make_cnn_weights(cfg), **synth.HYPER)
-    hb = {k: v.cpu().numpy() for k, v in data.items()}
-    nz = synth.make_noise(cfg, B, 0)
-    orc.update(hb, nz, 0)
-    t0 = time.perf_counter()
-    n = 0
-    while n < 3:
-        orc.update(hb, nz, n + 1); n += 1
-    dt = (time.perf_counter() - t0) / n
-    out["cpu_baseline"] = {"value": 1.0 / dt, "unit": "steps/s", "cores": torch.get_num_threads(), "kind": "port",
-                           "sample": f"{n} updates of batch {B}, {cpu_model()}"}
+if a.cpu:   # the CPU arm lives in bench.py (the one place outside tests/ and smoke() that may execute oracle/)
+    import bench
+    out["cpu_baseline"] = bench.time_cnn_cpu_port(cfg, B, {k: v.cpu().numpy() for k, v in data.items()})
 print(json.dumps(out))
