@@ -43,6 +43,8 @@ class ApproxContainer(nn.Module):
         if q_args["apprfunc"] != pi_args["apprfunc"]:
             raise NotImplementedError("value and policy approximators must be of the same type (both MLP or both CNN)")
         cnn = q_args["apprfunc"] == "CNN"
+        if cnn:   # the engine's DSAC_V1 step is wired for encoders too, but only the MLP configuration is pinned to the reference
+            raise NotImplementedError("DSAC_V1 on the B200 engine: MLP approximators (the CNN configuration is not validated)")
         mod = _cnn if cnn else _mlp
         q_cls, pi_cls = getattr(mod, q_args["name"], None), getattr(mod, pi_args["name"], None)
         if q_cls is None or pi_cls is None:

@@ -71,3 +71,43 @@ def test_no_cpu_fallback():
     alg = dsac_v2.DSAC_V2(**synth.reference_kwargs(synth.CONFIGS["tiny"]))
     with pytest.raises(_lib.DsactError):
         alg.local_update({"obs": torch.zeros(4, 5)}, 0)
+
+
+@pytest.mark.parametrize("variant", ["cnn_type2", "cnn_type1", "mlp_separated", "parameter", "v1_mlp"])
+def test_head_wise_layouts_match_the_dropin_modules(variant):
+    """The flat layout the head-wise engine reports (`dsact_cnn_query_layout`, no GPU needed) and the state_dict schema
+    `CnnEngine._schema` walks are those of the drop-in modules' own parameter order, for every variant it serves."""
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path[:0] = [os.path.join(root, "dsac-v2_b200", "dropin")]
+    import dsac_v1
+    import dsac_v2
+    from dsac_v2_b200.engine_cnn import CnnEngine
+    from dsac_v2_b200._lib import Layout
+    if variant.startswith("cnn"):
+        cfg = synth.CNN_CONFIGS["small_t1" if variant != "cnn_type2" else "carracing"]
+        kw = synth.cnn_reference_kwargs(cfg, replay_batch_size=4)
+    else:
+        cfg = synth.CONFIGS["ragged"]
+        over = {"algorithm": "DSAC_V1"} if variant == "v1_mlp" else {"policy_std_type": variant}
+        kw = synth.reference_kwargs(cfg, replay_batch_size=4, **over)
+    net = (dsac_v1 if variant.startswith("v1") else dsac_v2).ApproxContainer(**kw)
+    make = net._make if variant.startswith("v1") else None
+    if make is None:
+        from dsac_v2_b200.engine_cnn import make_cnn_config, make_heads_config
+        make = make_heads_config if net._heads_std else make_cnn_config
+    c = make(max_batch=4, **net._cfg_args)
+    lay = Layout()
+    assert _lib.load().dsact_cnn_query_layout(C.byref(c), C.byref(lay)) == 0
+    train, targ = net._flat_groups()
+    assert lay.n_params == sum(p.numel() for p in train) and lay.n_targets == sum(p.numel() for p in targ)
+
+    class Probe:   # _schema only reads the config
+        cfg = c
+    schema, n = CnnEngine._schema(Probe)
+    assert n == lay.n_targets
+    names = [k for k, p in net.named_parameters() if p.requires_grad and k != "log_alpha"]
+    assert [e[0] for e in schema] == names
+    sizes = dict(net.named_parameters())
+    assert all(tuple(sizes[e[0]].shape) == tuple(e[4]) and sizes[e[0]].numel() == e[3] for e in schema)
+    assert [e[1] for e in schema] == [k for k, p in net.named_parameters() if not p.requires_grad]
