@@ -51,3 +51,30 @@ def test_device_seed_mixes_run_seed_and_rank(monkeypatch):
             assert 0 <= s < 2 ** 64 and s == net.device_seed()
             seeds[(seed, rank)] = s
     assert len(set(seeds.values())) == len(seeds)
+
+
+def test_policy_span_of_the_trainer_covers_v2_and_v1_containers():
+    """`OffSerialTrainer._find_policy_span` (the slice of the flat parameter buffer mirrored to the CPU sampler): after both
+    critics of DSAC-T, after the single critic of DSAC_V1, for every policy std type."""
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path[:0] = [os.path.join(root, "dsac-v2_b200", "dropin")]
+    import dsac_v1
+    import dsac_v2
+    from dsac_v2_b200 import synth
+    from training.trainer import OffSerialTrainer
+    cfg = synth.CONFIGS["ragged"]
+    for mod, over in ((dsac_v2, {}), (dsac_v2, {"policy_std_type": "mlp_separated"}), (dsac_v2, {"policy_std_type": "parameter"}),
+                      (dsac_v1, {"algorithm": "DSAC_V1"})):
+        net = mod.ApproxContainer(**synth.reference_kwargs(cfg, replay_batch_size=8, **over))
+
+        class Probe:
+            networks = net
+        lo, hi = OffSerialTrainer._find_policy_span(Probe)
+        train, _ = net._flat_groups()
+        flat_names = []
+        for name in (("q1", "q2") if hasattr(net, "q1") else ("q",)) + ("policy",):
+            flat_names += [name] * sum(p.numel() for p in getattr(net, name).parameters())
+        assert flat_names[lo:hi] == ["policy"] * (hi - lo) and "policy" not in flat_names[:lo]
+        assert hi == sum(p.numel() for p in train) - 1     # log_alpha is the last element
