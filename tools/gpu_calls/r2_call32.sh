@@ -1,0 +1,3 @@
+#!/bin/bash
+timeout 200 python -m pytest tests/ -m gpu -x -q 2>&1 | grep -v "Warning\|^$\|Docs\|return float" | tail -4
+timeout 60 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -4
