@@ -45,6 +45,8 @@ class ApproxContainer(nn.Module):
         cnn = q_args["apprfunc"] == "CNN"
         if cnn:   # the engine's DSAC_V1 step is wired for encoders too, but only the MLP configuration is pinned to the reference
             raise NotImplementedError("DSAC_V1 on the B200 engine: MLP approximators (the CNN configuration is not validated)")
+        if pi_args["std_type"] != "mlp_shared":   # same reason: wired in the engine (pi_std 0 / 1 with algo = 1), no reference golden
+            raise NotImplementedError("DSAC_V1 on the B200 engine: policy std_type 'mlp_shared' (the reference's default for DSAC_V1)")
         mod = _cnn if cnn else _mlp
         q_cls, pi_cls = getattr(mod, q_args["name"], None), getattr(mod, pi_args["name"], None)
         if q_cls is None or pi_cls is None:
